@@ -1,0 +1,72 @@
+"""Scene and camera definitions shared by the golden generator and the tests.
+
+Everything is seeded and rebuilt identically on both sides, so the fixtures in ``tests/golden``
+only need to carry the reference's outputs.
+"""
+import datetime
+
+import numpy as np
+
+from glimpse_b200 import synthetic
+
+
+def camera_configs():
+    """Distortion cases of the reference's ``tests/test_camera.py:34-88`` on a map-scale camera,
+    plus a curvature/refraction case (``camera.py:1444-1449``)."""
+    base = dict(imgsz=(4288, 2848), f=(3700.0, 3690.0), c=(12.5, -8.25), xyz=(4.99e5, 6.77e6, 500.0),
+                viewdir=(60.0, -25.0, 1.5))
+    small = dict(imgsz=(100, 100), f=100.0, xyz=(1.0, 2.0, 3.0), viewdir=(10.0, 20.0, 30.0))
+    return {
+        "ideal": dict(base),
+        "k1": dict(base, k=(0.1, 0, 0, 0, 0, 0)),
+        "k1neg": dict(base, k=(-0.1, 0, 0, 0, 0, 0)),
+        "k123": dict(base, k=(0.05, -0.01, 0.001, 0, 0, 0)),
+        "k456": dict(base, k=(0, 0, 0, 0.002, 0.0005, -0.0001)),
+        "k6": dict(base, k=(0.1,) * 6),
+        "p": dict(base, p=(0.01, 0.01)),
+        "full": dict(base, k=synthetic.FULL_K, p=synthetic.FULL_P),
+        "full_corr": dict(base, k=synthetic.FULL_K, p=synthetic.FULL_P, correction=True),
+        "small_k1_extreme": dict(small, k=(2.0, 0, 0, 0, 0, 0)),
+        "small_k1_neg_extreme": dict(small, k=(-2.0, 0, 0, 0, 0, 0)),
+        "small_all": dict(small, k=(0.1,) * 6, p=(0.01, 0.01)),
+    }
+
+
+def add_second_observer(scene):
+    """Second station: same place, rolled 180 deg (image flipped both ways), RGB frames, radial-only
+    distortion, and images starting one frame later (staggered template start)."""
+    first = scene.observers[0]
+    frames, cams, dts = [], [], []
+    for t in range(1, len(first.frames)):
+        g = first.frames[t][::-1, ::-1]
+        rgb = np.stack([g, np.roll(g, 1, axis=1), np.roll(g, 1, axis=0)], axis=2)
+        frames.append(np.ascontiguousarray(rgb))
+        vec = first.cams[t].copy()
+        vec[3:6] = (0.0, -90.0, 180.0)
+        vec[18:20] = 0.0
+        cams.append(vec)
+        dts.append(first.datetimes[t])
+    scene.observers.append(synthetic.ObserverScene(frames, np.array(cams), dts, sigma=0.4))
+    return scene
+
+
+def track_cases():
+    return {
+        # config-1 shape, shrunk: 1 observer, Cartesian, full distortion
+        "track_c1": dict(
+            scene_kwargs=dict(seed=1, n_points=3, n_particles=300, n_frames=6, imgsz=(320, 240), margin_px=90),
+            seed=101,
+        ),
+        # config-3 shape, shrunk: 2 observers (RGB second, staggered), Cylindrical, dem_sigma > 0, covariances
+        "track_cyl2": dict(
+            scene_kwargs=dict(seed=3, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              kind="cylindrical", velocity_sigma=0.2),
+            seed=303, post=add_second_observer, return_covariances=True,
+        ),
+        # map-scale world coordinates + per-frame view-direction jitter
+        "track_jitter": dict(
+            scene_kwargs=dict(seed=5, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              jitter_deg=0.02, world_offset=(4.99e5, 6.77e6)),
+            seed=505,
+        ),
+    }
