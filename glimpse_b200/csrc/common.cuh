@@ -1,0 +1,122 @@
+// Shared device helpers: unfused IEEE arithmetic, warp/block reductions, cluster all-gather.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/glimpse_b200.h"
+
+namespace cg = cooperative_groups;
+
+#define GB_MAX_OBS 8
+#define GB_MAX_CLUSTER 8
+#define GB_XCH 36 /* doubles per CTA slot in the cluster exchange buffer */
+#define GB_MAX_BINS 1024
+
+// particle flag bits, in the order the reference would raise (tracker.py:106-119, observer.py:201,
+// raster.py:961-973)
+#define GB_F_VIEW_OOB 1u
+#define GB_F_NOT_VISIBLE 2u
+#define GB_F_NAN 4u
+#define GB_F_SAMPLE_OUTSIDE 8u
+#define GB_F_DEM_OOB 16u
+#define GB_F_WINDOW 32u
+#define GB_F_TEMPLATE 64u
+
+namespace gb {
+
+// NumPy evaluates element-wise expressions one rounded operation at a time; these keep nvcc from
+// contracting a*b+c into an FMA where bit-faithfulness to the reference is cheap to keep.
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double quo(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_xor(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += shfl_xor(v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmin(v, shfl_xor(v, d));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, shfl_xor(v, d));
+  return v;
+}
+
+// Fixed header at the start of dynamic shared memory.
+struct SmemHeader {
+  double xch[2][GB_MAX_CLUSTER][GB_XCH];  // cluster all-gather, double buffered by round parity
+  double red[32][GB_XCH];                 // per-warp partials of a block reduction
+  double bcast[GB_XCH];                   // block-wide broadcast values
+  double scan_warp[32];                   // warp totals of the block scan
+  double scan_carry;
+  double ref[6];                          // origin for the moment sums (parent particle 0)
+  int ibox[4];
+  int iflags[4];
+  gb_camera cam;
+  gb_motion motion;
+};
+
+struct ClusterCtx {
+  int rank;      // CTA rank within the cluster
+  int size;      // CTAs per point
+  int round;     // all-gather round counter (selects the exchange buffer)
+  SmemHeader* hdr;
+};
+
+// Block reduction of K per-thread doubles (OP 0: sum, 1: min); the result is left in
+// hdr->bcast[0..K), visible to all threads on return.  Maxima are reduced as minima of negatives.
+template <int K, int OP>
+__device__ __forceinline__ void block_reduce(double (&v)[K], SmemHeader* hdr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double x = OP == 0 ? warp_sum(v[k]) : warp_min(v[k]);
+    if (lane == 0) hdr->red[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    double x = hdr->red[0][k];
+    for (int w = 1; w < nwarp; ++w) {
+      const double y = hdr->red[w][k];
+      x = OP == 0 ? x + y : fmin(x, y);
+    }
+    hdr->bcast[k] = x;
+  }
+  __syncthreads();
+}
+
+// All-gather of hdr->bcast[0..K) across the CTAs of the cluster.  Returns the buffer
+// xch[buf][rank][k]; valid until the next-but-one all-gather.
+template <int K>
+__device__ __forceinline__ double (*cluster_allgather(ClusterCtx& cc))[GB_XCH] {
+  SmemHeader* hdr = cc.hdr;
+  const int buf = cc.round & 1;
+  cc.round++;
+  if (cc.size == 1) {
+    if (threadIdx.x < K) hdr->xch[buf][0][threadIdx.x] = hdr->bcast[threadIdx.x];
+    __syncthreads();
+    return hdr->xch[buf];
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  for (int idx = threadIdx.x; idx < K * cc.size; idx += blockDim.x) {
+    const int r = idx / K, k = idx - r * K;
+    double* remote = cluster.map_shared_rank(&hdr->xch[buf][cc.rank][k], r);
+    *remote = hdr->bcast[k];
+  }
+  cluster.sync();
+  return hdr->xch[buf];
+}
+
+}  // namespace gb

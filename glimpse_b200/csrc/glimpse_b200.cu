@@ -1,0 +1,1245 @@
+// glimpse_b200 — kernels and C ABI of the Tracker hot path (see include/glimpse_b200.h).
+//
+// One tracked point is owned by one thread-block cluster for one time step (k_step): the
+// cluster's CTAs split the point's particles, keep the evolved state, projected coordinates and
+// weights in shared memory, exchange the few cross-CTA scalars (bounding box, weight totals,
+// moments) through distributed shared memory, and stream the particle state in and out of HBM
+// exactly once (96 B per particle update).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "camera.cuh"
+#include "common.cuh"
+#include "motion.cuh"
+#include "tile.cuh"
+
+#define GB_THREADS 512
+#define GB_MAX_TEMPLATE 1024 /* template pixels handled by k_template */
+
+namespace gb {
+
+static thread_local char g_error[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_error, sizeof(g_error), fmt, detail);
+  return code;
+}
+#define GB_CUDA(expr)                                                               \
+  do {                                                                              \
+    cudaError_t err_ = (expr);                                                      \
+    if (err_ != cudaSuccess) return fail(GB_E_CUDA, #expr ": %s", cudaGetErrorString(err_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Kernel parameters
+// ---------------------------------------------------------------------------------------------
+struct StepParams {
+  int64_t P, N;
+  int T, O, S, t;
+  int tile_w, tile_h;
+  int cluster, n_local, particles_in_smem, tile_bytes;
+  int skip_evolve, viewshed, rng_mode, pad_;
+  uint64_t seed;
+  int64_t point_offset;
+  double tau, tau2;
+  int img[GB_MAX_OBS];       // global image index of each observer at time t, -1 = none
+  int tmpl_frame[GB_MAX_OBS]; // time index at which each observer's template is cut
+  double obs_scale[GB_MAX_OBS];
+  const gb_image* images;
+  const uint8_t* mask;
+  const int32_t* first;
+  const int32_t* last;
+  const gb_motion* motion;
+  const gb_surface* surfaces;
+  const double* init_normals;
+  const double* step_normals;
+  const double* uniforms;
+  double* state_a;
+  double* state_b;
+  double* weight_state;
+  double* scratch;
+  double* tmpl_tile;
+  double* tmpl_values;
+  double* tmpl_quantiles;
+  int32_t* tmpl_nvalues;
+  int32_t* tmpl_box;
+  double* tmpl_duv;
+  double* means;
+  double* sigmas;
+  double* covariances;
+  double* out_particles;
+  double* out_weights;
+  int32_t* status;
+  int32_t* status_time;
+  uint8_t* obs_flags;
+  int32_t* window_stats;
+  gb_stage_io io;
+};
+
+__device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
+
+__device__ __forceinline__ int status_from_flags(uint32_t f) {
+  if (f & GB_F_VIEW_OOB) return GB_ST_DEM_BOUNDS;
+  if (f & GB_F_NOT_VISIBLE) return GB_ST_NOT_VISIBLE;
+  if (f & GB_F_NAN) return GB_ST_NAN;
+  if (f & GB_F_TEMPLATE) return GB_ST_TEMPLATE_BOUNDS;
+  if (f & GB_F_WINDOW) return GB_ST_WINDOW_TOO_LARGE;
+  if (f & GB_F_SAMPLE_OUTSIDE) return GB_ST_SAMPLE_OUTSIDE;
+  if (f & GB_F_DEM_OOB) return GB_ST_DEM_BOUNDS;
+  return GB_ST_OK;
+}
+
+// tracker.py:106-119 for one particle
+__device__ __forceinline__ uint32_t test_particle(const StepParams& prm, const double (&s)[6]) {
+  uint32_t f = 0;
+  if (prm.viewshed >= 0) {
+    bool oob;
+    const double vis = surface_sample(prm.surfaces[prm.viewshed], s[0], s[1], 0, oob);
+    if (oob) f |= GB_F_VIEW_OOB;
+    else if (vis == 0.0) f |= GB_F_NOT_VISIBLE;
+  }
+  if (isnan(s[0]) | isnan(s[1]) | isnan(s[2]) | isnan(s[3]) | isnan(s[4]) | isnan(s[5])) f |= GB_F_NAN;
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weighted moments (tracker.py:72-104).  Sums are taken of d = particle - ref so that map-scale
+// coordinates do not cancel; NM = 13 (sigmas) or 28 (covariances) accumulators.
+// ---------------------------------------------------------------------------------------------
+template <bool COV>
+struct Moments {
+  static constexpr int NM = COV ? 28 : 13;
+  double a[NM];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < NM; ++k) a[k] = 0.0;
+  }
+  __device__ __forceinline__ void accumulate(double w, const double (&s)[6], const double* ref) {
+    double d[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = s[k] - ref[k];
+    a[0] += w;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[1 + k] = fma(w, d[k], a[1 + k]);
+    if (COV) {
+      int idx = 7;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int l = k; l < 6; ++l) a[idx++] = fma(w * d[k], d[l], a[idx]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[7 + k] = fma(w * d[k], d[k], a[7 + k]);
+    }
+  }
+};
+
+// Finalise from the summed accumulators `a` (NM doubles): mean[6], sigma[6] or cov[36].
+template <bool COV>
+__device__ inline void finalize_moments(const double* a, const double* ref, double* mean, double* sigma, double* cov) {
+  const double inv = 1.0 / a[0];
+  double m1[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    m1[k] = a[1 + k] * inv;
+    mean[k] = ref[k] + m1[k];
+  }
+  if (COV) {
+    int idx = 7;
+    for (int k = 0; k < 6; ++k)
+      for (int l = k; l < 6; ++l) {
+        const double c = a[idx++] * inv - m1[k] * m1[l];
+        cov[k * 6 + l] = c;
+        cov[l * 6 + k] = c;
+      }
+  } else {
+    for (int k = 0; k < 6; ++k) sigma[k] = sqrt(fmax(a[7 + k] * inv - m1[k] * m1[k], 0.0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small stand-alone kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_project(const __grid_constant__ gb_camera cam, const double* __restrict__ xyz, int64_t n,
+                          double* __restrict__ uv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double u, v;
+    project(cam, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], u, v);
+    uv[2 * i] = u;
+    uv[2 * i + 1] = v;
+  }
+}
+
+__global__ void k_unproject(const __grid_constant__ gb_camera cam, const double* __restrict__ uv, int64_t n,
+                            int directions, const double* __restrict__ depth, double* __restrict__ xyz) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double dx, dy, dz;
+    unproject(cam, uv[2 * i], uv[2 * i + 1], dx, dy, dz);
+    if (depth) {
+      const double d = depth[i];
+      dx = mul(dx, d);
+      dy = mul(dy, d);
+      dz = mul(dz, d);
+    }
+    if (!directions) {
+      dx = add(dx, cam.xyz[0]);
+      dy = add(dy, cam.xyz[1]);
+      dz = add(dz, cam.xyz[2]);
+    }
+    xyz[3 * i] = dx;
+    xyz[3 * i + 1] = dy;
+    xyz[3 * i + 2] = dz;
+  }
+}
+
+__global__ void k_gray_from_u8(const uint8_t* __restrict__ src, int height, int width, int nchan,
+                               uint16_t* __restrict__ dst, int pitch) {
+  const int64_t total = (int64_t)height * width;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
+    unsigned s = 0;
+    for (int k = 0; k < nchan; ++k) s += src[i * nchan + k];
+    dst[(int64_t)r * pitch + c] = (uint16_t)s;
+  }
+}
+
+__global__ void k_state_from_rows(const double* __restrict__ rows, int64_t npoints, int64_t n, double* __restrict__ state) {
+  const int64_t total = npoints * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / n, j = i - p * n;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) state[(p * 6 + c) * n + j] = rows[i * 6 + c];
+  }
+}
+
+__global__ void k_state_to_rows(const double* __restrict__ state, int64_t npoints, int64_t n, double* __restrict__ rows) {
+  const int64_t total = npoints * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / n, j = i - p * n;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) rows[i * 6 + c] = state[(p * 6 + c) * n + j];
+  }
+}
+
+// Motion.evolve_particles on SoA state with supplied normals (stage entry point + staggered
+// template path of gb_track, where t/first/last select the points that step at time t).
+__global__ void k_evolve(const gb_motion* __restrict__ motion, int64_t P, int64_t N, double tau, double tau2,
+                         const double* __restrict__ normals, int64_t normals_point_stride, double* __restrict__ state,
+                         const int32_t* first, const int32_t* last, const int32_t* status, int t, int rng_mode,
+                         uint64_t seed, int S, int64_t point_offset) {
+  const int64_t p = blockIdx.y;
+  if (first && (status[p] != 0 || t <= first[p] || t > last[p])) return;
+  const gb_motion m = motion[p];
+  const double* zn = normals ? normals + p * normals_point_stride + (first ? (int64_t)(t - first[p] - 1) * N * 3 : 0) : nullptr;
+  (void)S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    double s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = state[(p * 6 + c) * N + i];
+    double z0, z1, z2;
+    if (rng_mode == GB_RNG_SUPPLIED) {
+      z0 = zn[3 * i];
+      z1 = zn[3 * i + 1];
+      z2 = zn[3 * i + 2];
+    } else {
+      philox_normals3(seed, (uint64_t)(p + point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2);
+    }
+    evolve_particle(m, tau, tau2, z0, z1, z2, s);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) state[(p * 6 + c) * N + i] = s[c];
+  }
+}
+
+// Tracker.particle_mean / sigma / covariance for one row-major particle set (stage entry point).
+__global__ void __launch_bounds__(GB_THREADS) k_moments(const double* __restrict__ particles,
+                                                        const double* __restrict__ weights, int64_t n, double* mean,
+                                                        double* sigma, double* cov) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  double ref[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) ref[c] = particles[c];
+  Moments<true> mom;
+  mom.clear();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = particles[i * 6 + c];
+    mom.accumulate(weights[i], s, ref);
+  }
+  block_reduce<28, 0>(mom.a, hdr);
+  if (threadIdx.x == 0) {
+    double m[6], cv[36];
+    finalize_moments<true>(hdr->bcast, ref, m, nullptr, cv);
+    for (int c = 0; c < 6; ++c) {
+      mean[c] = m[c];
+      if (sigma) sigma[c] = sqrt(fmax(cv[c * 7], 0.0));
+    }
+    if (cov)
+      for (int c = 0; c < 36; ++c) cov[c] = cv[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First frame: initialize_particles + test_particles + unit weights + moments
+// (motion.py:149-163, 260-283; tracker.py:327-330, 350-357).  One CTA per point.
+// ---------------------------------------------------------------------------------------------
+template <bool COV>
+__global__ void __launch_bounds__(GB_THREADS) k_init(const __grid_constant__ StepParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  const int64_t p = blockIdx.x;
+  const int t = prm.t;
+  if (prm.status[p] != 0 || prm.first[p] != t || prm.last[p] < t) return;
+  const int64_t N = prm.N;
+  const gb_motion m = prm.motion[p];
+  double* state = state_buffer(prm, t) + p * 6 * N;
+  bool oob0, oob1;
+  double ref[6] = {m.xy[0], m.xy[1], surface_sample(prm.surfaces[m.dem], m.xy[0], m.xy[1], 1, oob0), 0.0, 0.0, 0.0};
+  (void)oob1;
+  if (isnan(ref[2])) ref[2] = 0.0;
+  if (m.kind == GB_MOTION_CYLINDRICAL) {
+    ref[3] = m.v[0] * cos(m.v[1]);
+    ref[4] = m.v[0] * sin(m.v[1]);
+  } else {
+    ref[3] = m.v[0];
+    ref[4] = m.v[1];
+  }
+  ref[5] = m.v[2];
+  Moments<COV> mom;
+  mom.clear();
+  uint32_t flags = 0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    double zn[6];
+    if (prm.rng_mode == GB_RNG_SUPPLIED) {
+      const double* src = prm.init_normals + (p * N + i) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) zn[c] = src[c];
+    } else {
+      philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 0u, zn[0], zn[1], zn[2]);
+      philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 1u, zn[3], zn[4], zn[5]);
+    }
+    double s[6];
+    init_particle(m, prm.surfaces, zn, s, flags);
+    flags |= test_particle(prm, s);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) state[c * N + i] = s[c];
+    if (prm.weight_state) prm.weight_state[p * N + i] = 1.0;
+    if (prm.out_particles) {
+      double* dst = prm.out_particles + ((p * prm.T + t) * N + i) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dst[c] = s[c];
+    }
+    if (prm.out_weights) prm.out_weights[(p * prm.T + t) * N + i] = 1.0;
+    mom.accumulate(1.0, s, ref);
+  }
+  const int any = __syncthreads_or((int)flags);
+  if (any) {
+    if (threadIdx.x == 0) {
+      prm.status[p] = status_from_flags((uint32_t)any);
+      prm.status_time[p] = t;
+    }
+    return;
+  }
+  block_reduce<Moments<COV>::NM, 0>(mom.a, hdr);
+  if (threadIdx.x == 0) {
+    double mean[6], sg[6], cv[36];
+    finalize_moments<COV>(hdr->bcast, ref, mean, sg, cv);
+    double* mo = prm.means + (p * prm.T + t) * 6;
+    for (int c = 0; c < 6; ++c) mo[c] = mean[c];
+    if (COV) {
+      double* co = prm.covariances + (p * prm.T + t) * 36;
+      for (int c = 0; c < 36; ++c) co[c] = cv[c];
+    } else {
+      double* so = prm.sigmas + (p * prm.T + t) * 6;
+      for (int c = 0; c < 6; ++c) so[c] = sg[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Template construction (tracker.py:536-561, 494-534): one CTA per (point, observer) due at t.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepParams prm) {
+  __shared__ double s_red[8][8];
+  __shared__ double s_mean[4];
+  __shared__ int s_box[4];
+  __shared__ int s_ok;
+  __shared__ double s_stats[2];
+  __shared__ uint16_t s_raw[GB_MAX_TEMPLATE];
+  __shared__ uint32_t s_hist[GB_MAX_BINS];
+  const int64_t p = blockIdx.x / prm.O;
+  const int o = (int)(blockIdx.x - p * prm.O);
+  const int t = prm.t;
+  if (prm.status[p] != 0 || prm.tmpl_frame[o] != t || !prm.mask[p * prm.O + o] || prm.img[o] < 0) return;
+  if (t < prm.first[p] || t > prm.last[p]) return;
+  const int64_t N = prm.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // particles as they are when the template is cut: just initialised (t == first) or evolved in place
+  const double* state = state_buffer(prm, prm.first[p] == t ? t : t - 1) + p * 6 * N;
+  const double* wts = prm.weight_state ? prm.weight_state + p * N : nullptr;
+  const double ref[3] = {state[0], state[N], state[2 * N]};
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = tid; i < N; i += blockDim.x) {
+    const double w = wts ? wts[i] : 1.0;
+    acc[0] += w;
+    acc[1] = fma(w, state[i] - ref[0], acc[1]);
+    acc[2] = fma(w, state[N + i] - ref[1], acc[2]);
+    acc[3] = fma(w, state[2 * N + i] - ref[2], acc[3]);
+  }
+  for (int k = 0; k < 4; ++k) {
+    const double x = warp_sum(acc[k]);
+    if (lane == 0) s_red[warp][k] = x;
+  }
+  __syncthreads();
+  const gb_image* img = prm.images + prm.img[o];
+  const int tw = prm.tile_w, th = prm.tile_h;
+  if (tid == 0) {
+    double tot[4] = {0, 0, 0, 0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+      for (int k = 0; k < 4; ++k) tot[k] += s_red[w][k];
+    const double mx = ref[0] + tot[1] / tot[0], my = ref[1] + tot[2] / tot[0], mz = ref[2] + tot[3] / tot[0];
+    double u, v;
+    project(img->cam, mx, my, mz, u, v);
+    // Observer.tile_box -> Grid.snap_box (observer.py:115-130, raster.py:390-421)
+    const double hw = tw * 0.5, hh = th * 0.5;
+    const double l = sub(u, hw), tp = sub(v, hh), r = add(u, hw), b = add(v, hh);
+    const double W = (double)img->cam.imgsz[0], H = (double)img->cam.imgsz[1];
+    const bool ok = (l >= 0.0) & (l <= W) & (r >= 0.0) & (r <= W) & (tp >= 0.0) & (tp <= H) & (b >= 0.0) & (b <= H);
+    s_ok = ok ? 1 : 0;
+    if (ok) {
+      s_box[0] = (int)floor(l + 0.5);
+      s_box[1] = (int)floor(tp + 0.5);
+      s_box[2] = (int)floor(r + 0.5);
+      s_box[3] = (int)floor(b + 0.5);
+      int32_t* gbox = prm.tmpl_box + (p * prm.O + o) * 4;
+      for (int k = 0; k < 4; ++k) gbox[k] = s_box[k];
+      double* duv = prm.tmpl_duv + (p * prm.O + o) * 2;
+      duv[0] = sub(u, (double)(s_box[0] + s_box[2]) / 2.0);
+      duv[1] = sub(v, (double)(s_box[1] + s_box[3]) / 2.0);
+    } else {
+      if (atomicCAS(&prm.status[p], 0, GB_ST_TEMPLATE_BOUNDS) == 0) prm.status_time[p] = t;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  // the snapped box always spans tile_w x tile_h pixels for integer sizes
+  const int bw = s_box[2] - s_box[0], bh = s_box[3] - s_box[1];
+  const int area = bw * bh;
+  const int nchan = img->nchan, nbins = 255 * nchan + 1;
+  for (int i = tid; i < nbins; i += blockDim.x) s_hist[i] = 0u;
+  for (int i = tid; i < area; i += blockDim.x) {
+    const int r = i / bw, c = i - r * bw;
+    // a box snapped onto the frame edge can reach one pixel outside only through rounding; clamp
+    const int rr = min(max(s_box[1] + r, 0), img->height - 1), cc = min(max(s_box[0] + c, 0), img->width - 1);
+    s_raw[i] = img->gray[(int64_t)rr * img->pitch + cc];
+  }
+  __syncthreads();
+  // grey mean and population std (helpers.py:324-344)
+  double sum = 0.0;
+  for (int i = tid; i < area; i += blockDim.x) {
+    sum += quo((double)s_raw[i], (double)nchan);
+    atomicAdd(&s_hist[s_raw[i]], 1u);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp][0] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w][0];
+    s_stats[0] = quo(tot, (double)area);
+  }
+  __syncthreads();
+  const double mean = s_stats[0];
+  double ss = 0.0;
+  for (int i = tid; i < area; i += blockDim.x) {
+    const double d = sub(quo((double)s_raw[i], (double)nchan), mean);
+    ss += mul(d, d);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[warp][1] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w][1];
+    s_stats[1] = quo(1.0, sqrt(quo(tot, (double)area)));
+  }
+  __syncthreads();
+  const double inv_std = s_stats[1];
+  // CDF over occupied grey levels (helpers.py:433-464): levels are visited in increasing order, and
+  // the normalised value is an increasing function of the level, so this is np.unique's order.
+  if (tid == 0) {
+    double* vals = prm.tmpl_values + (p * prm.O + o) * (int64_t)(tw * th);
+    double* qs = prm.tmpl_quantiles + (p * prm.O + o) * (int64_t)(tw * th);
+    int n = 0;
+    uint32_t run = 0;
+    for (int b = 0; b < nbins; ++b) {
+      if (!s_hist[b]) continue;
+      run += s_hist[b];
+      vals[n] = mul(sub(quo((double)b, (double)nchan), mean), inv_std);
+      qs[n] = quo((double)run, (double)area);
+      ++n;
+    }
+    prm.tmpl_nvalues[p * prm.O + o] = n;
+  }
+  // high-pass (tracker.py:530-531): value minus the 5x5 reflected median, taken on grey levels
+  double* tile = prm.tmpl_tile + (p * prm.O + o) * (int64_t)(tw * th);
+  for (int i = tid; i < area; i += blockDim.x) {
+    const int r = i / bw, c = i - r * bw;
+    const int med = median5x5(s_raw, bw, bh, r, c);
+    const double vn = mul(sub(quo((double)s_raw[i], (double)nchan), mean), inv_std);
+    const double vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
+    tile[i] = sub(vn, vm);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused update step (tracker.py:331-357 for one point and one time):
+//   evolve -> test -> per observer [project, search window, tile pipeline, spline sample]
+//   -> surface likelihood -> weights -> systematic resampling -> moments.
+// grid.x = P * cluster; one cluster per point.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double resample_position(int64_t j, double u, double inv_n) {
+  // (np.arange(n) + u) * (1 / n)  (tracker.py:173)
+  return mul(add((double)j, u), inv_n);
+}
+
+// Number of resampling positions <= c, i.e. the end of the child range of a particle whose
+// normalised cumulative weight is c (np.searchsorted(cumsum, positions, side='left')).
+__device__ __forceinline__ int count_positions_le(double c, double u, double inv_n, int64_t N) {
+  double g = floor(c * (double)N - u) + 1.0;
+  g = fmin(fmax(g, 0.0), (double)N);
+  int64_t e = (int64_t)g;
+  while (e > 0 && resample_position(e - 1, u, inv_n) > c) --e;
+  while (e < N && resample_position(e, u, inv_n) <= c) ++e;
+  return (int)e;
+}
+
+template <bool COV>
+__global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ StepParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  constexpr int HDR = (int)((sizeof(SmemHeader) + 15) / 16 * 16);
+  const int cs = prm.cluster;
+  const int rank = (int)(blockIdx.x % cs);
+  const int64_t p = blockIdx.x / cs;
+  const int t = prm.t, tid = threadIdx.x, B = blockDim.x;
+  const int64_t N = prm.N;
+  const bool forced = prm.io.force_evolved != nullptr;
+  if (prm.status[p] != 0 || t <= prm.first[p] || t > prm.last[p]) return;
+
+  ClusterCtx cc{rank, cs, 0, hdr};
+  const int nl = prm.n_local;
+  const int64_t i0 = (int64_t)rank * nl;
+  const int nv = (int)max((int64_t)0, min((int64_t)nl, N - i0));
+
+  double *ev, *uvb, *llb;
+  char* tile_base;
+  if (prm.particles_in_smem) {
+    ev = reinterpret_cast<double*>(smem_raw + HDR);
+    uvb = ev + 6 * (int64_t)nl;
+    llb = uvb + 2 * (int64_t)nl;
+    tile_base = reinterpret_cast<char*>(llb + nl);
+  } else {
+    ev = prm.scratch + (p * cs + rank) * 9 * (int64_t)nl;
+    uvb = ev + 6 * (int64_t)nl;
+    llb = uvb + 2 * (int64_t)nl;
+    tile_base = reinterpret_cast<char*>(smem_raw + HDR);
+  }
+  // motion parameters to shared memory
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&hdr->motion);
+    for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += B) dst[k] = src[k];
+  }
+  const double* sin_ = forced ? prm.io.force_evolved + p * 6 * N : state_buffer(prm, t - 1) + p * 6 * N;
+  if (tid < 6) hdr->ref[tid] = sin_[tid * N];
+  __syncthreads();
+
+  // ---- phase A: motion step and particle tests ----
+  uint32_t flags = 0;
+  {
+    const int s_idx = t - prm.first[p] - 1;
+    const double* zn = prm.step_normals ? prm.step_normals + ((p * prm.S + s_idx) * N + i0) * 3 : nullptr;
+    const bool evolve = !forced && !prm.skip_evolve;
+    for (int i = tid; i < nv; i += B) {
+      double s[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s[c] = sin_[c * N + i0 + i];
+      if (evolve) {
+        double z0, z1, z2;
+        if (prm.rng_mode == GB_RNG_SUPPLIED) {
+          z0 = zn[3 * i];
+          z1 = zn[3 * i + 1];
+          z2 = zn[3 * i + 2];
+        } else {
+          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)(i0 + i), 2u, z0, z1, z2);
+        }
+        evolve_particle(hdr->motion, prm.tau, prm.tau2, z0, z1, z2, s);
+      }
+      flags |= test_particle(prm, s);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) ev[c * nl + i] = s[c];
+      llb[i] = 0.0;
+      if (prm.io.dump_evolved) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) prm.io.dump_evolved[(p * 6 + c) * N + i0 + i] = s[c];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: observers ----
+  bool fatal = false;
+  if (!prm.io.force_weights) {
+    for (int o = 0; o < prm.O && !fatal; ++o) {
+      const int64_t po = p * prm.O + o;
+      uint8_t* oflag = prm.obs_flags + (p * prm.T + t) * prm.O + o;
+      if (prm.img[o] < 0 || !prm.mask[po]) {
+        if (rank == 0 && tid == 0) *oflag = GB_OBS_NO_IMAGE;
+        continue;
+      }
+      const gb_image* img = prm.images + prm.img[o];
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&img->cam);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&hdr->cam);
+        for (int k = tid; k < (int)(sizeof(gb_camera) / 4); k += B) dst[k] = src[k];
+      }
+      __syncthreads();
+      // project, bounding box of the cloud (tracker.py:581-583)
+      double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
+      int has_nan = 0;
+      for (int i = tid; i < nv; i += B) {
+        double u, v;
+        project(hdr->cam, ev[i], ev[nl + i], ev[2 * nl + i], u, v);
+        uvb[i] = u;
+        uvb[nl + i] = v;
+        has_nan |= (int)(isnan(u) | isnan(v));
+        mm[0] = fmin(mm[0], u);
+        mm[1] = fmin(mm[1], v);
+        mm[2] = fmin(mm[2], -u);
+        mm[3] = fmin(mm[3], -v);
+        if (prm.io.dump_uv) {
+          double* d = prm.io.dump_uv + (po * N + i0 + i) * 2;
+          d[0] = u;
+          d[1] = v;
+        }
+      }
+      has_nan = __syncthreads_or(has_nan);
+      block_reduce<4, 1>(mm, hdr);
+      if (tid == 0) hdr->bcast[4] = (double)has_nan;
+      __syncthreads();
+      double(*xg)[GB_XCH] = cluster_allgather<5>(cc);
+      if (tid == 0) {
+        double lo_u = xg[0][0], lo_v = xg[0][1], hi_u = xg[0][2], hi_v = xg[0][3], nanf = xg[0][4];
+        for (int r = 1; r < cs; ++r) {
+          lo_u = fmin(lo_u, xg[r][0]);
+          lo_v = fmin(lo_v, xg[r][1]);
+          hi_u = fmin(hi_u, xg[r][2]);
+          hi_v = fmin(hi_v, xg[r][3]);
+          nanf += xg[r][4];
+        }
+        hi_u = -hi_u;
+        hi_v = -hi_v;
+        // tracker.py:580-595 (kx = ky = 3)
+        const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
+        double bl = sub(lo_u, tw * 0.5), bt = sub(lo_v, th * 0.5), br = add(hi_u, tw * 0.5), bb = add(hi_v, th * 0.5);
+        const double ncols = sub(3.0, sub(sub(br, bl), tw));
+        if (ncols > 0.0) {
+          bl = add(bl, mul(-ncols, 0.5));
+          br = add(br, mul(ncols, 0.5));
+        }
+        const double nrows = sub(3.0, sub(sub(bb, bt), th));
+        if (nrows > 0.0) {
+          bt = add(bt, mul(-nrows, 0.5));
+          bb = add(bb, mul(nrows, 0.5));
+        }
+        const double fl = floor(bl), ft = floor(bt), cr = ceil(br), cb = ceil(bb);
+        const double W = (double)hdr->cam.imgsz[0], H = (double)hdr->cam.imgsz[1];
+        // Camera.inframe on both corners (camera.py:700-718); NaN fails every comparison
+        const bool ok = (nanf == 0.0) & (fl >= 0.0) & (fl <= W) & (ft >= 0.0) & (ft <= H) & (cr >= 0.0) & (cr <= W) &
+                        (cb >= 0.0) & (cb <= H);
+        hdr->iflags[0] = ok ? 1 : 0;
+        if (ok) {
+          hdr->ibox[0] = (int)fl;
+          hdr->ibox[1] = (int)ft;
+          hdr->ibox[2] = (int)cr;
+          hdr->ibox[3] = (int)cb;
+        }
+      }
+      __syncthreads();
+      if (!hdr->iflags[0]) {
+        if (rank == 0 && tid == 0) *oflag = GB_OBS_OUT_OF_FRAME;
+        __syncthreads();
+        continue;
+      }
+      TileWork w;
+      w.Su = hdr->ibox[2] - hdr->ibox[0];
+      w.Sv = hdr->ibox[3] - hdr->ibox[1];
+      w.tw = prm.tile_w;
+      w.th = prm.tile_h;
+      w.Mu = w.Su - w.tw + 1;
+      w.Mv = w.Sv - w.th + 1;
+      w.nbins = 255 * img->nchan + 1;
+      w.nvals = prm.tmpl_nvalues[po];
+      if (rank == 0 && tid == 0) {
+        *oflag = GB_OBS_USED;
+        if (prm.window_stats) {
+          int32_t* ws = prm.window_stats + ((p * prm.T + t) * prm.O + o) * 2;
+          ws[0] = w.Su;
+          ws[1] = w.Sv;
+        }
+        if (prm.io.dump_box) {
+          int32_t* d = prm.io.dump_box + po * 4;
+          for (int k = 0; k < 4; ++k) d[k] = hdr->ibox[k];
+        }
+      }
+      if (tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) > prm.tile_bytes || w.Mu > 256 || w.Mv > 256) {
+        flags |= GB_F_WINDOW;
+        fatal = true;
+        break;
+      }
+      tile_carve(tile_base, w);
+      const int64_t ta = (int64_t)w.tw * w.th;
+      const bool dumper = rank == 0;
+      tile_build_surface(img, hdr->ibox, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta, prm.tmpl_values + po * ta,
+                         w, (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
+                         (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap);
+      // geo-reference of the surface (tracker.py:615-620) and cell centres (observer.py:203-208)
+      const double eu = sub(mul((double)w.tw, 0.5), 0.5), evv = sub(mul((double)w.th, 0.5), 0.5);
+      const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
+      const double sl = add(add((double)hdr->ibox[0], eu), du_t), st = add(add((double)hdr->ibox[1], evv), dv_t);
+      const double sr = add(add((double)hdr->ibox[2], -eu), du_t), sb = add(add((double)hdr->ibox[3], -evv), dv_t);
+      const double cu0 = add(sl, mul(quo(sub(sr, sl), (double)w.Mu), 0.5));
+      const double cv0 = add(st, mul(quo(sub(sb, st), (double)w.Mv), 0.5));
+      const double cu1 = add(cu0, (double)(w.Mu - 1)), cv1 = add(cv0, (double)(w.Mv - 1));
+      const double scale = prm.obs_scale[o];
+      for (int i = tid; i < nv; i += B) {
+        const double u = uvb[i], v = uvb[nl + i];
+        if (!((u >= sl) & (u <= sr) & (v >= st) & (v <= sb))) flags |= GB_F_SAMPLE_OUTSIDE;
+        // FITPACK evaluates at the argument clamped to the first/last data site
+        const double x = fmin(fmax(u, cu0), cu1) - cu0, y = fmin(fmax(v, cv0), cv1) - cv0;
+        const double val = hermite_eval(w.herm, w.Mu, w.Mv, x, y);
+        llb[i] = add(llb[i], mul(val, scale));
+        if (prm.io.dump_sampled) prm.io.dump_sampled[po * N + i0 + i] = val;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- phase C: weights (tracker.py:143-149), block scan, totals ----
+  double wsum_local;
+  {
+    const double* fw = prm.io.force_weights ? prm.io.force_weights + p * N + i0 : nullptr;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = B >> 5;
+    if (tid == 0) hdr->scan_carry = 0.0;
+    __syncthreads();
+    for (int base = 0; base < nv; base += B) {
+      const int i = base + tid;
+      double w = 0.0;
+      if (i < nv) {
+        if (fw) {
+          w = fw[i];
+        } else {
+          const double ll = add(llb[i], surface_log_likelihood(hdr->motion, prm.surfaces, ev[i], ev[nl + i], ev[2 * nl + i], flags));
+          w = add(exp(-ll), 1e-300);
+        }
+        llb[i] = w;
+        if (prm.io.dump_weights) prm.io.dump_weights[p * N + i0 + i] = w;
+      }
+      double incl = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = shfl_up(incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) hdr->scan_warp[warp] = incl;
+      __syncthreads();
+      double woff = 0.0;
+      for (int k = 0; k < warp; ++k) woff += hdr->scan_warp[k];
+      const double carry = hdr->scan_carry;
+      const double l = carry + (woff + incl);
+      if (i < nv) uvb[i] = l;
+      __syncthreads();
+      if (tid == B - 1) hdr->scan_carry = l;  // running total (w = 0 past the end keeps it constant)
+      __syncthreads();
+      (void)nwarp;
+    }
+    wsum_local = hdr->scan_carry;
+  }
+  const int blockflags = __syncthreads_or((int)flags);
+  if (tid == 0) {
+    hdr->bcast[0] = wsum_local;
+    hdr->bcast[1] = (double)blockflags;
+  }
+  __syncthreads();
+  double prefix = 0.0, total = 0.0;
+  {
+    double(*xg)[GB_XCH] = cluster_allgather<2>(cc);
+    uint32_t allflags = 0;
+    for (int r = 0; r < cs; ++r) {
+      if (r == rank) prefix = total;
+      total += xg[r][0];
+      allflags |= (uint32_t)xg[r][1];
+    }
+    if (allflags) {
+      if (rank == 0 && tid == 0) {
+        prm.status[p] = status_from_flags(allflags);
+        prm.status_time[p] = t;
+      }
+      return;
+    }
+  }
+
+  // ---- phase D: systematic resampling (tracker.py:168-176, 222-223) ----
+  const double u01 = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[p * prm.S + (t - prm.first[p] - 1)]
+                                                      : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
+  const double inv_n = quo(1.0, (double)N);
+  int* E = reinterpret_cast<int*>(uvb + nl);
+  for (int i = tid; i < nv; i += B) E[i] = count_positions_le(quo(prefix + uvb[i], total), u01, inv_n, N);
+  const int J0 = rank == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
+  __syncthreads();
+  const int J1 = nv > 0 ? E[nv - 1] : J0;
+  {
+    double* sout = state_buffer(prm, t) + p * 6 * N;
+    for (int j = J0 + tid; j < J1; j += B) {
+      int lo = 0, hi = nv - 1;  // smallest local parent with E[parent] > j
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (E[mid] > j) hi = mid; else lo = mid + 1;
+      }
+      const int a = lo;
+      double s[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + a];
+      const double w = llb[a];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sout[c * N + j] = s[c];
+      if (prm.weight_state) prm.weight_state[p * N + j] = w;
+      if (prm.out_particles) {
+        double* d = prm.out_particles + ((p * prm.T + t) * N + j) * 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) d[c] = s[c];
+      }
+      if (prm.out_weights) prm.out_weights[(p * prm.T + t) * N + j] = w;
+      if (prm.io.dump_indices) prm.io.dump_indices[p * N + j] = (int)(i0 + a);
+    }
+  }
+
+  // ---- phase E: moments of the resampled set = parents weighted by (children x weight) ----
+  Moments<COV> mom;
+  mom.clear();
+  for (int i = tid; i < nv; i += B) {
+    const int cnt = E[i] - (i > 0 ? E[i - 1] : J0);
+    if (cnt > 0) {
+      double s[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + i];
+      mom.accumulate((double)cnt * llb[i], s, hdr->ref);
+    }
+  }
+  block_reduce<Moments<COV>::NM, 0>(mom.a, hdr);
+  {
+    double(*xg)[GB_XCH] = cluster_allgather<Moments<COV>::NM>(cc);
+    if (rank == 0 && tid == 0) {
+      double a[Moments<COV>::NM];
+      for (int k = 0; k < Moments<COV>::NM; ++k) {
+        double x = xg[0][k];
+        for (int r = 1; r < cs; ++r) x += xg[r][k];
+        a[k] = x;
+      }
+      double mean[6], sg[6], cv[36];
+      finalize_moments<COV>(a, hdr->ref, mean, sg, cv);
+      double* mo = prm.means + (p * prm.T + t) * 6;
+      for (int c = 0; c < 6; ++c) mo[c] = mean[c];
+      if (COV) {
+        double* co = prm.covariances + (p * prm.T + t) * 36;
+        for (int c = 0; c < 36; ++c) co[c] = cv[c];
+      } else {
+        double* so = prm.sigmas + (p * prm.T + t) * 6;
+        for (int c = 0; c < 6; ++c) so[c] = sg[c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static std::once_flag g_tables_once[16];
+
+static int ensure_tables() {
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(GB_E_INVALID, "device index out of range%s");
+  cudaError_t err = cudaSuccess;
+  std::call_once(g_tables_once[dev], [&]() {
+    double cp[256], inv[256];
+    cp[0] = 2.0;
+    inv[0] = 1.0;
+    for (int i = 1; i < 256; ++i) {
+      inv[i] = 1.0 / (4.0 - cp[i - 1]);
+      cp[i] = inv[i];
+    }
+    err = cudaMemcpyToSymbol(c_spline_cp, cp, sizeof(cp));
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_spline_inv, inv, sizeof(inv));
+  });
+  if (err != cudaSuccess) return fail(GB_E_CUDA, "spline tables: %s", cudaGetErrorString(err));
+  return GB_OK;
+}
+
+static int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > 148 * 16) g = 148 * 16;
+  return (int)g;
+}
+
+static constexpr int kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+static constexpr int kHeaderBytes = (int)((sizeof(SmemHeader) + 15) / 16 * 16);
+
+static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
+  memset(&prm, 0, sizeof(prm));
+  prm.P = d.P;
+  prm.N = d.N;
+  prm.T = d.T;
+  prm.O = d.O;
+  prm.S = d.T - 1;
+  prm.t = t;
+  prm.tile_w = d.tile_w;
+  prm.tile_h = d.tile_h;
+  prm.cluster = d.plan.cluster;
+  prm.n_local = d.plan.n_local;
+  prm.particles_in_smem = d.plan.particles_in_smem;
+  prm.tile_bytes = d.plan.tile_bytes;
+  prm.viewshed = d.viewshed;
+  prm.rng_mode = d.rng_mode;
+  prm.seed = d.seed;
+  prm.point_offset = d.point_offset;
+  if (t > 0) {
+    prm.tau = d.tau_host[t - 1];
+    prm.tau2 = d.tau2_host[t - 1];
+  }
+  for (int o = 0; o < d.O; ++o) {
+    const int idx = d.image_index_host[(int64_t)t * d.O + o];
+    prm.img[o] = idx >= 0 ? d.image_offset_host[o] + idx : -1;
+    prm.obs_scale[o] = d.obs_scale_host[o];
+    int tf = -1;
+    for (int tt = 0; tt < d.T; ++tt)
+      if (d.image_index_host[(int64_t)tt * d.O + o] >= 0) {
+        tf = tt;
+        break;
+      }
+    prm.tmpl_frame[o] = tf;
+  }
+  prm.images = d.images;
+  prm.mask = d.mask;
+  prm.first = d.first;
+  prm.last = d.last;
+  prm.motion = d.motion;
+  prm.surfaces = d.surfaces;
+  prm.init_normals = d.init_normals;
+  prm.step_normals = d.step_normals;
+  prm.uniforms = d.uniforms;
+  prm.state_a = d.state_a;
+  prm.state_b = d.state_b;
+  prm.weight_state = d.weight_state;
+  prm.scratch = d.scratch;
+  prm.tmpl_tile = d.tmpl_tile;
+  prm.tmpl_values = d.tmpl_values;
+  prm.tmpl_quantiles = d.tmpl_quantiles;
+  prm.tmpl_nvalues = d.tmpl_nvalues;
+  prm.tmpl_box = d.tmpl_box;
+  prm.tmpl_duv = d.tmpl_duv;
+  prm.means = d.means;
+  prm.sigmas = d.sigmas;
+  prm.covariances = d.covariances;
+  prm.out_particles = d.out_particles;
+  prm.out_weights = d.out_weights;
+  prm.status = d.status;
+  prm.status_time = d.status_time;
+  prm.obs_flags = d.obs_flags;
+  prm.window_stats = d.window_stats;
+}
+
+static int check_desc(const gb_track_desc& d) {
+  if (d.P <= 0 || d.N <= 0 || d.T < 2) return fail(GB_E_INVALID, "P, N must be positive and T >= 2%s");
+  if (d.O < 1 || d.O > GB_MAX_OBS) return fail(GB_E_INVALID, "between 1 and 8 observers are supported%s");
+  if (d.tile_w < 1 || d.tile_h < 1 || (int64_t)d.tile_w * d.tile_h > GB_MAX_TEMPLATE)
+    return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
+  if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");
+  if (!d.images || !d.mask || !d.first || !d.last || !d.motion || !d.surfaces || !d.state_a || !d.state_b || !d.means ||
+      !d.status || !d.status_time || !d.obs_flags || !d.tmpl_tile || !d.tmpl_values || !d.tmpl_quantiles ||
+      !d.tmpl_nvalues || !d.tmpl_box || !d.tmpl_duv)
+    return fail(GB_E_INVALID, "missing required buffer%s");
+  if (d.rng_mode == GB_RNG_SUPPLIED && (!d.init_normals || !d.step_normals || !d.uniforms))
+    return fail(GB_E_INVALID, "supplied-draw mode needs init_normals, step_normals and uniforms%s");
+  if (d.plan.cluster < 1 || d.plan.cluster > GB_MAX_CLUSTER || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
+    return fail(GB_E_INVALID, "invalid launch plan (use gb_step_plan)%s");
+  if (!d.plan.particles_in_smem && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
+  if ((int64_t)d.plan.cluster * d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
+  return GB_OK;
+}
+
+template <bool COV>
+static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t stream) {
+  GB_CUDA(cudaFuncSetAttribute(k_step<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(prm.P * plan.cluster), 1, 1);
+  cfg.blockDim = dim3(GB_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GB_CUDA(cudaLaunchKernelEx(&cfg, k_step<COV>, prm));
+  return GB_OK;
+}
+
+static int launch_init(const StepParams& prm, bool cov, cudaStream_t stream) {
+  const int smem = kHeaderBytes;
+  if (cov)
+    k_init<true><<<(unsigned)prm.P, GB_THREADS, smem, stream>>>(prm);
+  else
+    k_init<false><<<(unsigned)prm.P, GB_THREADS, smem, stream>>>(prm);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+static int launch_template(const StepParams& prm, cudaStream_t stream) {
+  k_template<<<(unsigned)(prm.P * prm.O), 256, 0, stream>>>(prm);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int gb_version(void) { return GB_VERSION; }
+const char* gb_last_error(void) { return g_error; }
+
+int gb_camera_from_vector(const double* v, const double* corr, gb_camera* out) {
+  if (!v || !out) return fail(GB_E_INVALID, "null argument%s");
+  memset(out, 0, sizeof(*out));
+  const double d2r = 3.14159265358979323846 / 180.0;
+  const double c1 = cos(v[3] * d2r), c2 = cos(v[4] * d2r), c3 = cos(v[5] * d2r);
+  const double s1 = sin(v[3] * d2r), s2 = sin(v[4] * d2r), s3 = sin(v[5] * d2r);
+  const double R[9] = {c1 * c3 + s1 * s2 * s3, c1 * s2 * s3 - c3 * s1, -c2 * s3,
+                       c3 * s1 * s2 - c1 * s3, s1 * s3 + c1 * c3 * s2, -c2 * c3,
+                       c2 * s1,                c1 * c2,                s2};
+  for (int i = 0; i < 9; ++i) out->R[i] = R[i];
+  for (int i = 0; i < 3; ++i) out->xyz[i] = v[i];
+  out->imgsz[0] = (int32_t)v[6];
+  out->imgsz[1] = (int32_t)v[7];
+  out->f[0] = v[8];
+  out->f[1] = v[9];
+  out->cc[0] = out->imgsz[0] / 2.0 + v[10];
+  out->cc[1] = out->imgsz[1] / 2.0 + v[11];
+  for (int i = 0; i < 6; ++i) out->k[i] = v[12 + i];
+  out->p[0] = v[18];
+  out->p[1] = v[19];
+  if (corr) {
+    out->has_corr = 1;
+    out->corr_c1 = corr[1] - 1.0;
+    out->corr_c2 = 2.0 * corr[0];
+  }
+  return GB_OK;
+}
+
+int gb_project(const gb_camera* cam, const double* xyz, int64_t n, double* uv, void* stream) {
+  if (!cam || (n > 0 && (!xyz || !uv))) return fail(GB_E_INVALID, "null argument%s");
+  if (n <= 0) return GB_OK;
+  k_project<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*cam, xyz, n, uv);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_unproject(const gb_camera* cam, const double* uv, int64_t n, int directions, const double* depth, double* xyz,
+                 void* stream) {
+  if (!cam || (n > 0 && (!xyz || !uv))) return fail(GB_E_INVALID, "null argument%s");
+  if (n <= 0) return GB_OK;
+  k_unproject<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*cam, uv, n, directions, depth, xyz);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_gray_from_u8(const uint8_t* src, int32_t height, int32_t width, int32_t nchan, uint16_t* dst, int32_t pitch,
+                    void* stream) {
+  if (!src || !dst || height <= 0 || width <= 0 || nchan < 1 || nchan > 4 || pitch < width)
+    return fail(GB_E_INVALID, "bad frame arguments (1..4 uint8 bands)%s");
+  k_gray_from_u8<<<grid_for((int64_t)height * width, 256), 256, 0, (cudaStream_t)stream>>>(src, height, width, nchan, dst, pitch);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_state_from_rows(const double* rows, int64_t npoints, int64_t n, double* state, void* stream) {
+  if (!rows || !state) return fail(GB_E_INVALID, "null argument%s");
+  k_state_from_rows<<<grid_for(npoints * n, 256), 256, 0, (cudaStream_t)stream>>>(rows, npoints, n, state);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* rows, void* stream) {
+  if (!rows || !state) return fail(GB_E_INVALID, "null argument%s");
+  k_state_to_rows<<<grid_for(npoints * n, 256), 256, 0, (cudaStream_t)stream>>>(state, npoints, n, rows);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t prefer_cluster,
+                 gb_plan* plan) {
+  if (!plan || n_particles <= 0 || tile_w < 1 || tile_h < 1) return fail(GB_E_INVALID, "bad plan arguments%s");
+  if ((int64_t)tile_w * tile_h > GB_MAX_TEMPLATE) return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
+  if (prefer_cluster != 0 && prefer_cluster != 1 && prefer_cluster != 2 && prefer_cluster != 4 && prefer_cluster != 8)
+    return fail(GB_E_INVALID, "cluster size must be 0 (auto), 1, 2, 4 or 8%s");
+  memset(plan, 0, sizeof(*plan));
+  plan->threads = GB_THREADS;
+  plan->max_template = tile_w * tile_h;
+  // tile capacity we want on chip: a search window that exceeds the template by 64 px each way
+  const int64_t want = tile_bytes_needed(tile_w + 64, tile_h + 64, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h);
+  const int avail = kMaxSmem - kHeaderBytes;
+  int chosen = 0;
+  for (int cs = 1; cs <= GB_MAX_CLUSTER; cs *= 2) {
+    if (prefer_cluster && cs != prefer_cluster) continue;
+    int64_t nl = (n_particles + cs - 1) / cs;
+    nl = (nl + 1) / 2 * 2;
+    const int64_t pbytes = nl * 72;
+    const bool fits = pbytes + (prefer_cluster ? tile_bytes_needed(tile_w + 3, tile_h + 3, tile_w, tile_h, 256, 16) : want) <= avail;
+    if (fits) {
+      chosen = cs;
+      plan->cluster = cs;
+      plan->n_local = (int32_t)nl;
+      plan->particles_in_smem = 1;
+      plan->tile_bytes = (int32_t)(avail - pbytes);
+      plan->smem_bytes = kMaxSmem;
+      plan->scratch_bytes = 0;
+      break;
+    }
+  }
+  if (!chosen) {
+    const int cs = prefer_cluster ? prefer_cluster : GB_MAX_CLUSTER;
+    int64_t nl = (n_particles + cs - 1) / cs;
+    nl = (nl + 1) / 2 * 2;
+    if (nl > 0x7fffffff / 16) return fail(GB_E_RESOURCE, "too many particles per point%s");
+    plan->cluster = cs;
+    plan->n_local = (int32_t)nl;
+    plan->particles_in_smem = 0;
+    plan->tile_bytes = avail;
+    plan->smem_bytes = kMaxSmem;
+    plan->scratch_bytes = npoints * cs * 9 * nl * (int64_t)sizeof(double);
+  }
+  return GB_OK;
+}
+
+int gb_track_init(const gb_track_desc* d, int32_t t, void* stream) {
+  if (!d) return fail(GB_E_INVALID, "null descriptor%s");
+  int rc = check_desc(*d);
+  if (rc) return rc;
+  if (t < 0 || t >= d->T) return fail(GB_E_INVALID, "time index out of range%s");
+  if ((rc = ensure_tables())) return rc;
+  StepParams prm;
+  fill_params(*d, t, prm);
+  if ((rc = launch_init(prm, d->covariances != nullptr, (cudaStream_t)stream))) return rc;
+  return launch_template(prm, (cudaStream_t)stream);
+}
+
+int gb_track_step(const gb_track_desc* d, int32_t t, const gb_stage_io* io, void* stream) {
+  if (!d) return fail(GB_E_INVALID, "null descriptor%s");
+  int rc = check_desc(*d);
+  if (rc) return rc;
+  if (t < 1 || t >= d->T) return fail(GB_E_INVALID, "time index out of range%s");
+  if ((rc = ensure_tables())) return rc;
+  StepParams prm;
+  fill_params(*d, t, prm);
+  if (io) prm.io = *io;
+  return d->covariances ? launch_step<true>(prm, d->plan, (cudaStream_t)stream)
+                        : launch_step<false>(prm, d->plan, (cudaStream_t)stream);
+}
+
+int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
+  if (!d) return fail(GB_E_INVALID, "null descriptor%s");
+  int rc = check_desc(*d);
+  if (rc) return rc;
+  if (!d->mask_host || !d->first_host || !d->last_host) return fail(GB_E_INVALID, "host copies of mask/first/last required%s");
+  if ((rc = ensure_tables())) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool cov = d->covariances != nullptr;
+  int64_t launches = 0;
+  // per-time work flags from the host copies (tracker.py:321-347)
+  StepParams probe;
+  fill_params(*d, 0, probe);
+  for (int t = 0; t < d->T; ++t) {
+    bool any_init = false, any_step = false, any_tmpl = false, staggered = false;
+    for (int64_t p = 0; p < d->P; ++p) {
+      const int f = d->first_host[p], l = d->last_host[p];
+      if (f == t && l >= t) any_init = true;
+      if (f < t && t <= l) any_step = true;
+      if (f <= t && t <= l)
+        for (int o = 0; o < d->O; ++o)
+          if (probe.tmpl_frame[o] == t && d->mask_host[p * d->O + o]) {
+            any_tmpl = true;
+            if (f < t) staggered = true;
+          }
+    }
+    if (!any_init && !any_step) continue;
+    StepParams prm;
+    fill_params(*d, t, prm);
+    if (any_init) {
+      if ((rc = launch_init(prm, cov, stream))) return rc;
+      ++launches;
+    }
+    if (staggered) {
+      if (!d->weight_state) return fail(GB_E_INVALID, "weight_state is required when a template starts after a point's first frame%s");
+      dim3 grid((unsigned)grid_for(d->N, 256), (unsigned)d->P, 1);
+      k_evolve<<<grid, 256, 0, stream>>>(d->motion, d->P, d->N, prm.tau, prm.tau2, d->step_normals, (int64_t)(d->T - 1) * d->N * 3,
+                                         ((t - 1) & 1) ? d->state_b : d->state_a, d->first, d->last, d->status, t, d->rng_mode,
+                                         d->seed, d->T - 1, d->point_offset);
+      GB_CUDA(cudaGetLastError());
+      ++launches;
+      prm.skip_evolve = 1;
+    }
+    if (any_tmpl) {
+      if ((rc = launch_template(prm, stream))) return rc;
+      ++launches;
+    }
+    if (any_step) {
+      rc = cov ? launch_step<true>(prm, d->plan, stream) : launch_step<false>(prm, d->plan, stream);
+      if (rc) return rc;
+      ++launches;
+    }
+  }
+  if (launches_out) *launches_out = launches;
+  return GB_OK;
+}
+
+int gb_evolve(const gb_motion* motion, int64_t P, int64_t N, double tau, double tau2, const double* normals, double* state,
+              void* stream) {
+  if (!motion || !normals || !state || P <= 0 || N <= 0) return fail(GB_E_INVALID, "bad arguments%s");
+  dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
+  k_evolve<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, P, N, tau, tau2, normals, N * 3, state, nullptr, nullptr, nullptr, 0,
+                                                   GB_RNG_SUPPLIED, 0, 0, 0);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_moments(const double* particles, const double* weights, int64_t n, double* mean, double* sigma, double* cov,
+               void* stream) {
+  if (!particles || !weights || !mean || n <= 0) return fail(GB_E_INVALID, "bad arguments%s");
+  k_moments<<<1, GB_THREADS, kHeaderBytes, (cudaStream_t)stream>>>(particles, weights, n, mean, sigma, cov);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""Frame holders: ``Image`` (photograph + per-frame Camera) and ``Raster`` (DEM / viewshed grid).
+
+Mirrors the parts of reference ``image.py:86-119,137-214,279-299`` and ``raster.py:30-421,891-1027``
+that the Tracker touches.  File decoding is host I/O and out of scope; in-memory arrays are the
+norm (``img.array = ndarray``), with an OpenCV read as a convenience when a path exists.
+"""
+from __future__ import annotations
+
+import datetime as _dt
+import os
+from typing import Iterable, Optional, Union
+
+import numpy as np
+
+from . import _lib
+from .camera import Camera
+
+
+class Image:
+    """Photograph taken by a :class:`Camera` at a known time (reference ``image.py:17-119``)."""
+
+    def __init__(self, path, cam: Union[dict, Camera] = None, datetime: _dt.datetime = None, exif=None) -> None:
+        self.path = str(path)
+        if isinstance(cam, dict):
+            cam = Camera(**cam)
+        if cam is None:
+            raise ValueError("Image needs a Camera (EXIF parsing is out of scope)")
+        if datetime is None:
+            raise ValueError("Image needs a datetime (EXIF parsing is out of scope)")
+        self.cam = cam
+        self.datetime = datetime
+        self.exif = exif
+        self.array: Optional[np.ndarray] = None
+
+    @property
+    def size(self) -> np.ndarray:
+        return self.cam.imgsz
+
+    def read(self, box: Iterable[int] = None, cache: bool = True) -> np.ndarray:
+        """Pixel array, optionally cropped to (left, top, right, bottom) (reference image.py:137-214)."""
+        array = self.array
+        if array is None:
+            if not os.path.exists(self.path):
+                raise FileNotFoundError(f"{self.path}: set Image.array or give a readable path")
+            import cv2
+
+            array = cv2.imread(self.path, cv2.IMREAD_UNCHANGED)
+            if array is None:
+                raise IOError(f"Could not decode {self.path}")
+            if array.ndim == 3:
+                array = array[:, :, ::-1]
+            w, h = (int(v) for v in self.cam.imgsz)
+            if (array.shape[1], array.shape[0]) != (w, h):
+                array = cv2.resize(array, (w, h), interpolation=cv2.INTER_AREA)
+            array = np.ascontiguousarray(array)
+            if cache:
+                self.array = array
+        if box is not None:
+            array = array[box[1]:box[3], box[0]:box[2]]
+        return array
+
+    def xyz_to_uv(self, xyz, **kwargs):
+        return self.cam.xyz_to_uv(xyz, **kwargs)
+
+    def uv_to_xyz(self, uv, directions: bool = False, **kwargs):
+        return self.cam.uv_to_xyz(uv, directions=directions, **kwargs)
+
+    def inbounds(self, uv):
+        return self.cam.inframe(uv)
+
+
+class Raster:
+    """Regular grid of values (reference ``raster.py:523-560``): DEM, DEM uncertainty or viewshed.
+
+    ``x`` / ``y`` are the outer limits (left, right) / (top, bottom) or cell-centre vectors, exactly
+    as the reference accepts them; a scalar ``array`` is the constant surface the motion models build
+    from numbers (reference ``track/motion.py:136-141``).
+    """
+
+    def __init__(self, array, x=None, y=None, datetime: _dt.datetime = None) -> None:
+        self.array = np.atleast_2d(np.asarray(array, dtype=float)) if np.ndim(array) else np.asarray(array, dtype=float)
+        self.datetime = datetime
+        shape = self.array.shape if self.array.ndim == 2 else (1, 1)
+        self.xlim = self._limits(x, shape[1])
+        self.ylim = self._limits(y, shape[0])
+
+    @staticmethod
+    def _limits(value, n) -> np.ndarray:
+        if value is None:
+            return np.array((0.0, float(n)))
+        value = np.atleast_1d(np.asarray(value, dtype=float))
+        if value.size > 2:  # cell centres
+            d = value[1] - value[0]
+            return np.array((value[0] - d / 2, value[-1] + d / 2))
+        return value.astype(float)
+
+    @property
+    def size(self) -> np.ndarray:
+        if self.array.ndim != 2:
+            return np.array((1, 1))
+        return np.array(self.array.shape[::-1])
+
+    @property
+    def constant(self) -> bool:
+        return self.array.ndim != 2 or self.array.size == 1
+
+    def lower(self, torch, device) -> "tuple[_lib.gb_surface, object]":
+        """-> (``gb_surface``, device tensor kept alive by the caller)."""
+        s = _lib.gb_surface()
+        s.xmin, s.xmax = float(min(self.xlim)), float(max(self.xlim))
+        s.ymin, s.ymax = float(min(self.ylim)), float(max(self.ylim))
+        if self.constant:
+            s.z = None
+            s.value = float(self.array.flat[0])
+            return s, None
+        ny, nx = self.array.shape
+        dx = (self.xlim[1] - self.xlim[0]) / nx
+        dy = (self.ylim[1] - self.ylim[0]) / ny
+        z = self.array.T  # (nx, ny)
+        if dx < 0:
+            z = z[::-1, :]
+        if dy < 0:
+            z = z[:, ::-1]
+        if nx < 2 or ny < 2:
+            raise NotImplementedError("1-D rasters are not supported on device")
+        tensor = torch.as_tensor(np.ascontiguousarray(z)).to(device)
+        s.z = tensor.data_ptr()
+        s.nx, s.ny = nx, ny
+        s.dx, s.dy = abs(dx), abs(dy)
+        s.x0, s.y0 = s.xmin + s.dx / 2, s.ymin + s.dy / 2
+        s.value = 0.0
+        return s, tensor

@@ -1,0 +1,94 @@
+"""Motion models (reference ``track/motion.py:92-311``) as parameter holders that the Tracker lowers
+to ``gb_motion`` structs; ``evolve_particles`` is also callable on its own (``gb_evolve``)."""
+from __future__ import annotations
+
+import ctypes as C
+import datetime as _dt
+from typing import Iterable, Union
+
+import numpy as np
+
+from . import _lib
+from .image import Raster
+
+Number = Union[int, float]
+
+
+def _as_raster(value) -> Raster:
+    if hasattr(value, "array") and hasattr(value, "xlim"):
+        return value
+    if value is None:
+        # reference motion.py:139-141 wraps None as well, and then fails on first use
+        raise ValueError("dem_sigma=None is not usable (the reference raises KeyError on it); pass 0")
+    return Raster(value, x=(-np.inf, np.inf), y=(-np.inf, np.inf))
+
+
+class CartesianMotion:
+    """Random-acceleration model with independent x, y, z components (reference motion.py:92-204)."""
+
+    kind = _lib.GB_MOTION_CARTESIAN
+
+    def __init__(self, xy, time_unit: _dt.timedelta, dem, dem_sigma=0.0, n: int = 1000, xy_sigma=(0, 0),
+                 vxyz=(0, 0, 0), vxyz_sigma=(0, 0, 0), axyz=(0, 0, 0), axyz_sigma=(0, 0, 0)) -> None:
+        self.xy = xy
+        self.time_unit = time_unit
+        self.dem = _as_raster(dem)
+        self.dem_sigma = _as_raster(dem_sigma)
+        self.n = n
+        self.xy_sigma = xy_sigma
+        self.vxyz = vxyz
+        self.vxyz_sigma = vxyz_sigma
+        self.axyz = axyz
+        self.axyz_sigma = axyz_sigma
+
+    def _velocity(self):
+        return self.vxyz, self.vxyz_sigma, self.axyz, self.axyz_sigma
+
+    def lower(self, dem_index: int, dem_sigma_index: int) -> _lib.gb_motion:
+        m = _lib.gb_motion()
+        m.kind = self.kind
+        m.dem, m.dem_sigma = dem_index, dem_sigma_index
+        v, vs, a, as_ = self._velocity()
+        m.xy[:] = np.asarray(self.xy, dtype=float).tolist()
+        m.xy_sigma[:] = np.broadcast_to(np.asarray(self.xy_sigma, dtype=float), (2,)).tolist()
+        m.v[:] = np.asarray(v, dtype=float).tolist()
+        m.v_sigma[:] = np.asarray(vs, dtype=float).tolist()
+        m.a[:] = np.asarray(a, dtype=float).tolist()
+        m.a_sigma[:] = np.asarray(as_, dtype=float).tolist()
+        return m
+
+    def evolve_particles(self, particles: np.ndarray, dt: _dt.timedelta) -> None:
+        """In-place motion step on (n, 6) particles with draws from ``np.random.randn(n, 3)`` — the
+        reference's call (motion.py:165-179) — evaluated by ``gb_evolve``."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        n = len(particles)
+        tau = dt.total_seconds() / self.time_unit.total_seconds()
+        normals = torch.as_tensor(np.random.randn(n, 3)).cuda()
+        state = torch.as_tensor(np.ascontiguousarray(particles.T)).cuda()  # [6][n]
+        motion = torch.frombuffer(bytearray(bytes(self.lower(0, 0))), dtype=torch.uint8).cuda()
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.gb_evolve(motion.data_ptr(), 1, n, tau, tau ** 2, normals.data_ptr(), state.data_ptr(), stream))
+        particles[:] = state.cpu().numpy().T
+
+
+class CylindricalMotion(CartesianMotion):
+    """Speed / heading / elevation components (reference motion.py:207-311)."""
+
+    kind = _lib.GB_MOTION_CYLINDRICAL
+
+    def __init__(self, xy, time_unit: _dt.timedelta, dem, dem_sigma=0.0, n: int = 1000, xy_sigma=(0, 0),
+                 vrthz=(0, 0, 0), vrthz_sigma=(0, 0, 0), arthz=(0, 0, 0), arthz_sigma=(0, 0, 0)) -> None:
+        self.xy = xy
+        self.time_unit = time_unit
+        self.dem = _as_raster(dem)
+        self.dem_sigma = _as_raster(dem_sigma)
+        self.n = n
+        self.xy_sigma = xy_sigma
+        self.vrthz = vrthz
+        self.vrthz_sigma = vrthz_sigma
+        self.arthz = arthz
+        self.arthz_sigma = arthz_sigma
+
+    def _velocity(self):
+        return self.vrthz, self.vrthz_sigma, self.arthz, self.arthz_sigma

@@ -1,0 +1,336 @@
+"""Device session of one ``Tracker.track`` call: uploads frames and models, owns every device
+buffer, fills the ``gb_track_desc`` and calls the C ABI.  Also used by the parity tests to drive
+single teacher-forced steps (``gb_track_init`` / ``gb_track_step``)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .camera import lower_camera
+from .image import Raster
+
+
+def _struct_array_to_device(torch, structs, ctype, device):
+    arr = (ctype * len(structs))(*structs)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def point_span(image_index: np.ndarray, observer_mask: np.ndarray):
+    """first / last time index with an image from a masked observer, per point (reference
+    tracker.py:321-325; argmax semantics: a point with no image at all spans the whole sequence)."""
+    has = image_index >= 0  # (T, O)
+    observed = (observer_mask.astype(np.int64) @ has.T.astype(np.int64)) > 0  # (P, T)
+    first = np.argmax(observed, axis=1)
+    last = observed.shape[1] - 1 - np.argmax(observed[:, ::-1], axis=1)
+    return first.astype(np.int32), last.astype(np.int32)
+
+
+def empty_result(P, T, O, return_covariances, return_particles, N=0) -> dict:
+    out = {
+        "means": np.full((P, T, 6), np.nan),
+        "sigmas": np.full((P, T, 6, 6) if return_covariances else (P, T, 6), np.nan),
+        "status": np.zeros(P, dtype=np.int32), "status_time": np.zeros(P, dtype=np.int32),
+        "obs_flags": np.zeros((P, T, O), dtype=np.uint8),
+    }
+    if return_particles:
+        out["particles"], out["weights"] = np.full((P, T, N, 6), np.nan), np.full((P, T, N), np.nan)
+    return out
+
+
+def reference_order_draws(P, N, steps_per_point):
+    """Draws from the legacy global NumPy generator in the reference's order: per point
+    randn(N,2), randn(N), randn(N,3); then per update randn(N,3) and one random()."""
+    S = int(max(steps_per_point)) if len(steps_per_point) else 0
+    init = np.empty((P, N, 6))
+    step = np.zeros((P, max(S, 1), N, 3))
+    unif = np.zeros((P, max(S, 1)))
+    for p in range(P):
+        init[p, :, 0:2] = np.random.randn(N, 2)
+        init[p, :, 2] = np.random.randn(N)
+        init[p, :, 3:6] = np.random.randn(N, 3)
+        for s in range(int(steps_per_point[p])):
+            step[p, s] = np.random.randn(N, 3)
+            unif[p, s] = np.random.random()
+    return init, step, unif
+
+
+class _Adopted:
+    """Reference motion-model object (duck-typed by attributes) presented through ``lower``."""
+
+    def __init__(self, model, kind):
+        self._m, self._kind = model, kind
+        self.dem, self.dem_sigma, self.n, self.time_unit = model.dem, model.dem_sigma, model.n, model.time_unit
+
+    def lower(self, dem_index, dem_sigma_index):
+        from .motion import CartesianMotion, CylindricalMotion
+
+        m = self._m
+        if self._kind == _lib.GB_MOTION_CARTESIAN:
+            tmp = CartesianMotion(m.xy, m.time_unit, 0.0, 0.0, m.n, m.xy_sigma, m.vxyz, m.vxyz_sigma, m.axyz, m.axyz_sigma)
+        else:
+            tmp = CylindricalMotion(m.xy, m.time_unit, 0.0, 0.0, m.n, m.xy_sigma, m.vrthz, m.vrthz_sigma, m.arthz, m.arthz_sigma)
+        return tmp.lower(dem_index, dem_sigma_index)
+
+
+def adopt_model(model):
+    """Built-in models of this package pass through; the reference's are recognised by class name and
+    attributes.  Anything else has no device kernel."""
+    if hasattr(model, "lower"):
+        return model
+    name = type(model).__name__
+    if name == "CartesianMotion" and hasattr(model, "vxyz"):
+        return _Adopted(model, _lib.GB_MOTION_CARTESIAN)
+    if name == "CylindricalMotion" and hasattr(model, "vrthz"):
+        return _Adopted(model, _lib.GB_MOTION_CYLINDRICAL)
+    raise NotImplementedError(f"motion model {name} has no device kernel (no CPU fallback)")
+
+
+class Session:
+    def __init__(self, tracker, models, image_index, taus, tile_size, observer_mask, return_covariances=False,
+                 return_particles=False, point_offset=0, draws=None):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.tracker = tracker
+        self.device = torch.device(tracker.device) if tracker.device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.P, self.T, self.O = len(models), image_index.shape[0], image_index.shape[1]
+        P, T, O = self.P, self.T, self.O
+        N = self.N = int(models[0].n)
+        if any(int(m.n) != N for m in models):
+            raise NotImplementedError("all motion models of one track() call must have the same number of particles")
+        if O > _lib.GB_MAX_OBS:
+            raise NotImplementedError(f"at most {_lib.GB_MAX_OBS} observers")
+        self.tw, self.th = (int(v) for v in tile_size)
+        self.return_covariances, self.return_particles = return_covariances, return_particles
+        self.image_index = np.ascontiguousarray(image_index, dtype=np.int32)
+        self.taus = np.ascontiguousarray(taus, dtype=float)
+        observer_mask = np.asarray(observer_mask, dtype=bool).reshape(P, O)
+        device = self.device
+        self.keep = []
+        with torch.cuda.device(device):
+            self.stream = torch.cuda.current_stream().cuda_stream
+            self.plan = _lib.gb_plan()
+            _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, int(tracker.cluster), C.byref(self.plan)))
+            self.h2d = 0
+            images_dev, self.offsets = self._upload_frames()
+            motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)
+            self.first, self.last = point_span(self.image_index, observer_mask)
+            self.tmpl_frame = np.array([int(np.argmax(self.image_index[:, o] >= 0)) if (self.image_index[:, o] >= 0).any() else -1
+                                        for o in range(O)])
+            tf = self.tmpl_frame[None, :]
+            staggered = bool(np.any(observer_mask & (tf > self.first[:, None]) & (tf >= 0) & (tf <= self.last[:, None])))
+            f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+            dev = dict(device=device)
+            self.mask_h = np.ascontiguousarray(observer_mask.astype(np.uint8))
+            self.scale_h = np.array([1 / (2 * obs.sigma ** 2) for obs in tracker.observers], dtype=float)
+            self.tau2_h = np.array([float(t) ** 2 for t in self.taus], dtype=float)
+            b = self.buf = {}
+            b["mask"] = torch.as_tensor(self.mask_h).to(device)
+            b["first"], b["last"] = torch.as_tensor(self.first).to(device), torch.as_tensor(self.last).to(device)
+            b["state_a"] = torch.empty((P, 6, N), dtype=f64, **dev)
+            b["state_b"] = torch.empty((P, 6, N), dtype=f64, **dev)
+            b["weight_state"] = torch.empty((P, N), dtype=f64, **dev) if (staggered or return_particles) else None
+            b["scratch"] = torch.empty((self.plan.scratch_bytes // 8,), dtype=f64, **dev) if self.plan.scratch_bytes else None
+            ta = self.tw * self.th
+            b["tmpl_tile"] = torch.zeros((P, O, ta), dtype=f64, **dev)
+            b["tmpl_values"] = torch.zeros((P, O, ta), dtype=f64, **dev)
+            b["tmpl_quantiles"] = torch.zeros((P, O, ta), dtype=f64, **dev)
+            b["tmpl_nvalues"] = torch.zeros((P, O), dtype=i32, **dev)
+            b["tmpl_box"] = torch.zeros((P, O, 4), dtype=i32, **dev)
+            b["tmpl_duv"] = torch.zeros((P, O, 2), dtype=f64, **dev)
+            nan = float("nan")
+            b["means"] = torch.full((P, T, 6), nan, dtype=f64, **dev)
+            b["sig"] = torch.full((P, T, 36 if return_covariances else 6), nan, dtype=f64, **dev)
+            b["particles"] = torch.full((P, T, N, 6), nan, dtype=f64, **dev) if return_particles else None
+            b["weights"] = torch.full((P, T, N), nan, dtype=f64, **dev) if return_particles else None
+            b["status"] = torch.zeros((P,), dtype=i32, **dev)
+            b["status_time"] = torch.zeros((P,), dtype=i32, **dev)
+            b["obs_flags"] = torch.zeros((P, T, O), dtype=u8, **dev)
+            b["window"] = torch.zeros((P, T, O, 2), dtype=i32, **dev)
+
+            d = self.desc = _lib.gb_track_desc()
+            d.P, d.N, d.T, d.O, d.tile_w, d.tile_h = P, N, T, O, self.tw, self.th
+            d.images = images_dev.data_ptr()
+            d.image_offset_host = self.offsets.ctypes.data
+            d.image_index_host = self.image_index.ctypes.data
+            d.obs_scale_host = self.scale_h.ctypes.data
+            d.mask, d.first, d.last = b["mask"].data_ptr(), b["first"].data_ptr(), b["last"].data_ptr()
+            d.mask_host, d.first_host, d.last_host = self.mask_h.ctypes.data, self.first.ctypes.data, self.last.ctypes.data
+            d.tau_host, d.tau2_host = self.taus.ctypes.data, self.tau2_h.ctypes.data
+            d.motion, d.surfaces, d.n_surfaces, d.viewshed = motion_dev.data_ptr(), surf_dev.data_ptr(), n_surf, viewshed
+            self.keep += [images_dev, motion_dev, surf_dev]
+            d.point_offset = int(point_offset)
+            if draws is not None or tracker.rng == "numpy":
+                d.rng_mode = _lib.GB_RNG_SUPPLIED
+                if draws is None:
+                    nbytes = P * max(T - 1, 1) * N * 24
+                    if nbytes > 8 << 30:
+                        raise MemoryError("rng='numpy' would need %.1f GiB of supplied normals; use rng='philox'" % (nbytes / 2 ** 30))
+                    draws = reference_order_draws(P, N, self.last - self.first)
+                init, step, unif = draws
+                S = T - 1
+                step_full = np.zeros((P, S, N, 3))
+                unif_full = np.zeros((P, S))
+                step_full[:, : step.shape[1]] = step[:, :S]
+                unif_full[:, : unif.shape[1]] = unif[:, :S]
+                b["init_normals"] = torch.as_tensor(np.ascontiguousarray(init)).to(device)
+                b["step_normals"] = torch.as_tensor(step_full).to(device)
+                b["uniforms"] = torch.as_tensor(unif_full).to(device)
+                d.init_normals, d.step_normals, d.uniforms = (b[k].data_ptr() for k in ("init_normals", "step_normals", "uniforms"))
+                self.h2d += (init.size + step_full.size + unif_full.size) * 8
+            elif tracker.rng == "philox":
+                d.rng_mode = _lib.GB_RNG_PHILOX
+                seed = tracker.seed if tracker.seed is not None else int(np.random.randint(0, 2 ** 62))
+                d.seed = int(seed) % (1 << 64)
+            else:
+                raise ValueError("rng must be 'philox' or 'numpy'")
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            d.state_a, d.state_b = ptr(b["state_a"]), ptr(b["state_b"])
+            d.weight_state, d.scratch = ptr(b["weight_state"]), ptr(b["scratch"])
+            d.tmpl_tile, d.tmpl_values, d.tmpl_quantiles = ptr(b["tmpl_tile"]), ptr(b["tmpl_values"]), ptr(b["tmpl_quantiles"])
+            d.tmpl_nvalues, d.tmpl_box, d.tmpl_duv = ptr(b["tmpl_nvalues"]), ptr(b["tmpl_box"]), ptr(b["tmpl_duv"])
+            d.means = ptr(b["means"])
+            if return_covariances:
+                d.covariances = ptr(b["sig"])
+            else:
+                d.sigmas = ptr(b["sig"])
+            d.out_particles, d.out_weights = ptr(b["particles"]), ptr(b["weights"])
+            d.status, d.status_time = ptr(b["status"]), ptr(b["status_time"])
+            d.obs_flags, d.window_stats = ptr(b["obs_flags"]), ptr(b["window"])
+            d.plan = self.plan
+        self.launches = 0
+        self.stats: dict = {}
+
+    # ---------------------------------------------------------------- uploads
+    def _upload_frames(self):
+        """Band-sum uint16 planes + per-image cameras for every image ``image_index`` references
+        (reference ``Observer.cache_images`` / ``Image.read``, tracker.py:295-299)."""
+        torch, device, tracker = self.torch, self.device, self.tracker
+        structs, offsets = [], [0]
+        for o, obs in enumerate(tracker.observers):
+            use_cache = bool(getattr(obs, "cache", True))
+            needed = set(int(v) for v in self.image_index[:, o] if v >= 0)
+            for i, img in enumerate(obs.images):
+                g = _lib.gb_image()
+                if i in needed:
+                    array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
+                    key = (o, i, id(array))
+                    cached = tracker._frame_cache.get(key) if use_cache else None
+                    if cached is None:
+                        if array.dtype != np.uint8:
+                            raise NotImplementedError("device frames must be uint8 (1-4 bands)")
+                        arr = np.ascontiguousarray(array)
+                        h, w = arr.shape[0], arr.shape[1]
+                        nchan = 1 if arr.ndim == 2 else arr.shape[2]
+                        src = torch.from_numpy(arr).to(device, non_blocking=True)
+                        self.h2d += arr.nbytes
+                        pitch = (w + 7) // 8 * 8
+                        plane = torch.empty((h, pitch), dtype=torch.int16, device=device)
+                        _lib.check(self.lib.gb_gray_from_u8(src.data_ptr(), h, w, nchan, plane.data_ptr(), pitch, self.stream))
+                        cached = (plane, w, h, pitch, nchan)
+                        if use_cache:
+                            tracker._frame_cache[key] = cached
+                    plane, w, h, pitch, nchan = cached
+                    self.keep.append(plane)
+                    g.gray = plane.data_ptr()
+                    g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
+                    g.cam = lower_camera(img.cam)
+                structs.append(g)
+            offsets.append(len(structs))
+        images_dev = _struct_array_to_device(torch, structs, _lib.gb_image, device)
+        self.h2d += images_dev.numel()
+        return images_dev, np.asarray(offsets, dtype=np.int32)
+
+    def _lower_models(self, models):
+        torch, device = self.torch, self.device
+        rasters, table = {}, []
+
+        def index_of(raster):
+            if not (hasattr(raster, "array") and hasattr(raster, "xlim")):
+                raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
+            arr = np.asarray(raster.array)
+            key = id(raster)
+            if arr.ndim != 2 or arr.size == 1:  # constant: share by value
+                key = ("const", float(arr.flat[0]), tuple(np.asarray(raster.xlim, dtype=float)),
+                       tuple(np.asarray(raster.ylim, dtype=float)))
+            if key not in rasters:
+                wrapped = raster if isinstance(raster, Raster) else Raster(raster.array, x=raster.xlim, y=raster.ylim)
+                s, tensor = wrapped.lower(torch, device)
+                rasters[key] = len(table)
+                table.append(s)
+                self.keep.append(tensor)
+            return rasters[key]
+
+        motions = []
+        for m in models:
+            m = adopt_model(m)
+            motions.append(m.lower(index_of(m.dem), index_of(m.dem_sigma)))
+        viewshed = index_of(self.tracker.viewshed) if self.tracker.viewshed is not None else -1
+        motion_dev = _struct_array_to_device(torch, motions, _lib.gb_motion, device)
+        surf_dev = _struct_array_to_device(torch, table, _lib.gb_surface, device)
+        self.h2d += motion_dev.numel() + surf_dev.numel()
+        return motion_dev, surf_dev, len(table), viewshed
+
+    # ---------------------------------------------------------------- C-ABI calls
+    def run(self) -> None:
+        """``gb_track``: every time step for every point, asynchronously on the current stream."""
+        launches = C.c_int64(0)
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.gb_track(C.byref(self.desc), self.stream, C.byref(launches)))
+        self.launches += int(launches.value)
+
+    def init(self, t: int) -> None:
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.gb_track_init(C.byref(self.desc), int(t), self.stream))
+
+    def step(self, t: int, io: Optional[_lib.gb_stage_io] = None) -> None:
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.gb_track_step(C.byref(self.desc), int(t), C.byref(io) if io is not None else None, self.stream))
+
+    # ---------------------------------------------------------------- results
+    def fetch(self) -> dict:
+        b, P, T = self.buf, self.P, self.T
+        out = {"means": b["means"].cpu().numpy()}
+        sig = b["sig"].cpu().numpy()
+        out["sigmas"] = sig.reshape(P, T, 6, 6) if self.return_covariances else sig
+        out["status"], out["status_time"] = b["status"].cpu().numpy(), b["status_time"].cpu().numpy()
+        out["obs_flags"] = b["obs_flags"].cpu().numpy()
+        d2h = b["means"].numel() * 8 + b["sig"].numel() * 8 + P * 8 + b["obs_flags"].numel()
+        if self.return_particles:
+            out["particles"], out["weights"] = b["particles"].cpu().numpy(), b["weights"].cpu().numpy()
+            d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
+        win = b["window"].cpu().numpy()
+        used = (out["obs_flags"] == 0) & (win[..., 0] > 0)
+        self.stats = {
+            "plan": {k: getattr(self.plan, k) for k, _ in self.plan._fields_}, "kernel_launches": self.launches,
+            "h2d_bytes": int(self.h2d), "d2h_bytes": int(d2h),
+            "window_width": win[..., 0][used], "window_height": win[..., 1][used],
+        }
+        return out
+
+    def final_state(self):
+        """What the reference leaves on the Tracker: particles / weights / templates of the last track."""
+        b = self.buf
+        final = b["state_b"] if (int(self.last[-1]) & 1) else b["state_a"]
+        particles = final[-1].T.contiguous().cpu().numpy()
+        weights = b["weight_state"][-1].cpu().numpy() if b["weight_state"] is not None else np.ones(self.N)
+        return particles, weights, self.templates(self.P - 1)
+
+    def templates(self, p: int):
+        b = self.buf
+        out = []
+        for o in range(self.O):
+            n_val = int(b["tmpl_nvalues"][p, o])
+            if n_val == 0:
+                out.append(None)
+                continue
+            out.append({
+                "obs": o, "img": int(self.image_index[self.tmpl_frame[o], o]), "box": b["tmpl_box"][p, o].cpu().numpy(),
+                "duv": b["tmpl_duv"][p, o].cpu().numpy(),
+                "tile": b["tmpl_tile"][p, o].cpu().numpy().reshape(self.th, self.tw),
+                "histogram": (b["tmpl_values"][p, o, :n_val].cpu().numpy(), b["tmpl_quantiles"][p, o, :n_val].cpu().numpy()),
+            })
+        return out

@@ -1,0 +1,265 @@
+"""``Tracker``: drop-in for the reference particle filter (``track/tracker.py:21-625``).
+
+Same constructor and ``track()`` signature, same returned :class:`Tracks`; the per-point,
+per-frame work (motion step, projection, tile pipeline, likelihood, resampling, moments) runs in
+the sm_100a kernels behind ``gb_track``.  The host keeps what the reference also does on the host:
+datetime matching, observer masks, error / warning materialisation.
+
+Differences a user can see (all documented in DESIGN.md):
+
+* ``rng="philox"`` (default) draws on the device from Philox4x32-10, keyed by ``seed`` (or by one
+  ``np.random.randint`` draw, so ``np.random.seed`` still makes runs reproducible).  ``rng="numpy"``
+  supplies the reference's exact legacy-MT19937 draw sequence (parity runs; ~2.5e7 normals/s).
+* ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
+  ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
+* Only the default ``resample_method`` / ``highpass`` / ``interpolation`` have kernels; other values
+  raise ``NotImplementedError`` (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime as _dt
+import warnings as _warnings
+from typing import Any, Callable, Iterable, List, Optional, Union
+
+import numpy as np
+
+from . import _lib
+from .tracks import Tracks
+
+OUT_OF_FRAME_MESSAGE = "Particles too close to or beyond image bounds, skipping image"
+
+
+def pairwise_distance_datetimes(x, y) -> np.ndarray:
+    """|x_i - y_j| in seconds (reference helpers.py:1831-1854)."""
+    xs = np.array([v.timestamp() for v in x], dtype=float)
+    ys = np.array([v.timestamp() for v in y], dtype=float)
+    return np.abs(xs[:, None] - ys[None, :])
+
+
+from .session import point_span  # noqa: E402,F401  (re-exported)
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int):
+    """Contiguous block [lo, hi) of ``n_items`` owned by ``rank`` (ceil-sized blocks)."""
+    per = -(-n_items // world_size)
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)
+
+
+class Tracker:
+    """Estimate the trajectory of world points through time (reference ``tracker.py:21-70``)."""
+
+    def __init__(
+        self,
+        observers: Iterable,
+        viewshed=None,
+        resample_method: str = "systematic",
+        highpass: dict = {"size": (5, 5)},
+        interpolation: dict = {"kx": 3, "ky": 3},
+        *,
+        rng: str = "philox",
+        seed: Optional[int] = None,
+        cluster: int = 0,
+        device=None,
+        distributed: bool = True,
+    ) -> None:
+        self.observers = list(observers)
+        self.viewshed = viewshed
+        self.resample_method = resample_method
+        self.highpass = highpass
+        self.interpolation = interpolation
+        self.rng = rng
+        self.seed = seed
+        self.cluster = cluster
+        self.device = device
+        self.distributed = distributed
+        self.particles = None
+        self.weights = None
+        self.templates = None
+        self.last_run: dict = {}
+        self._frame_cache: dict = {}
+
+    # ------------------------------------------------------------------ reference-visible state
+    @property
+    def particle_mean(self) -> np.ndarray:
+        return np.average(self.particles, weights=self.weights, axis=0)
+
+    @property
+    def particle_covariance(self) -> np.ndarray:
+        return np.cov(self.particles.T, aweights=self.weights, ddof=0)
+
+    @property
+    def datetimes(self) -> np.ndarray:
+        return np.unique(np.concatenate([obs.datetimes for obs in self.observers]))
+
+    def reset(self) -> None:
+        self.particles = None
+        self.weights = None
+        self.templates = None
+
+    def clear_device_cache(self) -> None:
+        self._frame_cache.clear()
+
+    # ------------------------------------------------------------------ host-side time logic
+    def parse_datetimes(self, datetimes, maxdt: _dt.timedelta = _dt.timedelta(0)) -> np.ndarray:
+        """(reference tracker.py:425-464)."""
+        datetimes = np.asarray(datetimes)
+        monotonic = (datetimes[1:] >= datetimes[:-1]).all() or (datetimes[1:] <= datetimes[:-1]).all()
+        if not monotonic:
+            raise ValueError("Datetimes must be monotonic")
+        selected = np.concatenate(((True,), datetimes[1:] != datetimes[:-1]))
+        if not all(selected):
+            _warnings.warn("Dropping duplicate datetimes")
+            datetimes = datetimes[selected]
+        distances = pairwise_distance_datetimes(datetimes, self.datetimes)
+        selected = distances.min(axis=1) <= abs(maxdt.total_seconds())
+        if not all(selected):
+            _warnings.warn("Dropping datetimes not matching any Observers")
+            datetimes = datetimes[selected]
+        if len(datetimes) < 2:
+            raise ValueError("Fewer than two valid datetimes")
+        return datetimes
+
+    def match_datetimes(self, datetimes, maxdt: _dt.timedelta = _dt.timedelta(0)) -> np.ndarray:
+        """Grid (T, O) of matching image indices, ``None`` = no match (reference tracker.py:466-492)."""
+        matches = np.full((len(datetimes), len(self.observers)), None)
+        for i, observer in enumerate(self.observers):
+            distances = pairwise_distance_datetimes(datetimes, observer.datetimes)
+            nearest = np.argmin(distances, axis=1)
+            matches[:, i] = nearest
+            too_far = distances[np.arange(distances.shape[0]), nearest] > abs(maxdt.total_seconds())
+            matches[too_far, i] = None
+        return matches
+
+    # ------------------------------------------------------------------ the public entry point
+    def track(
+        self,
+        motion_models: Iterable,
+        datetimes: Iterable[_dt.datetime] = None,
+        maxdt: _dt.timedelta = _dt.timedelta(0),
+        tile_size: Iterable[int] = (15, 15),
+        observer_mask: np.ndarray = None,
+        return_covariances: bool = False,
+        return_particles: bool = False,
+        reduce_particles: Callable[[np.ndarray, np.ndarray], Any] = None,
+        parallel: Union[bool, int] = False,
+    ) -> Tracks:
+        """Track particles through time (reference ``tracker.py:225-417``)."""
+        if reduce_particles:
+            return_particles = True
+        params = dict(motion_models=motion_models, datetimes=datetimes, maxdt=maxdt, tile_size=tile_size,
+                      observer_mask=observer_mask, return_covariances=return_covariances,
+                      return_particles=return_particles, reduce_particles=reduce_particles, parallel=parallel)
+        motion_models = list(motion_models)
+        time_unit = motion_models[0].time_unit
+        for model in motion_models[1:]:
+            if model.time_unit != time_unit:
+                raise ValueError("Motion models must have equal time units")
+        if self.resample_method != "systematic":
+            raise NotImplementedError("only resample_method='systematic' has a device kernel")
+        if tuple(self.highpass.get("size", ())) != (5, 5) or set(self.highpass) - {"size"}:
+            raise NotImplementedError("only highpass={'size': (5, 5)} has a device kernel")
+        if self.interpolation.get("kx", 3) != 3 or self.interpolation.get("ky", 3) != 3 or set(self.interpolation) - {"kx", "ky"}:
+            raise NotImplementedError("only interpolation={'kx': 3, 'ky': 3} has a device kernel")
+        self.reset()
+        ntracks = len(motion_models)
+        raise_errors = ntracks < 2
+        if datetimes is None:
+            datetimes = self.datetimes
+        else:
+            datetimes = self.parse_datetimes(datetimes=datetimes, maxdt=maxdt)
+        if observer_mask is None:
+            observer_mask = np.ones((ntracks, len(self.observers)), dtype=bool)
+        observer_mask = np.asarray(observer_mask, dtype=bool).reshape(ntracks, len(self.observers))
+        matching_images = self.match_datetimes(datetimes=datetimes, maxdt=maxdt)
+        image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching_images], dtype=np.int32)
+        unit = time_unit.total_seconds()
+        taus = np.array([dt.total_seconds() / unit for dt in np.diff(datetimes)], dtype=float)
+
+        # points owned by this rank
+        lo, hi, world, rank = 0, ntracks, 1, 0
+        dist = None
+        if self.distributed:
+            try:
+                import torch.distributed as dist_mod
+
+                if dist_mod.is_available() and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
+                    dist = dist_mod
+                    world, rank = dist.get_world_size(), dist.get_rank()
+                    lo, hi = shard_bounds(ntracks, world, rank)
+            except ImportError:
+                pass
+        local = self._track_local(motion_models[lo:hi], image_index, taus, tuple(int(v) for v in tile_size),
+                                  observer_mask[lo:hi], return_covariances, return_particles, point_offset=lo)
+        if dist is not None:
+            local = self._gather(dist, local, ntracks, world)
+
+        # materialise errors / warnings the way the reference reports them (tracker.py:358-368)
+        errors: List[Optional[BaseException]] = []
+        all_warnings: List[Optional[tuple]] = []
+        status, status_time, flags = local["status"], local["status_time"], local["obs_flags"]
+        for p in range(ntracks):
+            err = None
+            limit = flags.shape[1]
+            if status[p] != 0:
+                cls, msg = _lib.GB_ST_MESSAGES[int(status[p])]
+                err = cls(f"{msg} (track {p}, time index {int(status_time[p])})")
+                limit = int(status_time[p])
+            errors.append(err)
+            caught = tuple(UserWarning(OUT_OF_FRAME_MESSAGE) for _ in np.argwhere(flags[p, :limit] == _lib.GB_OBS_OUT_OF_FRAME))
+            all_warnings.append(caught if caught else None)
+        if raise_errors and errors and errors[0] is not None:
+            raise errors[0]
+        kwargs = dict(time_unit=time_unit, datetimes=datetimes, means=local["means"], tracker=self,
+                      images=matching_images, params=params, errors=errors, warnings=all_warnings)
+        particles, weights = local.get("particles"), local.get("weights")
+        reduced = None
+        if reduce_particles:
+            reduced = [reduce_particles(particles[p], weights[p]) for p in range(ntracks)]
+            particles = weights = None
+        kwargs["particles"], kwargs["weights"] = particles, weights
+        if return_covariances:
+            kwargs["covariances"] = local["sigmas"]
+        else:
+            kwargs["sigmas"] = local["sigmas"]
+        tracks = Tracks(**kwargs)
+        if reduced is not None:
+            tracks.reduced = reduced
+        return tracks
+
+    # ------------------------------------------------------------------ device plumbing
+    def _track_local(self, models, image_index, taus, tile_size, observer_mask, return_covariances, return_particles,
+                     point_offset=0) -> dict:
+        """Run the filter for ``models`` on this process's GPU; returns host arrays."""
+        from .session import Session, empty_result
+
+        if len(models) == 0:
+            return empty_result(0, image_index.shape[0], image_index.shape[1], return_covariances, return_particles)
+        session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
+                          return_particles, point_offset=point_offset)
+        session.run()
+        out = session.fetch()
+        self.last_run = session.stats
+        self.particles, self.weights, self.templates = session.final_state()
+        return out
+
+    # ------------------------------------------------------------------ multi-GPU: one final gather
+    @staticmethod
+    def _gather(dist, local: dict, ntracks: int, world: int) -> dict:
+        """All-gather the per-rank result blocks (points are independent: no per-step collective)."""
+        import torch
+
+        backend = dist.get_backend()
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        per = -(-ntracks // world)
+        merged = {}
+        for key, value in local.items():
+            arr = np.ascontiguousarray(value)
+            pad = np.zeros((per,) + arr.shape[1:], dtype=arr.dtype)
+            pad[: arr.shape[0]] = arr
+            mine = torch.as_tensor(pad).to(device)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            merged[key] = np.concatenate([p.cpu().numpy() for p in parts], axis=0)[:ntracks]
+        return merged

@@ -1,0 +1,278 @@
+/* glimpse_b200 — C ABI of the B200-native `glimpse.Tracker` hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  Every entry point
+ * names the reference interface it replaces (paths relative to /root/reference/src/glimpse).  The
+ * Python host layer (`glimpse_b200/`) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - All functions return 0 on success, a negative GB_E_* code on API misuse / CUDA failure
+ *    (text via gb_last_error()).  Per-point algorithmic failures (the reference's exceptions) are
+ *    reported in `status[P]` as positive GB_ST_* codes, never by the return value.
+ *  - Pointers are DEVICE pointers unless the parameter name ends in `_host`.  The caller owns every
+ *    buffer; the library keeps no pointer after a call returns and never frees caller memory.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are stream-ordered
+ *    and asynchronous unless stated otherwise.
+ *  - Particle state layout ("SoA"): double state[P][6][N], component-major (x, y, z, vx, vy, vz),
+ *    so a warp reads 32 consecutive particles of one component.  The reference's (n, 6) row-major
+ *    arrays (track/tracker.py:37-38) are converted with gb_state_from_rows / gb_state_to_rows.
+ */
+#ifndef GLIMPSE_B200_H
+#define GLIMPSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 1
+
+/* ---- return codes ---- */
+#define GB_OK 0
+#define GB_E_INVALID (-1)   /* bad argument */
+#define GB_E_CUDA (-2)      /* CUDA runtime error */
+#define GB_E_RESOURCE (-3)  /* problem does not fit the on-chip layout (see gb_step_plan) */
+
+/* ---- per-point status (reference exceptions on the path) ---- */
+#define GB_ST_OK 0
+#define GB_ST_NOT_VISIBLE 1     /* ValueError: particles on non-visible viewshed cells (tracker.py:114-117) */
+#define GB_ST_NAN 2             /* ValueError: particles have missing (NaN) values (tracker.py:118-119) */
+#define GB_ST_DEM_BOUNDS 3      /* ValueError: sampling coordinates out of bounds (raster.py:961-973) */
+#define GB_ST_SAMPLE_OUTSIDE 4  /* ValueError: sampling points are outside box (observer.py:201-202) */
+#define GB_ST_TEMPLATE_BOUNDS 5 /* IndexError: box extends beyond grid bounds (raster.py:417-418) */
+#define GB_ST_WINDOW_TOO_LARGE 6 /* search window exceeds the on-chip tile capacity of this launch plan */
+
+/* ---- per-(point, time, observer) flags ---- */
+#define GB_OBS_USED 0
+#define GB_OBS_NO_IMAGE 1    /* masked or no matching image (tracker.py:574-575) */
+#define GB_OBS_OUT_OF_FRAME 2 /* warning: particles too close to or beyond image bounds (tracker.py:597-601) */
+
+#define GB_MOTION_CARTESIAN 0   /* track/motion.py:92-204 */
+#define GB_MOTION_CYLINDRICAL 1 /* track/motion.py:207-311 */
+
+#define GB_RNG_SUPPLIED 0 /* normals / uniforms provided in the reference's draw order */
+#define GB_RNG_PHILOX 1   /* counter-based Philox4x32-10 on device */
+
+/* Camera of one image, already lowered from the reference's 20-vector
+ * [xyz, viewdir, imgsz, f, c, k1..k6, p1, p2] (camera.py:101,127-198): R is `Camera.R`
+ * (camera.py:239-280), cc = imgsz / 2 + c (camera.py:1507).  corr_* implement
+ * helpers.elevation_corrections (helpers.py:1771-1790): dz += corr_c1 * d2 / corr_c2 with
+ * corr_c1 = refraction - 1 and corr_c2 = 2 * radius; has_corr = 0 disables it. */
+typedef struct gb_camera {
+  double R[9];
+  double xyz[3];
+  double f[2];
+  double cc[2];
+  double k[6];
+  double p[2];
+  double corr_c1, corr_c2;
+  int32_t imgsz[2];
+  int32_t has_corr;
+  int32_t pad_;
+} gb_camera;
+
+/* One cached frame (image.py:137-214 with cache=True): `gray` holds the per-pixel SUM over the
+ * `nchan` bands as uint16, so mean(axis=2) (tracker.py:523-524) is gray / nchan.  Row pitch in
+ * elements; pixel (row r, col c) is gray[r * pitch + c]. */
+typedef struct gb_image {
+  const uint16_t* gray;
+  int32_t width, height, pitch, nchan;
+  gb_camera cam;
+} gb_image;
+
+/* DEM / DEM-sigma / viewshed raster in point-sampling form (raster.py:891-1027).  A constant
+ * surface (reference 0-D raster, motion.py:136-141) has z == NULL and returns `value` everywhere.
+ * Otherwise z[ix * ny + iy] on cell centres x0 + ix * dx, y0 + iy * dy (dx, dy > 0, increasing),
+ * and [xmin, xmax] x [ymin, ymax] are the outer limits used for the bounds error. */
+typedef struct gb_surface {
+  const double* z;
+  int32_t nx, ny;
+  double x0, dx, y0, dy;
+  double xmin, xmax, ymin, ymax;
+  double value;
+} gb_surface;
+
+/* Motion-model parameters of one tracked point (CartesianMotion motion.py:122-147 /
+ * CylindricalMotion motion.py:239-258).  For the cylindrical kind v/a are (vr, theta, vz) and
+ * (ar, dtheta/dt, az).  dem / dem_sigma index the `surfaces` table of the call. */
+typedef struct gb_motion {
+  int32_t kind;
+  int32_t dem, dem_sigma;
+  int32_t pad_;
+  double xy[2], xy_sigma[2];
+  double v[3], v_sigma[3];
+  double a[3], a_sigma[3];
+} gb_motion;
+
+/* ------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------ */
+int gb_version(void);
+const char* gb_last_error(void);
+/* Build a gb_camera from the reference 20-vector on the host (libm sin/cos).  corr_host = {radius,
+ * refraction} or NULL.  Replaces Camera.__init__ + Camera.R (camera.py:74-123, 239-280). */
+int gb_camera_from_vector(const double* vec20_host, const double* corr_host, gb_camera* out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Camera (stage entry points; also used by the host-side Camera class)
+ * ------------------------------------------------------------------------------------------ */
+/* Camera.xyz_to_uv (camera.py:591-628): xyz[n][3] -> uv[n][2]; NaN behind the camera. */
+int gb_project(const gb_camera* cam_host, const double* xyz, int64_t n, double* uv, void* stream);
+/* Camera.uv_to_xyz (camera.py:630-663): uv[n][2] -> xyz[n][3].  depth == NULL means depth 1;
+ * otherwise depth[n].  directions != 0 returns ray directions, else adds the camera position. */
+int gb_unproject(const gb_camera* cam_host, const double* uv, int64_t n, int directions, const double* depth,
+                 double* xyz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frames
+ * ------------------------------------------------------------------------------------------ */
+/* uint8 frame (H, W, C) row-major -> uint16 band-sum plane with the given pitch (Image.read +
+ * tile.mean(axis=2) hoisted to upload time; image.py:137-214, tracker.py:523-524). */
+int gb_gray_from_u8(const uint8_t* src, int32_t height, int32_t width, int32_t nchan, uint16_t* dst, int32_t pitch,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * State layout helpers
+ * ------------------------------------------------------------------------------------------ */
+int gb_state_from_rows(const double* rows, int64_t npoints, int64_t n, double* state, void* stream);
+int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The filter
+ * ------------------------------------------------------------------------------------------ */
+/* Launch plan chosen by gb_step_plan: cluster size (CTAs per tracked point), threads per CTA,
+ * dynamic shared memory and how it is split between particle arrays and tile buffers. */
+typedef struct gb_plan {
+  int32_t cluster;          /* CTAs per point (1, 2, 4 or 8) */
+  int32_t threads;          /* threads per CTA */
+  int32_t n_local;          /* particles per CTA */
+  int32_t particles_in_smem; /* 1: evolved state / uv / weights live in shared memory; 0: in `scratch` */
+  int32_t smem_bytes;       /* dynamic shared memory per CTA */
+  int32_t tile_bytes;       /* bytes of it available to the tile pipeline */
+  int32_t max_template;     /* template pixels the plan was sized for */
+  int32_t pad_;
+  int64_t scratch_bytes;    /* global scratch the caller must provide (0 if particles_in_smem) */
+} gb_plan;
+
+/* Size a launch plan for N particles per point and a w x h template.  `prefer_cluster` = 0 lets
+ * the library choose; otherwise forces 1/2/4/8. */
+int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t prefer_cluster,
+                 gb_plan* plan_host);
+
+/* Everything one Tracker.track call needs (track/tracker.py:225-417).  Shapes use P points,
+ * N particles, T times, O observers, S = T - 1 update steps, w x h template. */
+typedef struct gb_track_desc {
+  int64_t P, N;
+  int32_t T, O;
+  int32_t tile_w, tile_h;
+
+  /* frames and cameras: images[image_offset_host[o] + i] is image i of observer o */
+  const gb_image* images;          /* device array */
+  const int32_t* image_offset_host; /* [O + 1] */
+  const int32_t* image_index_host; /* [T][O] image of observer o matched to time t, -1 = none (tracker.py:466-492) */
+  const double* obs_scale_host;    /* [O] 1 / (2 sigma^2) (tracker.py:625) */
+  const uint8_t* mask;             /* device [P][O] observer mask (tracker.py:289-290) */
+  const int32_t* first;            /* device [P] first / last time index with a masked observer image (tracker.py:321-325) */
+  const int32_t* last;
+  const uint8_t* mask_host;        /* host copies of the three arrays above (drive the per-time launch decisions) */
+  const int32_t* first_host;
+  const int32_t* last_host;
+  const double* tau_host;          /* [S] dt / time_unit (motion.py:173) */
+  const double* tau2_host;         /* [S] tau ** 2 as the host language rounds it */
+
+  /* motion models and surfaces */
+  const gb_motion* motion;         /* device [P] */
+  const gb_surface* surfaces;      /* device table */
+  int32_t n_surfaces;
+  int32_t viewshed;                /* index into surfaces, -1 = none (tracker.py:114-117) */
+
+  /* random draws */
+  int32_t rng_mode;                /* GB_RNG_* */
+  int32_t pad0_;
+  uint64_t seed;                   /* Philox key */
+  int64_t point_offset;            /* global index of point 0 (Philox counters use global indices, so results do not depend on sharding) */
+  const double* init_normals;      /* supplied: [P][N][6] = randn(N,2) | randn(N) | randn(N,3) per particle */
+  const double* step_normals;      /* supplied: [P][S][N][3] */
+  const double* uniforms;          /* supplied: [P][S] one np.random.random() per update */
+
+  /* work buffers (caller-allocated) */
+  double* state_a;                 /* [P][6][N] */
+  double* state_b;                 /* [P][6][N] */
+  double* weight_state;            /* [P][N] or NULL; required when an observer's template starts after a point's first frame, or with out_weights */
+  double* scratch;                 /* plan.scratch_bytes or NULL */
+  /* templates (tracker.py:536-561), filled by the call */
+  double* tmpl_tile;               /* [P][O][h*w] high-passed template */
+  double* tmpl_values;             /* [P][O][h*w] sorted unique normalised values (helpers.py:433-464) */
+  double* tmpl_quantiles;          /* [P][O][h*w] */
+  int32_t* tmpl_nvalues;           /* [P][O] */
+  int32_t* tmpl_box;               /* [P][O][4] left, top, right, bottom */
+  double* tmpl_duv;                /* [P][O][2] */
+
+  /* outputs (caller pre-fills floating outputs with NaN, as tracker.py:306-313 does) */
+  double* means;                   /* [P][T][6] */
+  double* sigmas;                  /* [P][T][6] or NULL */
+  double* covariances;             /* [P][T][36] or NULL */
+  double* out_particles;           /* [P][T][N][6] or NULL (return_particles) */
+  double* out_weights;             /* [P][T][N] or NULL */
+  int32_t* status;                 /* [P] GB_ST_*; must be zero on entry */
+  int32_t* status_time;            /* [P] time index at which status was raised */
+  uint8_t* obs_flags;              /* [P][T][O] GB_OBS_* */
+  int32_t* window_stats;           /* [P][T][O][2] realised search-window (width, height), or NULL */
+
+  gb_plan plan;
+} gb_track_desc;
+
+/* Tracker.track for all points, all times (tracker.py:225-417): enqueues the per-time kernels on
+ * `stream` and returns without synchronising.  `kernel_launches_host` (optional) receives the
+ * number of kernels launched. */
+int gb_track(const gb_track_desc* desc_host, void* stream, int64_t* kernel_launches_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Teacher-forced stage entry point for parity tests
+ * ------------------------------------------------------------------------------------------ */
+/* Runs ONE update of the production step kernel for `P` points at time index `t` with any subset
+ * of its intermediate values forced to caller-supplied ones and/or dumped:
+ *   force_evolved  [P][6][N]   use these particles instead of evolving state_a (a3/a4 skipped)
+ *   force_weights  [P][N]      use these weights instead of exp(-ll) (a8..a16 skipped)
+ *   dump_evolved   [P][6][N]   particles after the motion step (motion.py:165-179)
+ *   dump_uv        [P][O][N][2]  projected particles (camera.py:591-628)
+ *   dump_box       [P][O][4]   search window (tracker.py:576-595)
+ *   dump_search    [P][O][cap] high-passed, CDF-matched search tile as float32 (tracker.py:605-611)
+ *   dump_sse       [P][O][cap] area-normalised SSE surface, float32 (tracker.py:609-614)
+ *   dump_sampled   [P][O][N]   spline-sampled SSE (observer.py:178-214)
+ *   dump_weights   [P][N]      weights before resampling (tracker.py:145-149)
+ *   dump_indices   [P][N]      resampled ancestor indices (tracker.py:168-176)
+ * Any pointer may be NULL.  `dump_cap` is the per-(point, observer) capacity of dump_search/dump_sse. */
+typedef struct gb_stage_io {
+  const double* force_evolved;
+  const double* force_weights;
+  double* dump_evolved;
+  double* dump_uv;
+  int32_t* dump_box;
+  float* dump_search;
+  float* dump_sse;
+  double* dump_sampled;
+  double* dump_weights;
+  int32_t* dump_indices;
+  int64_t dump_cap;
+} gb_stage_io;
+
+int gb_track_step(const gb_track_desc* desc_host, int32_t t, const gb_stage_io* io_host, void* stream);
+/* First-frame initialisation (motion.py:149-163, 260-283 + tracker.py:327-330) for points whose
+ * first time index is `t`, and template construction (tracker.py:536-561) for templates due at t. */
+int gb_track_init(const gb_track_desc* desc_host, int32_t t, void* stream);
+
+/* Motion.evolve_particles as a stand-alone call (motion.py:165-179, 285-311) on SoA state
+ * [P][6][N] in place; normals[P][N][3] supplied. */
+int gb_evolve(const gb_motion* motion, int64_t P, int64_t N, double tau, double tau2, const double* normals,
+              double* state, void* stream);
+/* Tracker.particle_mean / compute_particle_sigma / particle_covariance (tracker.py:72-104) on
+ * row-major particles[n][6], weights[n]: mean[6], sigma[6] (or NULL), cov[36] (or NULL). */
+int gb_moments(const double* particles, const double* weights, int64_t n, double* mean, double* sigma, double* cov,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIMPSE_B200_H */

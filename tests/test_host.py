@@ -1,0 +1,238 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the ctypes mirrors
+match the header's layout, and the host logic of the Tracker (time matching, spans, sharding,
+final gather over gloo) behaves like the reference."""
+import ctypes as C
+import datetime
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "glimpse_b200.h")
+
+
+def test_library_exports_every_declared_symbol():
+    from glimpse_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    text = open(HEADER).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(gb_\w+)\s*\(", text, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gb_version() == 1
+
+
+def test_ctypes_layout_matches_header():
+    from glimpse_b200 import _lib
+
+    names = ["gb_camera", "gb_image", "gb_surface", "gb_motion", "gb_plan", "gb_track_desc", "gb_stage_io"]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "glimpse_b200.h"\nint main(void){\n'
+    for n in names:
+        prog += f'printf("{n} %zu\\n", sizeof({n}));\n'
+    prog += 'printf("desc.plan %zu\\n", offsetof(gb_track_desc, plan));\n'
+    prog += 'printf("desc.means %zu\\n", offsetof(gb_track_desc, means));\n'
+    prog += 'printf("desc.seed %zu\\n", offsetof(gb_track_desc, seed));\n'
+    prog += 'printf("image.cam %zu\\n", offsetof(gb_image, cam));\nreturn 0;}\n'
+    with tempfile.TemporaryDirectory() as tmp:
+        src, exe = os.path.join(tmp, "s.c"), os.path.join(tmp, "s")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    for n in names:
+        assert int(out[n]) == C.sizeof(getattr(_lib, n)), n
+    assert int(out["desc.plan"]) == _lib.gb_track_desc.plan.offset
+    assert int(out["desc.means"]) == _lib.gb_track_desc.means.offset
+    assert int(out["desc.seed"]) == _lib.gb_track_desc.seed.offset
+    assert int(out["image.cam"]) == _lib.gb_image.cam.offset
+
+
+def test_camera_from_vector_matches_numpy_rotation():
+    from glimpse_b200 import _lib, camera, synthetic
+
+    lib = _lib.load()
+    vec = synthetic.camera_vector(imgsz=(4288, 2848), f=(3700, 3690), c=(12.5, -8.25), xyz=(4.99e5, 6.77e6, 500.0),
+                                  viewdir=(60.0, -25.0, 1.5), k=synthetic.FULL_K, p=synthetic.FULL_P)
+    out = _lib.gb_camera()
+    corr = np.array([6.3781e6, 0.13])
+    assert lib.gb_camera_from_vector(vec.ctypes.data, corr.ctypes.data, C.byref(out)) == 0
+    np.testing.assert_allclose(np.array(out.R[:]).reshape(3, 3), camera.rotation_matrix(vec[3:6]), atol=1e-15)
+    assert list(out.imgsz[:]) == [4288, 2848]
+    np.testing.assert_allclose(out.cc[:], [2144 + 12.5, 1424 - 8.25])
+    assert out.has_corr == 1 and out.corr_c1 == 0.13 - 1 and out.corr_c2 == 2 * 6.3781e6
+
+
+def test_plan_sizes():
+    from glimpse_b200 import _lib
+
+    lib = _lib.load()
+    plan = _lib.gb_plan()
+    assert lib.gb_step_plan(1000, 15, 15, 10, 0, C.byref(plan)) == 0
+    assert plan.cluster == 1 and plan.particles_in_smem == 1 and plan.n_local >= 1000
+    assert lib.gb_step_plan(10000, 15, 15, 1000, 0, C.byref(plan)) == 0
+    assert plan.particles_in_smem == 1 and plan.cluster * plan.n_local >= 10000 and plan.smem_bytes <= 232448
+    assert plan.tile_bytes >= 64 * 1024  # room for search windows well beyond 41 x 41
+    assert lib.gb_step_plan(100000, 31, 31, 1000, 0, C.byref(plan)) == 0
+    assert plan.particles_in_smem == 0 and plan.scratch_bytes == 1000 * plan.cluster * 9 * plan.n_local * 8
+    assert lib.gb_step_plan(1000, 40, 40, 10, 0, C.byref(plan)) == -3  # template > 1024 px
+    assert lib.gb_step_plan(1000, 15, 15, 10, 3, C.byref(plan)) == -1
+    assert b"cluster" in lib.gb_last_error()
+
+
+def test_point_span_and_shards():
+    from glimpse_b200.session import point_span
+    from glimpse_b200.tracker import shard_bounds
+
+    index = np.array([[-1, -1], [0, -1], [1, 0], [-1, 1], [-1, -1]])
+    mask = np.array([[True, True], [True, False], [False, True], [False, False]])
+    first, last = point_span(index, mask)
+    np.testing.assert_array_equal(first, [1, 1, 2, 0])
+    np.testing.assert_array_equal(last, [3, 2, 3, 4])  # no image at all: argmax semantics of the reference
+    blocks = [shard_bounds(10, 4, r) for r in range(4)]
+    assert blocks == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [shard_bounds(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def _observers(n_frames=4, offset_days=0):
+    import glimpse_b200 as gb
+
+    t0 = datetime.datetime(2020, 1, 1) + datetime.timedelta(days=offset_days)
+    images = []
+    for i in range(n_frames):
+        img = gb.Image(f"f{i}", cam=gb.Camera(imgsz=(20, 10), f=10), datetime=t0 + datetime.timedelta(days=i))
+        img.array = np.zeros((10, 20), dtype=np.uint8)
+        images.append(img)
+    return gb.Observer(images)
+
+
+def test_datetime_matching_follows_reference():
+    import glimpse_b200 as gb
+
+    a, b = _observers(4), _observers(3, offset_days=2)
+    tracker = gb.Tracker([a, b])
+    assert len(tracker.datetimes) == 5
+    m = tracker.match_datetimes(tracker.datetimes)
+    assert [v for v in m[:, 0]] == [0, 1, 2, 3, None]
+    assert [v for v in m[:, 1]] == [None, None, 0, 1, 2]
+    t0 = datetime.datetime(2020, 1, 1)
+    with pytest.raises(ValueError, match="monotonic"):
+        tracker.parse_datetimes([t0, t0 + datetime.timedelta(days=2), t0 + datetime.timedelta(days=1)])
+    with pytest.raises(ValueError, match="Fewer than two"):
+        tracker.parse_datetimes([t0 + datetime.timedelta(days=40), t0 + datetime.timedelta(days=41)])
+    with pytest.warns(UserWarning, match="duplicate"):
+        out = tracker.parse_datetimes([t0, t0, t0 + datetime.timedelta(days=1)])
+    assert len(out) == 2
+    back = tracker.parse_datetimes(tracker.datetimes[::-1])  # backward tracking is legal
+    assert back[0] > back[-1]
+
+
+def test_observer_validation_and_tile_box():
+    import glimpse_b200 as gb
+
+    obs = _observers(3)
+    with pytest.raises(ValueError, match="two or greater"):
+        gb.Observer(obs.images[:1])
+    with pytest.raises(ValueError, match="stricly increasing"):
+        gb.Observer(obs.images[::-1])
+    np.testing.assert_array_equal(obs.tile_box((10.2, 5.4), (4, 4), img=0), [8, 3, 12, 7])
+    with pytest.raises(IndexError):
+        obs.tile_box((1.0, 5.0), (4, 4), img=0)
+    assert obs.index(obs.images[1]) == 1 and obs.index(obs.datetimes[2]) == 2
+
+
+def test_unsupported_options_raise_instead_of_falling_back():
+    import glimpse_b200 as gb
+
+    obs = _observers(3)
+    day = datetime.timedelta(days=1)
+    models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
+    for kw in (dict(resample_method="residual"), dict(highpass={"size": (3, 3)}), dict(interpolation={"kx": 1, "ky": 1})):
+        with pytest.raises(NotImplementedError):
+            gb.Tracker([obs], **kw).track(models)
+    with pytest.raises(ValueError, match="equal time units"):
+        gb.Tracker([obs]).track(models + [gb.CartesianMotion(xy=(0, 0), time_unit=2 * day, dem=0.0, n=10)])
+
+    class Custom:
+        n, time_unit = 10, day
+
+    from glimpse_b200.session import adopt_model
+
+    with pytest.raises(NotImplementedError, match="no device kernel"):
+        adopt_model(Custom())
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    import glimpse_b200 as gb
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cam = gb.Camera(imgsz=10, f=10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cam.xyz_to_uv(np.zeros((1, 3)))
+    obs = _observers(3)
+    models = [gb.CartesianMotion(xy=(0, 0), time_unit=datetime.timedelta(days=1), dem=0.0, n=10)] * 2
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gb.Tracker([obs]).track(models)
+
+
+WORKER = r"""
+import os, sys, datetime
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+import glimpse_b200 as gb
+from test_host import _observers
+obs = _observers(4)
+day = datetime.timedelta(days=1)
+models = [gb.CartesianMotion(xy=(float(i), 0), time_unit=day, dem=0.0, n=8) for i in range(5)]
+tracker = gb.Tracker([obs])
+seen = {}
+def fake_local(models, image_index, taus, tile_size, mask, cov, parts, point_offset=0):
+    # stands in for the GPU compute: encodes (global point index, time) so the gather can be checked
+    from glimpse_b200.session import empty_result
+    P, T, O = len(models), image_index.shape[0], image_index.shape[1]
+    out = empty_result(P, T, O, cov, parts, N=8)
+    for i, m in enumerate(models):
+        out["means"][i] = m.xy[0] * 100 + np.arange(T)[:, None]
+        out["sigmas"][i] = point_offset + i
+    if P:
+        out["status"][-1] = 5 if point_offset == 0 else 0
+        out["status_time"][-1] = 2
+    seen["block"] = (point_offset, P)
+    return out
+tracker._track_local = fake_local
+tracks = tracker.track(models)
+assert seen["block"] == ((0, 3) if dist.get_rank() == 0 else (3, 2)), seen
+assert tracks.means.shape == (5, 4, 6)
+for i in range(5):
+    assert np.all(tracks.means[i] == i * 100 + np.arange(4)[:, None]) and np.all(tracks.sigmas[i] == i)
+assert isinstance(tracks.errors[2], IndexError) and all(tracks.errors[i] is None for i in (0, 1, 3, 4))
+dist.barrier(); dist.destroy_process_group()
+print("rank", sys.argv[3], "ok")
+"""
+
+
+def test_points_shard_across_ranks_and_gather_over_gloo():
+    """world_size 2 on CPU: contiguous blocks of points per rank, one final all-gather, every rank
+    returns the full Tracks (the compute itself is stubbed: it has no CPU path)."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, "-c", WORKER, ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out
+        assert f"rank {r} ok" in out
