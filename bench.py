@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the Tracker hot path on B200 (BASELINE.json metric: particle-updates/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (``config.workload``): BASELINE.json configs[1] — single nadir observer, CartesianMotion,
+1 000 points x 10 000 particles x 100 frames, full k1-k6/p1/p2 distortion, 15x15 template, synthetic
+translated-texture 4288x2848 uint8 frames.  One "step" = one whole ``track`` of that workload.
+
+* ``value``   device-resident inputs (frames already in HBM), CUDA-event time of the per-time kernel
+              sequence (gb_track_init + gb_track_step for t = 1..T-1, the same launches gb_track makes),
+              plus — for N > 1 — the final NCCL all-gather of the results.  Points x particles x frames
+              of ALL ranks / max-over-ranks time.  Weak scaling: every rank tracks its own 1 000 points.
+* ``e2e``     the same metric through the public ``Tracker.track`` call with the frames in pinned HOST
+              memory: per step the H2D copy of all frames + model tables and the D2H read of means /
+              sigmas / status are inside the timed region.
+* ``roofline`` for the dominant kernel ``k_step``: algorithmic bytes per launch (96 B x P x N, SURVEY.md
+              §8d) / its mean CUDA-event duration, against MEASURED_PEAKS.json ``hbm_gbs``.
+* ``cpu_baseline`` the NumPy/SciPy/OpenCV oracle (a port of the Python reference, ``oracle/``) timed on one
+              host core on a bounded sub-sample of the same workload (full N, fewer points and frames).
+* ``--impl reference`` times that CPU port with every host core (fork pool over points, the reference's
+              own parallel axis) and prints the same JSON line with ``"impl": "reference"``.
+"""
+import argparse
+import datetime
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "particle_updates_per_s"
+UNIT = "particle-updates/s"
+ALGORITHMIC_BYTES_PER_UPDATE = 96.0  # read 6 x f64 parent state + write 6 x f64 child state
+
+WORKLOAD = dict(n_points=1000, n_particles=10000, n_frames=100, imgsz=(4288, 2848), velocity_sigma=0.2, seed=2,
+                margin_px=200)
+WORKLOAD_NAME = ("configs[1]: 1 observer, CartesianMotion, 1000 points x 10000 particles x 100 frames, "
+                 "full k1-k6/p1/p2, 15x15 template, 4288x2848 uint8 frames")
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_scene(n_points, n_frames, pinned=False):
+    from glimpse_b200 import synthetic
+
+    kw = dict(WORKLOAD)
+    kw.update(n_points=n_points, n_frames=n_frames)
+    scene = synthetic.nadir_scene(**kw)
+    if pinned:
+        import torch
+
+        for obs in scene.observers:
+            frames = []
+            for f in obs.frames:
+                t = torch.empty(f.shape, dtype=torch.uint8).pin_memory()
+                t.numpy()[...] = f
+                frames.append(t.numpy())
+            obs.frames = frames
+    return scene
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (oracle = NumPy/SciPy/OpenCV port of the Python reference)
+# --------------------------------------------------------------------------------------------------
+_SCENE = None  # inherited by forked workers (frames are not pickled)
+
+
+def _cpu_track_block(args):
+    import warnings
+
+    import helpers
+    from oracle import tracker_oracle as orc
+
+    lo, hi, seed = args
+    scene = _SCENE
+    try:
+        import cv2
+
+        cv2.setNumThreads(1)
+    except Exception:
+        pass
+    obs, models, taus, index = helpers.oracle_inputs(scene, points=range(lo, hi))
+    np.random.seed(seed + lo)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = orc.track(obs, models, taus, index, tile_size=scene.tile_size, raise_errors=False)
+    return int(np.isfinite(res.means[:, -1, 0]).sum())
+
+
+def cpu_rate(scene, n_points, cores):
+    """particle-updates/s of the CPU port on `cores` processes (points split into contiguous blocks)."""
+    global _SCENE
+    _SCENE = scene
+    T = len(scene.observers[0].frames)
+    t0 = time.perf_counter()
+    if cores == 1:
+        _cpu_track_block((0, n_points, 11))
+    else:
+        import multiprocessing as mp
+
+        per = -(-n_points // cores)
+        blocks = [(lo, min(lo + per, n_points), 11) for lo in range(0, n_points, per)]
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_track_block, blocks)
+    dt = time.perf_counter() - t0
+    return n_points * scene.n_particles * T / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    cores = min(cores, 64)
+    n_points, n_frames = 8 * cores, 12
+    scene = build_scene(n_points, n_frames)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt = cpu_rate(scene, n_points, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = n_points * scene.n_particles * n_frames / (ms / 1e3)
+    sample = f"{n_points} points x {scene.n_particles} particles x {n_frames} frames of the workload, fork pool over points"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+
+    import glimpse_b200 as gb
+    from glimpse_b200 import _lib, synthetic
+    from glimpse_b200.session import Session
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    P, N, T = WORKLOAD["n_points"], WORKLOAD["n_particles"], WORKLOAD["n_frames"]
+    if args.small:
+        P, T = 64, 12
+    if args.points:
+        P, args.small = args.points, True
+    if args.frames:
+        T, args.small = args.frames, True
+    scene = build_scene(P * world, T, pinned=True)
+    observers, models = synthetic.build(scene, gb)
+    tracker = gb.Tracker(observers, seed=20260101, cluster=args.cluster)
+    datetimes = tracker.datetimes
+    matching = tracker.match_datetimes(datetimes)
+    image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
+    unit = scene.time_unit.total_seconds()
+    taus = np.array([dt.total_seconds() / unit for dt in np.diff(datetimes)])
+    lo, hi = rank * P, (rank + 1) * P
+    mask = np.ones((P, 1), dtype=bool)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: device-resident inputs, CUDA events on the launching stream ----------
+    session = Session(tracker, models[lo:hi], image_index, taus, scene.tile_size, mask, point_offset=lo)
+    gathered = None
+    if dist is not None:
+        gathered = [torch.empty((world,) + tuple(session.buf[k].shape), dtype=torch.float64, device=device)
+                    for k in ("means", "sig")]
+
+    def one_track(events=None):
+        session.buf["status"].zero_()
+        session.init(0)
+        for t in range(1, T):
+            if events is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                session.step(t)
+                b.record()
+                events.append((a, b))
+            else:
+                session.step(t)
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered[0], session.buf["means"])
+            dist.all_gather_into_tensor(gathered[1], session.buf["sig"])
+
+    for _ in range(args.warmup):
+        one_track()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    step_events = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        one_track(step_events)
+    end.record()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(start.elapsed_time(end)) / args.steps
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
+    status = session.buf["status"].cpu().numpy()
+    session.launches = 0
+    stats_out = session.fetch()
+    failed = int((status != 0).sum())
+    value = world * P * N * T / (dev_ms / 1e3)
+    launches_per_step = 2 + (T - 1)  # k_init + k_template + (T - 1) x k_step
+    peak, peak_src = hbm_peak()
+    achieved = ALGORITHMIC_BYTES_PER_UPDATE * P * N / (kernel_ms / 1e3) / 1e9
+    win_w, win_h = session.stats["window_width"], session.stats["window_height"]
+
+    # ---------------- e2e: public API, host frames, copies inside the timed region -----------------
+    def e2e_once():
+        tracker.clear_device_cache()
+        return tracker.track(models, tile_size=scene.tile_size)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(1 if args.warmup else 0):
+        e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tracks = e2e_once()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = world * P * N * T / e2e_s
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tracker.last_run["h2d_bytes"]),
+           "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps}
+    v_err = float(np.nanmedian(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0])))
+
+    # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sub_points, sub_frames = 12, 12
+        sub = build_scene(sub_points, sub_frames)
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        rate, dt = cpu_rate(sub, sub_points, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+               "sample": f"{sub_points} points x {N} particles x {sub_frames} frames of the workload (oracle/tracker_oracle.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD_NAME if not args.small else f"SMALL smoke variant: {P} points x {N} particles x {T} frames",
+                "points_per_gpu": P, "particles": N, "frames": T, "rng": "philox (device)",
+                "cache": "inputs larger than L2 (particle state 2 x %.0f MB per GPU, no flush needed)" % (P * N * 48 / 1e6),
+                "plan": session.stats["plan"],
+                "search_window_px": {"median_w": float(np.median(win_w)) if len(win_w) else None,
+                                     "median_h": float(np.median(win_h)) if len(win_h) else None,
+                                     "p90_w": float(np.percentile(win_w, 90)) if len(win_w) else None,
+                                     "p99_w": float(np.percentile(win_w, 99)) if len(win_w) else None,
+                                     "max_w": int(win_w.max()) if len(win_w) else None,
+                                     "max_h": int(win_h.max()) if len(win_h) else None},
+                "failed_points": failed, "median_abs_velocity_error_m_per_day": v_err,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="glimpse_b200", choices=["glimpse_b200", "reference"])
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--small", action="store_true", help="tiny variant for smoke-testing the script (not a bench value)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--points", type=int, default=0, help="override points per GPU (profiling only; not a bench value)")
+    ap.add_argument("--frames", type=int, default=0, help="override frame count (profiling only; not a bench value)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

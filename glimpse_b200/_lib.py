@@ -59,8 +59,8 @@ class gb_motion(C.Structure):
 class gb_plan(C.Structure):
     _fields_ = [
         ("cluster", C.c_int32), ("threads", C.c_int32), ("n_local", C.c_int32), ("particles_in_smem", C.c_int32),
-        ("smem_bytes", C.c_int32), ("tile_bytes", C.c_int32), ("max_template", C.c_int32), ("pad_", C.c_int32),
-        ("scratch_bytes", C.c_int64),
+        ("smem_bytes", C.c_int32), ("tile_bytes", C.c_int32), ("max_template", C.c_int32), ("n_slabs", C.c_int32),
+        ("slab_bytes", C.c_int64), ("particle_scratch_bytes", C.c_int64), ("scratch_bytes", C.c_int64),
     ]
 
 
@@ -88,7 +88,7 @@ class gb_stage_io(C.Structure):
     _fields_ = [
         ("force_evolved", C.c_void_p), ("force_weights", C.c_void_p), ("dump_evolved", C.c_void_p),
         ("dump_uv", C.c_void_p), ("dump_box", C.c_void_p), ("dump_search", C.c_void_p), ("dump_sse", C.c_void_p),
-        ("dump_sampled", C.c_void_p), ("dump_weights", C.c_void_p), ("dump_indices", C.c_void_p), ("dump_cap", C.c_int64),
+        ("dump_sampled", C.c_void_p), ("dump_weights", C.c_void_p), ("dump_indices", C.c_void_p), ("dump_clocks", C.c_void_p), ("dump_cap", C.c_int64),
     ]
 
 

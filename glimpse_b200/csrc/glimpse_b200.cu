@@ -17,7 +17,7 @@
 #include "motion.cuh"
 #include "tile.cuh"
 
-#define GB_THREADS 512
+#define GB_THREADS 1024
 #define GB_MAX_TEMPLATE 1024 /* template pixels handled by k_template */
 
 namespace gb {
@@ -42,6 +42,8 @@ struct StepParams {
   int T, O, S, t;
   int tile_w, tile_h;
   int cluster, n_local, particles_in_smem, tile_bytes;
+  int n_slabs, pad2_;
+  int64_t slab_bytes, particle_scratch_bytes;
   int skip_evolve, viewshed, rng_mode, pad_;
   uint64_t seed;
   int64_t point_offset;
@@ -531,6 +533,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
   const int64_t N = prm.N;
   const bool forced = prm.io.force_evolved != nullptr;
   if (prm.status[p] != 0 || t <= prm.first[p] || t > prm.last[p]) return;
+  long long* clk = (prm.io.dump_clocks && rank == 0) ? reinterpret_cast<long long*>(prm.io.dump_clocks) + p * 16 : nullptr;
+#define GB_CLK(i) do { if (clk && tid == 0) clk[i] = clock64(); } while (0)
+  GB_CLK(0);
 
   ClusterCtx cc{rank, cs, 0, hdr};
   const int nl = prm.n_local;
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
   }
   __syncthreads();
+  GB_CLK(1);
 
   // ---- phase B: observers ----
   bool fatal = false;
@@ -634,6 +640,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       if (tid == 0) hdr->bcast[4] = (double)has_nan;
       __syncthreads();
       double(*xg)[GB_XCH] = cluster_allgather<5>(cc);
+      GB_CLK(2);
       if (tid == 0) {
         double lo_u = xg[0][0], lo_v = xg[0][1], hi_u = xg[0][2], hi_v = xg[0][3], nanf = xg[0][4];
         for (int r = 1; r < cs; ++r) {
@@ -698,17 +705,29 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
           for (int k = 0; k < 4; ++k) d[k] = hdr->ibox[k];
         }
       }
-      if (tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) > prm.tile_bytes || w.Mu > 256 || w.Mv > 256) {
-        flags |= GB_F_WINDOW;
-        fatal = true;
-        break;
+      char* tbase = tile_base;
+      {
+        const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
+        if (need > prm.tile_bytes) {
+          // overflow: this CTA's tile buffers go to its SM's slab in global memory (L2-resident)
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          if (need > prm.slab_bytes || w.Mu > 256 || w.Mv > 256 || (int)smid >= prm.n_slabs) {
+            flags |= GB_F_WINDOW;
+            fatal = true;
+            break;
+          }
+          tbase = reinterpret_cast<char*>(prm.scratch) + prm.particle_scratch_bytes + (int64_t)smid * prm.slab_bytes;
+        }
       }
-      tile_carve(tile_base, w);
+      tile_carve(tbase, w);
       const int64_t ta = (int64_t)w.tw * w.th;
       const bool dumper = rank == 0;
       tile_build_surface(img, hdr->ibox, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta, prm.tmpl_values + po * ta,
                          w, (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
-                         (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap);
+                         (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap,
+                         clk ? clk + 3 : nullptr);
+      GB_CLK(6);
       // geo-reference of the surface (tracker.py:615-620) and cell centres (observer.py:203-208)
       const double eu = sub(mul((double)w.tw, 0.5), 0.5), evv = sub(mul((double)w.th, 0.5), 0.5);
       const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
@@ -731,6 +750,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
   }
 
+  GB_CLK(7);
   // ---- phase C: weights (tracker.py:143-149), block scan, totals ----
   double wsum_local;
   {
@@ -771,6 +791,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
     wsum_local = hdr->scan_carry;
   }
+  GB_CLK(8);
   const int blockflags = __syncthreads_or((int)flags);
   if (tid == 0) {
     hdr->bcast[0] = wsum_local;
@@ -795,6 +816,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
   }
 
+  GB_CLK(9);
   // ---- phase D: systematic resampling (tracker.py:168-176, 222-223) ----
   const double u01 = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[p * prm.S + (t - prm.first[p] - 1)]
                                                       : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
@@ -803,6 +825,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
   for (int i = tid; i < nv; i += B) E[i] = count_positions_le(quo(prefix + uvb[i], total), u01, inv_n, N);
   const int J0 = rank == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
   __syncthreads();
+  GB_CLK(10);
   const int J1 = nv > 0 ? E[nv - 1] : J0;
   {
     double* sout = state_buffer(prm, t) + p * 6 * N;
@@ -830,6 +853,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
   }
 
+  GB_CLK(11);
   // ---- phase E: moments of the resampled set = parents weighted by (children x weight) ----
   Moments<COV> mom;
   mom.clear();
@@ -865,6 +889,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       }
     }
   }
+  GB_CLK(12);
+#undef GB_CLK
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -916,6 +942,9 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.n_local = d.plan.n_local;
   prm.particles_in_smem = d.plan.particles_in_smem;
   prm.tile_bytes = d.plan.tile_bytes;
+  prm.n_slabs = d.plan.n_slabs;
+  prm.slab_bytes = d.plan.slab_bytes;
+  prm.particle_scratch_bytes = d.plan.particle_scratch_bytes;
   prm.viewshed = d.viewshed;
   prm.rng_mode = d.rng_mode;
   prm.seed = d.seed;
@@ -980,7 +1009,7 @@ static int check_desc(const gb_track_desc& d) {
     return fail(GB_E_INVALID, "supplied-draw mode needs init_normals, step_normals and uniforms%s");
   if (d.plan.cluster < 1 || d.plan.cluster > GB_MAX_CLUSTER || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
     return fail(GB_E_INVALID, "invalid launch plan (use gb_step_plan)%s");
-  if (!d.plan.particles_in_smem && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
+  if (d.plan.scratch_bytes > 0 && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
   if ((int64_t)d.plan.cluster * d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
   return GB_OK;
 }
@@ -1107,25 +1136,25 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
   memset(plan, 0, sizeof(*plan));
   plan->threads = GB_THREADS;
   plan->max_template = tile_w * tile_h;
-  // tile capacity we want on chip: a search window that exceeds the template by 64 px each way
-  const int64_t want = tile_bytes_needed(tile_w + 64, tile_h + 64, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h);
+  plan->smem_bytes = kMaxSmem;
+  plan->n_slabs = 160;
+  plan->slab_bytes = (tile_bytes_needed(tile_w + 255, tile_h + 255, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
+  // on-chip tile capacity we insist on: a search window 24 px larger than the template each way;
+  // bigger windows spill to the per-SM slabs
+  const int64_t want = tile_bytes_needed(tile_w + 24, tile_h + 24, tile_w, tile_h, 256, tile_w * tile_h);
   const int avail = kMaxSmem - kHeaderBytes;
-  int chosen = 0;
-  for (int cs = 1; cs <= GB_MAX_CLUSTER; cs *= 2) {
+  bool chosen = false;
+  for (int cs = 1; cs <= GB_MAX_CLUSTER && !chosen; cs *= 2) {
     if (prefer_cluster && cs != prefer_cluster) continue;
     int64_t nl = (n_particles + cs - 1) / cs;
     nl = (nl + 1) / 2 * 2;
     const int64_t pbytes = nl * 72;
-    const bool fits = pbytes + (prefer_cluster ? tile_bytes_needed(tile_w + 3, tile_h + 3, tile_w, tile_h, 256, 16) : want) <= avail;
-    if (fits) {
-      chosen = cs;
+    if (pbytes + want <= avail) {
+      chosen = true;
       plan->cluster = cs;
       plan->n_local = (int32_t)nl;
       plan->particles_in_smem = 1;
       plan->tile_bytes = (int32_t)(avail - pbytes);
-      plan->smem_bytes = kMaxSmem;
-      plan->scratch_bytes = 0;
-      break;
     }
   }
   if (!chosen) {
@@ -1137,9 +1166,9 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     plan->n_local = (int32_t)nl;
     plan->particles_in_smem = 0;
     plan->tile_bytes = avail;
-    plan->smem_bytes = kMaxSmem;
-    plan->scratch_bytes = npoints * cs * 9 * nl * (int64_t)sizeof(double);
+    plan->particle_scratch_bytes = npoints * cs * 9 * nl * (int64_t)sizeof(double);
   }
+  plan->scratch_bytes = plan->particle_scratch_bytes + plan->n_slabs * plan->slab_bytes;
   return GB_OK;
 }
 

@@ -155,7 +155,7 @@ __device__ __forceinline__ double hermite_eval(const float4* herm, int Mu, int M
 // the capacity and carved `w`.
 __device__ inline void tile_build_surface(const gb_image* img, const int* box, const double* g_tmpl,
                                           const double* g_tq, const double* g_tv, TileWork& w, float* dump_search,
-                                          float* dump_sse, int64_t dump_cap) {
+                                          float* dump_sse, int64_t dump_cap, long long* clk) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int Su = w.Su, Sv = w.Sv, Mu = w.Mu, Mv = w.Mv;
   const int area = Su * Sv;
@@ -205,6 +205,7 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
     if (cle) w.lut[b] = interp_clamped(quo((double)cle, (double)area), w.tq, w.tv, w.nvals);
   }
   __syncthreads();
+  if (clk && threadIdx.x == 0) clk[0] = clock64();
   // 5. high-pass: matched value minus the matched 5x5 median (tracker.py:530-531), cast to
   //    float32 as the reference does for matchTemplate (tracker.py:610)
   for (int i = tid; i < area; i += nthr) {
@@ -215,6 +216,7 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
     if (dump_search && i < dump_cap) dump_search[i] = v;
   }
   __syncthreads();
+  if (clk && threadIdx.x == 0) clk[1] = clock64();
   // 6. area-normalised sum of squared differences (tracker.py:609-614)
   {
     const double inv_area = 1.0 / (double)(w.tw * w.th);
@@ -238,6 +240,7 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
     }
   }
   __syncthreads();
+  if (clk && threadIdx.x == 0) clk[2] = clock64();
   // 7. Hermite data: dF/du along rows and dF/dv along columns, then the cross derivative
   {
     float* base = reinterpret_cast<float*>(w.herm);

@@ -151,8 +151,10 @@ typedef struct gb_plan {
   int32_t smem_bytes;       /* dynamic shared memory per CTA */
   int32_t tile_bytes;       /* bytes of it available to the tile pipeline */
   int32_t max_template;     /* template pixels the plan was sized for */
-  int32_t pad_;
-  int64_t scratch_bytes;    /* global scratch the caller must provide (0 if particles_in_smem) */
+  int32_t n_slabs;          /* per-SM overflow slabs for search windows that do not fit tile_bytes */
+  int64_t slab_bytes;       /* bytes per slab (windows up to 256 + template - 1 pixels a side) */
+  int64_t particle_scratch_bytes; /* global particle arrays when !particles_in_smem */
+  int64_t scratch_bytes;    /* total global scratch the caller must provide: particle_scratch_bytes + n_slabs * slab_bytes */
 } gb_plan;
 
 /* Size a launch plan for N particles per point and a w x h template.  `prefer_cluster` = 0 lets
@@ -243,6 +245,7 @@ int gb_track(const gb_track_desc* desc_host, void* stream, int64_t* kernel_launc
  *   dump_sampled   [P][O][N]   spline-sampled SSE (observer.py:178-214)
  *   dump_weights   [P][N]      weights before resampling (tracker.py:145-149)
  *   dump_indices   [P][N]      resampled ancestor indices (tracker.py:168-176)
+ *   dump_clocks    [P][16]     clock64() of rank-0 CTA at the phase boundaries of the step (profiling aid)
  * Any pointer may be NULL.  `dump_cap` is the per-(point, observer) capacity of dump_search/dump_sse. */
 typedef struct gb_stage_io {
   const double* force_evolved;
@@ -255,6 +258,7 @@ typedef struct gb_stage_io {
   double* dump_sampled;
   double* dump_weights;
   int32_t* dump_indices;
+  int64_t* dump_clocks;
   int64_t dump_cap;
 } gb_stage_io;
 

@@ -37,7 +37,7 @@ def case_scene(name):
     return scene, case
 
 
-def make_session(scene, case, golden, return_particles=False, cluster=0):
+def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None):
     import glimpse_b200 as gb
     from glimpse_b200.session import Session, reference_order_draws
 
@@ -59,6 +59,9 @@ def make_session(scene, case, golden, return_particles=False, cluster=0):
     session = Session(tracker, models, image_index, taus, scene.tile_size, mask,
                       return_covariances=bool(case.get("return_covariances", False)),
                       return_particles=return_particles, draws=draws)
+    if tile_bytes is not None:  # shrink the on-chip tile capacity: every search window overflows to the slabs
+        session.plan.tile_bytes = tile_bytes
+        session.desc.plan.tile_bytes = tile_bytes
     return session, draws
 
 
@@ -95,14 +98,15 @@ def test_templates_match_reference(cuda, name):
             k += 1
 
 
-@pytest.mark.parametrize("name,cluster", [(n, 0) for n in scenes.track_cases()] + [("track_c1", 2), ("track_cyl2", 4), ("track_jitter", 8)])
-def test_step_teacher_forced(cuda, name, cluster):
+@pytest.mark.parametrize("name,cluster,tile_bytes", [(n, 0, None) for n in scenes.track_cases()]
+                         + [("track_c1", 2, None), ("track_cyl2", 4, None), ("track_jitter", 8, None), ("track_c1", 4, 2048)])
+def test_step_teacher_forced(cuda, name, cluster, tile_bytes):
     from glimpse_b200 import _lib
 
     torch = cuda
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
-    session, draws = make_session(scene, case, g, cluster=cluster)
+    session, draws = make_session(scene, case, g, cluster=cluster, tile_bytes=tile_bytes)
     assert cluster == 0 or session.plan.cluster == cluster
     P, N, T, O = session.P, session.N, session.T, session.O
     per = int(g["n_steps"]) // P
