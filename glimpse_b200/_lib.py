@@ -67,7 +67,7 @@ class gb_plan(C.Structure):
 class gb_track_desc(C.Structure):
     _fields_ = [
         ("P", C.c_int64), ("N", C.c_int64), ("T", C.c_int32), ("O", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
-        ("images", C.c_void_p), ("image_offset_host", C.c_void_p), ("image_index_host", C.c_void_p),
+        ("images", C.c_void_p), ("images_host", C.c_void_p), ("image_offset_host", C.c_void_p), ("image_index_host", C.c_void_p),
         ("obs_scale_host", C.c_void_p), ("mask", C.c_void_p), ("first", C.c_void_p), ("last", C.c_void_p),
         ("mask_host", C.c_void_p), ("first_host", C.c_void_p), ("last_host", C.c_void_p),
         ("tau_host", C.c_void_p), ("tau2_host", C.c_void_p),

@@ -66,6 +66,64 @@ __device__ __forceinline__ void project(const gb_camera& c, double px, double py
   v = add(mul(yd, c.f[1]), c.cc[1]);
 }
 
+// Camera + distortion flags as the step kernel receives it (kernel-parameter / constant bank).
+struct CamK {
+  gb_camera c;
+  int32_t any_k, any_p, has_den, pad_;
+};
+
+__host__ inline void camk_from(const gb_camera& c, CamK& out) {
+  out.c = c;
+  out.any_k = (c.k[0] != 0.0) || (c.k[1] != 0.0) || (c.k[2] != 0.0) || (c.k[3] != 0.0) || (c.k[4] != 0.0) || (c.k[5] != 0.0);
+  out.has_den = (c.k[3] != 0.0) || (c.k[4] != 0.0) || (c.k[5] != 0.0);
+  out.any_p = (c.p[0] != 0.0) || (c.p[1] != 0.0);
+  out.pad_ = 0;
+}
+
+// Same mapping as project(), arranged for throughput in the fused step kernel: one division
+// instead of three and fused multiply-adds.  With s = xc^2 + yc^2 and z2 = zc^2 the rational radial
+// factor is N / D, N = z2^3 + k1 s z2^2 + k2 s^2 z2 + k3 s^3 (D likewise with k4..k6), so
+//   x' = xc N / (zc D) + tx / z2,   q = 1 / (z2 D)  ->  1 / (zc D) = q zc,  1 / z2 = q D.
+// Differs from project() by a few ulp (~1e-12 px at map scale; tests/test_gpu_track.py bounds it).
+__device__ __forceinline__ void project_fast(const CamK& k, double px, double py, double pz, double& u, double& v) {
+  const gb_camera& c = k.c;
+  const double dx = px - c.xyz[0], dy = py - c.xyz[1];
+  double dz = pz - c.xyz[2];
+  if (c.has_corr) dz = add(dz, quo(mul(c.corr_c1, add(mul(dx, dx), mul(dy, dy))), c.corr_c2));
+  const double xc = fma(c.R[2], dz, fma(c.R[1], dy, c.R[0] * dx));
+  const double yc = fma(c.R[5], dz, fma(c.R[4], dy, c.R[3] * dx));
+  const double zc = fma(c.R[8], dz, fma(c.R[7], dy, c.R[6] * dx));
+  double xd, yd;
+  if (!k.any_k && !k.any_p) {
+    const double iz = 1.0 / zc;
+    xd = xc * iz;
+    yd = yc * iz;
+  } else {
+    const double z2 = zc * zc, s = fma(xc, xc, yc * yc);
+    const double s2 = s * s, z4 = z2 * z2;
+    const double s3 = s2 * s, z6 = z4 * z2;
+    const double sz4 = s * z4, s2z2 = s2 * z2;
+    const double Nn = fma(c.k[2], s3, fma(c.k[1], s2z2, fma(c.k[0], sz4, z6)));
+    const double Dd = k.has_den ? fma(c.k[5], s3, fma(c.k[4], s2z2, fma(c.k[3], sz4, z6))) : z6;
+    const double q = 1.0 / (z2 * Dd);
+    const double izd = q * zc * Nn;  // radial factor / zc
+    xd = xc * izd;
+    yd = yc * izd;
+    if (k.any_p) {
+      const double iz2 = q * Dd;
+      const double xy2 = 2.0 * xc * yc;
+      xd = fma(fma(c.p[1], fma(2.0 * xc, xc, s), xy2 * c.p[0]), iz2, xd);
+      yd = fma(fma(c.p[0], fma(2.0 * yc, yc, s), xy2 * c.p[1]), iz2, yd);
+    }
+  }
+  u = fma(xd, c.f[0], c.cc[0]);
+  v = fma(yd, c.f[1], c.cc[1]);
+  if (!(zc > 0.0)) {
+    u = CUDART_NAN;
+    v = CUDART_NAN;
+  }
+}
+
 // Inverse distortion (camera.py:1198-1264, 1305-1337).
 __device__ inline void undistort(const gb_camera& c, double x, double y, double& xu, double& yu) {
   const bool any_k = (c.k[0] != 0.0) | (c.k[1] != 0.0) | (c.k[2] != 0.0) | (c.k[3] != 0.0) | (c.k[4] != 0.0) |

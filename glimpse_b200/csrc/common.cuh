@@ -58,7 +58,7 @@ struct SmemHeader {
   double xch[2][GB_MAX_CLUSTER][GB_XCH];  // cluster all-gather, double buffered by round parity
   double red[32][GB_XCH];                 // per-warp partials of a block reduction
   double bcast[GB_XCH];                   // block-wide broadcast values
-  double scan_warp[32];                   // warp totals of the block scan
+  double scan_tot[256];                   // per-(chunk, warp) totals of the block scan, then their exclusive prefix
   double scan_carry;
   double ref[6];                          // origin for the moment sums (parent particle 0)
   int ibox[4];
@@ -76,6 +76,7 @@ struct ClusterCtx {
 
 // Block reduction of K per-thread doubles (OP 0: sum, 1: min); the result is left in
 // hdr->bcast[0..K), visible to all threads on return.  Maxima are reduced as minima of negatives.
+// Stage 1: shuffles inside each warp; stage 2: warp k combines the per-warp partials of value k.
 template <int K, int OP>
 __device__ __forceinline__ void block_reduce(double (&v)[K], SmemHeader* hdr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -85,14 +86,10 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], SmemHeader* hdr) {
     if (lane == 0) hdr->red[warp][k] = x;
   }
   __syncthreads();
-  if (threadIdx.x < K) {
-    const int k = threadIdx.x;
-    double x = hdr->red[0][k];
-    for (int w = 1; w < nwarp; ++w) {
-      const double y = hdr->red[w][k];
-      x = OP == 0 ? x + y : fmin(x, y);
-    }
-    hdr->bcast[k] = x;
+  for (int k = warp; k < K; k += nwarp) {
+    double x = lane < nwarp ? hdr->red[lane][k] : (OP == 0 ? 0.0 : CUDART_INF);
+    x = OP == 0 ? warp_sum(x) : warp_min(x);
+    if (lane == 0) hdr->bcast[k] = x;
   }
   __syncthreads();
 }

@@ -17,7 +17,7 @@
 #include "motion.cuh"
 #include "tile.cuh"
 
-#define GB_THREADS 1024
+#define GB_THREADS 512
 #define GB_MAX_TEMPLATE 1024 /* template pixels handled by k_template */
 
 namespace gb {
@@ -49,6 +49,9 @@ struct StepParams {
   int64_t point_offset;
   double tau, tau2;
   int img[GB_MAX_OBS];       // global image index of each observer at time t, -1 = none
+  CamK cam[GB_MAX_OBS];      // that image's camera (constant bank: operands without loads)
+  const uint16_t* gray[GB_MAX_OBS];
+  int pitch[GB_MAX_OBS], nchan[GB_MAX_OBS];
   int tmpl_frame[GB_MAX_OBS]; // time index at which each observer's template is cut
   double obs_scale[GB_MAX_OBS];
   const gb_image* images;
@@ -505,20 +508,55 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
 //   -> surface likelihood -> weights -> systematic resampling -> moments.
 // grid.x = P * cluster; one cluster per point.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double resample_position(int64_t j, double u, double inv_n) {
+__device__ __forceinline__ double resample_position(int j, double u, double inv_n) {
   // (np.arange(n) + u) * (1 / n)  (tracker.py:173)
   return mul(add((double)j, u), inv_n);
 }
 
 // Number of resampling positions <= c, i.e. the end of the child range of a particle whose
-// normalised cumulative weight is c (np.searchsorted(cumsum, positions, side='left')).
-__device__ __forceinline__ int count_positions_le(double c, double u, double inv_n, int64_t N) {
-  double g = floor(c * (double)N - u) + 1.0;
-  g = fmin(fmax(g, 0.0), (double)N);
-  int64_t e = (int64_t)g;
-  while (e > 0 && resample_position(e - 1, u, inv_n) > c) --e;
-  while (e < N && resample_position(e, u, inv_n) <= c) ++e;
-  return (int)e;
+// normalised cumulative weight is c (np.searchsorted(cumsum, positions, side='left')).  The guess
+// from c * N - u is verified against the reference's own position formula and walked if needed.
+__device__ __forceinline__ int count_positions_le(double c, double u, double inv_n, int N) {
+  int e = __double2int_rd(c * (double)N - u) + 1;
+  e = min(max(e, 0), N);
+  const bool ok = (e == 0 || resample_position(e - 1, u, inv_n) <= c) && (e == N || resample_position(e, u, inv_n) > c);
+  if (!ok) {
+    while (e > 0 && resample_position(e - 1, u, inv_n) > c) --e;
+    while (e < N && resample_position(e, u, inv_n) <= c) ++e;
+  }
+  return e;
+}
+
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_up(v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// Block-wide integer min of K values (maxima as minima of negatives): REDUX inside the warp,
+// then one warp over the per-warp partials.  Result in hdr->bcast[0..K) as doubles.
+template <int K>
+__device__ __forceinline__ void block_min_int(const int (&v)[K], SmemHeader* hdr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int* red = reinterpret_cast<int*>(hdr->red);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int x = __reduce_min_sync(0xffffffffu, v[k]);
+    if (lane == 0) red[warp * K + k] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int x = lane < nwarp ? red[lane * K + k] : 0x7fffffff;
+      x = __reduce_min_sync(0xffffffffu, x);
+      if (lane == 0) hdr->bcast[k] = (double)x;
+    }
+  }
+  __syncthreads();
 }
 
 template <bool COV>
@@ -529,8 +567,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
   const int cs = prm.cluster;
   const int rank = (int)(blockIdx.x % cs);
   const int64_t p = blockIdx.x / cs;
-  const int t = prm.t, tid = threadIdx.x, B = blockDim.x;
-  const int64_t N = prm.N;
+  const int t = prm.t, tid = threadIdx.x, B = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = B >> 5;
+  const int N = (int)prm.N, O = prm.O;
   const bool forced = prm.io.force_evolved != nullptr;
   if (prm.status[p] != 0 || t <= prm.first[p] || t > prm.last[p]) return;
   long long* clk = (prm.io.dump_clocks && rank == 0) ? reinterpret_cast<long long*>(prm.io.dump_clocks) + p * 16 : nullptr;
@@ -539,15 +577,15 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
 
   ClusterCtx cc{rank, cs, 0, hdr};
   const int nl = prm.n_local;
-  const int64_t i0 = (int64_t)rank * nl;
-  const int nv = (int)max((int64_t)0, min((int64_t)nl, N - i0));
+  const int i0 = rank * nl;
+  const int nv = max(0, min(nl, N - i0));
 
   double *ev, *uvb, *llb;
   char* tile_base;
   if (prm.particles_in_smem) {
     ev = reinterpret_cast<double*>(smem_raw + HDR);
-    uvb = ev + 6 * (int64_t)nl;
-    llb = uvb + 2 * (int64_t)nl;
+    uvb = ev + 6 * nl;
+    llb = uvb + 2 * nl;
     tile_base = reinterpret_cast<char*>(llb + nl);
   } else {
     ev = prm.scratch + (p * cs + rank) * 9 * (int64_t)nl;
@@ -555,106 +593,163 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     llb = uvb + 2 * (int64_t)nl;
     tile_base = reinterpret_cast<char*>(smem_raw + HDR);
   }
-  // motion parameters to shared memory
+  // motion parameters and the moment origin to shared memory
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&hdr->motion);
     for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += B) dst[k] = src[k];
   }
-  const double* sin_ = forced ? prm.io.force_evolved + p * 6 * N : state_buffer(prm, t - 1) + p * 6 * N;
-  if (tid < 6) hdr->ref[tid] = sin_[tid * N];
+  const double* sin_ = forced ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
+  if (tid < 6) hdr->ref[tid] = sin_[tid * (int64_t)N];
+  // observers that have an image for this point at this time (block-uniform)
+  int first_obs = -1;
+  for (int o = O - 1; o >= 0; --o)
+    if (prm.img[o] >= 0 && prm.mask[p * O + o]) first_obs = o;
+  const bool use_obs = !prm.io.force_weights;
   __syncthreads();
+  const bool surface_ll = !(prm.surfaces[hdr->motion.dem_sigma].z == nullptr && prm.surfaces[hdr->motion.dem_sigma].value == 0.0);
+  const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
 
-  // ---- phase A: motion step and particle tests ----
   uint32_t flags = 0;
+  // integer bounding box of the cloud: floor(min - half) = min floor(u - half) (monotone rounding)
+  int ib[5] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff, 0};  // left, top, -right, -bottom, -(any NaN)
+  // ---- phase A: motion step, particle tests and (fused) projection into the first observer ----
   {
     const int s_idx = t - prm.first[p] - 1;
-    const double* zn = prm.step_normals ? prm.step_normals + ((p * prm.S + s_idx) * N + i0) * 3 : nullptr;
+    const double* zn = prm.step_normals ? prm.step_normals + (((int64_t)p * prm.S + s_idx) * N + i0) * 3 : nullptr;
     const bool evolve = !forced && !prm.skip_evolve;
-    for (int i = tid; i < nv; i += B) {
-      double s[6];
+    const bool proj = use_obs && first_obs >= 0;
+    const int fo = proj ? first_obs : 0;
+    const double* src = sin_ + i0;
+    // two particles per trip: two independent dependency chains in flight per thread
+    for (int ia = tid; ia < nv; ia += 2 * B) {
+      const int ibx = ia + B;
+      const bool vb = ibx < nv;
+      const int ii[2] = {ia, vb ? ibx : ia};
+      double s[2][6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) s[c] = sin_[c * N + i0 + i];
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s[q][c] = src[c * (int64_t)N + ii[q]];
       if (evolve) {
-        double z0, z1, z2;
-        if (prm.rng_mode == GB_RNG_SUPPLIED) {
-          z0 = zn[3 * i];
-          z1 = zn[3 * i + 1];
-          z2 = zn[3 * i + 2];
-        } else {
-          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)(i0 + i), 2u, z0, z1, z2);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          double z0, z1, z2;
+          if (prm.rng_mode == GB_RNG_SUPPLIED) {
+            z0 = zn[3 * ii[q]];
+            z1 = zn[3 * ii[q] + 1];
+            z2 = zn[3 * ii[q] + 2];
+          } else {
+            philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)(i0 + ii[q]), 2u, z0, z1, z2);
+          }
+          evolve_particle(hdr->motion, prm.tau, prm.tau2, z0, z1, z2, s[q]);
         }
-        evolve_particle(hdr->motion, prm.tau, prm.tau2, z0, z1, z2, s);
       }
-      flags |= test_particle(prm, s);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) ev[c * nl + i] = s[c];
-      llb[i] = 0.0;
-      if (prm.io.dump_evolved) {
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !vb) break;
+        const int i = ii[q];
+        flags |= test_particle(prm, s[q]);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) prm.io.dump_evolved[(p * 6 + c) * N + i0 + i] = s[c];
+        for (int c = 0; c < 6; ++c) ev[c * nl + i] = s[q][c];
+        llb[i] = 0.0;
+        if (prm.io.dump_evolved) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) prm.io.dump_evolved[((int64_t)p * 6 + c) * N + i0 + i] = s[q][c];
+        }
+      }
+      if (proj) {
+        double u[2], v[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) project_fast(prm.cam[fo], s[q][0], s[q][1], s[q][2], u[q], v[q]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !vb) break;
+          const int i = ii[q];
+          uvb[i] = u[q];
+          uvb[nl + i] = v[q];
+          if (isnan(u[q]) | isnan(v[q])) ib[4] = -1;
+          ib[0] = min(ib[0], __double2int_rd(u[q] - hw));
+          ib[1] = min(ib[1], __double2int_rd(v[q] - hh));
+          ib[2] = min(ib[2], -__double2int_ru(u[q] + hw));
+          ib[3] = min(ib[3], -__double2int_ru(v[q] + hh));
+          if (prm.io.dump_uv) {
+            double* d = prm.io.dump_uv + (((int64_t)p * O + first_obs) * N + i0 + i) * 2;
+            d[0] = u[q];
+            d[1] = v[q];
+          }
+        }
       }
     }
   }
-  __syncthreads();
   GB_CLK(1);
 
   // ---- phase B: observers ----
   bool fatal = false;
-  if (!prm.io.force_weights) {
-    for (int o = 0; o < prm.O && !fatal; ++o) {
-      const int64_t po = p * prm.O + o;
-      uint8_t* oflag = prm.obs_flags + (p * prm.T + t) * prm.O + o;
+  if (use_obs) {
+    for (int o = 0; o < O && !fatal; ++o) {
+      const int64_t po = p * O + o;
+      uint8_t* oflag = prm.obs_flags + ((int64_t)p * prm.T + t) * O + o;
       if (prm.img[o] < 0 || !prm.mask[po]) {
         if (rank == 0 && tid == 0) *oflag = GB_OBS_NO_IMAGE;
         continue;
       }
-      const gb_image* img = prm.images + prm.img[o];
-      {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&img->cam);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&hdr->cam);
-        for (int k = tid; k < (int)(sizeof(gb_camera) / 4); k += B) dst[k] = src[k];
-      }
-      __syncthreads();
-      // project, bounding box of the cloud (tracker.py:581-583)
-      double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
-      int has_nan = 0;
-      for (int i = tid; i < nv; i += B) {
-        double u, v;
-        project(hdr->cam, ev[i], ev[nl + i], ev[2 * nl + i], u, v);
-        uvb[i] = u;
-        uvb[nl + i] = v;
-        has_nan |= (int)(isnan(u) | isnan(v));
-        mm[0] = fmin(mm[0], u);
-        mm[1] = fmin(mm[1], v);
-        mm[2] = fmin(mm[2], -u);
-        mm[3] = fmin(mm[3], -v);
-        if (prm.io.dump_uv) {
-          double* d = prm.io.dump_uv + (po * N + i0 + i) * 2;
-          d[0] = u;
-          d[1] = v;
+      if (o != first_obs) {
+        __syncthreads();  // everyone is done with the previous observer's tile buffers
+        ib[0] = ib[1] = ib[2] = ib[3] = 0x7fffffff;
+        ib[4] = 0;
+        for (int i = tid; i < nv; i += B) {
+          double u, v;
+          project_fast(prm.cam[o], ev[i], ev[nl + i], ev[2 * nl + i], u, v);
+          uvb[i] = u;
+          uvb[nl + i] = v;
+          if (isnan(u) | isnan(v)) ib[4] = -1;
+          ib[0] = min(ib[0], __double2int_rd(u - hw));
+          ib[1] = min(ib[1], __double2int_rd(v - hh));
+          ib[2] = min(ib[2], -__double2int_ru(u + hw));
+          ib[3] = min(ib[3], -__double2int_ru(v + hh));
+          if (prm.io.dump_uv) {
+            double* d = prm.io.dump_uv + ((po * N) + i0 + i) * 2;
+            d[0] = u;
+            d[1] = v;
+          }
         }
       }
-      has_nan = __syncthreads_or(has_nan);
-      block_reduce<4, 1>(mm, hdr);
-      if (tid == 0) hdr->bcast[4] = (double)has_nan;
-      __syncthreads();
+      block_min_int<5>(ib, hdr);
       double(*xg)[GB_XCH] = cluster_allgather<5>(cc);
-      GB_CLK(2);
-      if (tid == 0) {
-        double lo_u = xg[0][0], lo_v = xg[0][1], hi_u = xg[0][2], hi_v = xg[0][3], nanf = xg[0][4];
+      int bx[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        double x = xg[0][k];
+        for (int r = 1; r < cs; ++r) x = fmin(x, xg[r][k]);
+        bx[k] = (int)x;
+      }
+      int box_l = bx[0], box_t = bx[1], box_r = -bx[2], box_b = -bx[3];
+      bool nan_any = bx[4] != 0;
+      // The reference widens the box when the cloud spans less than 3 px (tracker.py:584-594); that needs
+      // the exact extents.  Rare: take the exact double-precision route only then (cluster-uniform test).
+      if (!nan_any && ((box_r - box_l) - prm.tile_w < 5 || (box_b - box_t) - prm.tile_h < 5)) {
+        double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
+        for (int i = tid; i < nv; i += B) {
+          const double u = uvb[i], v = uvb[nl + i];
+          mm[0] = fmin(mm[0], u);
+          mm[1] = fmin(mm[1], v);
+          mm[2] = fmin(mm[2], -u);
+          mm[3] = fmin(mm[3], -v);
+        }
+        block_reduce<4, 1>(mm, hdr);
+        double(*xm)[GB_XCH] = cluster_allgather<4>(cc);
+        double lo_u = xm[0][0], lo_v = xm[0][1], hi_u = xm[0][2], hi_v = xm[0][3];
         for (int r = 1; r < cs; ++r) {
-          lo_u = fmin(lo_u, xg[r][0]);
-          lo_v = fmin(lo_v, xg[r][1]);
-          hi_u = fmin(hi_u, xg[r][2]);
-          hi_v = fmin(hi_v, xg[r][3]);
-          nanf += xg[r][4];
+          lo_u = fmin(lo_u, xm[r][0]);
+          lo_v = fmin(lo_v, xm[r][1]);
+          hi_u = fmin(hi_u, xm[r][2]);
+          hi_v = fmin(hi_v, xm[r][3]);
         }
         hi_u = -hi_u;
         hi_v = -hi_v;
-        // tracker.py:580-595 (kx = ky = 3)
         const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
-        double bl = sub(lo_u, tw * 0.5), bt = sub(lo_v, th * 0.5), br = add(hi_u, tw * 0.5), bb = add(hi_v, th * 0.5);
+        double bl = sub(lo_u, hw), bt = sub(lo_v, hh), br = add(hi_u, hw), bb = add(hi_v, hh);
         const double ncols = sub(3.0, sub(sub(br, bl), tw));
         if (ncols > 0.0) {
           bl = add(bl, mul(-ncols, 0.5));
@@ -665,44 +760,48 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
           bt = add(bt, mul(-nrows, 0.5));
           bb = add(bb, mul(nrows, 0.5));
         }
-        const double fl = floor(bl), ft = floor(bt), cr = ceil(br), cb = ceil(bb);
-        const double W = (double)hdr->cam.imgsz[0], H = (double)hdr->cam.imgsz[1];
-        // Camera.inframe on both corners (camera.py:700-718); NaN fails every comparison
-        const bool ok = (nanf == 0.0) & (fl >= 0.0) & (fl <= W) & (ft >= 0.0) & (ft <= H) & (cr >= 0.0) & (cr <= W) &
-                        (cb >= 0.0) & (cb <= H);
-        hdr->iflags[0] = ok ? 1 : 0;
-        if (ok) {
-          hdr->ibox[0] = (int)fl;
-          hdr->ibox[1] = (int)ft;
-          hdr->ibox[2] = (int)cr;
-          hdr->ibox[3] = (int)cb;
-        }
+        box_l = __double2int_rd(bl);
+        box_t = __double2int_rd(bt);
+        box_r = __double2int_ru(br);
+        box_b = __double2int_ru(bb);
       }
-      __syncthreads();
-      if (!hdr->iflags[0]) {
+      GB_CLK(2);
+      // Camera.inframe on both corners (camera.py:700-718); NaN fails every comparison
+      const int W = prm.cam[o].c.imgsz[0], H = prm.cam[o].c.imgsz[1];
+      const bool inframe = !nan_any && box_l >= 0 && box_l <= W && box_t >= 0 && box_t <= H && box_r >= 0 && box_r <= W &&
+                           box_b >= 0 && box_b <= H;
+      if (!inframe) {
         if (rank == 0 && tid == 0) *oflag = GB_OBS_OUT_OF_FRAME;
-        __syncthreads();
         continue;
       }
+      if (tid == 0) {
+        hdr->ibox[0] = box_l;
+        hdr->ibox[1] = box_t;
+        hdr->ibox[2] = box_r;
+        hdr->ibox[3] = box_b;
+      }
       TileWork w;
-      w.Su = hdr->ibox[2] - hdr->ibox[0];
-      w.Sv = hdr->ibox[3] - hdr->ibox[1];
+      w.Su = box_r - box_l;
+      w.Sv = box_b - box_t;
       w.tw = prm.tile_w;
       w.th = prm.tile_h;
       w.Mu = w.Su - w.tw + 1;
       w.Mv = w.Sv - w.th + 1;
-      w.nbins = 255 * img->nchan + 1;
+      w.nbins = 255 * prm.nchan[o] + 1;
       w.nvals = prm.tmpl_nvalues[po];
       if (rank == 0 && tid == 0) {
         *oflag = GB_OBS_USED;
         if (prm.window_stats) {
-          int32_t* ws = prm.window_stats + ((p * prm.T + t) * prm.O + o) * 2;
+          int32_t* ws = prm.window_stats + (((int64_t)p * prm.T + t) * O + o) * 2;
           ws[0] = w.Su;
           ws[1] = w.Sv;
         }
         if (prm.io.dump_box) {
           int32_t* d = prm.io.dump_box + po * 4;
-          for (int k = 0; k < 4; ++k) d[k] = hdr->ibox[k];
+          d[0] = box_l;
+          d[1] = box_t;
+          d[2] = box_r;
+          d[3] = box_b;
         }
       }
       char* tbase = tile_base;
@@ -723,16 +822,18 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       tile_carve(tbase, w);
       const int64_t ta = (int64_t)w.tw * w.th;
       const bool dumper = rank == 0;
-      tile_build_surface(img, hdr->ibox, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta, prm.tmpl_values + po * ta,
-                         w, (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
+      const int boxv[4] = {box_l, box_t, box_r, box_b};
+      tile_build_surface(prm.gray[o], prm.pitch[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+                         prm.tmpl_values + po * ta, w,
+                         (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
                          (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap,
                          clk ? clk + 3 : nullptr);
       GB_CLK(6);
       // geo-reference of the surface (tracker.py:615-620) and cell centres (observer.py:203-208)
       const double eu = sub(mul((double)w.tw, 0.5), 0.5), evv = sub(mul((double)w.th, 0.5), 0.5);
       const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
-      const double sl = add(add((double)hdr->ibox[0], eu), du_t), st = add(add((double)hdr->ibox[1], evv), dv_t);
-      const double sr = add(add((double)hdr->ibox[2], -eu), du_t), sb = add(add((double)hdr->ibox[3], -evv), dv_t);
+      const double sl = add(add((double)box_l, eu), du_t), st = add(add((double)box_t, evv), dv_t);
+      const double sr = add(add((double)box_r, -eu), du_t), sb = add(add((double)box_b, -evv), dv_t);
       const double cu0 = add(sl, mul(quo(sub(sr, sl), (double)w.Mu), 0.5));
       const double cv0 = add(st, mul(quo(sub(sb, st), (double)w.Mv), 0.5));
       const double cu1 = add(cu0, (double)(w.Mu - 1)), cv1 = add(cv0, (double)(w.Mv - 1));
@@ -742,59 +843,68 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
         if (!((u >= sl) & (u <= sr) & (v >= st) & (v <= sb))) flags |= GB_F_SAMPLE_OUTSIDE;
         // FITPACK evaluates at the argument clamped to the first/last data site
         const double x = fmin(fmax(u, cu0), cu1) - cu0, y = fmin(fmax(v, cv0), cv1) - cv0;
-        const double val = hermite_eval(w.herm, w.Mu, w.Mv, x, y);
+        const double val = (double)hermite_eval(w.herm, w.Mp, w.Mu, w.Mv, x, y);
         llb[i] = add(llb[i], mul(val, scale));
         if (prm.io.dump_sampled) prm.io.dump_sampled[po * N + i0 + i] = val;
       }
-      __syncthreads();
     }
   }
-
   GB_CLK(7);
-  // ---- phase C: weights (tracker.py:143-149), block scan, totals ----
-  double wsum_local;
+
+  // ---- phase C: weights (tracker.py:143-149) and their inclusive prefix within the CTA ----
+  // Particle i = k * B + tid: chunk k is contiguous across the block.  Warp scans first, then one
+  // warp turns the per-(chunk, warp) totals into offsets: two block barriers per 8 chunks.
   {
-    const double* fw = prm.io.force_weights ? prm.io.force_weights + p * N + i0 : nullptr;
-    const int lane = tid & 31, warp = tid >> 5, nwarp = B >> 5;
-    if (tid == 0) hdr->scan_carry = 0.0;
-    __syncthreads();
-    for (int base = 0; base < nv; base += B) {
-      const int i = base + tid;
-      double w = 0.0;
-      if (i < nv) {
-        if (fw) {
-          w = fw[i];
-        } else {
-          const double ll = add(llb[i], surface_log_likelihood(hdr->motion, prm.surfaces, ev[i], ev[nl + i], ev[2 * nl + i], flags));
-          w = add(exp(-ll), 1e-300);
+    const double* fw = prm.io.force_weights ? prm.io.force_weights + (int64_t)p * N + i0 : nullptr;
+    double carry = 0.0;
+    for (int base = 0; base < nv; base += 8 * B) {
+      const int nchunk = min(8, (nv - base + B - 1) / B);
+      for (int k = 0; k < nchunk; ++k) {
+        const int i = base + k * B + tid;
+        double w = 0.0;
+        if (i < nv) {
+          if (fw) {
+            w = fw[i];
+          } else {
+            double ll = llb[i];
+            if (surface_ll) ll = add(ll, surface_log_likelihood(hdr->motion, prm.surfaces, ev[i], ev[nl + i], ev[2 * nl + i], flags));
+            else ll = add(ll, 0.0);
+            w = add(exp(-ll), 1e-300);
+          }
+          llb[i] = w;
+          if (prm.io.dump_weights) prm.io.dump_weights[(int64_t)p * N + i0 + i] = w;
         }
-        llb[i] = w;
-        if (prm.io.dump_weights) prm.io.dump_weights[p * N + i0 + i] = w;
+        const double incl = warp_inclusive_scan(w, lane);
+        if (i < nv) uvb[i] = incl;
+        if (lane == 31) hdr->scan_tot[k * nwarp + warp] = incl;
       }
-      double incl = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double o = shfl_up(incl, d);
-        if (lane >= d) incl += o;
+      __syncthreads();
+      if (warp == 0) {
+        double run = carry;
+        for (int b0 = 0; b0 < nchunk * nwarp; b0 += 32) {
+          const double v = (b0 + lane < nchunk * nwarp) ? hdr->scan_tot[b0 + lane] : 0.0;
+          const double incl = warp_inclusive_scan(v, lane);
+          double excl = shfl_up(incl, 1);
+          if (lane == 0) excl = 0.0;
+          if (b0 + lane < nchunk * nwarp) hdr->scan_tot[b0 + lane] = run + excl;
+          run = run + __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) hdr->scan_carry = run;
       }
-      if (lane == 31) hdr->scan_warp[warp] = incl;
       __syncthreads();
-      double woff = 0.0;
-      for (int k = 0; k < warp; ++k) woff += hdr->scan_warp[k];
-      const double carry = hdr->scan_carry;
-      const double l = carry + (woff + incl);
-      if (i < nv) uvb[i] = l;
+      for (int k = 0; k < nchunk; ++k) {
+        const int i = base + k * B + tid;
+        if (i < nv) uvb[i] = hdr->scan_tot[k * nwarp + warp] + uvb[i];
+      }
+      carry = hdr->scan_carry;
       __syncthreads();
-      if (tid == B - 1) hdr->scan_carry = l;  // running total (w = 0 past the end keeps it constant)
-      __syncthreads();
-      (void)nwarp;
     }
-    wsum_local = hdr->scan_carry;
   }
   GB_CLK(8);
   const int blockflags = __syncthreads_or((int)flags);
+  // the CTA total is, by definition, the prefix of its last particle (keeps child ranges seamless)
   if (tid == 0) {
-    hdr->bcast[0] = wsum_local;
+    hdr->bcast[0] = nv > 0 ? uvb[nv - 1] : 0.0;
     hdr->bcast[1] = (double)blockflags;
   }
   __syncthreads();
@@ -815,10 +925,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       return;
     }
   }
-
   GB_CLK(9);
-  // ---- phase D: systematic resampling (tracker.py:168-176, 222-223) ----
-  const double u01 = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[p * prm.S + (t - prm.first[p] - 1)]
+
+  // ---- phase D: systematic resampling (tracker.py:168-176): child range [E[i-1], E[i]) of every parent ----
+  const double u01 = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
                                                       : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
   const double inv_n = quo(1.0, (double)N);
   int* E = reinterpret_cast<int*>(uvb + nl);
@@ -826,35 +936,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
   const int J0 = rank == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
   __syncthreads();
   GB_CLK(10);
-  const int J1 = nv > 0 ? E[nv - 1] : J0;
-  {
-    double* sout = state_buffer(prm, t) + p * 6 * N;
-    for (int j = J0 + tid; j < J1; j += B) {
-      int lo = 0, hi = nv - 1;  // smallest local parent with E[parent] > j
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (E[mid] > j) hi = mid; else lo = mid + 1;
-      }
-      const int a = lo;
-      double s[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + a];
-      const double w = llb[a];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) sout[c * N + j] = s[c];
-      if (prm.weight_state) prm.weight_state[p * N + j] = w;
-      if (prm.out_particles) {
-        double* d = prm.out_particles + ((p * prm.T + t) * N + j) * 6;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) d[c] = s[c];
-      }
-      if (prm.out_weights) prm.out_weights[(p * prm.T + t) * N + j] = w;
-      if (prm.io.dump_indices) prm.io.dump_indices[p * N + j] = (int)(i0 + a);
-    }
-  }
 
-  GB_CLK(11);
   // ---- phase E: moments of the resampled set = parents weighted by (children x weight) ----
+  // (before the child stores, so that no global store is in flight at the cluster barrier)
   Moments<COV> mom;
   mom.clear();
   for (int i = tid; i < nv; i += B) {
@@ -869,23 +953,55 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
   block_reduce<Moments<COV>::NM, 0>(mom.a, hdr);
   {
     double(*xg)[GB_XCH] = cluster_allgather<Moments<COV>::NM>(cc);
-    if (rank == 0 && tid == 0) {
-      double a[Moments<COV>::NM];
-      for (int k = 0; k < Moments<COV>::NM; ++k) {
-        double x = xg[0][k];
-        for (int r = 1; r < cs; ++r) x += xg[r][k];
-        a[k] = x;
+    if (rank == 0 && tid < Moments<COV>::NM) {
+      double x = xg[0][tid];
+      for (int r = 1; r < cs; ++r) x += xg[r][tid];
+      hdr->bcast[tid] = x;
+    }
+    if (rank == 0) {
+      __syncthreads();
+      if (tid == 0) {
+        double mean[6], sg[6], cv[36];
+        finalize_moments<COV>(hdr->bcast, hdr->ref, mean, sg, cv);
+        double* mo = prm.means + ((int64_t)p * prm.T + t) * 6;
+        for (int c = 0; c < 6; ++c) mo[c] = mean[c];
+        if (COV) {
+          double* co = prm.covariances + ((int64_t)p * prm.T + t) * 36;
+          for (int c = 0; c < 36; ++c) co[c] = cv[c];
+        } else {
+          double* so = prm.sigmas + ((int64_t)p * prm.T + t) * 6;
+          for (int c = 0; c < 6; ++c) so[c] = sg[c];
+        }
       }
-      double mean[6], sg[6], cv[36];
-      finalize_moments<COV>(a, hdr->ref, mean, sg, cv);
-      double* mo = prm.means + (p * prm.T + t) * 6;
-      for (int c = 0; c < 6; ++c) mo[c] = mean[c];
-      if (COV) {
-        double* co = prm.covariances + (p * prm.T + t) * 36;
-        for (int c = 0; c < 36; ++c) co[c] = cv[c];
-      } else {
-        double* so = prm.sigmas + (p * prm.T + t) * 6;
-        for (int c = 0; c < 6; ++c) so[c] = sg[c];
+    }
+  }
+  GB_CLK(11);
+
+  // ---- phase F: every parent writes its children (tracker.py:222-223); no search, no further barrier ----
+  {
+    double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
+    double* wst = prm.weight_state ? prm.weight_state + (int64_t)p * N : nullptr;
+    double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
+    double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
+    int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
+    for (int i = tid; i < nv; i += B) {
+      const int j1 = E[i];
+      int j = i > 0 ? E[i - 1] : J0;
+      if (j >= j1) continue;
+      double s[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + i];
+      const double w = llb[i];
+      for (; j < j1; ++j) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
+        if (wst) wst[j] = w;
+        if (outp) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
+        }
+        if (outw) outw[j] = w;
+        if (outi) outi[j] = i0 + i;
       }
     }
   }
@@ -956,6 +1072,13 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   for (int o = 0; o < d.O; ++o) {
     const int idx = d.image_index_host[(int64_t)t * d.O + o];
     prm.img[o] = idx >= 0 ? d.image_offset_host[o] + idx : -1;
+    if (idx >= 0 && d.images_host) {
+      const gb_image& im = d.images_host[prm.img[o]];
+      camk_from(im.cam, prm.cam[o]);
+      prm.gray[o] = im.gray;
+      prm.pitch[o] = im.pitch;
+      prm.nchan[o] = im.nchan;
+    }
     prm.obs_scale[o] = d.obs_scale_host[o];
     int tf = -1;
     for (int tt = 0; tt < d.T; ++tt)
@@ -1001,6 +1124,7 @@ static int check_desc(const gb_track_desc& d) {
   if (d.tile_w < 1 || d.tile_h < 1 || (int64_t)d.tile_w * d.tile_h > GB_MAX_TEMPLATE)
     return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
   if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");
+  if (!d.images_host) return fail(GB_E_INVALID, "images_host is required%s");
   if (!d.images || !d.mask || !d.first || !d.last || !d.motion || !d.surfaces || !d.state_a || !d.state_b || !d.means ||
       !d.status || !d.status_time || !d.obs_flags || !d.tmpl_tile || !d.tmpl_values || !d.tmpl_quantiles ||
       !d.tmpl_nvalues || !d.tmpl_box || !d.tmpl_duv)

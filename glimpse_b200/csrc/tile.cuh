@@ -10,7 +10,8 @@
 //  * CDF matching only depends on pixel ranks, so the matched tile is LUT[raw] with one LUT entry
 //    per grey level: LUT[g] = interp(count(raw <= g) / size, template_quantiles, template_values).
 //  * LUT is non-decreasing and the median of 25 values is one of them, so
-//    median5x5(LUT[raw]) == LUT[median5x5(raw)]; the median runs on integers.
+//    median5x5(LUT[raw]) == LUT[median5x5(raw)]; the median runs on integers, two vertically
+//    adjacent pixels at a time in the halves of one 32-bit word (VIMNMX.U16x2).
 #pragma once
 #include "common.cuh"
 #include "median25.cuh"
@@ -23,46 +24,52 @@ __constant__ double c_spline_cp[256];
 __constant__ double c_spline_inv[256];
 
 struct TileWork {
-  float4* herm;    // [Mv * Mu] (F, dF/du, dF/dv, d2F/dudv)
-  double* lut;     // [nbins]
-  double* tq;      // [nvals] template quantiles
-  double* tv;      // [nvals] template values
-  float* hp;       // [Sv * Su] high-passed search tile
-  float* tmpl;     // [th * tw] high-passed template
-  uint32_t* hist;  // [nbins]
-  uint16_t* raw;   // [Sv * Su]
-  int Su, Sv, Mu, Mv, nbins, nvals, tw, th;
+  float4* herm;      // [Mv][Mp] (F, dF/du, dF/dv, d2F/dudv); Mp odd keeps row solves off the same banks
+  uint32_t* packed;  // [Sv + 4][Su + 4] reflect-padded window, row r in the low and r + 1 in the high half; aliases herm
+  double* lut;       // [nbins]
+  double* tq;        // [nvals] template quantiles
+  double* tv;        // [nvals] template values
+  float* hp;         // [Sv][Sp] high-passed search tile, Sp = Su rounded up to 4
+  uint16_t* raw;     // [Sv][Su] raw window; aliases hp (dead before hp is written)
+  float* tmpl;       // [th][Tp] high-passed template, Tp = tw rounded up to 4
+  uint32_t* hist;    // [nbins]
+  int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
 };
 
+__host__ __device__ inline int64_t align16(int64_t b) { return (b + 15) / 16 * 16; }
+
 __host__ __device__ inline int64_t tile_bytes_needed(int Su, int Sv, int tw, int th, int nbins, int nvals) {
-  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1;
-  int64_t b = 0;
-  b += ((Mu * Mv * 16 + 15) / 16) * 16;
-  b += (int64_t)nbins * 8 + (int64_t)nvals * 16;
-  b += ((int64_t)Su * Sv * 4 + 15) / 16 * 16;
-  b += ((int64_t)tw * th * 4 + 15) / 16 * 16;
-  b += (int64_t)nbins * 4;
-  b += ((int64_t)Su * Sv * 2 + 15) / 16 * 16;
+  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mp = Mu | 1, Sp = (Su + 3) / 4 * 4, Tp = (tw + 3) / 4 * 4;
+  const int64_t herm = Mv * Mp * 16, packed = (int64_t)(Sv + 4) * (Su + 4) * 4;
+  int64_t b = align16(herm > packed ? herm : packed);
+  b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
+  b += align16((int64_t)Sv * Sp * 4);
+  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)nbins * 4);
   return b;
 }
 
 __device__ inline void tile_carve(char* base, TileWork& w) {
+  w.Mp = w.Mu | 1;
+  w.Sp = (w.Su + 3) / 4 * 4;
+  w.Tp = (w.tw + 3) / 4 * 4;
   char* p = base;
+  const int64_t herm = (int64_t)w.Mv * w.Mp * 16, packed = (int64_t)(w.Sv + 4) * (w.Su + 4) * 4;
   w.herm = reinterpret_cast<float4*>(p);
-  p += (((int64_t)w.Mu * w.Mv * 16 + 15) / 16) * 16;
+  w.packed = reinterpret_cast<uint32_t*>(p);
+  p += align16(herm > packed ? herm : packed);
   w.lut = reinterpret_cast<double*>(p);
-  p += (int64_t)w.nbins * 8;
+  p += align16((int64_t)w.nbins * 8);
   w.tq = reinterpret_cast<double*>(p);
-  p += (int64_t)w.nvals * 8;
+  p += align16((int64_t)w.nvals * 8);
   w.tv = reinterpret_cast<double*>(p);
-  p += (int64_t)w.nvals * 8;
+  p += align16((int64_t)w.nvals * 8);
   w.hp = reinterpret_cast<float*>(p);
-  p += ((int64_t)w.Su * w.Sv * 4 + 15) / 16 * 16;
-  w.tmpl = reinterpret_cast<float*>(p);
-  p += ((int64_t)w.tw * w.th * 4 + 15) / 16 * 16;
-  w.hist = reinterpret_cast<uint32_t*>(p);
-  p += (int64_t)w.nbins * 4;
   w.raw = reinterpret_cast<uint16_t*>(p);
+  p += align16((int64_t)w.Sv * w.Sp * 4);
+  w.tmpl = reinterpret_cast<float*>(p);
+  p += align16((int64_t)w.th * w.Tp * 4);
+  w.hist = reinterpret_cast<uint32_t*>(p);
 }
 
 // np.interp(q, xp, fp) for one abscissa (numpy compiled_base.c arr_interp): clamped at the ends,
@@ -85,10 +92,11 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
   // scipy.ndimage 'reflect': d c b a | a b c d | d c b a
   if (i < 0) i = -i - 1;
   if (i >= n) i = 2 * n - i - 1;
-  return i;
+  return min(max(i, 0), n - 1);
 }
 
-// Median of the 5x5 neighbourhood of (r, c) in an integer tile with reflected borders.
+// Median of the 5x5 neighbourhood of (r, c) in an integer tile with reflected borders (scalar
+// version, used by the template kernel).
 __device__ __forceinline__ int median5x5(const uint16_t* raw, int Su, int Sv, int r, int c) {
   int v[25];
   int cols[5];
@@ -104,16 +112,33 @@ __device__ __forceinline__ int median5x5(const uint16_t* raw, int Su, int Sv, in
 }
 
 // Solve the not-a-knot slope system along one line of the Hermite array (stride in floats).
-// `in` holds the samples, `out` receives the slopes; intermediate values pass through `out`.
-__device__ inline void spline_slopes_line(const float* in, float* out, int stride, int m) {
+// `in` holds the samples, `out` receives the slopes; the forward-sweep values pass through `out`
+// as floats.  The loop-carried chain is one DFMA per element in each direction.
+__device__ __forceinline__ void spline_slopes_line(const float* __restrict__ in, float* __restrict__ out, int stride, int m) {
   const double f0 = in[0], f1 = in[stride], f2 = in[2 * stride];
   double d = 0.5 * (5.0 * (f1 - f0) + (f2 - f1));
   out[0] = (float)d;
   double prev = f0, cur = f1;
-  for (int i = 1; i < m - 1; ++i) {
+  int i = 1;
+  for (; i + 3 < m - 1; i += 4) {  // four elements per trip: loads and rhs products are off the chain
+    const double n0 = in[(i + 1) * stride], n1 = in[(i + 2) * stride], n2 = in[(i + 3) * stride], n3 = in[(i + 4) * stride];
+    const double v0 = c_spline_inv[i], v1 = c_spline_inv[i + 1], v2 = c_spline_inv[i + 2], v3 = c_spline_inv[i + 3];
+    const double a0 = 3.0 * (n0 - prev) * v0, a1 = 3.0 * (n1 - cur) * v1, a2 = 3.0 * (n2 - n0) * v2, a3 = 3.0 * (n3 - n1) * v3;
+    const double d0 = fma(-v0, d, a0);
+    const double d1 = fma(-v1, d0, a1);
+    const double d2 = fma(-v2, d1, a2);
+    d = fma(-v3, d2, a3);
+    out[i * stride] = (float)d0;
+    out[(i + 1) * stride] = (float)d1;
+    out[(i + 2) * stride] = (float)d2;
+    out[(i + 3) * stride] = (float)d;
+    prev = n2;
+    cur = n3;
+  }
+  for (; i < m - 1; ++i) {
     const double next = in[(i + 1) * stride];
-    const double rhs = 3.0 * (next - prev);
-    d = (rhs - d) * c_spline_inv[i];
+    const double v = c_spline_inv[i];
+    d = fma(-v, d, 3.0 * (next - prev) * v);
     out[i * stride] = (float)d;
     prev = cur;
     cur = next;
@@ -125,60 +150,84 @@ __device__ inline void spline_slopes_line(const float* in, float* out, int strid
   }
   double s = d;
   out[(m - 1) * stride] = (float)s;
-  for (int i = m - 2; i >= 0; --i) {
-    s = (double)out[i * stride] - c_spline_cp[i] * s;
+  i = m - 2;
+  for (; i - 3 >= 0; i -= 4) {
+    const double e0 = out[i * stride], e1 = out[(i - 1) * stride], e2 = out[(i - 2) * stride], e3 = out[(i - 3) * stride];
+    const double s0 = fma(-c_spline_cp[i], s, e0);
+    const double s1 = fma(-c_spline_cp[i - 1], s0, e1);
+    const double s2 = fma(-c_spline_cp[i - 2], s1, e2);
+    s = fma(-c_spline_cp[i - 3], s2, e3);
+    out[i * stride] = (float)s0;
+    out[(i - 1) * stride] = (float)s1;
+    out[(i - 2) * stride] = (float)s2;
+    out[(i - 3) * stride] = (float)s;
+  }
+  for (; i >= 0; --i) {
+    s = fma(-c_spline_cp[i], s, (double)out[i * stride]);
     out[i * stride] = (float)s;
   }
 }
 
-// Bicubic Hermite evaluation at (x, y) measured from the first cell centre, in cell units.
-__device__ __forceinline__ double hermite_eval(const float4* herm, int Mu, int Mv, double x, double y) {
-  int j = min((int)floor(x), Mu - 2), i = min((int)floor(y), Mv - 2);
+// Bicubic Hermite evaluation at (x, y) measured from the first cell centre, in cell units.  The cell
+// index and the in-cell offset are taken in double; the 16-term patch is evaluated in float (the
+// data are float32: the SSE surface is cv2.matchTemplate's float32 output in the reference).
+__device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, int Mp, int Mu, int Mv, double x, double y) {
+  int j = min((int)x, Mu - 2), i = min((int)y, Mv - 2);  // x, y >= 0
   j = max(j, 0);
   i = max(i, 0);
-  const double tx = x - (double)j, ty = y - (double)i;
-  const double tx2 = tx * tx, tx3 = tx2 * tx, ty2 = ty * ty, ty3 = ty2 * ty;
-  const double a0 = 2.0 * tx3 - 3.0 * tx2 + 1.0, a1 = tx3 - 2.0 * tx2 + tx, a2 = -2.0 * tx3 + 3.0 * tx2, a3 = tx3 - tx2;
-  const double b0 = 2.0 * ty3 - 3.0 * ty2 + 1.0, b1 = ty3 - 2.0 * ty2 + ty, b2 = -2.0 * ty3 + 3.0 * ty2, b3 = ty3 - ty2;
-  const float4 h00 = herm[i * Mu + j], h01 = herm[i * Mu + j + 1];
-  const float4 h10 = herm[(i + 1) * Mu + j], h11 = herm[(i + 1) * Mu + j + 1];
+  const float tx = (float)(x - (double)j), ty = (float)(y - (double)i);
+  const float tx2 = tx * tx, tx3 = tx2 * tx, ty2 = ty * ty, ty3 = ty2 * ty;
+  const float a2 = 3.0f * tx2 - 2.0f * tx3, a0 = 1.0f - a2, a3 = tx3 - tx2, a1 = a3 - tx2 + tx;
+  const float b2 = 3.0f * ty2 - 2.0f * ty3, b0 = 1.0f - b2, b3 = ty3 - ty2, b1 = b3 - ty2 + ty;
+  const float4* row0 = herm + i * Mp + j;
+  const float4 h00 = row0[0], h01 = row0[1], h10 = row0[Mp], h11 = row0[Mp + 1];
   // rows of the patch: value and u-slope interpolated along u, for f and for df/dv
-  const double top_f = a0 * h00.x + a2 * h01.x + a1 * h00.y + a3 * h01.y;
-  const double bot_f = a0 * h10.x + a2 * h11.x + a1 * h10.y + a3 * h11.y;
-  const double top_v = a0 * h00.z + a2 * h01.z + a1 * h00.w + a3 * h01.w;
-  const double bot_v = a0 * h10.z + a2 * h11.z + a1 * h10.w + a3 * h11.w;
+  const float top_f = a0 * h00.x + a2 * h01.x + a1 * h00.y + a3 * h01.y;
+  const float bot_f = a0 * h10.x + a2 * h11.x + a1 * h10.y + a3 * h11.y;
+  const float top_v = a0 * h00.z + a2 * h01.z + a1 * h00.w + a3 * h01.w;
+  const float bot_v = a0 * h10.z + a2 * h11.z + a1 * h10.w + a3 * h11.w;
   return b0 * top_f + b2 * bot_f + b1 * top_v + b3 * bot_v;
 }
 
 // Build the Hermite surface for one search window.  All threads of the CTA participate.
-// `box` = (left, top, right, bottom); template data in global memory.  The caller has verified
-// the capacity and carved `w`.
-__device__ inline void tile_build_surface(const gb_image* img, const int* box, const double* g_tmpl,
-                                          const double* g_tq, const double* g_tv, TileWork& w, float* dump_search,
-                                          float* dump_sse, int64_t dump_cap, long long* clk) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int Su = w.Su, Sv = w.Sv, Mu = w.Mu, Mv = w.Mv;
+// `box` = (left, top, right, bottom); template data in global memory.  The caller has verified the
+// capacity and carved `w`.
+__device__ inline void tile_build_surface(const uint16_t* __restrict__ gray_plane, int pitch, const int* box, const double* __restrict__ g_tmpl,
+                                          const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
+                                          float* dump_search, float* dump_sse, int64_t dump_cap, long long* clk) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int Su = w.Su, Sv = w.Sv, Mu = w.Mu, Mv = w.Mv, Mp = w.Mp, Sp = w.Sp, Tp = w.Tp;
   const int area = Su * Sv;
-  // 1. raw window, template, template CDF; clear histogram
+  // 1. raw window (a warp per row: consecutive lanes read consecutive pixels), template and its
+  //    CDF; clear the histogram
   {
-    const uint16_t* gray = img->gray;
-    const int pitch = img->pitch, left = box[0], top = box[1];
-    for (int i = tid; i < area; i += nthr) {
-      const int r = i / Su, c = i - r * Su;
-      w.raw[i] = gray[(int64_t)(top + r) * pitch + left + c];
-    }
+    const uint16_t* gray = gray_plane + (int64_t)box[1] * pitch + box[0];
+    for (int r = warp; r < Sv; r += nwarp)
+      for (int c = lane; c < Su; c += 32) w.raw[r * Su + c] = gray[(int64_t)r * pitch + c];
     for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
-    for (int i = tid; i < w.tw * w.th; i += nthr) w.tmpl[i] = (float)g_tmpl[i];
+    for (int i = tid; i < w.tw * w.th; i += nthr) {
+      const int r = i / w.tw, c = i - r * w.tw;
+      w.tmpl[r * Tp + c] = (float)g_tmpl[i];
+    }
     for (int i = tid; i < w.nvals; i += nthr) {
       w.tq[i] = g_tq[i];
       w.tv[i] = g_tv[i];
     }
   }
   __syncthreads();
-  // 2. histogram of grey levels
+  // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
   for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
+  {
+    const int PW = Su + 4, PH = Sv + 4;
+    for (int i = tid; i < PW * PH; i += nthr) {
+      const int pr = i / PW, pc = i - pr * PW;
+      const int cc = reflect_index(pc - 2, Su);
+      const uint32_t lo = w.raw[reflect_index(pr - 2, Sv) * Su + cc], hi = w.raw[reflect_index(pr - 1, Sv) * Su + cc];
+      w.packed[i] = lo | (hi << 16);
+    }
+  }
   __syncthreads();
-  // 3. inclusive cumulative counts (one warp; nbins <= 1024)
+  // 3. inclusive cumulative counts (one warp; nbins <= 1024); empty levels are marked with 0
   if (tid < 32) {
     const int per = (w.nbins + 31) / 32;
     const int b0 = tid * per, b1 = min(b0 + per, w.nbins);
@@ -194,7 +243,6 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
     for (int b = b0; b < b1; ++b) {
       const uint32_t h = w.hist[b];
       run += h;
-      // keep the count of the level in the top bit-free range; mark empty levels with 0
       w.hist[b] = h ? run : 0u;
     }
   }
@@ -206,36 +254,90 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
   }
   __syncthreads();
   if (clk && threadIdx.x == 0) clk[0] = clock64();
-  // 5. high-pass: matched value minus the matched 5x5 median (tracker.py:530-531), cast to
-  //    float32 as the reference does for matchTemplate (tracker.py:610)
-  for (int i = tid; i < area; i += nthr) {
-    const int r = i / Su, c = i - r * Su;
-    const int med = median5x5(w.raw, Su, Sv, r, c);
-    const float v = (float)sub(w.lut[w.raw[i]], w.lut[med]);
-    w.hp[i] = v;
-    if (dump_search && i < dump_cap) dump_search[i] = v;
+  // 5. high-pass: matched value minus the matched 5x5 median (tracker.py:530-531), cast to float32
+  //    as the reference does for matchTemplate (tracker.py:610).  One thread = pixels (r, c), (r+1, c).
+  {
+    const int PW = Su + 4, pairs = ((Sv + 1) / 2) * Su;
+    for (int i = tid; i < pairs; i += nthr) {
+      const int rp = i / Su, c = i - rp * Su, r = 2 * rp;
+      uint32_t v[25];
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        const uint32_t* row = w.packed + (r + a) * PW + c;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) v[a * 5 + b] = row[b];
+      }
+      const uint32_t self = v[12];
+      const uint32_t med = gb_median25_u16x2(v);
+      {
+        const float o = (float)sub(w.lut[self & 0xffffu], w.lut[med & 0xffffu]);
+        w.hp[r * Sp + c] = o;
+        if (dump_search && r * Su + c < dump_cap) dump_search[r * Su + c] = o;
+      }
+      if (r + 1 < Sv) {
+        const float o = (float)sub(w.lut[self >> 16], w.lut[med >> 16]);
+        w.hp[(r + 1) * Sp + c] = o;
+        if (dump_search && (r + 1) * Su + c < dump_cap) dump_search[(r + 1) * Su + c] = o;
+      }
+    }
   }
   __syncthreads();
   if (clk && threadIdx.x == 0) clk[1] = clock64();
-  // 6. area-normalised sum of squared differences (tracker.py:609-614)
+  // 6. area-normalised sum of squared differences (tracker.py:609-614).  One warp owns a block of
+  //    4 output rows x 32 output columns and a slice of the template columns: lanes run along the
+  //    image row (conflict-free loads, template values broadcast) and each lane keeps the four row
+  //    outputs in registers while the template column slides past.  Slices land in the unused
+  //    components of the Hermite cells and are summed in a fixed order (bit-reproducible).
   {
-    const double inv_area = 1.0 / (double)(w.tw * w.th);
     const int tw = w.tw, th = w.th;
-    for (int o = tid; o < Mu * Mv; o += nthr) {
-      const int r = o / Mu, c = o - r * Mu;
-      float acc = 0.0f;
-      for (int i = 0; i < th; ++i) {
-        const float* srow = w.hp + (r + i) * Su + c;
-        const float* trow = w.tmpl + i * tw;
-        float racc = 0.0f;
-        for (int j = 0; j < tw; ++j) {
-          const float d = srow[j] - trow[j];
-          racc = fmaf(d, d, racc);
+    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    int JP = 1;
+    while (JP < 4 && JP * 2 * RG * CB <= nwarp && JP * 2 <= tw) JP *= 2;
+    const int jper = (tw + JP - 1) / JP;
+    const int items = RG * CB * JP;
+    float* hf = reinterpret_cast<float*>(w.herm);
+    for (int item = warp; item < items; item += nwarp) {
+      const int jp = item % JP, blk = item / JP;
+      const int rg = blk / CB, cb = blk - rg * CB;
+      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
+      const int kmax = min(4, Mv - r0);  // valid output rows in this block
+      const int jlo = jp * jper, jhi = min(jlo + jper, tw);
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      for (int j = jlo; j < jhi; ++j) {
+        const float* Icol = w.hp + r0 * Sp + c + j;
+        const float* Tcol = w.tmpl + j;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+        const int nrow = th + kmax - 1;
+        for (int ip = 0; ip < nrow; ++ip) {
+          t3 = t2;
+          t2 = t1;
+          t1 = t0;
+          t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
+          const float iv = Icol[ip * Sp];
+          // output row k uses template row ip - k
+          if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
+          if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
+          if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
+          if (ip >= 3) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
         }
-        acc += racc;
       }
+      if (cb * 32 + lane < Mu) {
+        const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < kmax) hf[((r0 + k) * Mp + c) * 4 + jp] = acc[k];
+      }
+    }
+    __syncthreads();
+    const double inv_area = 1.0 / (double)(tw * th);
+    for (int o = tid; o < Mu * Mv; o += nthr) {
+      const int r = o / Mu, cc = o - r * Mu;
+      const float4 part = w.herm[r * Mp + cc];
+      float acc = part.x;
+      if (JP > 1) acc += part.y;
+      if (JP > 2) acc = (acc + part.z) + part.w;
       const float sse = (float)((double)acc * inv_area);
-      w.herm[o] = make_float4(sse, 0.0f, 0.0f, 0.0f);
+      w.herm[r * Mp + cc] = make_float4(sse, 0.0f, 0.0f, 0.0f);
       if (dump_sse && o < dump_cap) dump_sse[o] = sse;
     }
   }
@@ -247,14 +349,14 @@ __device__ inline void tile_build_surface(const gb_image* img, const int* box, c
     const int Mvp = 32 * ((Mv + 31) / 32);  // rows and columns on separate warps
     for (int line = tid; line < Mvp + Mu; line += nthr) {
       if (line < Mv) {
-        spline_slopes_line(base + (int64_t)line * Mu * 4, base + (int64_t)line * Mu * 4 + 1, 4, Mu);
+        spline_slopes_line(base + (int64_t)line * Mp * 4, base + (int64_t)line * Mp * 4 + 1, 4, Mu);
       } else if (line >= Mvp) {
         const int c = line - Mvp;
-        spline_slopes_line(base + (int64_t)c * 4, base + (int64_t)c * 4 + 2, Mu * 4, Mv);
+        spline_slopes_line(base + (int64_t)c * 4, base + (int64_t)c * 4 + 2, Mp * 4, Mv);
       }
     }
     __syncthreads();
-    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mu * 4, Mv);
+    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mp * 4, Mv);
   }
   __syncthreads();
 }

@@ -154,6 +154,7 @@ class Session:
             d = self.desc = _lib.gb_track_desc()
             d.P, d.N, d.T, d.O, d.tile_w, d.tile_h = P, N, T, O, self.tw, self.th
             d.images = images_dev.data_ptr()
+            d.images_host = C.addressof(self.images_host)
             d.image_offset_host = self.offsets.ctypes.data
             d.image_index_host = self.image_index.ctypes.data
             d.obs_scale_host = self.scale_h.ctypes.data
@@ -240,7 +241,8 @@ class Session:
                     g.cam = lower_camera(img.cam)
                 structs.append(g)
             offsets.append(len(structs))
-        images_dev = _struct_array_to_device(torch, structs, _lib.gb_image, device)
+        self.images_host = (_lib.gb_image * len(structs))(*structs)
+        images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
         self.h2d += images_dev.numel()
         return images_dev, np.asarray(offsets, dtype=np.int32)
 

@@ -171,6 +171,7 @@ typedef struct gb_track_desc {
 
   /* frames and cameras: images[image_offset_host[o] + i] is image i of observer o */
   const gb_image* images;          /* device array */
+  const gb_image* images_host;     /* host copy of the same table (cameras travel to the kernels as launch parameters) */
   const int32_t* image_offset_host; /* [O + 1] */
   const int32_t* image_index_host; /* [T][O] image of observer o matched to time t, -1 = none (tracker.py:466-492) */
   const double* obs_scale_host;    /* [O] 1 / (2 sigma^2) (tracker.py:625) */

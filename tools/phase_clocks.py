@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 NAMES = ["A evolve+test", "project+box allgather", "box,load,hist,LUT", "median highpass", "SSD", "hermite solve",
-         "spline eval", "weights+scan", "W allgather", "child ranges E", "children write", "moments+allgather"]
+         "spline eval", "weights+scan", "W allgather", "child ranges E", "moments+allgather", "children write"]
 # clock slots: 0 start, 1 after A, 2 after box allgather, 3 after LUT, 4 after median, 5 after SSD, 6 after hermite,
 #              7 after eval, 8 after scan, 9 after W allgather, 10 after E, 11 after children, 12 end
 ORDER = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (9, 10), (10, 11), (11, 12)]
