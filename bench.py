@@ -227,7 +227,7 @@ def run_gpu_arm(args):
         T, args.small = args.frames, True
     scene = build_scene(P * world, T, pinned=True)
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, seed=20260101, cluster=args.cluster)
+    tracker = gb.Tracker(observers, seed=20260101, cluster=args.cluster, mode=args.mode)
     datetimes = tracker.datetimes
     matching = tracker.match_datetimes(datetimes)
     image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
@@ -292,7 +292,8 @@ def run_gpu_arm(args):
     stats_out = session.fetch()
     failed = int((status != 0).sum())
     value = world * P * N * T / (dev_ms / 1e3)
-    launches_per_step = 2 + (T - 1)  # k_init + k_template + (T - 1) x k_step
+    per_update = 6 if args.mode == "stream" else 1
+    launches_per_step = 2 + per_update * (T - 1)  # k_init + k_template + (T - 1) updates
     peak, peak_src = hbm_peak()
     achieved = ALGORITHMIC_BYTES_PER_UPDATE * P * N / (kernel_ms / 1e3) / 1e9
     win_w, win_h = session.stats["window_width"], session.stats["window_height"]
@@ -333,7 +334,7 @@ def run_gpu_arm(args):
             "data": "synthetic",
             "config": {
                 "workload": WORKLOAD_NAME if not args.small else f"SMALL smoke variant: {P} points x {N} particles x {T} frames",
-                "points_per_gpu": P, "particles": N, "frames": T, "rng": "philox (device)",
+                "points_per_gpu": P, "particles": N, "frames": T, "rng": "philox (device)", "mode": args.mode,
                 "cache": "inputs larger than L2 (particle state 2 x %.0f MB per GPU, no flush needed)" % (P * N * 48 / 1e6),
                 "plan": session.stats["plan"],
                 "search_window_px": {"median_w": float(np.median(win_w)) if len(win_w) else None,
@@ -345,7 +346,7 @@ def run_gpu_arm(args):
                 "failed_points": failed, "median_abs_velocity_error_m_per_day": v_err,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "traffic": None, "kernel": "k_step" if args.mode == "fused" else "update = k_s0..k_s5", "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N},
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -365,6 +366,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="glimpse_b200", choices=["glimpse_b200", "reference"])
     ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--mode", default="stream", choices=["stream", "fused"])
     ap.add_argument("--small", action="store_true", help="tiny variant for smoke-testing the script (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (profiling only; not a bench value)")

@@ -22,6 +22,7 @@ GB_ST_MESSAGES = {
 }
 GB_OBS_OUT_OF_FRAME = 2
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
+GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL = 0, 1
 
 
@@ -61,6 +62,8 @@ class gb_plan(C.Structure):
         ("cluster", C.c_int32), ("threads", C.c_int32), ("n_local", C.c_int32), ("particles_in_smem", C.c_int32),
         ("smem_bytes", C.c_int32), ("tile_bytes", C.c_int32), ("max_template", C.c_int32), ("n_slabs", C.c_int32),
         ("slab_bytes", C.c_int64), ("particle_scratch_bytes", C.c_int64), ("scratch_bytes", C.c_int64),
+        ("mode", C.c_int32), ("stream_block", C.c_int32), ("stream_nblk", C.c_int32), ("n_observers", C.c_int32),
+        ("surf_bytes", C.c_int64),
     ]
 
 
@@ -102,7 +105,7 @@ SIGNATURES = {
     "gb_gray_from_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "gb_state_from_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_state_to_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
-    "gb_step_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(gb_plan)]),
+    "gb_step_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(gb_plan)]),
     "gb_track": (C.c_int, [C.POINTER(gb_track_desc), C.c_void_p, C.POINTER(C.c_int64)]),
     "gb_track_step": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.POINTER(gb_stage_io), C.c_void_p]),
     "gb_track_init": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.c_void_p]),

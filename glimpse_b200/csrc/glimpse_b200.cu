@@ -83,6 +83,19 @@ struct StepParams {
   uint8_t* obs_flags;
   int32_t* window_stats;
   gb_stage_io io;
+  // GB_MODE_STREAM buffers (carved from `scratch` by the host)
+  double* s_ev;      // [P][6][N]   particles after the motion step
+  double* s_uv;      // [P][O][2][N] projected particles
+  double* s_w;       // [P][N]      weights
+  double* s_bsum;    // [P][nblk]   per-CTA weight totals
+  double* s_pm;      // [P][nblk][28] per-CTA moment sums
+  int* s_ibox;       // [P][O][5]   integer cloud box (left, top, -right, -bottom, -(any NaN))
+  int* s_pflags;     // [P]         GB_F_* raised during this update
+  uint8_t* s_act;    // [P]         GB_ACT_* bits of this update
+  int* s_meta;       // [P][O][8]   surface meta: box[4], Mu, Mv, Mp, ok
+  char* s_surf;      // [P][O] surface regions of surf_bytes each (Hermite array first)
+  int64_t surf_bytes;
+  int s_block, s_nblk;
 };
 
 __device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
@@ -1009,6 +1022,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
 #undef GB_CLK
 }
 
+#include "stream.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -1133,6 +1148,8 @@ static int check_desc(const gb_track_desc& d) {
     return fail(GB_E_INVALID, "supplied-draw mode needs init_normals, step_normals and uniforms%s");
   if (d.plan.cluster < 1 || d.plan.cluster > GB_MAX_CLUSTER || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
     return fail(GB_E_INVALID, "invalid launch plan (use gb_step_plan)%s");
+  if (d.plan.mode == GB_MODE_STREAM && (d.plan.n_observers != d.O || d.plan.stream_nblk < 1 || d.plan.surf_bytes <= 0))
+    return fail(GB_E_INVALID, "streaming plan does not match the descriptor (use gb_step_plan)%s");
   if (d.plan.scratch_bytes > 0 && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
   if ((int64_t)d.plan.cluster * d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
   return GB_OK;
@@ -1156,6 +1173,79 @@ static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t 
   cfg.numAttrs = 1;
   GB_CUDA(cudaLaunchKernelEx(&cfg, k_step<COV>, prm));
   return GB_OK;
+}
+
+struct StreamLayout {
+  int64_t ev, uv, w, bsum, pm, ibox, pflags, act, meta, surf, total;
+};
+
+static StreamLayout stream_layout(int64_t P, int64_t N, int64_t O, int64_t nblk, int64_t surf_bytes) {
+  StreamLayout L;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    const int64_t at = off;
+    off += (bytes + 255) / 256 * 256;
+    return at;
+  };
+  L.ev = take(P * 6 * N * 8);
+  L.uv = take(P * O * 2 * N * 8);
+  L.w = take(P * N * 8);
+  L.bsum = take(P * nblk * 8);
+  L.pm = take(P * nblk * 28 * 8);
+  L.ibox = take(P * O * 5 * 4);
+  L.pflags = take(P * 4);
+  L.act = take(P);
+  L.meta = take(P * O * 8 * 4);
+  L.surf = take(P * O * surf_bytes);
+  L.total = off;
+  return L;
+}
+
+static void stream_bind(const gb_track_desc& d, StepParams& prm) {
+  const gb_plan& pl = d.plan;
+  const StreamLayout L = stream_layout(d.P, d.N, d.O, pl.stream_nblk, pl.surf_bytes);
+  char* base = reinterpret_cast<char*>(d.scratch);
+  prm.s_ev = reinterpret_cast<double*>(base + L.ev);
+  prm.s_uv = reinterpret_cast<double*>(base + L.uv);
+  prm.s_w = reinterpret_cast<double*>(base + L.w);
+  prm.s_bsum = reinterpret_cast<double*>(base + L.bsum);
+  prm.s_pm = reinterpret_cast<double*>(base + L.pm);
+  prm.s_ibox = reinterpret_cast<int*>(base + L.ibox);
+  prm.s_pflags = reinterpret_cast<int*>(base + L.pflags);
+  prm.s_act = reinterpret_cast<uint8_t*>(base + L.act);
+  prm.s_meta = reinterpret_cast<int*>(base + L.meta);
+  prm.s_surf = base + L.surf;
+  prm.surf_bytes = pl.surf_bytes;
+  prm.s_block = pl.stream_block;
+  prm.s_nblk = pl.stream_nblk;
+}
+
+static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2_surface (3 CTAs per SM)
+
+template <bool COV>
+static int launch_stream_step(const StepParams& prm, cudaStream_t stream, int64_t* launches) {
+  const unsigned nb = (unsigned)(prm.P * prm.s_nblk);
+  k_s0_reset<<<grid_for(prm.P * prm.O * 5, 256), 256, 0, stream>>>(prm);
+  k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  GB_CUDA(cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem));
+  k_s2_surface<<<(unsigned)(prm.P * prm.O), GB_SBLOCK_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
+  k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  k_s5_finalize<COV><<<(unsigned)((prm.P + 3) / 4), 128, 0, stream>>>(prm);
+  GB_CUDA(cudaGetLastError());
+  if (launches) *launches += 6;
+  return GB_OK;
+}
+
+// One update for all points in the organisation the plan asks for.
+static int launch_update(const gb_track_desc& d, StepParams& prm, cudaStream_t stream, int64_t* launches) {
+  const bool cov = d.covariances != nullptr;
+  if (d.plan.mode == GB_MODE_STREAM) {
+    stream_bind(d, prm);
+    return cov ? launch_stream_step<true>(prm, stream, launches) : launch_stream_step<false>(prm, stream, launches);
+  }
+  if (launches) *launches += 1;
+  return cov ? launch_step<true>(prm, d.plan, stream) : launch_step<false>(prm, d.plan, stream);
 }
 
 static int launch_init(const StepParams& prm, bool cov, cudaStream_t stream) {
@@ -1251,16 +1341,33 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
   return GB_OK;
 }
 
-int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t prefer_cluster,
-                 gb_plan* plan) {
+int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
+                 int32_t prefer_cluster, int32_t mode, gb_plan* plan) {
   if (!plan || n_particles <= 0 || tile_w < 1 || tile_h < 1) return fail(GB_E_INVALID, "bad plan arguments%s");
   if ((int64_t)tile_w * tile_h > GB_MAX_TEMPLATE) return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
   if (prefer_cluster != 0 && prefer_cluster != 1 && prefer_cluster != 2 && prefer_cluster != 4 && prefer_cluster != 8)
     return fail(GB_E_INVALID, "cluster size must be 0 (auto), 1, 2, 4 or 8%s");
+  if (n_observers < 1 || n_observers > GB_MAX_OBS) return fail(GB_E_INVALID, "between 1 and 8 observers are supported%s");
+  if (mode != GB_MODE_FUSED && mode != GB_MODE_STREAM) return fail(GB_E_INVALID, "unknown mode%s");
   memset(plan, 0, sizeof(*plan));
+  plan->mode = mode;
+  plan->n_observers = n_observers;
   plan->threads = GB_THREADS;
   plan->max_template = tile_w * tile_h;
   plan->smem_bytes = kMaxSmem;
+  if (mode == GB_MODE_STREAM) {
+    if (n_particles > 0x7fffffff / 4) return fail(GB_E_RESOURCE, "too many particles per point%s");
+    plan->cluster = 1;
+    plan->n_local = (int32_t)n_particles;
+    plan->particles_in_smem = 0;
+    plan->tile_bytes = kSurfaceSmem;
+    plan->stream_block = 2 * GB_SBLOCK_THREADS;
+    plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
+    // surface regions sized for search windows up to 191 px larger than the template
+    plan->surf_bytes = (tile_bytes_needed(tile_w + 191, tile_h + 191, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
+    plan->scratch_bytes = stream_layout(npoints, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
+    return GB_OK;
+  }
   plan->n_slabs = 160;
   plan->slab_bytes = (tile_bytes_needed(tile_w + 255, tile_h + 255, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
   // on-chip tile capacity we insist on: a search window 24 px larger than the template each way;
@@ -1317,8 +1424,7 @@ int gb_track_step(const gb_track_desc* d, int32_t t, const gb_stage_io* io, void
   StepParams prm;
   fill_params(*d, t, prm);
   if (io) prm.io = *io;
-  return d->covariances ? launch_step<true>(prm, d->plan, (cudaStream_t)stream)
-                        : launch_step<false>(prm, d->plan, (cudaStream_t)stream);
+  return launch_update(*d, prm, (cudaStream_t)stream, nullptr);
 }
 
 int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
@@ -1368,9 +1474,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
       ++launches;
     }
     if (any_step) {
-      rc = cov ? launch_step<true>(prm, d->plan, stream) : launch_step<false>(prm, d->plan, stream);
-      if (rc) return rc;
-      ++launches;
+      if ((rc = launch_update(*d, prm, stream, &launches))) return rc;
     }
   }
   if (launches_out) *launches_out = launches;

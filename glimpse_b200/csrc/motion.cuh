@@ -46,7 +46,9 @@ __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t point, u
   const float u0 = ((float)r[0] + 0.5f) * two_neg32, u1 = ((float)r[2] + 0.5f) * two_neg32;
   // u in (0, 1]: clamp the fp32 rounding of values next to 1 and 0
   const float a0 = fminf(fmaxf(u0, 1.0e-10f), 1.0f), a1 = fminf(fmaxf(u1, 1.0e-10f), 1.0f);
-  const float rad0 = sqrtf(-2.0f * __logf(a0)), rad1 = sqrtf(-2.0f * __logf(a1));
+  // sqrt(x) as x * rsqrt(x) (MUFU.RSQ); x = -2 ln(u) is floored at 1e-30 so that u == 1 gives 0, not NaN
+  const float e0 = fmaxf(-2.0f * __logf(a0), 1.0e-30f), e1 = fmaxf(-2.0f * __logf(a1), 1.0e-30f);
+  const float rad0 = e0 * rsqrtf(e0), rad1 = e1 * rsqrtf(e1);
   float s0, c0, s1, c1;
   __sincosf(6.283185307179586f * ((float)(r[1] >> 8) * 5.9604644775390625e-08f), &s0, &c0);
   __sincosf(6.283185307179586f * ((float)(r[3] >> 8) * 5.9604644775390625e-08f), &s1, &c1);

@@ -1,0 +1,619 @@
+// GB_MODE_STREAM kernels (included by glimpse_b200.cu after StepParams / Moments are defined).
+#pragma once
+// (already inside namespace gb)
+
+// ---------------------------------------------------------------------------------------------
+// GB_MODE_STREAM: the same update as five kernels over all points.  Intermediates (evolved
+// particles, projected coordinates, weights, spline surfaces) go through global memory / L2; every
+// kernel is embarrassingly parallel with full occupancy and no intra-kernel serial stage.
+//   s1 propagate  evolve + test + project + integer cloud box        (per particle)
+//   s2 surface    search window + tile pipeline -> Hermite surface    (one CTA per point-observer)
+//   s3 weights    spline sample + surface likelihood -> weights, CTA totals (per particle)
+//   s4 resample   prefix of the weights, child ranges, child writes, moment partials (per particle)
+//   s5 finalise   moments, status                                      (per point)
+// ---------------------------------------------------------------------------------------------
+#define GB_SBLOCK_THREADS 256
+
+// Per-point byte written by k_s0_reset: bit 0 = the point is updated at this time, bit 1 = its motion
+// model has a non-trivial surface likelihood.  One load instead of a chain of dependent ones.
+#define GB_ACT_ACTIVE 1
+#define GB_ACT_SURFACE_LL 2
+__device__ __forceinline__ bool stream_point_active(const StepParams& prm, int64_t p) {
+  return (prm.s_act[p] & GB_ACT_ACTIVE) != 0;
+}
+
+__global__ void k_s0_reset(const __grid_constant__ StepParams prm) {
+  const int64_t n = prm.P * prm.O * 5;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    prm.s_ibox[i] = (i % 5 == 4) ? 0 : 0x7fffffff;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.P; i += (int64_t)gridDim.x * blockDim.x) {
+    prm.s_pflags[i] = 0;
+    const bool active = prm.status[i] == 0 && prm.t > prm.first[i] && prm.t <= prm.last[i];
+    const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
+    const bool sll = !(sg.z == nullptr && sg.value == 0.0);
+    prm.s_act[i] = (uint8_t)((active ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0));
+  }
+}
+
+// Warp-transposed reduction of K per-lane doubles (K = 16 or 32): recursive halving, 16 (31) shuffles
+// instead of 5 K.  On return lane l holds in v[0] the warp total of value index
+// transposed_index(l) = lane bits [4..1] (K = 16, both lanes of a pair) or [4..0] (K = 32).
+template <int K>
+__device__ __forceinline__ void warp_reduce_transpose(double (&v)[K], int lane) {
+#pragma unroll
+  for (int half = K / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const double send = upper ? v[k] : v[k + half];
+      const double keep = upper ? v[k + half] : v[k];
+      v[k] = keep + shfl_xor(send, bit);
+    }
+  }
+  if (K == 16) v[0] += shfl_xor(v[0], 1);
+}
+template <int K>
+__device__ __forceinline__ int transposed_index(int lane) {
+  return K == 16 ? (lane >> 1) : lane;
+}
+
+// s1: two consecutive particles per thread (16-byte loads / stores), one CTA = s_block particles of a point.
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __grid_constant__ StepParams prm) {
+  __shared__ gb_motion s_motion;
+  __shared__ int s_box[GB_MAX_OBS][5];
+  const int64_t p = blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  if (!stream_point_active(prm, p)) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = (int)prm.N, O = prm.O, t = prm.t;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
+    for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
+    if (tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
+  }
+  __syncthreads();
+  const bool forced = prm.io.force_evolved != nullptr;
+  const double* sin_ = forced ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
+  double* ev = prm.s_ev + p * 6 * (int64_t)N;
+  const int s_idx = t - prm.first[p] - 1;
+  const double* zn = prm.step_normals ? prm.step_normals + (((int64_t)p * prm.S + s_idx) * N) * 3 : nullptr;
+  const bool evolve = !forced && !prm.skip_evolve;
+  const bool use_obs = !prm.io.force_weights;
+  const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
+  const int ia = b * prm.s_block + 2 * tid;  // particles ia, ia + 1
+  const bool va = ia < N, vb = ia + 1 < N;
+  const bool vec = (N & 1) == 0;  // 16-byte aligned pairs
+  uint32_t flags = 0;
+  if (va) {
+    double s[2][6];
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double2 x = *reinterpret_cast<const double2*>(sin_ + c * (int64_t)N + ia);
+        s[0][c] = x.x;
+        s[1][c] = x.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        s[0][c] = sin_[c * (int64_t)N + ia];
+        s[1][c] = vb ? sin_[c * (int64_t)N + ia + 1] : s[0][c];
+      }
+    }
+    if (evolve) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double z0, z1, z2;
+        const int i = (q == 1 && !vb) ? ia : ia + q;
+        if (prm.rng_mode == GB_RNG_SUPPLIED) {
+          z0 = zn[3 * (int64_t)i];
+          z1 = zn[3 * (int64_t)i + 1];
+          z2 = zn[3 * (int64_t)i + 2];
+        } else {
+          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2);
+        }
+        evolve_particle(s_motion, prm.tau, prm.tau2, z0, z1, z2, s[q]);
+      }
+    }
+    flags |= test_particle(prm, s[0]);
+    if (vb) flags |= test_particle(prm, s[1]);
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) *reinterpret_cast<double2*>(ev + c * (int64_t)N + ia) = make_double2(s[0][c], s[1][c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        ev[c * (int64_t)N + ia] = s[0][c];
+        if (vb) ev[c * (int64_t)N + ia + 1] = s[1][c];
+      }
+    }
+    if (prm.io.dump_evolved) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        prm.io.dump_evolved[((int64_t)p * 6 + c) * N + ia] = s[0][c];
+        if (vb) prm.io.dump_evolved[((int64_t)p * 6 + c) * N + ia + 1] = s[1][c];
+      }
+    }
+    if (use_obs) {
+      for (int o = 0; o < O; ++o) {
+        const int64_t po = p * O + o;
+        if (prm.img[o] < 0 || !prm.mask[po]) continue;  // block-uniform
+        double* uv = prm.s_uv + po * 2 * (int64_t)N;
+        double u[2], v[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) project_fast(prm.cam[o], s[q][0], s[q][1], s[q][2], u[q], v[q]);
+        if (!vb) {
+          u[1] = u[0];
+          v[1] = v[0];
+        }
+        if (vec) {
+          *reinterpret_cast<double2*>(uv + ia) = make_double2(u[0], u[1]);
+          *reinterpret_cast<double2*>(uv + (int64_t)N + ia) = make_double2(v[0], v[1]);
+        } else {
+          uv[ia] = u[0];
+          uv[(int64_t)N + ia] = v[0];
+          if (vb) {
+            uv[ia + 1] = u[1];
+            uv[(int64_t)N + ia + 1] = v[1];
+          }
+        }
+        int ib[5];
+        ib[4] = (isnan(u[0]) | isnan(v[0]) | isnan(u[1]) | isnan(v[1])) ? -1 : 0;
+        ib[0] = min(__double2int_rd(u[0] - hw), __double2int_rd(u[1] - hw));
+        ib[1] = min(__double2int_rd(v[0] - hh), __double2int_rd(v[1] - hh));
+        ib[2] = -max(__double2int_ru(u[0] + hw), __double2int_ru(u[1] + hw));
+        ib[3] = -max(__double2int_ru(v[0] + hh), __double2int_ru(v[1] + hh));
+        const unsigned mask = __activemask();
+        int red[5], mine = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          red[k] = __reduce_min_sync(mask, ib[k]);
+          if (lane == k) mine = red[k];
+        }
+        // lanes 0..4 of a warp publish one value each; a tail warp without them lets its first lane do all five
+        if ((mask & 0x1fu) == 0x1fu) {
+          if (lane < 5) atomicMin(&s_box[o][lane], mine);
+        } else if (lane == (__ffs(mask) - 1)) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) atomicMin(&s_box[o][k], red[k]);
+        }
+        if (prm.io.dump_uv) {
+          double* d = prm.io.dump_uv + (po * N + ia) * 2;
+          d[0] = u[0];
+          d[1] = v[0];
+          if (vb) {
+            d[2] = u[1];
+            d[3] = v[1];
+          }
+        }
+      }
+    }
+  }
+  const int any = __syncthreads_or((int)flags);
+  if (any && tid == 0) atomicOr(&prm.s_pflags[p], any);
+  if (use_obs && tid < O * 5) {
+    const int o = tid / 5, k = tid - o * 5;
+    const int64_t po = p * O + o;
+    if (prm.img[o] >= 0 && prm.mask[po]) atomicMin(&prm.s_ibox[po * 5 + k], s_box[o][k]);
+  }
+}
+
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS) k_s2_surface(const __grid_constant__ StepParams prm, int smem_budget) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_mm[GB_SBLOCK_THREADS / 32][4];
+  __shared__ int s_box[4];
+  const int64_t po = blockIdx.x;
+  const int64_t p = po / prm.O;
+  const int o = (int)(po - p * prm.O);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
+  int* meta = prm.s_meta + po * 8;
+  if (tid == 0) meta[7] = 0;
+  if (!stream_point_active(prm, p) || prm.io.force_weights) return;
+  uint8_t* oflag = prm.obs_flags + ((int64_t)p * prm.T + t) * prm.O + o;
+  if (prm.img[o] < 0 || !prm.mask[po]) {
+    if (tid == 0) *oflag = GB_OBS_NO_IMAGE;
+    return;
+  }
+  if (prm.s_pflags[p] != 0) return;  // the point failed its particle tests: reference raises before any observer work
+  const int N = (int)prm.N;
+  const int* ib = prm.s_ibox + po * 5;
+  int box_l = ib[0], box_t = ib[1], box_r = -ib[2], box_b = -ib[3];
+  const bool nan_any = ib[4] != 0;
+  if (!nan_any && ((box_r - box_l) - prm.tile_w < 5 || (box_b - box_t) - prm.tile_h < 5)) {
+    // cloud narrower than ~3 px: the reference widens the box from the exact extents (tracker.py:584-594)
+    const double* uv = prm.s_uv + po * 2 * (int64_t)N;
+    double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
+    for (int i = tid; i < N; i += blockDim.x) {
+      const double u = uv[i], v = uv[(int64_t)N + i];
+      mm[0] = fmin(mm[0], u);
+      mm[1] = fmin(mm[1], v);
+      mm[2] = fmin(mm[2], -u);
+      mm[3] = fmin(mm[3], -v);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double x = warp_min(mm[k]);
+      if (lane == 0) s_mm[warp][k] = x;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double e[4];
+      for (int k = 0; k < 4; ++k) {
+        e[k] = s_mm[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) e[k] = fmin(e[k], s_mm[w][k]);
+      }
+      const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
+      const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
+      double bl = sub(e[0], hw), bt = sub(e[1], hh), br = add(-e[2], hw), bb = add(-e[3], hh);
+      const double ncols = sub(3.0, sub(sub(br, bl), tw));
+      if (ncols > 0.0) {
+        bl = add(bl, mul(-ncols, 0.5));
+        br = add(br, mul(ncols, 0.5));
+      }
+      const double nrows = sub(3.0, sub(sub(bb, bt), th));
+      if (nrows > 0.0) {
+        bt = add(bt, mul(-nrows, 0.5));
+        bb = add(bb, mul(nrows, 0.5));
+      }
+      s_box[0] = __double2int_rd(bl);
+      s_box[1] = __double2int_rd(bt);
+      s_box[2] = __double2int_ru(br);
+      s_box[3] = __double2int_ru(bb);
+    }
+    __syncthreads();
+    box_l = s_box[0];
+    box_t = s_box[1];
+    box_r = s_box[2];
+    box_b = s_box[3];
+  }
+  const int W = prm.cam[o].c.imgsz[0], H = prm.cam[o].c.imgsz[1];
+  const bool inframe = !nan_any && box_l >= 0 && box_l <= W && box_t >= 0 && box_t <= H && box_r >= 0 && box_r <= W &&
+                       box_b >= 0 && box_b <= H;
+  if (!inframe) {
+    if (tid == 0) *oflag = GB_OBS_OUT_OF_FRAME;
+    return;
+  }
+  TileWork w;
+  w.Su = box_r - box_l;
+  w.Sv = box_b - box_t;
+  w.tw = prm.tile_w;
+  w.th = prm.tile_h;
+  w.Mu = w.Su - w.tw + 1;
+  w.Mv = w.Sv - w.th + 1;
+  w.nbins = 255 * prm.nchan[o] + 1;
+  w.nvals = prm.tmpl_nvalues[po];
+  if (tid == 0) {
+    *oflag = GB_OBS_USED;
+    if (prm.window_stats) {
+      int32_t* ws = prm.window_stats + (((int64_t)p * prm.T + t) * prm.O + o) * 2;
+      ws[0] = w.Su;
+      ws[1] = w.Sv;
+    }
+    if (prm.io.dump_box) {
+      int32_t* d = prm.io.dump_box + po * 4;
+      d[0] = box_l;
+      d[1] = box_t;
+      d[2] = box_r;
+      d[3] = box_b;
+    }
+  }
+  char* region = prm.s_surf + po * prm.surf_bytes;
+  const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
+  if (need > prm.surf_bytes || w.Mu > 256 || w.Mv > 256) {
+    if (tid == 0) atomicOr(&prm.s_pflags[p], (int)GB_F_WINDOW);
+    return;
+  }
+  const bool in_smem = need <= smem_budget;
+  tile_carve(in_smem ? reinterpret_cast<char*>(smem_raw) : region, w);
+  const int64_t ta = (int64_t)w.tw * w.th;
+  const int boxv[4] = {box_l, box_t, box_r, box_b};
+  tile_build_surface(prm.gray[o], prm.pitch[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+                     prm.tmpl_values + po * ta, w, prm.io.dump_search ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
+                     prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap, nullptr);
+  if (in_smem) {
+    float4* dst = reinterpret_cast<float4*>(region);
+    for (int i = tid; i < w.Mv * w.Mp; i += blockDim.x) dst[i] = w.herm[i];
+  }
+  if (tid == 0) {
+    meta[0] = box_l;
+    meta[1] = box_t;
+    meta[2] = box_r;
+    meta[3] = box_b;
+    meta[4] = w.Mu;
+    meta[5] = w.Mv;
+    meta[6] = w.Mp;
+    meta[7] = 1;
+  }
+}
+
+// Exclusive offsets of one value per thread across the CTA (warp shuffles + one pass over the
+// warp totals).  Returns the offset of the calling thread.
+__device__ __forceinline__ double block_exclusive_offset(double v, double* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double incl = warp_inclusive_scan(v, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  double off = 0.0;
+#pragma unroll
+  for (int k = 0; k < GB_SBLOCK_THREADS / 32; ++k) off += k < warp ? s_warp[k] : 0.0;
+  double excl = shfl_up(incl, 1);
+  if (lane == 0) excl = 0.0;
+  return off + excl;
+}
+
+// Per-(CTA, observer) constants of the spline surface: geo-reference (tracker.py:615-620) and cell
+// centres (observer.py:203-208).
+struct SurfaceRef {
+  double sl, st, sr, sb, cu0, cv0, cu1, cv1, scale;
+  const float4* herm;
+  int Mu, Mv, Mp, ok;
+};
+
+// s3: spline sample + surface likelihood -> weight; two consecutive particles per thread.
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __grid_constant__ StepParams prm) {
+  __shared__ gb_motion s_motion;
+  __shared__ SurfaceRef s_ref[GB_MAX_OBS];
+  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
+  const int64_t p = blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  const int act = prm.s_act[p];
+  if (!(act & GB_ACT_ACTIVE) || prm.s_pflags[p] != 0) return;
+  const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = (int)prm.N, O = prm.O;
+  {
+    if (surface_ll) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
+      for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    if (tid < O) {
+      const int o = tid;
+      const int64_t po = p * O + o;
+      const int* meta = prm.s_meta + po * 8;
+      SurfaceRef r;
+      r.ok = meta[7];
+      r.Mu = meta[4];
+      r.Mv = meta[5];
+      r.Mp = meta[6];
+      const double eu = sub(mul((double)prm.tile_w, 0.5), 0.5), evv = sub(mul((double)prm.tile_h, 0.5), 0.5);
+      const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
+      r.sl = add(add((double)meta[0], eu), du_t);
+      r.st = add(add((double)meta[1], evv), dv_t);
+      r.sr = add(add((double)meta[2], -eu), du_t);
+      r.sb = add(add((double)meta[3], -evv), dv_t);
+      r.cu0 = add(r.sl, mul(quo(sub(r.sr, r.sl), (double)max(r.Mu, 1)), 0.5));
+      r.cv0 = add(r.st, mul(quo(sub(r.sb, r.st), (double)max(r.Mv, 1)), 0.5));
+      r.cu1 = add(r.cu0, (double)(r.Mu - 1));
+      r.cv1 = add(r.cv0, (double)(r.Mv - 1));
+      r.scale = prm.obs_scale[o];
+      r.herm = reinterpret_cast<const float4*>(prm.s_surf + po * prm.surf_bytes);
+      s_ref[o] = r;
+    }
+  }
+  __syncthreads();
+  const double* ev = prm.s_ev + p * 6 * (int64_t)N;
+  const double* fw = prm.io.force_weights ? prm.io.force_weights + (int64_t)p * N : nullptr;
+  const int ia = b * prm.s_block + 2 * tid;
+  const bool va = ia < N, vb = ia + 1 < N, vec = (N & 1) == 0;
+  uint32_t flags = 0;
+  double w[2] = {0.0, 0.0};
+  if (va) {
+    if (fw) {
+      w[0] = fw[ia];
+      w[1] = vb ? fw[ia + 1] : 0.0;
+    } else {
+      double ll[2] = {0.0, 0.0};
+      for (int o = 0; o < O; ++o) {
+        const SurfaceRef& r = s_ref[o];
+        if (!r.ok) continue;
+        const double* uv = prm.s_uv + (p * O + o) * 2 * (int64_t)N;
+        double u[2], v[2];
+        if (vec) {
+          const double2 a = *reinterpret_cast<const double2*>(uv + ia), c = *reinterpret_cast<const double2*>(uv + (int64_t)N + ia);
+          u[0] = a.x;
+          u[1] = a.y;
+          v[0] = c.x;
+          v[1] = c.y;
+        } else {
+          u[0] = uv[ia];
+          v[0] = uv[(int64_t)N + ia];
+          u[1] = vb ? uv[ia + 1] : u[0];
+          v[1] = vb ? uv[(int64_t)N + ia + 1] : v[0];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (!((u[q] >= r.sl) & (u[q] <= r.sr) & (v[q] >= r.st) & (v[q] <= r.sb))) flags |= GB_F_SAMPLE_OUTSIDE;
+          // FITPACK evaluates at the argument clamped to the first/last data site
+          const double x = fmin(fmax(u[q], r.cu0), r.cu1) - r.cu0, y = fmin(fmax(v[q], r.cv0), r.cv1) - r.cv0;
+          const double val = (double)hermite_eval(r.herm, r.Mp, r.Mu, r.Mv, x, y);
+          ll[q] = add(ll[q], mul(val, r.scale));
+          if (prm.io.dump_sampled && (q == 0 || vb)) prm.io.dump_sampled[(p * O + o) * N + ia + q] = val;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !vb) break;
+        const int i = ia + q;
+        double l = ll[q];
+        if (surface_ll) l = add(l, surface_log_likelihood(s_motion, prm.surfaces, ev[i], ev[(int64_t)N + i], ev[2 * (int64_t)N + i], flags));
+        else l = add(l, 0.0);
+        w[q] = add(exp(-l), 1e-300);
+      }
+    }
+    double* wd = prm.s_w + (int64_t)p * N;
+    if (vec) {
+      *reinterpret_cast<double2*>(wd + ia) = make_double2(w[0], w[1]);
+    } else {
+      wd[ia] = w[0];
+      if (vb) wd[ia + 1] = w[1];
+    }
+    if (prm.io.dump_weights) {
+      prm.io.dump_weights[(int64_t)p * N + ia] = w[0];
+      if (vb) prm.io.dump_weights[(int64_t)p * N + ia + 1] = w[1];
+    }
+  }
+  // CTA total of the weights (fixed association: pair, warp butterfly, warps in order)
+  double tsum = warp_sum(w[0] + w[1]);
+  if (lane == 0) s_warp[warp] = tsum;
+  const int any = __syncthreads_or((int)flags);
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_warp[k];
+    prm.s_bsum[p * prm.s_nblk + b] = tot;
+    if (any) atomicOr(&prm.s_pflags[p], any);
+  }
+}
+
+// s4: prefix of the weights and child ranges (two consecutive parents per thread), then one thread per
+// CHILD: find the parent in the CTA's sorted range ends, gather its state, write coalesced, and add it to
+// the moment partials (sum over children == sum over parents weighted by their child counts).
+template <bool COV>
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __grid_constant__ StepParams prm) {
+  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16;
+  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
+  __shared__ double s_pref[5];
+  __shared__ double s_red[GB_SBLOCK_THREADS / 32][KP];
+  __shared__ double s_w[2 * GB_SBLOCK_THREADS];
+  __shared__ int s_end[2 * GB_SBLOCK_THREADS];
+  __shared__ int s_j0;
+  const int64_t p = blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  if (!stream_point_active(prm, p) || prm.s_pflags[p] != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
+  const int N = (int)prm.N;
+  // prefix of the preceding CTAs and the point total, summed in CTA order by one thread (every CTA of the
+  // point computes the same chain, so child ranges meet exactly at CTA boundaries)
+  if (tid == 0) {
+    const double* bs = prm.s_bsum + p * prm.s_nblk;
+    double run = 0.0, pre = 0.0, nxt = 0.0;
+    for (int k = 0; k < prm.s_nblk; ++k) {
+      if (k == b) pre = run;
+      run += bs[k];
+      if (k == b) nxt = run;
+    }
+    s_pref[0] = pre;
+    s_pref[1] = run;
+    s_pref[2] = nxt;
+    s_pref[3] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
+                                                : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
+    s_pref[4] = quo(1.0, (double)N);
+  }
+  const double* wsrc = prm.s_w + (int64_t)p * N;
+  const int base = b * prm.s_block;
+  const int ia = base + 2 * tid;
+  const bool va = ia < N, vb = ia + 1 < N, vec = (N & 1) == 0;
+  const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA
+  double w0 = 0.0, w1 = 0.0;
+  if (va) {
+    if (vec) {
+      const double2 x = *reinterpret_cast<const double2*>(wsrc + ia);
+      w0 = x.x;
+      w1 = x.y;
+    } else {
+      w0 = wsrc[ia];
+      w1 = vb ? wsrc[ia + 1] : 0.0;
+    }
+  }
+  s_w[2 * tid] = w0;
+  s_w[2 * tid + 1] = w1;
+  const double off = block_exclusive_offset(w0 + w1, s_warp);  // contains a __syncthreads(): s_pref is visible
+  const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4];
+  // The last parent of the CTA takes the next CTA's prefix as its cumulative weight, so that child ranges
+  // are seamless across CTAs whatever the association of the in-CTA sums.
+  const int last_i = base + n_here - 1;
+  double c0 = prefix + (off + w0), c1 = prefix + ((off + w0) + w1);
+  if (ia == last_i) c0 = next_prefix;
+  if (ia + 1 == last_i) c1 = next_prefix;
+  if (va) s_end[2 * tid] = count_positions_le(quo(c0, total), u01, inv_n, N);
+  if (vb) s_end[2 * tid + 1] = count_positions_le(quo(c1, total), u01, inv_n, N);
+  if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
+  __syncthreads();
+  const int J0 = s_j0, J1 = n_here > 0 ? s_end[n_here - 1] : J0;
+  const double* ev = prm.s_ev + p * 6 * (int64_t)N + base;
+  const double* sin0 = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
+  double ref[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) ref[c] = sin0[c * (int64_t)N];
+  double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
+  double* wst = prm.weight_state ? prm.weight_state + (int64_t)p * N : nullptr;
+  double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
+  double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
+  int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
+  Moments<COV> mom;
+  mom.clear();
+  for (int j = J0 + tid; j < J1; j += GB_SBLOCK_THREADS) {
+    int lo = 0, hi = n_here - 1;  // smallest parent whose range end exceeds j
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    double s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = ev[c * (int64_t)N + lo];
+    const double w = s_w[lo];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
+    mom.accumulate(w, s, ref);
+    if (wst) wst[j] = w;
+    if (outp) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
+    }
+    if (outw) outw[j] = w;
+    if (outi) outi[j] = base + lo;
+  }
+  // per-CTA moment partials, combined in CTA order by s5 (bit-reproducible)
+  double r[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) r[k] = k < NM ? mom.a[k] : 0.0;
+  warp_reduce_transpose<KP>(r, lane);
+  if (KP == 32 || (lane & 1) == 0) s_red[warp][transposed_index<KP>(lane)] = r[0];
+  __syncthreads();
+  if (tid < NM) {
+    double x = s_red[0][tid];
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) x += s_red[wv][tid];
+    prm.s_pm[(p * prm.s_nblk + b) * 28 + tid] = x;
+  }
+}
+
+// s5: one warp per point: lane k sums moment k over the CTAs in order, lane 0 finalises.
+template <bool COV>
+__global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {
+  const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= prm.P || !stream_point_active(prm, p)) return;
+  const int t = prm.t;
+  const int f = prm.s_pflags[p];
+  if (f) {
+    if (lane == 0) {
+      prm.status[p] = status_from_flags((uint32_t)f);
+      prm.status_time[p] = t;
+    }
+    return;
+  }
+  constexpr int NM = Moments<COV>::NM;
+  double x = 0.0;
+  if (lane < NM)
+    for (int b = 0; b < prm.s_nblk; ++b) x += prm.s_pm[(p * prm.s_nblk + b) * 28 + lane];
+  double a[NM];
+#pragma unroll
+  for (int k = 0; k < NM; ++k) a[k] = __shfl_sync(0xffffffffu, x, k);
+  if (lane != 0) return;
+  const int64_t N = prm.N;
+  const double* sin_ = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * N : state_buffer(prm, t - 1) + p * 6 * N;
+  double ref[6];
+  for (int c = 0; c < 6; ++c) ref[c] = sin_[c * N];
+  double mean[6], sg[6], cv[36];
+  finalize_moments<COV>(a, ref, mean, sg, cv);
+  double* mo = prm.means + ((int64_t)p * prm.T + t) * 6;
+  for (int c = 0; c < 6; ++c) mo[c] = mean[c];
+  if (COV) {
+    double* co = prm.covariances + ((int64_t)p * prm.T + t) * 36;
+    for (int c = 0; c < 36; ++c) co[c] = cv[c];
+  } else {
+    double* so = prm.sigmas + ((int64_t)p * prm.T + t) * 6;
+    for (int c = 0; c < 6; ++c) so[c] = sg[c];
+  }
+}

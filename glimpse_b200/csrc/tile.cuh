@@ -306,19 +306,60 @@ __device__ inline void tile_build_surface(const uint16_t* __restrict__ gray_plan
       for (int j = jlo; j < jhi; ++j) {
         const float* Icol = w.hp + r0 * Sp + c + j;
         const float* Tcol = w.tmpl + j;
-        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
         const int nrow = th + kmax - 1;
-        for (int ip = 0; ip < nrow; ++ip) {
-          t3 = t2;
-          t2 = t1;
-          t1 = t0;
-          t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
-          const float iv = Icol[ip * Sp];
-          // output row k uses template row ip - k
-          if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
-          if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
-          if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
-          if (ip >= 3) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
+        if (th >= 4) {
+          // ta, tb, tc = template rows ip-1, ip-2, ip-3; output row k pairs image row ip with template row ip-k
+          float ta, tb, tc;
+          {
+            const float t_0 = Tcol[0], t_1 = Tcol[Tp], t_2 = Tcol[2 * Tp];
+            const float i_0 = Icol[0], i_1 = Icol[Sp], i_2 = Icol[2 * Sp];
+            float d = i_0 - t_0; a0 = fmaf(d, d, a0);
+            d = i_1 - t_1; a0 = fmaf(d, d, a0);
+            d = i_1 - t_0; a1 = fmaf(d, d, a1);
+            d = i_2 - t_2; a0 = fmaf(d, d, a0);
+            d = i_2 - t_1; a1 = fmaf(d, d, a1);
+            d = i_2 - t_0; a2 = fmaf(d, d, a2);
+            ta = t_2; tb = t_1; tc = t_0;
+          }
+#pragma unroll 4
+          for (int ip = 3; ip < th; ++ip) {
+            const float tn = Tcol[ip * Tp];
+            const float iv = Icol[ip * Sp];
+            float d = iv - tn; a0 = fmaf(d, d, a0);
+            d = iv - ta; a1 = fmaf(d, d, a1);
+            d = iv - tb; a2 = fmaf(d, d, a2);
+            d = iv - tc; a3 = fmaf(d, d, a3);
+            tc = tb; tb = ta; ta = tn;
+          }
+          // tail: image rows th .. th + kmax - 2 only feed output rows 1..3
+          if (th < nrow) {
+            const float iv = Icol[th * Sp];
+            float d = iv - ta; a1 = fmaf(d, d, a1);
+            d = iv - tb; a2 = fmaf(d, d, a2);
+            d = iv - tc; a3 = fmaf(d, d, a3);
+          }
+          if (th + 1 < nrow) {
+            const float iv = Icol[(th + 1) * Sp];
+            float d = iv - ta; a2 = fmaf(d, d, a2);
+            d = iv - tb; a3 = fmaf(d, d, a3);
+          }
+          if (th + 2 < nrow) {
+            const float iv = Icol[(th + 2) * Sp];
+            const float d = iv - ta; a3 = fmaf(d, d, a3);
+          }
+        } else {
+          float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+          for (int ip = 0; ip < nrow; ++ip) {
+            t3 = t2;
+            t2 = t1;
+            t1 = t0;
+            t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
+            const float iv = Icol[ip * Sp];
+            if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
+            if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
+            if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
+            if (ip >= 3 && ip <= th + 2) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
+          }
         }
       }
       if (cb * 32 + lane < Mu) {

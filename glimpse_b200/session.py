@@ -113,7 +113,8 @@ class Session:
         with torch.cuda.device(device):
             self.stream = torch.cuda.current_stream().cuda_stream
             self.plan = _lib.gb_plan()
-            _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, int(tracker.cluster), C.byref(self.plan)))
+            mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[getattr(tracker, "mode", "stream")]
+            _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, O, int(tracker.cluster), mode, C.byref(self.plan)))
             self.h2d = 0
             images_dev, self.offsets = self._upload_frames()
             motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)

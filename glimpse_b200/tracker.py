@@ -10,6 +10,9 @@ Differences a user can see (all documented in DESIGN.md):
 * ``rng="philox"`` (default) draws on the device from Philox4x32-10, keyed by ``seed`` (or by one
   ``np.random.randint`` draw, so ``np.random.seed`` still makes runs reproducible).  ``rng="numpy"``
   supplies the reference's exact legacy-MT19937 draw sequence (parity runs; ~2.5e7 normals/s).
+* ``mode="stream"`` (default) runs each update as five massively parallel kernels; ``mode="fused"`` runs
+  it as one thread-block-cluster kernel per update with the particle intermediates kept on chip
+  (``cluster`` = CTAs per point, 0 = automatic).  Same results up to floating-point association.
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
 * Only the default ``resample_method`` / ``highpass`` / ``interpolation`` have kernels; other values
@@ -61,6 +64,7 @@ class Tracker:
         rng: str = "philox",
         seed: Optional[int] = None,
         cluster: int = 0,
+        mode: str = "stream",
         device=None,
         distributed: bool = True,
     ) -> None:
@@ -72,6 +76,7 @@ class Tracker:
         self.rng = rng
         self.seed = seed
         self.cluster = cluster
+        self.mode = mode
         self.device = device
         self.distributed = distributed
         self.particles = None

@@ -141,6 +141,14 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
 /* ------------------------------------------------------------------------------------------
  * The filter
  * ------------------------------------------------------------------------------------------ */
+/* Two device organisations of the same update (identical results up to floating-point association):
+ *  GB_MODE_FUSED  one thread-block cluster owns a point for a whole update; particle intermediates
+ *                 stay in (distributed) shared memory, state streams through HBM once (96 B/update).
+ *  GB_MODE_STREAM five massively parallel kernels per update over all points (propagate, surface,
+ *                 weights, resample, finalise); intermediates go through global memory / L2. */
+#define GB_MODE_FUSED 0
+#define GB_MODE_STREAM 1
+
 /* Launch plan chosen by gb_step_plan: cluster size (CTAs per tracked point), threads per CTA,
  * dynamic shared memory and how it is split between particle arrays and tile buffers. */
 typedef struct gb_plan {
@@ -154,13 +162,18 @@ typedef struct gb_plan {
   int32_t n_slabs;          /* per-SM overflow slabs for search windows that do not fit tile_bytes */
   int64_t slab_bytes;       /* bytes per slab (windows up to 256 + template - 1 pixels a side) */
   int64_t particle_scratch_bytes; /* global particle arrays when !particles_in_smem */
-  int64_t scratch_bytes;    /* total global scratch the caller must provide: particle_scratch_bytes + n_slabs * slab_bytes */
+  int64_t scratch_bytes;    /* total global scratch the caller must provide */
+  int32_t mode;             /* GB_MODE_* */
+  int32_t stream_block;     /* GB_MODE_STREAM: particles per CTA of the per-particle kernels */
+  int32_t stream_nblk;      /* GB_MODE_STREAM: CTAs per point */
+  int32_t n_observers;
+  int64_t surf_bytes;       /* GB_MODE_STREAM: bytes of the per-(point, observer) surface region */
 } gb_plan;
 
-/* Size a launch plan for N particles per point and a w x h template.  `prefer_cluster` = 0 lets
- * the library choose; otherwise forces 1/2/4/8. */
-int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t prefer_cluster,
-                 gb_plan* plan_host);
+/* Size a launch plan for N particles per point, a w x h template, P points and O observers.
+ * `prefer_cluster` = 0 lets the library choose the cluster size of GB_MODE_FUSED; otherwise forces 1/2/4/8. */
+int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
+                 int32_t prefer_cluster, int32_t mode, gb_plan* plan_host);
 
 /* Everything one Tracker.track call needs (track/tracker.py:225-417).  Shapes use P points,
  * N particles, T times, O observers, S = T - 1 update steps, w x h template. */

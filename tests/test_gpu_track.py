@@ -37,12 +37,12 @@ def case_scene(name):
     return scene, case
 
 
-def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None):
+def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None, mode="stream"):
     import glimpse_b200 as gb
     from glimpse_b200.session import Session, reference_order_draws
 
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster)
+    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode)
     datetimes = tracker.datetimes
     matching = tracker.match_datetimes(datetimes)
     image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
@@ -72,11 +72,12 @@ def golden_steps(g, P, T_steps):
     return per
 
 
+@pytest.mark.parametrize("mode", ["stream", "fused"])
 @pytest.mark.parametrize("name", list(scenes.track_cases()))
-def test_templates_match_reference(cuda, name):
+def test_templates_match_reference(cuda, name, mode):
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
-    session, _ = make_session(scene, case, g)
+    session, _ = make_session(scene, case, g, mode=mode)
     # run the whole track so that staggered templates (observer starting later) are built too
     session.run()
     cuda.cuda.synchronize()
@@ -98,15 +99,18 @@ def test_templates_match_reference(cuda, name):
             k += 1
 
 
-@pytest.mark.parametrize("name,cluster,tile_bytes", [(n, 0, None) for n in scenes.track_cases()]
-                         + [("track_c1", 2, None), ("track_cyl2", 4, None), ("track_jitter", 8, None), ("track_c1", 4, 2048)])
-def test_step_teacher_forced(cuda, name, cluster, tile_bytes):
+@pytest.mark.parametrize("name,mode,cluster,tile_bytes",
+                         [(n, "stream", 0, None) for n in scenes.track_cases()]
+                         + [(n, "fused", 0, None) for n in scenes.track_cases()]
+                         + [("track_c1", "fused", 2, None), ("track_cyl2", "fused", 4, None), ("track_jitter", "fused", 8, None),
+                            ("track_c1", "fused", 4, 2048)])
+def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
     from glimpse_b200 import _lib
 
     torch = cuda
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
-    session, draws = make_session(scene, case, g, cluster=cluster, tile_bytes=tile_bytes)
+    session, draws = make_session(scene, case, g, cluster=cluster, tile_bytes=tile_bytes, mode=mode)
     assert cluster == 0 or session.plan.cluster == cluster
     P, N, T, O = session.P, session.N, session.T, session.O
     per = int(g["n_steps"]) // P
@@ -207,15 +211,16 @@ def test_step_teacher_forced(cuda, name, cluster, tile_bytes):
     assert worst["sigma"] <= 1e-7
 
 
+@pytest.mark.parametrize("mode", ["stream", "fused"])
 @pytest.mark.parametrize("name", list(scenes.track_cases()))
-def test_track_free_running_matches_reference(cuda, name):
+def test_track_free_running_matches_reference(cuda, name, mode):
     """Whole Tracker.track with the reference's draw sequence (rng='numpy')."""
     import glimpse_b200 as gb
 
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, rng="numpy")
+    tracker = gb.Tracker(observers, rng="numpy", mode=mode)
     np.random.seed(int(g["seed"]))
     cov = bool(case.get("return_covariances", False))
     tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True, return_covariances=cov)
@@ -234,20 +239,21 @@ def test_track_free_running_matches_reference(cuda, name):
         assert np.nanmax(np.abs(tracks.sigmas[ok] - g["sigmas"][ok]) / g["sigmas"][ok]) < 0.05
 
 
-def test_philox_run_recovers_velocity(cuda):
+@pytest.mark.parametrize("mode", ["stream", "fused"])
+def test_philox_run_recovers_velocity(cuda, mode):
     """Device RNG: the filter recovers the synthetic ground-truth velocity (0.4 m/d along +x)."""
     import glimpse_b200 as gb
 
     scene = synthetic.nadir_scene(seed=9, n_points=12, n_particles=2000, n_frames=10, imgsz=(600, 400))
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, seed=1234)
+    tracker = gb.Tracker(observers, seed=1234, mode=mode)
     tracks = tracker.track(models, tile_size=scene.tile_size)
     assert all(e is None for e in tracks.errors)
     v = tracks.vxyz[:, -1]
     assert np.all(np.abs(v[:, 0] - scene.truth_velocity[0]) < 0.03), v
     assert np.all(np.abs(v[:, 1] - scene.truth_velocity[1]) < 0.03), v
     # determinism: same seed, same answer; other seed, other answer
-    again = gb.Tracker(observers, seed=1234).track(models, tile_size=scene.tile_size)
+    again = gb.Tracker(observers, seed=1234, mode=mode).track(models, tile_size=scene.tile_size)
     np.testing.assert_array_equal(again.means, tracks.means)
-    other = gb.Tracker(observers, seed=99).track(models, tile_size=scene.tile_size)
+    other = gb.Tracker(observers, seed=99, mode=mode).track(models, tile_size=scene.tile_size)
     assert not np.array_equal(other.means, tracks.means)

@@ -74,17 +74,17 @@ def test_plan_sizes():
 
     lib = _lib.load()
     plan = _lib.gb_plan()
-    assert lib.gb_step_plan(1000, 15, 15, 10, 0, C.byref(plan)) == 0
+    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 0, 0, C.byref(plan)) == 0
     assert plan.cluster == 1 and plan.particles_in_smem == 1 and plan.n_local >= 1000
-    assert lib.gb_step_plan(10000, 15, 15, 1000, 0, C.byref(plan)) == 0
+    assert lib.gb_step_plan(10000, 15, 15, 1000, 1, 0, 0, C.byref(plan)) == 0
     assert plan.particles_in_smem == 1 and plan.cluster * plan.n_local >= 10000 and plan.smem_bytes <= 232448
     assert plan.cluster == 4 and plan.tile_bytes >= 24 * 1024  # 39 x 39 windows on chip, larger ones spill to slabs
     assert plan.scratch_bytes == plan.n_slabs * plan.slab_bytes and plan.slab_bytes > 1 << 20
-    assert lib.gb_step_plan(100000, 31, 31, 1000, 0, C.byref(plan)) == 0
+    assert lib.gb_step_plan(100000, 31, 31, 1000, 1, 0, 0, C.byref(plan)) == 0
     assert plan.particles_in_smem == 0 and plan.particle_scratch_bytes == 1000 * plan.cluster * 9 * plan.n_local * 8
     assert plan.scratch_bytes == plan.particle_scratch_bytes + plan.n_slabs * plan.slab_bytes
-    assert lib.gb_step_plan(1000, 40, 40, 10, 0, C.byref(plan)) == -3  # template > 1024 px
-    assert lib.gb_step_plan(1000, 15, 15, 10, 3, C.byref(plan)) == -1
+    assert lib.gb_step_plan(1000, 40, 40, 10, 1, 0, 0, C.byref(plan)) == -3  # template > 1024 px
+    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 3, 0, C.byref(plan)) == -1
     assert b"cluster" in lib.gb_last_error()
 
 
