@@ -36,7 +36,7 @@ class gb_camera(C.Structure):
 
 class gb_image(C.Structure):
     _fields_ = [
-        ("gray", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("nchan", C.c_int32),
+        ("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("nchan", C.c_int32),
         ("cam", gb_camera),
     ]
 
@@ -70,7 +70,7 @@ class gb_plan(C.Structure):
 class gb_track_desc(C.Structure):
     _fields_ = [
         ("P", C.c_int64), ("N", C.c_int64), ("T", C.c_int32), ("O", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
-        ("images", C.c_void_p), ("images_host", C.c_void_p), ("image_offset_host", C.c_void_p), ("image_index_host", C.c_void_p),
+        ("images", C.c_void_p), ("images_host", C.c_void_p), ("image_events_host", C.c_void_p), ("image_offset_host", C.c_void_p), ("image_index_host", C.c_void_p),
         ("obs_scale_host", C.c_void_p), ("mask", C.c_void_p), ("first", C.c_void_p), ("last", C.c_void_p),
         ("mask_host", C.c_void_p), ("first_host", C.c_void_p), ("last_host", C.c_void_p),
         ("tau_host", C.c_void_p), ("tau2_host", C.c_void_p),
@@ -102,7 +102,6 @@ SIGNATURES = {
     "gb_camera_from_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(gb_camera)]),
     "gb_project": (C.c_int, [C.POINTER(gb_camera), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_unproject": (C.c_int, [C.POINTER(gb_camera), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "gb_gray_from_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "gb_state_from_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_state_to_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_step_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(gb_plan)]),

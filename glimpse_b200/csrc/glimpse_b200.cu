@@ -50,7 +50,7 @@ struct StepParams {
   double tau, tau2;
   int img[GB_MAX_OBS];       // global image index of each observer at time t, -1 = none
   CamK cam[GB_MAX_OBS];      // that image's camera (constant bank: operands without loads)
-  const uint16_t* gray[GB_MAX_OBS];
+  const uint8_t* pixels[GB_MAX_OBS];
   int pitch[GB_MAX_OBS], nchan[GB_MAX_OBS];
   int tmpl_frame[GB_MAX_OBS]; // time index at which each observer's template is cut
   double obs_scale[GB_MAX_OBS];
@@ -211,17 +211,6 @@ __global__ void k_unproject(const __grid_constant__ gb_camera cam, const double*
     xyz[3 * i] = dx;
     xyz[3 * i + 1] = dy;
     xyz[3 * i + 2] = dz;
-  }
-}
-
-__global__ void k_gray_from_u8(const uint8_t* __restrict__ src, int height, int width, int nchan,
-                               uint16_t* __restrict__ dst, int pitch) {
-  const int64_t total = (int64_t)height * width;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
-    unsigned s = 0;
-    for (int k = 0; k < nchan; ++k) s += src[i * nchan + k];
-    dst[(int64_t)r * pitch + c] = (uint16_t)s;
   }
 }
 
@@ -454,7 +443,10 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
     const int r = i / bw, c = i - r * bw;
     // a box snapped onto the frame edge can reach one pixel outside only through rounding; clamp
     const int rr = min(max(s_box[1] + r, 0), img->height - 1), cc = min(max(s_box[0] + c, 0), img->width - 1);
-    s_raw[i] = img->gray[(int64_t)rr * img->pitch + cc];
+    const uint8_t* px = img->pixels + (int64_t)rr * img->pitch + (int64_t)cc * img->nchan;
+    unsigned sum = 0;
+    for (int k = 0; k < img->nchan; ++k) sum += px[k];
+    s_raw[i] = (uint16_t)sum;
   }
   __syncthreads();
   // grey mean and population std (helpers.py:324-344)
@@ -836,7 +828,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       const int64_t ta = (int64_t)w.tw * w.th;
       const bool dumper = rank == 0;
       const int boxv[4] = {box_l, box_t, box_r, box_b};
-      tile_build_surface(prm.gray[o], prm.pitch[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+      tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
                          prm.tmpl_values + po * ta, w,
                          (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
                          (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap,
@@ -1090,7 +1082,7 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
     if (idx >= 0 && d.images_host) {
       const gb_image& im = d.images_host[prm.img[o]];
       camk_from(im.cam, prm.cam[o]);
-      prm.gray[o] = im.gray;
+      prm.pixels[o] = im.pixels;
       prm.pitch[o] = im.pitch;
       prm.nchan[o] = im.nchan;
     }
@@ -1228,7 +1220,7 @@ static int launch_stream_step(const StepParams& prm, cudaStream_t stream, int64_
   k_s0_reset<<<grid_for(prm.P * prm.O * 5, 256), 256, 0, stream>>>(prm);
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   GB_CUDA(cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem));
-  k_s2_surface<<<(unsigned)(prm.P * prm.O), GB_SBLOCK_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
+  k_s2_surface<<<(unsigned)(prm.P * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
   k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s5_finalize<COV><<<(unsigned)((prm.P + 3) / 4), 128, 0, stream>>>(prm);
@@ -1318,15 +1310,6 @@ int gb_unproject(const gb_camera* cam, const double* uv, int64_t n, int directio
   return GB_OK;
 }
 
-int gb_gray_from_u8(const uint8_t* src, int32_t height, int32_t width, int32_t nchan, uint16_t* dst, int32_t pitch,
-                    void* stream) {
-  if (!src || !dst || height <= 0 || width <= 0 || nchan < 1 || nchan > 4 || pitch < width)
-    return fail(GB_E_INVALID, "bad frame arguments (1..4 uint8 bands)%s");
-  k_gray_from_u8<<<grid_for((int64_t)height * width, 256), 256, 0, (cudaStream_t)stream>>>(src, height, width, nchan, dst, pitch);
-  GB_CUDA(cudaGetLastError());
-  return GB_OK;
-}
-
 int gb_state_from_rows(const double* rows, int64_t npoints, int64_t n, double* state, void* stream) {
   if (!rows || !state) return fail(GB_E_INVALID, "null argument%s");
   k_state_from_rows<<<grid_for(npoints * n, 256), 256, 0, (cudaStream_t)stream>>>(rows, npoints, n, state);
@@ -1361,7 +1344,7 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     plan->n_local = (int32_t)n_particles;
     plan->particles_in_smem = 0;
     plan->tile_bytes = kSurfaceSmem;
-    plan->stream_block = 2 * GB_SBLOCK_THREADS;
+    plan->stream_block = GB_S4_PPT * GB_SBLOCK_THREADS;
     plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
     // surface regions sized for search windows up to 191 px larger than the template
     plan->surf_bytes = (tile_bytes_needed(tile_w + 191, tile_h + 191, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
@@ -1455,6 +1438,10 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
     if (!any_init && !any_step) continue;
     StepParams prm;
     fill_params(*d, t, prm);
+    if (d->image_events_host)
+      for (int o = 0; o < d->O; ++o)
+        if (prm.img[o] >= 0 && d->image_events_host[prm.img[o]])
+          GB_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)d->image_events_host[prm.img[o]], 0));
     if (any_init) {
       if ((rc = launch_init(prm, cov, stream))) return rc;
       ++launches;

@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __g
   const bool evolve = !forced && !prm.skip_evolve;
   const bool use_obs = !prm.io.force_weights;
   const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
-  const int ia = b * prm.s_block + 2 * tid;  // particles ia, ia + 1
-  const bool va = ia < N, vb = ia + 1 < N;
   const bool vec = (N & 1) == 0;  // 16-byte aligned pairs
   uint32_t flags = 0;
+  for (int sub = 0; sub < prm.s_block; sub += 2 * GB_SBLOCK_THREADS) {
+  const int ia = b * prm.s_block + sub + 2 * tid;  // particles ia, ia + 1
+  const bool va = ia < N, vb = ia + 1 < N;
   if (va) {
     double s[2][6];
     if (vec) {
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __g
       }
     }
   }
+  }
   const int any = __syncthreads_or((int)flags);
   if (any && tid == 0) atomicOr(&prm.s_pflags[p], any);
   if (use_obs && tid < O * 5) {
@@ -199,9 +201,10 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __g
   }
 }
 
-__global__ void __launch_bounds__(GB_SBLOCK_THREADS) k_s2_surface(const __grid_constant__ StepParams prm, int smem_budget) {
+#define GB_S2_THREADS 512
+__global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_constant__ StepParams prm, int smem_budget) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double s_mm[GB_SBLOCK_THREADS / 32][4];
+  __shared__ double s_mm[GB_S2_THREADS / 32][4];
   __shared__ int s_box[4];
   const int64_t po = blockIdx.x;
   const int64_t p = po / prm.O;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS) k_s2_surface(const __grid_c
   tile_carve(in_smem ? reinterpret_cast<char*>(smem_raw) : region, w);
   const int64_t ta = (int64_t)w.tw * w.th;
   const int boxv[4] = {box_l, box_t, box_r, box_b};
-  tile_build_surface(prm.gray[o], prm.pitch[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+  tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
                      prm.tmpl_values + po * ta, w, prm.io.dump_search ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
                      prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap, nullptr);
   if (in_smem) {
@@ -395,9 +398,12 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   __syncthreads();
   const double* ev = prm.s_ev + p * 6 * (int64_t)N;
   const double* fw = prm.io.force_weights ? prm.io.force_weights + (int64_t)p * N : nullptr;
-  const int ia = b * prm.s_block + 2 * tid;
-  const bool va = ia < N, vb = ia + 1 < N, vec = (N & 1) == 0;
+  const bool vec = (N & 1) == 0;
   uint32_t flags = 0;
+  double wacc = 0.0;
+  for (int sub = 0; sub < prm.s_block; sub += 2 * GB_SBLOCK_THREADS) {
+  const int ia = b * prm.s_block + sub + 2 * tid;
+  const bool va = ia < N, vb = ia + 1 < N;
   double w[2] = {0.0, 0.0};
   if (va) {
     if (fw) {
@@ -454,8 +460,10 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
       if (vb) prm.io.dump_weights[(int64_t)p * N + ia + 1] = w[1];
     }
   }
-  // CTA total of the weights (fixed association: pair, warp butterfly, warps in order)
-  double tsum = warp_sum(w[0] + w[1]);
+  wacc += w[0] + w[1];
+  }
+  // CTA total of the weights (fixed association: per thread, warp butterfly, warps in order)
+  double tsum = warp_sum(wacc);
   if (lane == 0) s_warp[warp] = tsum;
   const int any = __syncthreads_or((int)flags);
   if (tid == 0) {
@@ -466,17 +474,18 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   }
 }
 
-// s4: prefix of the weights and child ranges (two consecutive parents per thread), then one thread per
-// CHILD: find the parent in the CTA's sorted range ends, gather its state, write coalesced, and add it to
-// the moment partials (sum over children == sum over parents weighted by their child counts).
+// s4: prefix of the weights and child ranges (GB_S4_PPT consecutive parents per thread), then one thread
+// per CHILD: find the parent in the CTA's sorted range ends, gather its state, write coalesced, and add it
+// to the moment partials (sum over children == sum over parents weighted by their child counts).
+#define GB_S4_PPT 8
 template <bool COV>
 __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __grid_constant__ StepParams prm) {
-  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16;
+  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4_PPT, CAP = PPT * GB_SBLOCK_THREADS;
   __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
-  __shared__ double s_pref[5];
+  __shared__ double s_pref[6];
   __shared__ double s_red[GB_SBLOCK_THREADS / 32][KP];
-  __shared__ double s_w[2 * GB_SBLOCK_THREADS];
-  __shared__ int s_end[2 * GB_SBLOCK_THREADS];
+  __shared__ double s_w[CAP];
+  __shared__ int s_end[CAP];
   __shared__ int s_j0;
   const int64_t p = blockIdx.x / prm.s_nblk;
   const int b = (int)(blockIdx.x - p * prm.s_nblk);
@@ -502,32 +511,39 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __gr
   }
   const double* wsrc = prm.s_w + (int64_t)p * N;
   const int base = b * prm.s_block;
-  const int ia = base + 2 * tid;
-  const bool va = ia < N, vb = ia + 1 < N, vec = (N & 1) == 0;
-  const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA
-  double w0 = 0.0, w1 = 0.0;
-  if (va) {
-    if (vec) {
-      const double2 x = *reinterpret_cast<const double2*>(wsrc + ia);
-      w0 = x.x;
-      w1 = x.y;
-    } else {
-      w0 = wsrc[ia];
-      w1 = vb ? wsrc[ia + 1] : 0.0;
+  const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA (<= CAP)
+  const int k0 = PPT * tid;                                      // first local parent of this thread
+  double w[PPT];
+  if ((N & 1) == 0 && k0 + PPT <= n_here) {
+#pragma unroll
+    for (int q = 0; q < PPT; q += 2) {
+      const double2 x = *reinterpret_cast<const double2*>(wsrc + base + k0 + q);
+      w[q] = x.x;
+      w[q + 1] = x.y;
     }
+  } else {
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) w[q] = (k0 + q < n_here) ? wsrc[base + k0 + q] : 0.0;
   }
-  s_w[2 * tid] = w0;
-  s_w[2 * tid + 1] = w1;
-  const double off = block_exclusive_offset(w0 + w1, s_warp);  // contains a __syncthreads(): s_pref is visible
+  double tsum = 0.0;
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    if (k0 + q < CAP) s_w[k0 + q] = w[q];
+    tsum += w[q];
+    w[q] = tsum;  // inclusive prefix inside the thread
+  }
+  const double off = block_exclusive_offset(tsum, s_warp);  // contains a __syncthreads(): s_pref is visible
   const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4];
   // The last parent of the CTA takes the next CTA's prefix as its cumulative weight, so that child ranges
   // are seamless across CTAs whatever the association of the in-CTA sums.
-  const int last_i = base + n_here - 1;
-  double c0 = prefix + (off + w0), c1 = prefix + ((off + w0) + w1);
-  if (ia == last_i) c0 = next_prefix;
-  if (ia + 1 == last_i) c1 = next_prefix;
-  if (va) s_end[2 * tid] = count_positions_le(quo(c0, total), u01, inv_n, N);
-  if (vb) s_end[2 * tid + 1] = count_positions_le(quo(c1, total), u01, inv_n, N);
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int k = k0 + q;
+    if (k < n_here) {
+      const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
+      s_end[k] = count_positions_le(quo(c, total), u01, inv_n, N);
+    }
+  }
   if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
   __syncthreads();
   const int J0 = s_j0, J1 = n_here > 0 ? s_end[n_here - 1] : J0;
@@ -552,16 +568,16 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __gr
     double s[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) s[c] = ev[c * (int64_t)N + lo];
-    const double w = s_w[lo];
+    const double wj = s_w[lo];
 #pragma unroll
     for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
-    mom.accumulate(w, s, ref);
-    if (wst) wst[j] = w;
+    mom.accumulate(wj, s, ref);
+    if (wst) wst[j] = wj;
     if (outp) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
     }
-    if (outw) outw[j] = w;
+    if (outw) outw[j] = wj;
     if (outi) outi[j] = base + lo;
   }
   // per-CTA moment partials, combined in CTA order by s5 (bit-reproducible)

@@ -192,7 +192,7 @@ __device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, i
 // Build the Hermite surface for one search window.  All threads of the CTA participate.
 // `box` = (left, top, right, bottom); template data in global memory.  The caller has verified the
 // capacity and carved `w`.
-__device__ inline void tile_build_surface(const uint16_t* __restrict__ gray_plane, int pitch, const int* box, const double* __restrict__ g_tmpl,
+__device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
                                           const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
                                           float* dump_search, float* dump_sse, int64_t dump_cap, long long* clk) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -201,9 +201,19 @@ __device__ inline void tile_build_surface(const uint16_t* __restrict__ gray_plan
   // 1. raw window (a warp per row: consecutive lanes read consecutive pixels), template and its
   //    CDF; clear the histogram
   {
-    const uint16_t* gray = gray_plane + (int64_t)box[1] * pitch + box[0];
-    for (int r = warp; r < Sv; r += nwarp)
-      for (int c = lane; c < Su; c += 32) w.raw[r * Su + c] = gray[(int64_t)r * pitch + c];
+    const uint8_t* px = pixels + (int64_t)box[1] * pitch + (int64_t)box[0] * nchan;
+    if (nchan == 1) {
+      for (int r = warp; r < Sv; r += nwarp)
+        for (int c = lane; c < Su; c += 32) w.raw[r * Su + c] = px[(int64_t)r * pitch + c];
+    } else {
+      for (int r = warp; r < Sv; r += nwarp)
+        for (int c = lane; c < Su; c += 32) {
+          const uint8_t* q = px + (int64_t)r * pitch + c * nchan;
+          unsigned sum = 0;
+          for (int k = 0; k < nchan; ++k) sum += q[k];
+          w.raw[r * Su + c] = (uint16_t)sum;
+        }
+    }
     for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
     for (int i = tid; i < w.tw * w.th; i += nthr) {
       const int r = i / w.tw, c = i - r * w.tw;

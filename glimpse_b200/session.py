@@ -156,6 +156,7 @@ class Session:
             d.P, d.N, d.T, d.O, d.tile_w, d.tile_h = P, N, T, O, self.tw, self.th
             d.images = images_dev.data_ptr()
             d.images_host = C.addressof(self.images_host)
+            d.image_events_host = C.addressof(self.image_events)
             d.image_offset_host = self.offsets.ctypes.data
             d.image_index_host = self.image_index.ctypes.data
             d.obs_scale_host = self.scale_h.ctypes.data
@@ -208,41 +209,59 @@ class Session:
 
     # ---------------------------------------------------------------- uploads
     def _upload_frames(self):
-        """Band-sum uint16 planes + per-image cameras for every image ``image_index`` references
-        (reference ``Observer.cache_images`` / ``Image.read``, tracker.py:295-299)."""
+        """Copy every frame ``image_index`` references to the device as it is (uint8, 1-4 bands; reference
+        ``Observer.cache_images`` / ``Image.read``, tracker.py:295-299).  Copies go to a side stream in
+        time order, each followed by an event that ``gb_track`` waits on before the first kernel that reads
+        the frame, so the upload of later frames overlaps the tracking of earlier ones."""
         torch, device, tracker = self.torch, self.device, self.tracker
-        structs, offsets = [], [0]
+        structs, offsets, order = [], [0], []
         for o, obs in enumerate(tracker.observers):
-            use_cache = bool(getattr(obs, "cache", True))
-            needed = set(int(v) for v in self.image_index[:, o] if v >= 0)
+            first_use = {}
+            for t, v in enumerate(self.image_index[:, o]):
+                if v >= 0:
+                    first_use.setdefault(int(v), t)
             for i, img in enumerate(obs.images):
-                g = _lib.gb_image()
-                if i in needed:
-                    array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
-                    key = (o, i, id(array))
-                    cached = tracker._frame_cache.get(key) if use_cache else None
-                    if cached is None:
-                        if array.dtype != np.uint8:
-                            raise NotImplementedError("device frames must be uint8 (1-4 bands)")
-                        arr = np.ascontiguousarray(array)
-                        h, w = arr.shape[0], arr.shape[1]
-                        nchan = 1 if arr.ndim == 2 else arr.shape[2]
-                        src = torch.from_numpy(arr).to(device, non_blocking=True)
-                        self.h2d += arr.nbytes
-                        pitch = (w + 7) // 8 * 8
-                        plane = torch.empty((h, pitch), dtype=torch.int16, device=device)
-                        _lib.check(self.lib.gb_gray_from_u8(src.data_ptr(), h, w, nchan, plane.data_ptr(), pitch, self.stream))
-                        cached = (plane, w, h, pitch, nchan)
-                        if use_cache:
-                            tracker._frame_cache[key] = cached
-                    plane, w, h, pitch, nchan = cached
-                    self.keep.append(plane)
-                    g.gray = plane.data_ptr()
-                    g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
-                    g.cam = lower_camera(img.cam)
-                structs.append(g)
+                if i in first_use:
+                    order.append((first_use[i], len(structs)))
+                structs.append((o, i, img, i in first_use))
             offsets.append(len(structs))
-        self.images_host = (_lib.gb_image * len(structs))(*structs)
+        out = [_lib.gb_image() for _ in structs]
+        self.image_events = (C.c_void_p * len(structs))()
+        self.keep_events = []
+        copy_stream = getattr(tracker, "_copy_stream", None)
+        if copy_stream is None or copy_stream.device != device:
+            copy_stream = tracker._copy_stream = torch.cuda.Stream(device=device)
+        compute_stream = torch.cuda.current_stream(device)
+        copy_stream.wait_stream(compute_stream)
+        for _, k in sorted(order):
+            o, i, img, _used = structs[k]
+            obs = tracker.observers[o]
+            use_cache = bool(getattr(obs, "cache", True))
+            array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
+            key = (o, i, id(array))
+            cached = tracker._frame_cache.get(key) if use_cache else None
+            if cached is None:
+                if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
+                    raise NotImplementedError("device frames must be uint8 with 1-4 bands")
+                arr = np.ascontiguousarray(array)
+                with torch.cuda.stream(copy_stream):
+                    dev = torch.from_numpy(arr).to(device, non_blocking=True)
+                    event = torch.cuda.Event()
+                    event.record(copy_stream)
+                dev.record_stream(compute_stream)
+                self.h2d += arr.nbytes
+                cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
+                if use_cache:
+                    tracker._frame_cache[key] = cached
+            dev, w, h, pitch, nchan, event = cached
+            self.keep.append(dev)
+            self.keep_events.append(event)
+            g = out[k]
+            g.pixels = dev.data_ptr()
+            g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
+            g.cam = lower_camera(img.cam)
+            self.image_events[k] = event.cuda_event
+        self.images_host = (_lib.gb_image * len(out))(*out)
         images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
         self.h2d += images_dev.numel()
         return images_dev, np.asarray(offsets, dtype=np.int32)
@@ -285,11 +304,19 @@ class Session:
             _lib.check(self.lib.gb_track(C.byref(self.desc), self.stream, C.byref(launches)))
         self.launches += int(launches.value)
 
+    def _await_uploads(self) -> None:
+        """Per-time entry points do not take the frame events: wait for the whole copy stream once."""
+        if not getattr(self, "_uploads_awaited", False):
+            self.torch.cuda.current_stream(self.device).wait_stream(self.tracker._copy_stream)
+            self._uploads_awaited = True
+
     def init(self, t: int) -> None:
+        self._await_uploads()
         with self.torch.cuda.device(self.device):
             _lib.check(self.lib.gb_track_init(C.byref(self.desc), int(t), self.stream))
 
     def step(self, t: int, io: Optional[_lib.gb_stage_io] = None) -> None:
+        self._await_uploads()
         with self.torch.cuda.device(self.device):
             _lib.check(self.lib.gb_track_step(C.byref(self.desc), int(t), C.byref(io) if io is not None else None, self.stream))
 

@@ -72,11 +72,12 @@ typedef struct gb_camera {
   int32_t pad_;
 } gb_camera;
 
-/* One cached frame (image.py:137-214 with cache=True): `gray` holds the per-pixel SUM over the
- * `nchan` bands as uint16, so mean(axis=2) (tracker.py:523-524) is gray / nchan.  Row pitch in
- * elements; pixel (row r, col c) is gray[r * pitch + c]. */
+/* One cached frame (image.py:137-214 with cache=True): the uint8 pixel array exactly as the host holds
+ * it, (height, width, nchan) row-major with `pitch` BYTES per row.  The tile loaders sum the `nchan`
+ * bands on the fly, so tile.mean(axis=2) (tracker.py:523-524) is that sum / nchan; no converted copy
+ * of the frame is ever written. */
 typedef struct gb_image {
-  const uint16_t* gray;
+  const uint8_t* pixels;
   int32_t width, height, pitch, nchan;
   gb_camera cam;
 } gb_image;
@@ -123,14 +124,6 @@ int gb_project(const gb_camera* cam_host, const double* xyz, int64_t n, double* 
  * otherwise depth[n].  directions != 0 returns ray directions, else adds the camera position. */
 int gb_unproject(const gb_camera* cam_host, const double* uv, int64_t n, int directions, const double* depth,
                  double* xyz, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * Frames
- * ------------------------------------------------------------------------------------------ */
-/* uint8 frame (H, W, C) row-major -> uint16 band-sum plane with the given pitch (Image.read +
- * tile.mean(axis=2) hoisted to upload time; image.py:137-214, tracker.py:523-524). */
-int gb_gray_from_u8(const uint8_t* src, int32_t height, int32_t width, int32_t nchan, uint16_t* dst, int32_t pitch,
-                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * State layout helpers
@@ -185,6 +178,8 @@ typedef struct gb_track_desc {
   /* frames and cameras: images[image_offset_host[o] + i] is image i of observer o */
   const gb_image* images;          /* device array */
   const gb_image* images_host;     /* host copy of the same table (cameras travel to the kernels as launch parameters) */
+  void* const* image_events_host;  /* optional [n_images] cudaEvent_t: gb_track makes `stream` wait for event i before the first
+                                    * kernel that reads image i (lets the caller overlap frame uploads with tracking); NULL = none */
   const int32_t* image_offset_host; /* [O + 1] */
   const int32_t* image_index_host; /* [T][O] image of observer o matched to time t, -1 = none (tracker.py:466-492) */
   const double* obs_scale_host;    /* [O] 1 / (2 sigma^2) (tracker.py:625) */
