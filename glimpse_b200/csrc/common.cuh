@@ -74,6 +74,19 @@ struct ClusterCtx {
   SmemHeader* hdr;
 };
 
+// Bitwise OR of one word per thread across the CTA (__syncthreads_or only tells whether any is non-zero).
+// `slot` is one shared-memory word owned by the caller.
+__device__ __forceinline__ unsigned block_or(unsigned v, unsigned* slot) {
+  if (threadIdx.x == 0) *slot = 0u;
+  __syncthreads();
+  v = __reduce_or_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicOr(slot, v);
+  __syncthreads();
+  const unsigned out = *slot;
+  __syncthreads();
+  return out;
+}
+
 // Block reduction of K per-thread doubles (OP 0: sum, 1: min); the result is left in
 // hdr->bcast[0..K), visible to all threads on return.  Maxima are reduced as minima of negatives.
 // Stage 1: shuffles inside each warp; stage 2: warp k combines the per-warp partials of value k.

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_init(const __grid_constant__ Ste
     if (prm.out_weights) prm.out_weights[(p * prm.T + t) * N + i] = 1.0;
     mom.accumulate(1.0, s, ref);
   }
-  const int any = __syncthreads_or((int)flags);
+  const int any = (int)block_or(flags, reinterpret_cast<unsigned*>(&hdr->iflags[1]));
   if (any) {
     if (threadIdx.x == 0) {
       prm.status[p] = status_from_flags((uint32_t)any);
@@ -430,6 +430,11 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
       duv[1] = sub(v, (double)(s_box[1] + s_box[3]) / 2.0);
     } else {
       if (atomicCAS(&prm.status[p], 0, GB_ST_TEMPLATE_BOUNDS) == 0) prm.status_time[p] = t;
+      // the reference raises inside initialize_template, before the moments of this time are stored (tracker.py:336-354)
+      double* mo = prm.means + (p * prm.T + t) * 6;
+      for (int c = 0; c < 6; ++c) mo[c] = CUDART_NAN;
+      if (prm.sigmas) for (int c = 0; c < 6; ++c) prm.sigmas[(p * prm.T + t) * 6 + c] = CUDART_NAN;
+      if (prm.covariances) for (int c = 0; c < 36; ++c) prm.covariances[(p * prm.T + t) * 36 + c] = CUDART_NAN;
     }
   }
   __syncthreads();
@@ -906,7 +911,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
     }
   }
   GB_CLK(8);
-  const int blockflags = __syncthreads_or((int)flags);
+  const int blockflags = (int)block_or(flags, reinterpret_cast<unsigned*>(&hdr->iflags[1]));
   // the CTA total is, by definition, the prefix of its last particle (keeps child ranges seamless)
   if (tid == 0) {
     hdr->bcast[0] = nv > 0 ? uvb[nv - 1] : 0.0;

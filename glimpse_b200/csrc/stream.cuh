@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __g
     }
   }
   }
-  const int any = __syncthreads_or((int)flags);
+  __shared__ unsigned s_or;
+  const int any = (int)block_or(flags, &s_or);
   if (any && tid == 0) atomicOr(&prm.s_pflags[p], any);
   if (use_obs && tid < O * 5) {
     const int o = tid / 5, k = tid - o * 5;
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   // CTA total of the weights (fixed association: per thread, warp butterfly, warps in order)
   double tsum = warp_sum(wacc);
   if (lane == 0) s_warp[warp] = tsum;
-  const int any = __syncthreads_or((int)flags);
+  __shared__ unsigned s_or;
+  const int any = (int)block_or(flags, &s_or);
   if (tid == 0) {
     double tot = 0.0;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_warp[k];

@@ -1,0 +1,207 @@
+"""Edge cases and size-independent properties of the device Tracker, checked against the oracle
+(free-running with the reference's draw order) or against invariants of the algorithm."""
+import datetime
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers
+from glimpse_b200 import synthetic
+from oracle import tracker_oracle as orc
+
+pytestmark = pytest.mark.gpu
+MODES = ["stream", "fused"]
+
+
+def run_both(scene, seed, mode, points=None, viewshed=None, oracle_viewshed=None, exact=True, **track_kw):
+    import glimpse_b200 as gb
+
+    observers, models = synthetic.build(scene, gb, points=points)
+    tracker = gb.Tracker(observers, viewshed=viewshed, rng="numpy", mode=mode)
+    np.random.seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tracks = tracker.track(models, tile_size=scene.tile_size, **track_kw)
+    obs, specs, taus, index = helpers.oracle_inputs(scene, points=points)
+    np.random.seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = orc.track(obs, specs, taus, index, tile_size=scene.tile_size, viewshed=oracle_viewshed, exact=exact,
+                        return_covariances=track_kw.get("return_covariances", False),
+                        observer_mask=track_kw.get("observer_mask"))
+    return tracks, ref, tracker
+
+
+def assert_close_to_oracle(tracks, ref, sig_tol=0.05):
+    sig = ref.sigmas if ref.sigmas.ndim == 3 else np.sqrt(np.einsum("ptii->pti", ref.sigmas))
+    both = ~np.isnan(ref.means[..., 0])
+    assert np.array_equal(~np.isnan(tracks.means[..., 0]), both)
+    d = np.abs(tracks.means - ref.means) / np.maximum(sig, 1e-9)
+    assert np.nanmax(d[..., [0, 1, 3, 4]]) < sig_tol
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_template_beyond_image_is_an_index_error(cuda, mode):
+    """raster.py:417-418 via observer.py:115-130: captured per track with >= 2 tracks, raised with one."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=4, n_points=3, n_particles=256, n_frames=4, imgsz=(320, 240), margin_px=90)
+    # (the failing track goes last: a track that stops early leaves its later draws unconsumed in the reference,
+    #  so tracks after it see a shifted random stream)
+    scene.points[2, 0] = (320 / 2 - 3) * 0.2  # 3 px from the right edge: the 15 x 15 template does not fit
+    tracks, ref, _ = run_both(scene, 11, mode)
+    assert [type(e).__name__ if e else None for e in tracks.errors] == [None, None, "IndexError"]
+    assert isinstance(ref.errors[2], IndexError)
+    assert np.isnan(tracks.means[2]).all() and not np.isnan(tracks.means[:2]).any()
+    assert_close_to_oracle(tracks, ref)
+    observers, models = synthetic.build(scene, gb, points=[2])
+    with pytest.raises(IndexError, match="Box extends beyond grid bounds"):
+        gb.Tracker(observers, rng="numpy", mode=mode).track(models, tile_size=scene.tile_size)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_particles_leaving_the_frame_skip_the_image_with_a_warning(cuda, mode):
+    """tracker.py:597-601: the observer contributes nothing, the filter keeps running on the motion model."""
+    scene = synthetic.nadir_scene(seed=6, n_points=2, n_particles=256, n_frames=6, imgsz=(320, 240), margin_px=100,
+                                  velocity_sigma=0.3)
+    scene.points[0, 0] = (320 / 2 - 24) * 0.2  # template fits, the growing cloud does not
+    scene.motion["vxyz"] = (2.0, 0.0, 0.0)      # 10 px / day towards the edge
+    tracks, ref, _ = run_both(scene, 21, mode)
+    assert tracks.errors[0] is None and tracks.warnings[0] is not None
+    assert all("too close to or beyond image bounds" in str(w) for w in tracks.warnings[0])
+    assert (ref.skipped[0] == 2).sum() == len(tracks.warnings[0]) > 0
+    assert_close_to_oracle(tracks, ref)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_viewshed_and_gridded_dem(cuda, mode):
+    """tracker.py:114-117 (nearest viewshed sample) and motion.py:181-204 with a 2-D DEM / DEM sigma
+    (bilinear Raster.sample, raster.py:891-1027)."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=8, n_points=3, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=90)
+    rng = np.random.RandomState(0)
+    dem = 0.5 * rng.rand(12, 16)
+    sig = 0.5 + 0.1 * rng.rand(12, 16)
+    x, y = (-40.0, 40.0), (30.0, -30.0)  # north-up raster: y decreasing
+    scene.motion.update(dem=gb.Raster(dem, x=x, y=y), dem_sigma=gb.Raster(sig, x=x, y=y))
+    scene.points = scene.points[[0, 2, 1]]  # the eastern point last (see the note on draw order above)
+    vis = np.ones((12, 16))
+    vis[:, 10:] = 0  # the eastern point (x = +14 m) starts on non-visible cells
+    viewshed = gb.Raster(vis, x=x, y=y)
+    observers, models = synthetic.build(scene, gb)
+    scene.motion.update(dem=0.0, dem_sigma=0.0)  # placeholders for the oracle specs, replaced below
+    tracker = gb.Tracker(observers, viewshed=viewshed, rng="numpy", mode=mode)
+    np.random.seed(5)
+    tracks = tracker.track(models, tile_size=scene.tile_size)
+    obs, specs, taus, index = helpers.oracle_inputs(scene)
+    for sp in specs:
+        sp.dem, sp.dem_sigma = orc.Surface(dem, x, y), orc.Surface(sig, x, y)
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = orc.track(obs, specs, taus, index, tile_size=scene.tile_size, viewshed=orc.Surface(vis, x, y), exact=True)
+    kinds = [type(e).__name__ if e else None for e in tracks.errors]
+    assert kinds == [type(e).__name__ if e else None for e in ref.errors]
+    assert "ValueError" in kinds and None in kinds
+    assert "non-visible viewshed" in str([e for e in tracks.errors if e][0])
+    assert_close_to_oracle(tracks, ref)
+    z_ok = ~np.isnan(ref.means[..., 2])
+    assert np.max(np.abs(tracks.means[..., 2][z_ok] - ref.means[..., 2][z_ok])) < 0.05 * np.nanmax(ref.sigmas[..., 2])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cylindrical_zero_speed_gives_nan_error(cuda, mode):
+    """motion.py:296-303: vr = 0 -> 0/0 -> 'Some particles have missing (NaN) values'."""
+    scene = synthetic.nadir_scene(seed=3, n_points=2, n_particles=128, n_frames=4, imgsz=(320, 240), margin_px=100,
+                                  kind="cylindrical")
+    scene.motion.update(vrthz=(0.0, 0.0, 0.0), vrthz_sigma=(0.0, 0.0, 0.0))
+    tracks, ref, _ = run_both(scene, 2, mode)
+    assert all(isinstance(e, ValueError) and "NaN" in str(e) for e in tracks.errors)
+    assert all(isinstance(e, ValueError) for e in ref.errors)
+    assert not np.isnan(tracks.means[:, 0]).any() and np.isnan(tracks.means[:, 1:]).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_large_template_many_particles_and_mask(cuda, mode):
+    """config-4 shape shrunk (31 x 31 template, N = 20 000: scratch / multi-CTA paths), covariances,
+    and an observer mask that removes the only observer for one point (motion-only track)."""
+    scene = synthetic.nadir_scene(seed=12, n_points=3, n_particles=20000, n_frames=4, imgsz=(400, 300), margin_px=130,
+                                  tile_size=(31, 31), velocity_sigma=0.5)
+    mask = np.array([[True], [True], [False]])
+    tracks, ref, tracker = run_both(scene, 9, mode, return_covariances=True, observer_mask=mask)
+    assert all(e is None for e in tracks.errors)
+    assert tracks.covariances.shape == (3, 4, 6, 6) and tracks.sigmas is None
+    assert_close_to_oracle(tracks, ref)
+    c_ref, c = ref.sigmas, tracks.covariances
+    scale = np.sqrt(np.einsum("ptii,ptjj->ptij", c_ref, c_ref))
+    ok = scale > 0
+    assert np.max(np.abs(c - c_ref)[ok] / scale[ok]) < 0.05
+    # the unobserved point: weights stay uniform, positions follow the motion model only
+    assert np.allclose(tracks.means[2, :, 3], scene.truth_velocity[0], atol=0.02)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_backward_tracking_and_api_shapes(cuda, mode):
+    """Decreasing datetimes are legal (tracker.py:446-450): negative time steps."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=14, n_points=2, n_particles=400, n_frames=6, imgsz=(320, 240), margin_px=100)
+    observers, models = synthetic.build(scene, gb)
+    tracker = gb.Tracker(observers, seed=3, mode=mode)
+    back = tracker.track(models, datetimes=tracker.datetimes[::-1], tile_size=scene.tile_size, return_particles=True)
+    assert back.datetimes[0] > back.datetimes[-1]
+    assert back.particles.shape == (2, 6, 400, 6) and back.weights.shape == (2, 6, 400)
+    assert np.all(np.abs(back.vxyz[:, -1, 0] - scene.truth_velocity[0]) < 0.05)  # velocity keeps its sign, time runs backwards
+    # reported moments are those of the returned (resampled) particles and weights (tracker.py:350-354)
+    for p in range(2):
+        for t in range(6):
+            m = np.average(back.particles[p, t], weights=back.weights[p, t], axis=0)
+            assert np.max(np.abs(m - back.means[p, t]) / np.maximum(np.abs(m), 1e-3)) < 1e-11
+            s = np.sqrt(np.average((back.particles[p, t] - m) ** 2, weights=back.weights[p, t], axis=0))
+            assert np.allclose(s, back.sigmas[p, t], rtol=1e-7, atol=1e-12)
+    reduced = tracker.track(models, tile_size=scene.tile_size, reduce_particles=lambda ps, ws: ps.shape + ws.shape)
+    assert reduced.particles is None and reduced.reduced == [(6, 400, 6, 6, 400)] * 2
+    assert tracker.particles.shape == (400, 6) and tracker.templates[0]["tile"].shape == (15, 15)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_resampling_properties_at_scale(cuda, mode):
+    """Size-independent invariants of systematic resampling at N = 100 000 through the production kernel:
+    uniform weights -> identity; any weights -> sorted ancestors with |count_i - N w_i / W| < 1."""
+    import ctypes as C
+
+    import glimpse_b200 as gb
+    from glimpse_b200 import _lib
+    from glimpse_b200.session import Session
+
+    torch = cuda
+    N, P = 100000, 3
+    scene = synthetic.nadir_scene(seed=1, n_points=P, n_particles=N, n_frames=3, imgsz=(320, 240), margin_px=100)
+    observers, models = synthetic.build(scene, gb)
+    tracker = gb.Tracker(observers, seed=7, mode=mode)
+    index = np.array([[0], [1], [2]], dtype=np.int32)
+    s = Session(tracker, models, index, np.ones(2), scene.tile_size, np.ones((P, 1), dtype=bool))
+    s.init(0)
+    rng = np.random.RandomState(3)
+    w = np.ones((P, N))
+    w[1] = rng.rand(N) ** 6
+    w[2] = 1e-300
+    w[2, 77] = 1.0  # degenerate: one particle takes everything
+    fw = torch.as_tensor(w).to(s.device)
+    idx = torch.full((P, N), -1, dtype=torch.int32, device=s.device)
+    io = _lib.gb_stage_io()
+    io.force_weights, io.dump_indices = fw.data_ptr(), idx.data_ptr()
+    s.step(1, io)
+    torch.cuda.synchronize()
+    assert (s.buf["status"].cpu().numpy() == 0).all()
+    got = idx.cpu().numpy()
+    np.testing.assert_array_equal(got[0], np.arange(N))
+    assert np.all(np.diff(got[1]) >= 0) and got[1].min() >= 0 and got[1].max() < N
+    counts = np.bincount(got[1], minlength=N)
+    assert np.all(np.abs(counts - N * w[1] / w[1].sum()) < 1.0 + 1e-6)
+    assert np.all(got[2] == 77)
+    # the state written for the next step is the gathered one
+    state = (s.buf["state_b"] if 1 & 1 else s.buf["state_a"]).cpu().numpy()
+    assert np.all(state[2] == state[2][:, :1])
