@@ -258,16 +258,22 @@ def run_gpu_arm(args):
 
     def one_track(events=None):
         session.buf["status"].zero_()
-        session.init(0)
-        for t in range(1, T):
-            if events is not None:
+        if args.per_step_events:
+            session.init(0)
+            for t in range(1, T):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 session.step(t)
                 b.record()
+                if events is not None:
+                    events.append((a, b))
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            session.run()  # gb_track: every update of every point, asynchronously
+            b.record()
+            if events is not None:
                 events.append((a, b))
-            else:
-                session.step(t)
         if dist is not None:
             dist.all_gather_into_tensor(gathered[0], session.buf["means"])
             dist.all_gather_into_tensor(gathered[1], session.buf["sig"])
@@ -287,12 +293,15 @@ def run_gpu_arm(args):
     clocks = sampler.stop()
     dev_ms = max_over_ranks(start.elapsed_time(end)) / args.steps
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))
+    if not args.per_step_events:
+        kernel_ms /= (T - 1)  # gb_track = init + templates + (T - 1) updates; the updates are > 99 % of it
     status = session.buf["status"].cpu().numpy()
     session.launches = 0
     stats_out = session.fetch()
     failed = int((status != 0).sum())
     value = world * P * N * T / (dev_ms / 1e3)
-    per_update = 6 if args.mode == "stream" else 1
+    nbatch = -(-P // max(1, session.stats["plan"].get("stream_batch", P) or P)) if args.mode == "stream" else 1
+    per_update = 6 * nbatch if args.mode == "stream" else 1
     launches_per_step = 2 + per_update * (T - 1)  # k_init + k_template + (T - 1) updates
     peak, peak_src = hbm_peak()
     achieved = ALGORITHMIC_BYTES_PER_UPDATE * P * N / (kernel_ms / 1e3) / 1e9
@@ -369,6 +378,7 @@ def main():
     ap.add_argument("--mode", default="stream", choices=["stream", "fused"])
     ap.add_argument("--small", action="store_true", help="tiny variant for smoke-testing the script (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--per-step-events", action="store_true", help="drive the updates one gb_track_step at a time with CUDA events around each")
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (profiling only; not a bench value)")
     ap.add_argument("--frames", type=int, default=0, help="override frame count (profiling only; not a bench value)")
     args = ap.parse_args()

@@ -63,7 +63,7 @@ class gb_plan(C.Structure):
         ("smem_bytes", C.c_int32), ("tile_bytes", C.c_int32), ("max_template", C.c_int32), ("n_slabs", C.c_int32),
         ("slab_bytes", C.c_int64), ("particle_scratch_bytes", C.c_int64), ("scratch_bytes", C.c_int64),
         ("mode", C.c_int32), ("stream_block", C.c_int32), ("stream_nblk", C.c_int32), ("n_observers", C.c_int32),
-        ("surf_bytes", C.c_int64),
+        ("surf_bytes", C.c_int64), ("stream_batch", C.c_int32), ("stream_slots", C.c_int32),
     ]
 
 

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -96,6 +97,7 @@ struct StepParams {
   char* s_surf;      // [P][O] surface regions of surf_bytes each (Hermite array first)
   int64_t surf_bytes;
   int s_block, s_nblk;
+  int64_t p0, pb;    // batch of points handled by this launch
 };
 
 __device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
@@ -1053,6 +1055,7 @@ static int grid_for(int64_t n, int threads) {
   return (int)g;
 }
 
+static constexpr int kMaxSlots = 8;   // side streams / scratch slots of GB_MODE_STREAM
 static constexpr int kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 static constexpr int kHeaderBytes = (int)((sizeof(SmemHeader) + 15) / 16 * 16);
 
@@ -1145,7 +1148,8 @@ static int check_desc(const gb_track_desc& d) {
     return fail(GB_E_INVALID, "supplied-draw mode needs init_normals, step_normals and uniforms%s");
   if (d.plan.cluster < 1 || d.plan.cluster > GB_MAX_CLUSTER || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
     return fail(GB_E_INVALID, "invalid launch plan (use gb_step_plan)%s");
-  if (d.plan.mode == GB_MODE_STREAM && (d.plan.n_observers != d.O || d.plan.stream_nblk < 1 || d.plan.surf_bytes <= 0))
+  if (d.plan.mode == GB_MODE_STREAM && (d.plan.n_observers != d.O || d.plan.stream_nblk < 1 || d.plan.surf_bytes <= 0 ||
+                                        d.plan.stream_batch < 1 || d.plan.stream_slots < 1 || d.plan.stream_slots > kMaxSlots))
     return fail(GB_E_INVALID, "streaming plan does not match the descriptor (use gb_step_plan)%s");
   if (d.plan.scratch_bytes > 0 && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
   if ((int64_t)d.plan.cluster * d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
@@ -1176,7 +1180,8 @@ struct StreamLayout {
   int64_t ev, uv, w, bsum, pm, ibox, pflags, act, meta, surf, total;
 };
 
-static StreamLayout stream_layout(int64_t P, int64_t N, int64_t O, int64_t nblk, int64_t surf_bytes) {
+// Layout of one batch slot of `B` points.
+static StreamLayout stream_layout(int64_t B, int64_t N, int64_t O, int64_t nblk, int64_t surf_bytes) {
   StreamLayout L;
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
@@ -1184,63 +1189,137 @@ static StreamLayout stream_layout(int64_t P, int64_t N, int64_t O, int64_t nblk,
     off += (bytes + 255) / 256 * 256;
     return at;
   };
-  L.ev = take(P * 6 * N * 8);
-  L.uv = take(P * O * 2 * N * 8);
-  L.w = take(P * N * 8);
-  L.bsum = take(P * nblk * 8);
-  L.pm = take(P * nblk * 28 * 8);
-  L.ibox = take(P * O * 5 * 4);
-  L.pflags = take(P * 4);
-  L.act = take(P);
-  L.meta = take(P * O * 8 * 4);
-  L.surf = take(P * O * surf_bytes);
+  L.ev = take(B * 6 * N * 8);
+  L.uv = take(B * O * 2 * N * 8);
+  L.w = take(B * N * 8);
+  L.bsum = take(B * nblk * 8);
+  L.pm = take(B * nblk * 28 * 8);
+  L.ibox = take(B * O * 5 * 4);
+  L.pflags = take(B * 4);
+  L.act = take(B);
+  L.meta = take(B * O * 8 * 4);
+  L.surf = take(B * O * surf_bytes);
   L.total = off;
   return L;
 }
 
-static void stream_bind(const gb_track_desc& d, StepParams& prm) {
+// Point the kernel's scratch arrays at batch slot `slot` for the points [p0, p0 + pb).  The kernels index
+// them with the GLOBAL point number, so every base is shifted back by p0 elements.
+static void stream_bind(const gb_track_desc& d, StepParams& prm, int slot, int64_t p0, int64_t pb) {
   const gb_plan& pl = d.plan;
-  const StreamLayout L = stream_layout(d.P, d.N, d.O, pl.stream_nblk, pl.surf_bytes);
-  char* base = reinterpret_cast<char*>(d.scratch);
-  prm.s_ev = reinterpret_cast<double*>(base + L.ev);
-  prm.s_uv = reinterpret_cast<double*>(base + L.uv);
-  prm.s_w = reinterpret_cast<double*>(base + L.w);
-  prm.s_bsum = reinterpret_cast<double*>(base + L.bsum);
-  prm.s_pm = reinterpret_cast<double*>(base + L.pm);
-  prm.s_ibox = reinterpret_cast<int*>(base + L.ibox);
-  prm.s_pflags = reinterpret_cast<int*>(base + L.pflags);
-  prm.s_act = reinterpret_cast<uint8_t*>(base + L.act);
-  prm.s_meta = reinterpret_cast<int*>(base + L.meta);
-  prm.s_surf = base + L.surf;
+  const int64_t N = d.N, O = d.O, nblk = pl.stream_nblk;
+  const StreamLayout L = stream_layout(pl.stream_batch, N, O, nblk, pl.surf_bytes);
+  char* base = reinterpret_cast<char*>(d.scratch) + (int64_t)slot * L.total;
+  prm.s_ev = reinterpret_cast<double*>(base + L.ev) - p0 * 6 * N;
+  prm.s_uv = reinterpret_cast<double*>(base + L.uv) - p0 * O * 2 * N;
+  prm.s_w = reinterpret_cast<double*>(base + L.w) - p0 * N;
+  prm.s_bsum = reinterpret_cast<double*>(base + L.bsum) - p0 * nblk;
+  prm.s_pm = reinterpret_cast<double*>(base + L.pm) - p0 * nblk * 28;
+  prm.s_ibox = reinterpret_cast<int*>(base + L.ibox) - p0 * O * 5;
+  prm.s_pflags = reinterpret_cast<int*>(base + L.pflags) - p0;
+  prm.s_act = reinterpret_cast<uint8_t*>(base + L.act) - p0;
+  prm.s_meta = reinterpret_cast<int*>(base + L.meta) - p0 * O * 8;
+  prm.s_surf = base + L.surf - p0 * O * pl.surf_bytes;
   prm.surf_bytes = pl.surf_bytes;
   prm.s_block = pl.stream_block;
   prm.s_nblk = pl.stream_nblk;
+  prm.p0 = p0;
+  prm.pb = pb;
 }
 
 static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2_surface (3 CTAs per SM)
 
+// Side streams on which batches of points advance independently (points never interact).  One pool per device.
+struct StreamPool {
+  cudaStream_t side[kMaxSlots] = {};
+  cudaEvent_t fork = nullptr, join[kMaxSlots] = {};
+  bool ready = false;
+};
+static StreamPool g_pools[16];
+static std::mutex g_pool_mutex;
+
+static int get_pool(StreamPool** out) {
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(GB_E_INVALID, "device index out of range%s");
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  StreamPool& pool = g_pools[dev];
+  if (!pool.ready) {
+    for (int k = 0; k < kMaxSlots; ++k) {
+      GB_CUDA(cudaStreamCreateWithFlags(&pool.side[k], cudaStreamNonBlocking));
+      GB_CUDA(cudaEventCreateWithFlags(&pool.join[k], cudaEventDisableTiming));
+    }
+    GB_CUDA(cudaEventCreateWithFlags(&pool.fork, cudaEventDisableTiming));
+    pool.ready = true;
+  }
+  *out = &pool;
+  return GB_OK;
+}
+
 template <bool COV>
-static int launch_stream_step(const StepParams& prm, cudaStream_t stream, int64_t* launches) {
-  const unsigned nb = (unsigned)(prm.P * prm.s_nblk);
-  k_s0_reset<<<grid_for(prm.P * prm.O * 5, 256), 256, 0, stream>>>(prm);
+static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
+  const unsigned nb = (unsigned)(prm.pb * prm.s_nblk);
+  k_s0_reset<<<grid_for(prm.pb * prm.O * 5, 256), 256, 0, stream>>>(prm);
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
-  GB_CUDA(cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem));
-  k_s2_surface<<<(unsigned)(prm.P * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
+  k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
   k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
-  k_s5_finalize<COV><<<(unsigned)((prm.P + 3) / 4), 128, 0, stream>>>(prm);
+  k_s5_finalize<COV><<<(unsigned)((prm.pb + 3) / 4), 128, 0, stream>>>(prm);
   GB_CUDA(cudaGetLastError());
-  if (launches) *launches += 6;
+  return GB_OK;
+}
+
+// One update of all points in GB_MODE_STREAM: the points are cut into batches whose intermediates fit the
+// L2 cache; batch b runs on side stream b % slots with scratch slot b % slots.  `fork`: make the side streams
+// wait for everything enqueued on `stream` so far; `join`: make `stream` wait for the side streams.
+static int launch_stream_update(const gb_track_desc& d, StepParams& prm, cudaStream_t stream, bool fork, bool join,
+                                int64_t* launches) {
+  static std::once_flag attr_once[16];
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  cudaError_t aerr = cudaSuccess;
+  std::call_once(attr_once[dev & 15], [&]() {
+    aerr = cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem);
+  });
+  if (aerr != cudaSuccess) return fail(GB_E_CUDA, "k_s2_surface attributes: %s", cudaGetErrorString(aerr));
+  const bool cov = d.covariances != nullptr;
+  const int slots = d.plan.stream_slots;
+  const int64_t batch = d.plan.stream_batch;
+  const int64_t nbatch = (d.P + batch - 1) / batch;
+  StreamPool* pool = nullptr;
+  int rc = get_pool(&pool);
+  if (rc) return rc;
+  const int used = (int)(nbatch < slots ? nbatch : slots);
+  if (fork) {
+    GB_CUDA(cudaEventRecord(pool->fork, stream));
+    for (int k = 0; k < used; ++k) GB_CUDA(cudaStreamWaitEvent(pool->side[k], pool->fork, 0));
+  }
+  if (d.image_events_host)
+    for (int o = 0; o < d.O; ++o)
+      if (prm.img[o] >= 0 && d.image_events_host[prm.img[o]])
+        for (int k = 0; k < used; ++k)
+          GB_CUDA(cudaStreamWaitEvent(pool->side[k], (cudaEvent_t)d.image_events_host[prm.img[o]], 0));
+  for (int64_t b = 0; b < nbatch; ++b) {
+    const int slot = (int)(b % slots);
+    const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
+    stream_bind(d, prm, slot, p0, pb);
+    rc = cov ? launch_stream_batch<true>(prm, pool->side[slot]) : launch_stream_batch<false>(prm, pool->side[slot]);
+    if (rc) return rc;
+    if (launches) *launches += 6;
+  }
+  if (join) {
+    for (int k = 0; k < used; ++k) {
+      GB_CUDA(cudaEventRecord(pool->join[k], pool->side[k]));
+      GB_CUDA(cudaStreamWaitEvent(stream, pool->join[k], 0));
+    }
+  }
   return GB_OK;
 }
 
 // One update for all points in the organisation the plan asks for.
-static int launch_update(const gb_track_desc& d, StepParams& prm, cudaStream_t stream, int64_t* launches) {
+static int launch_update(const gb_track_desc& d, StepParams& prm, cudaStream_t stream, bool fork, bool join, int64_t* launches) {
+  if (d.plan.mode == GB_MODE_STREAM) return launch_stream_update(d, prm, stream, fork, join, launches);
   const bool cov = d.covariances != nullptr;
-  if (d.plan.mode == GB_MODE_STREAM) {
-    stream_bind(d, prm);
-    return cov ? launch_stream_step<true>(prm, stream, launches) : launch_stream_step<false>(prm, stream, launches);
-  }
   if (launches) *launches += 1;
   return cov ? launch_step<true>(prm, d.plan, stream) : launch_step<false>(prm, d.plan, stream);
 }
@@ -1353,7 +1432,20 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
     // surface regions sized for search windows up to 191 px larger than the template
     plan->surf_bytes = (tile_bytes_needed(tile_w + 191, tile_h + 191, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
-    plan->scratch_bytes = stream_layout(npoints, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
+    // Points are independent: they are cut into `slots` batches that advance on their own side streams, so the
+    // low-occupancy tails of one batch's kernels (a few very large search windows) overlap the other batches' work.
+    // (Batches small enough to keep the intermediates L2-resident were measured slower: launch-bound.)
+    int slots = 4;
+    int64_t batch = (npoints + slots - 1) / slots;
+    if (const char* e = getenv("GB_STREAM_BATCH")) batch = atoll(e);   // tuning overrides
+    if (const char* e = getenv("GB_STREAM_SLOTS")) slots = atoi(e);
+    if (batch < 1) batch = 1;
+    if (batch > npoints) batch = npoints;
+    if (slots < 1) slots = 1;
+    if (slots > kMaxSlots) slots = kMaxSlots;
+    plan->stream_batch = (int32_t)batch;
+    plan->stream_slots = slots;
+    plan->scratch_bytes = plan->stream_slots * stream_layout(batch, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
     return GB_OK;
   }
   plan->n_slabs = 160;
@@ -1412,7 +1504,7 @@ int gb_track_step(const gb_track_desc* d, int32_t t, const gb_stage_io* io, void
   StepParams prm;
   fill_params(*d, t, prm);
   if (io) prm.io = *io;
-  return launch_update(*d, prm, (cudaStream_t)stream, nullptr);
+  return launch_update(*d, prm, (cudaStream_t)stream, true, true, nullptr);
 }
 
 int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
@@ -1427,6 +1519,24 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   // per-time work flags from the host copies (tracker.py:321-347)
   StepParams probe;
   fill_params(*d, 0, probe);
+  // In GB_MODE_STREAM the updates run on side streams that advance batch by batch without meeting; the
+  // caller's stream forks them after its own kernels (init, templates, in-place evolve) and joins them
+  // before the next such kernel and at the end.
+  bool forked = false, need_fork = true;
+  const bool streaming = d->plan.mode == GB_MODE_STREAM;
+  auto join_sides = [&]() -> int {
+    if (!streaming || !forked) return GB_OK;
+    StreamPool* pool = nullptr;
+    int rcj = get_pool(&pool);
+    if (rcj) return rcj;
+    for (int k = 0; k < d->plan.stream_slots; ++k) {
+      GB_CUDA(cudaEventRecord(pool->join[k], pool->side[k]));
+      GB_CUDA(cudaStreamWaitEvent(stream, pool->join[k], 0));
+    }
+    forked = false;
+    need_fork = true;
+    return GB_OK;
+  };
   for (int t = 0; t < d->T; ++t) {
     bool any_init = false, any_step = false, any_tmpl = false, staggered = false;
     for (int64_t p = 0; p < d->P; ++p) {
@@ -1443,10 +1553,13 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
     if (!any_init && !any_step) continue;
     StepParams prm;
     fill_params(*d, t, prm);
-    if (d->image_events_host)
-      for (int o = 0; o < d->O; ++o)
-        if (prm.img[o] >= 0 && d->image_events_host[prm.img[o]])
-          GB_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)d->image_events_host[prm.img[o]], 0));
+    if (any_init || staggered || any_tmpl) {
+      if ((rc = join_sides())) return rc;
+      if (d->image_events_host)
+        for (int o = 0; o < d->O; ++o)
+          if (prm.img[o] >= 0 && d->image_events_host[prm.img[o]])
+            GB_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)d->image_events_host[prm.img[o]], 0));
+    }
     if (any_init) {
       if ((rc = launch_init(prm, cov, stream))) return rc;
       ++launches;
@@ -1466,9 +1579,16 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
       ++launches;
     }
     if (any_step) {
-      if ((rc = launch_update(*d, prm, stream, &launches))) return rc;
+      if (!streaming && d->image_events_host)
+        for (int o = 0; o < d->O; ++o)
+          if (prm.img[o] >= 0 && d->image_events_host[prm.img[o]])
+            GB_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)d->image_events_host[prm.img[o]], 0));
+      if ((rc = launch_update(*d, prm, stream, need_fork, false, &launches))) return rc;
+      forked = true;
+      need_fork = false;
     }
   }
+  if ((rc = join_sides())) return rc;
   if (launches_out) *launches_out = launches;
   return GB_OK;
 }

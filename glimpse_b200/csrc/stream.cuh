@@ -23,10 +23,12 @@ __device__ __forceinline__ bool stream_point_active(const StepParams& prm, int64
 }
 
 __global__ void k_s0_reset(const __grid_constant__ StepParams prm) {
-  const int64_t n = prm.P * prm.O * 5;
+  // scratch arrays are indexed by the global point number; the host pre-shifts their base pointers so
+  // that the batch [p0, p0 + pb) lands in the batch's slot
+  const int64_t lo5 = prm.p0 * prm.O * 5, n = prm.pb * prm.O * 5;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    prm.s_ibox[i] = (i % 5 == 4) ? 0 : 0x7fffffff;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.P; i += (int64_t)gridDim.x * blockDim.x) {
+    prm.s_ibox[lo5 + i] = (i % 5 == 4) ? 0 : 0x7fffffff;
+  for (int64_t i = prm.p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.p0 + prm.pb; i += (int64_t)gridDim.x * blockDim.x) {
     prm.s_pflags[i] = 0;
     const bool active = prm.status[i] == 0 && prm.t > prm.first[i] && prm.t <= prm.last[i];
     const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
@@ -61,8 +63,8 @@ __device__ __forceinline__ int transposed_index(int lane) {
 __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ int s_box[GB_MAX_OBS][5];
-  const int64_t p = blockIdx.x / prm.s_nblk;
-  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
   if (!stream_point_active(prm, p)) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = (int)prm.N, O = prm.O, t = prm.t;
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __g
     if (vec) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const double2 x = *reinterpret_cast<const double2*>(sin_ + c * (int64_t)N + ia);
+        const double2 x = __ldcs(reinterpret_cast<const double2*>(sin_ + c * (int64_t)N + ia));  // read once: evict first
         s[0][c] = x.x;
         s[1][c] = x.y;
       }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_mm[GB_S2_THREADS / 32][4];
   __shared__ int s_box[4];
-  const int64_t po = blockIdx.x;
+  const int64_t po = prm.p0 * prm.O + blockIdx.x;
   const int64_t p = po / prm.O;
   const int o = (int)(po - p * prm.O);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
@@ -359,8 +361,8 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   __shared__ gb_motion s_motion;
   __shared__ SurfaceRef s_ref[GB_MAX_OBS];
   __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
-  const int64_t p = blockIdx.x / prm.s_nblk;
-  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
   const int act = prm.s_act[p];
   if (!(act & GB_ACT_ACTIVE) || prm.s_pflags[p] != 0) return;
   const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
@@ -489,8 +491,8 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __gr
   __shared__ double s_w[CAP];
   __shared__ int s_end[CAP];
   __shared__ int s_j0;
-  const int64_t p = blockIdx.x / prm.s_nblk;
-  const int b = (int)(blockIdx.x - p * prm.s_nblk);
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
   if (!stream_point_active(prm, p) || prm.s_pflags[p] != 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
   const int N = (int)prm.N;
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __gr
     for (int c = 0; c < 6; ++c) s[c] = ev[c * (int64_t)N + lo];
     const double wj = s_w[lo];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
+    for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);  // next read is a whole update away
     mom.accumulate(wj, s, ref);
     if (wst) wst[j] = wj;
     if (outp) {
@@ -599,9 +601,9 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __gr
 // s5: one warp per point: lane k sums moment k over the CTAs in order, lane 0 finalises.
 template <bool COV>
 __global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {
-  const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = prm.p0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (p >= prm.P || !stream_point_active(prm, p)) return;
+  if (p >= prm.p0 + prm.pb || !stream_point_active(prm, p)) return;
   const int t = prm.t;
   const int f = prm.s_pflags[p];
   if (f) {

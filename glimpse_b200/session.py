@@ -62,7 +62,15 @@ class _Adopted:
 
     def __init__(self, model, kind):
         self._m, self._kind = model, kind
+        self.kind = kind
         self.dem, self.dem_sigma, self.n, self.time_unit = model.dem, model.dem_sigma, model.n, model.time_unit
+        self.xy, self.xy_sigma = model.xy, model.xy_sigma
+
+    def _velocity(self):
+        m = self._m
+        if self._kind == _lib.GB_MOTION_CARTESIAN:
+            return m.vxyz, m.vxyz_sigma, m.axyz, m.axyz_sigma
+        return m.vrthz, m.vrthz_sigma, m.arthz, m.arthz_sigma
 
     def lower(self, dem_index, dem_sigma_index):
         from .motion import CartesianMotion, CylindricalMotion
@@ -233,34 +241,34 @@ class Session:
             copy_stream = tracker._copy_stream = torch.cuda.Stream(device=device)
         compute_stream = torch.cuda.current_stream(device)
         copy_stream.wait_stream(compute_stream)
-        for _, k in sorted(order):
-            o, i, img, _used = structs[k]
-            obs = tracker.observers[o]
-            use_cache = bool(getattr(obs, "cache", True))
-            array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
-            key = (o, i, id(array))
-            cached = tracker._frame_cache.get(key) if use_cache else None
-            if cached is None:
-                if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
-                    raise NotImplementedError("device frames must be uint8 with 1-4 bands")
-                arr = np.ascontiguousarray(array)
-                with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream):
+            for _, k in sorted(order):
+                o, i, img, _used = structs[k]
+                obs = tracker.observers[o]
+                use_cache = bool(getattr(obs, "cache", True))
+                array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
+                key = (o, i, id(array))
+                cached = tracker._frame_cache.get(key) if use_cache else None
+                if cached is None:
+                    if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
+                        raise NotImplementedError("device frames must be uint8 with 1-4 bands")
+                    arr = array if array.flags.c_contiguous else np.ascontiguousarray(array)
                     dev = torch.from_numpy(arr).to(device, non_blocking=True)
                     event = torch.cuda.Event()
                     event.record(copy_stream)
-                dev.record_stream(compute_stream)
-                self.h2d += arr.nbytes
-                cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
-                if use_cache:
-                    tracker._frame_cache[key] = cached
-            dev, w, h, pitch, nchan, event = cached
-            self.keep.append(dev)
-            self.keep_events.append(event)
-            g = out[k]
-            g.pixels = dev.data_ptr()
-            g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
-            g.cam = lower_camera(img.cam)
-            self.image_events[k] = event.cuda_event
+                    dev.record_stream(compute_stream)
+                    self.h2d += arr.nbytes
+                    cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
+                    if use_cache:
+                        tracker._frame_cache[key] = cached
+                dev, w, h, pitch, nchan, event = cached
+                self.keep.append(dev)
+                self.keep_events.append(event)
+                g = out[k]
+                g.pixels = dev.data_ptr()
+                g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
+                g.cam = lower_camera(img.cam)
+                self.image_events[k] = event.cuda_event
         self.images_host = (_lib.gb_image * len(out))(*out)
         images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
         self.h2d += images_dev.numel()
@@ -270,7 +278,16 @@ class Session:
         torch, device = self.torch, self.device
         rasters, table = {}, []
 
+        memo = {}
+
         def index_of(raster):
+            hit = memo.get(id(raster))
+            if hit is not None:
+                return hit
+            memo[id(raster)] = out = _index_of(raster)
+            return out
+
+        def _index_of(raster):
             if not (hasattr(raster, "array") and hasattr(raster, "xlim")):
                 raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
             arr = np.asarray(raster.array)
@@ -286,12 +303,23 @@ class Session:
                 self.keep.append(tensor)
             return rasters[key]
 
-        motions = []
-        for m in models:
-            m = adopt_model(m)
-            motions.append(m.lower(index_of(m.dem), index_of(m.dem_sigma)))
+        # gb_motion table as one structured array (field layout of include/glimpse_b200.h)
+        dt = np.dtype([("kind", "<i4"), ("dem", "<i4"), ("dem_sigma", "<i4"), ("pad_", "<i4"), ("xy", "<f8", 2),
+                       ("xy_sigma", "<f8", 2), ("v", "<f8", 3), ("v_sigma", "<f8", 3), ("a", "<f8", 3), ("a_sigma", "<f8", 3)])
+        assert dt.itemsize == C.sizeof(_lib.gb_motion)
+        table_m = np.zeros(len(models), dtype=dt)
+        adopted = [adopt_model(m) for m in models]
+        vel = [m._velocity() for m in adopted]
+        table_m["kind"] = [m.kind for m in adopted]
+        table_m["dem"] = [index_of(m.dem) for m in adopted]
+        table_m["dem_sigma"] = [index_of(m.dem_sigma) for m in adopted]
+        table_m["xy"] = np.array([m.xy for m in adopted], dtype=float)
+        xs = np.array([m.xy_sigma for m in adopted], dtype=float)
+        table_m["xy_sigma"] = xs if xs.ndim == 2 else xs[:, None]
+        for k, name in enumerate(("v", "v_sigma", "a", "a_sigma")):
+            table_m[name] = np.array([v[k] for v in vel], dtype=float)
         viewshed = index_of(self.tracker.viewshed) if self.tracker.viewshed is not None else -1
-        motion_dev = _struct_array_to_device(torch, motions, _lib.gb_motion, device)
+        motion_dev = torch.from_numpy(table_m.view(np.uint8).reshape(-1)).to(device)
         surf_dev = _struct_array_to_device(torch, table, _lib.gb_surface, device)
         self.h2d += motion_dev.numel() + surf_dev.numel()
         return motion_dev, surf_dev, len(table), viewshed

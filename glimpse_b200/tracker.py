@@ -201,19 +201,19 @@ class Tracker:
             local = self._gather(dist, local, ntracks, world)
 
         # materialise errors / warnings the way the reference reports them (tracker.py:358-368)
-        errors: List[Optional[BaseException]] = []
-        all_warnings: List[Optional[tuple]] = []
+        errors: List[Optional[BaseException]] = [None] * ntracks
+        all_warnings: List[Optional[tuple]] = [None] * ntracks
         status, status_time, flags = local["status"], local["status_time"], local["obs_flags"]
-        for p in range(ntracks):
-            err = None
-            limit = flags.shape[1]
-            if status[p] != 0:
-                cls, msg = _lib.GB_ST_MESSAGES[int(status[p])]
-                err = cls(f"{msg} (track {p}, time index {int(status_time[p])})")
-                limit = int(status_time[p])
-            errors.append(err)
-            caught = tuple(UserWarning(OUT_OF_FRAME_MESSAGE) for _ in np.argwhere(flags[p, :limit] == _lib.GB_OBS_OUT_OF_FRAME))
-            all_warnings.append(caught if caught else None)
+        for p in np.nonzero(status)[0]:
+            cls, msg = _lib.GB_ST_MESSAGES[int(status[p])]
+            errors[p] = cls(f"{msg} (track {p}, time index {int(status_time[p])})")
+        flagged = flags == _lib.GB_OBS_OUT_OF_FRAME
+        if flagged.any():
+            # warnings raised before a track failed are kept, later ones never happened in the reference
+            limit = np.where(status != 0, status_time, flags.shape[1])
+            flagged &= np.arange(flags.shape[1])[None, :, None] < limit[:, None, None]
+            for p in np.nonzero(flagged.any(axis=(1, 2)))[0]:
+                all_warnings[p] = tuple(UserWarning(OUT_OF_FRAME_MESSAGE) for _ in range(int(flagged[p].sum())))
         if raise_errors and errors and errors[0] is not None:
             raise errors[0]
         kwargs = dict(time_unit=time_unit, datetimes=datetimes, means=local["means"], tracker=self,

@@ -161,6 +161,8 @@ typedef struct gb_plan {
   int32_t stream_nblk;      /* GB_MODE_STREAM: CTAs per point */
   int32_t n_observers;
   int64_t surf_bytes;       /* GB_MODE_STREAM: bytes of the per-(point, observer) surface region */
+  int32_t stream_batch;     /* GB_MODE_STREAM: points per batch (intermediates of one batch stay L2-resident) */
+  int32_t stream_slots;     /* GB_MODE_STREAM: batches in flight (side streams / scratch slots) */
 } gb_plan;
 
 /* Size a launch plan for N particles per point, a w x h template, P points and O observers.
