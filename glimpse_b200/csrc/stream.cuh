@@ -60,7 +60,7 @@ __device__ __forceinline__ int transposed_index(int lane) {
 }
 
 // s1: two consecutive particles per thread (16-byte loads / stores), one CTA = s_block particles of a point.
-__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s1_propagate(const __grid_constant__ StepParams prm) {
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ int s_box[GB_MAX_OBS][5];
   const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
 // to the moment partials (sum over children == sum over parents weighted by their child counts).
 #define GB_S4_PPT 8
 template <bool COV>
-__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 3) k_s4_resample(const __grid_constant__ StepParams prm) {
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __grid_constant__ StepParams prm) {
   constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4_PPT, CAP = PPT * GB_SBLOCK_THREADS;
   __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
   __shared__ double s_pref[6];

@@ -83,6 +83,9 @@ class Raster:
         shape = self.array.shape if self.array.ndim == 2 else (1, 1)
         self.xlim = self._limits(x, shape[1])
         self.ylim = self._limits(y, shape[0])
+        # identity used to share one device surface between equal constant rasters
+        self._const_key = (("const", float(self.array.flat[0]), tuple(self.xlim.tolist()), tuple(self.ylim.tolist()))
+                           if self.constant else None)
 
     @staticmethod
     def _limits(value, n) -> np.ndarray:

@@ -124,8 +124,9 @@ class Session:
             mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[getattr(tracker, "mode", "stream")]
             _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, O, int(tracker.cluster), mode, C.byref(self.plan)))
             self.h2d = 0
-            images_dev, self.offsets = self._upload_frames()
+            # small tables first: once the frame uploads are queued they keep the copy engine busy for tens of ms
             motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)
+            images_dev, self.offsets = self._upload_frames()
             self.first, self.last = point_span(self.image_index, observer_mask)
             self.tmpl_frame = np.array([int(np.argmax(self.image_index[:, o] >= 0)) if (self.image_index[:, o] >= 0).any() else -1
                                         for o in range(O)])
@@ -212,8 +213,21 @@ class Session:
             d.status, d.status_time = ptr(b["status"]), ptr(b["status_time"])
             d.obs_flags, d.window_stats = ptr(b["obs_flags"]), ptr(b["window"])
             d.plan = self.plan
+            self._start_frame_copies()
         self.launches = 0
         self.stats: dict = {}
+
+    def _start_frame_copies(self) -> None:
+        """Queue the frame uploads (in time order) on the copy stream, each followed by its event.  Called after
+        every small table is on the device: the big copies keep the copy engine busy for tens of milliseconds."""
+        torch, copy_stream = self.torch, self.tracker._copy_stream
+        with torch.cuda.stream(copy_stream):
+            for dev, arr, event in self._pending_copies:
+                dev.copy_(torch.from_numpy(arr), non_blocking=True)
+                event.record(copy_stream)
+        for k, event in self._pending_events:
+            self.image_events[k] = event.cuda_event
+        self._pending_copies = []
 
     # ---------------------------------------------------------------- uploads
     def _upload_frames(self):
@@ -236,6 +250,8 @@ class Session:
         out = [_lib.gb_image() for _ in structs]
         self.image_events = (C.c_void_p * len(structs))()
         self.keep_events = []
+        self._pending_copies = []
+        self._pending_events = []
         copy_stream = getattr(tracker, "_copy_stream", None)
         if copy_stream is None or copy_stream.device != device:
             copy_stream = tracker._copy_stream = torch.cuda.Stream(device=device)
@@ -253,9 +269,9 @@ class Session:
                     if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
                         raise NotImplementedError("device frames must be uint8 with 1-4 bands")
                     arr = array if array.flags.c_contiguous else np.ascontiguousarray(array)
-                    dev = torch.from_numpy(arr).to(device, non_blocking=True)
+                    dev = torch.empty(arr.shape, dtype=torch.uint8, device=device)  # allocated on the copy stream
                     event = torch.cuda.Event()
-                    event.record(copy_stream)
+                    self._pending_copies.append((dev, arr, event))
                     dev.record_stream(compute_stream)
                     self.h2d += arr.nbytes
                     cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
@@ -268,7 +284,7 @@ class Session:
                 g.pixels = dev.data_ptr()
                 g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
                 g.cam = lower_camera(img.cam)
-                self.image_events[k] = event.cuda_event
+                self._pending_events.append((k, event))
         self.images_host = (_lib.gb_image * len(out))(*out)
         images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
         self.h2d += images_dev.numel()
@@ -288,6 +304,9 @@ class Session:
             return out
 
         def _index_of(raster):
+            key = getattr(raster, "_const_key", None)
+            if key is not None and key in rasters:
+                return rasters[key]
             if not (hasattr(raster, "array") and hasattr(raster, "xlim")):
                 raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
             arr = np.asarray(raster.array)
