@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "camera.cuh"
 #include "common.cuh"
@@ -85,7 +86,10 @@ struct StepParams {
   int32_t* window_stats;
   gb_stage_io io;
   // GB_MODE_STREAM buffers (carved from `scratch` by the host)
-  double* s_ev;      // [P][6][N]   particles after the motion step
+  double* s_ev;      // [P][6][N]   particles after the motion step (this time's parity)
+  double* s_ev_next; // [P][6][N]   pipelined flow: particles advanced to the next time (other parity)
+  double* s_ref;     // [P][6]      pipelined flow: fixed origin of the moment sums
+  int* s_pflags_next; // [P]        pipelined flow: flags of the next time
   double* s_uv;      // [P][O][2][N] projected particles
   double* s_w;       // [P][N]      weights
   double* s_bsum;    // [P][nblk]   per-CTA weight totals
@@ -97,7 +101,15 @@ struct StepParams {
   char* s_surf;      // [P][O] surface regions of surf_bytes each (Hermite array first)
   int64_t surf_bytes;
   int s_block, s_nblk;
+  int tmpl_from_ev, pad3_;  // k_template: staggered templates read the evolved particles from s_ev (pipelined flow)
   int64_t p0, pb;    // batch of points handled by this launch
+};
+
+// What k_s4p needs to know about the NEXT time to advance the particles to it.
+struct NextParams {
+  double tau, tau2;
+  int img[GB_MAX_OBS];
+  CamK cam[GB_MAX_OBS];
 };
 
 __device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
@@ -319,6 +331,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_init(const __grid_constant__ Ste
     ref[4] = m.v[1];
   }
   ref[5] = m.v[2];
+  if (prm.s_ref && threadIdx.x < 6) prm.s_ref[p * 6 + threadIdx.x] = ref[threadIdx.x];
   Moments<COV> mom;
   mom.clear();
   uint32_t flags = 0;
@@ -389,7 +402,8 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   const int64_t N = prm.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // particles as they are when the template is cut: just initialised (t == first) or evolved in place
-  const double* state = state_buffer(prm, prm.first[p] == t ? t : t - 1) + p * 6 * N;
+  const double* state = prm.first[p] == t ? state_buffer(prm, t) + p * 6 * N
+                        : (prm.tmpl_from_ev ? prm.s_ev + p * 6 * N : state_buffer(prm, t - 1) + p * 6 * N);
   const double* wts = prm.weight_state ? prm.weight_state + p * N : nullptr;
   const double ref[3] = {state[0], state[N], state[2 * N]};
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1177,10 +1191,10 @@ static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t 
 }
 
 struct StreamLayout {
-  int64_t ev, uv, w, bsum, pm, ibox, pflags, act, meta, surf, total;
+  int64_t ev[2], uv, w, bsum, pm, ibox, pflags[2], act, meta, ref, surf, total;
 };
 
-// Layout of one batch slot of `B` points.
+// Scratch of GB_MODE_STREAM for `B` points.
 static StreamLayout stream_layout(int64_t B, int64_t N, int64_t O, int64_t nblk, int64_t surf_bytes) {
   StreamLayout L;
   int64_t off = 0;
@@ -1189,37 +1203,42 @@ static StreamLayout stream_layout(int64_t B, int64_t N, int64_t O, int64_t nblk,
     off += (bytes + 255) / 256 * 256;
     return at;
   };
-  L.ev = take(B * 6 * N * 8);
+  L.ev[0] = take(B * 6 * N * 8);
+  L.ev[1] = take(B * 6 * N * 8);
   L.uv = take(B * O * 2 * N * 8);
   L.w = take(B * N * 8);
   L.bsum = take(B * nblk * 8);
   L.pm = take(B * nblk * 28 * 8);
   L.ibox = take(B * O * 5 * 4);
-  L.pflags = take(B * 4);
+  L.pflags[0] = take(B * 4);
+  L.pflags[1] = take(B * 4);
   L.act = take(B);
   L.meta = take(B * O * 8 * 4);
+  L.ref = take(B * 6 * 8);
   L.surf = take(B * O * surf_bytes);
   L.total = off;
   return L;
 }
 
-// Point the kernel's scratch arrays at batch slot `slot` for the points [p0, p0 + pb).  The kernels index
-// them with the GLOBAL point number, so every base is shifted back by p0 elements.
-static void stream_bind(const gb_track_desc& d, StepParams& prm, int slot, int64_t p0, int64_t pb) {
+// Point the kernels at the scratch arrays (indexed by the global point number) for time parity `par`, and at
+// the batch of points [p0, p0 + pb).
+static void stream_bind(const gb_track_desc& d, StepParams& prm, int par, int64_t p0, int64_t pb) {
   const gb_plan& pl = d.plan;
-  const int64_t N = d.N, O = d.O, nblk = pl.stream_nblk;
-  const StreamLayout L = stream_layout(pl.stream_batch, N, O, nblk, pl.surf_bytes);
-  char* base = reinterpret_cast<char*>(d.scratch) + (int64_t)slot * L.total;
-  prm.s_ev = reinterpret_cast<double*>(base + L.ev) - p0 * 6 * N;
-  prm.s_uv = reinterpret_cast<double*>(base + L.uv) - p0 * O * 2 * N;
-  prm.s_w = reinterpret_cast<double*>(base + L.w) - p0 * N;
-  prm.s_bsum = reinterpret_cast<double*>(base + L.bsum) - p0 * nblk;
-  prm.s_pm = reinterpret_cast<double*>(base + L.pm) - p0 * nblk * 28;
-  prm.s_ibox = reinterpret_cast<int*>(base + L.ibox) - p0 * O * 5;
-  prm.s_pflags = reinterpret_cast<int*>(base + L.pflags) - p0;
-  prm.s_act = reinterpret_cast<uint8_t*>(base + L.act) - p0;
-  prm.s_meta = reinterpret_cast<int*>(base + L.meta) - p0 * O * 8;
-  prm.s_surf = base + L.surf - p0 * O * pl.surf_bytes;
+  const StreamLayout L = stream_layout(d.P, d.N, d.O, pl.stream_nblk, pl.surf_bytes);
+  char* base = reinterpret_cast<char*>(d.scratch);
+  prm.s_ev = reinterpret_cast<double*>(base + L.ev[par & 1]);
+  prm.s_ev_next = reinterpret_cast<double*>(base + L.ev[(par + 1) & 1]);
+  prm.s_uv = reinterpret_cast<double*>(base + L.uv);
+  prm.s_w = reinterpret_cast<double*>(base + L.w);
+  prm.s_bsum = reinterpret_cast<double*>(base + L.bsum);
+  prm.s_pm = reinterpret_cast<double*>(base + L.pm);
+  prm.s_ibox = reinterpret_cast<int*>(base + L.ibox);
+  prm.s_pflags = reinterpret_cast<int*>(base + L.pflags[par & 1]);
+  prm.s_pflags_next = reinterpret_cast<int*>(base + L.pflags[(par + 1) & 1]);
+  prm.s_act = reinterpret_cast<uint8_t*>(base + L.act);
+  prm.s_meta = reinterpret_cast<int*>(base + L.meta);
+  prm.s_ref = reinterpret_cast<double*>(base + L.ref);
+  prm.s_surf = base + L.surf;
   prm.surf_bytes = pl.surf_bytes;
   prm.s_block = pl.stream_block;
   prm.s_nblk = pl.stream_nblk;
@@ -1231,6 +1250,7 @@ static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2
 
 // Side streams on which batches of points advance independently (points never interact).  One pool per device.
 struct StreamPool {
+  std::mutex busy;  // one streaming call at a time per device: the fork / join events are shared
   cudaStream_t side[kMaxSlots] = {};
   cudaEvent_t fork = nullptr, join[kMaxSlots] = {};
   bool ready = false;
@@ -1290,6 +1310,7 @@ static int launch_stream_update(const gb_track_desc& d, StepParams& prm, cudaStr
   int rc = get_pool(&pool);
   if (rc) return rc;
   const int used = (int)(nbatch < slots ? nbatch : slots);
+  std::lock_guard<std::mutex> guard(pool->busy);
   if (fork) {
     GB_CUDA(cudaEventRecord(pool->fork, stream));
     for (int k = 0; k < used; ++k) GB_CUDA(cudaStreamWaitEvent(pool->side[k], pool->fork, 0));
@@ -1302,7 +1323,7 @@ static int launch_stream_update(const gb_track_desc& d, StepParams& prm, cudaStr
   for (int64_t b = 0; b < nbatch; ++b) {
     const int slot = (int)(b % slots);
     const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
-    stream_bind(d, prm, slot, p0, pb);
+    stream_bind(d, prm, prm.t, p0, pb);
     rc = cov ? launch_stream_batch<true>(prm, pool->side[slot]) : launch_stream_batch<false>(prm, pool->side[slot]);
     if (rc) return rc;
     if (launches) *launches += 6;
@@ -1314,6 +1335,144 @@ static int launch_stream_update(const gb_track_desc& d, StepParams& prm, cudaStr
     }
   }
   return GB_OK;
+}
+
+static int launch_init(const StepParams& prm, bool cov, cudaStream_t stream);
+static int launch_template(const StepParams& prm, cudaStream_t stream);
+
+// gb_track in GB_MODE_STREAM: the pipelined flow of stream.cuh.  Points are cut into `slots` batches that
+// advance on their own side streams without meeting; the caller's stream runs the kernels that need all
+// batches to be at the same time (first-frame initialisation, template construction) between a join and a fork.
+static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t* launches) {
+  static std::once_flag attr_once[16];
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  cudaError_t aerr = cudaSuccess;
+  std::call_once(attr_once[dev & 15], [&]() {
+    aerr = cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem);
+  });
+  if (aerr != cudaSuccess) return fail(GB_E_CUDA, "k_s2_surface attributes: %s", cudaGetErrorString(aerr));
+  const bool cov = d.covariances != nullptr;
+  const int slots = d.plan.stream_slots;
+  const int64_t batch = d.plan.stream_batch;
+  const int64_t nbatch = (d.P + batch - 1) / batch;
+  const int used = (int)(nbatch < slots ? nbatch : slots);
+  StreamPool* pool = nullptr;
+  int rc = get_pool(&pool);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> guard(pool->busy);
+  StepParams probe;
+  fill_params(d, 0, probe);
+  // what happens at each time (host copies of first / last / mask)
+  const int T = d.T;
+  std::vector<uint8_t> has_init(T, 0), has_tmpl(T, 0), has_update(T, 0), has_prop(T, 0);
+  bool staggered_any = false;
+  for (int64_t p = 0; p < d.P; ++p) {
+    const int f = d.first_host[p], l = d.last_host[p];
+    if (f < 0 || f >= T || l < f) continue;
+    has_init[f] = 1;
+    for (int t = f; t <= l && t < T; ++t) {
+      if (t > f) has_update[t] = 1;
+      if (t < l) has_prop[t] = 1;
+    }
+    for (int o = 0; o < d.O; ++o) {
+      const int tf = probe.tmpl_frame[o];
+      if (tf >= f && tf <= l && d.mask_host[p * d.O + o]) {
+        has_tmpl[tf] = 1;
+        if (tf > f) staggered_any = true;
+      }
+    }
+  }
+  if (staggered_any && !d.weight_state)
+    return fail(GB_E_INVALID, "weight_state is required when a template starts after a point's first frame%s");
+  auto wait_images = [&](cudaStream_t s, const StepParams& prm) -> int {
+    if (!d.image_events_host) return GB_OK;
+    for (int o = 0; o < d.O; ++o)
+      if (prm.img[o] >= 0 && d.image_events_host[prm.img[o]])
+        GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)d.image_events_host[prm.img[o]], 0));
+    return GB_OK;
+  };
+  bool forked = false, need_fork = true;
+  auto join_sides = [&]() -> int {
+    if (!forked) return GB_OK;
+    for (int k = 0; k < used; ++k) {
+      GB_CUDA(cudaEventRecord(pool->join[k], pool->side[k]));
+      GB_CUDA(cudaStreamWaitEvent(stream, pool->join[k], 0));
+    }
+    forked = false;
+    need_fork = true;
+    return GB_OK;
+  };
+  {
+    StepParams prm;
+    fill_params(d, 0, prm);
+    stream_bind(d, prm, 0, 0, d.P);
+    k_s0p_reset<<<grid_for(d.P * d.O * 5, 256), 256, 0, stream>>>(prm);
+    GB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+  }
+  for (int t = 0; t < T; ++t) {
+    if (!has_init[t] && !has_update[t] && !has_prop[t]) continue;
+    StepParams prm;
+    fill_params(d, t, prm);
+    NextParams nxt;
+    memset(&nxt, 0, sizeof(nxt));
+    for (int o = 0; o < GB_MAX_OBS; ++o) nxt.img[o] = -1;
+    if (t + 1 < T) {
+      StepParams pn;
+      fill_params(d, t + 1, pn);
+      nxt.tau = pn.tau;
+      nxt.tau2 = pn.tau2;
+      for (int o = 0; o < d.O; ++o) {
+        nxt.img[o] = pn.img[o];
+        nxt.cam[o] = pn.cam[o];
+      }
+    }
+    if (has_init[t] || has_tmpl[t]) {
+      if ((rc = join_sides())) return rc;
+      if ((rc = wait_images(stream, prm))) return rc;
+      stream_bind(d, prm, t, 0, d.P);
+      prm.tmpl_from_ev = 1;
+      if (has_init[t]) {
+        if ((rc = launch_init(prm, cov, stream))) return rc;
+        if (launches) ++*launches;
+      }
+      if (has_tmpl[t]) {
+        if ((rc = launch_template(prm, stream))) return rc;
+        if (launches) ++*launches;
+      }
+    }
+    if (need_fork) {
+      GB_CUDA(cudaEventRecord(pool->fork, stream));
+      for (int k = 0; k < used; ++k) GB_CUDA(cudaStreamWaitEvent(pool->side[k], pool->fork, 0));
+      forked = true;
+      need_fork = false;
+    }
+    if (has_update[t])
+      for (int k = 0; k < used; ++k)
+        if ((rc = wait_images(pool->side[k], prm))) return rc;
+    for (int64_t b = 0; b < nbatch; ++b) {
+      cudaStream_t ss = pool->side[b % slots];
+      const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
+      stream_bind(d, prm, t, p0, pb);
+      const unsigned nb = (unsigned)(pb * prm.s_nblk);
+      k_s0p_activity<<<grid_for(pb, 256), 256, 0, ss>>>(prm);
+      if (has_update[t]) {
+        k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, kSurfaceSmem);
+        k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm);
+      }
+      if (cov) {
+        k_s4p_resample_propagate<true><<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm, nxt);
+        k_s5p_finalize<true><<<(unsigned)((pb + 3) / 4), 128, 0, ss>>>(prm);
+      } else {
+        k_s4p_resample_propagate<false><<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm, nxt);
+        k_s5p_finalize<false><<<(unsigned)((pb + 3) / 4), 128, 0, ss>>>(prm);
+      }
+      GB_CUDA(cudaGetLastError());
+      if (launches) *launches += has_update[t] ? 5 : 3;
+    }
+  }
+  return join_sides();
 }
 
 // One update for all points in the organisation the plan asks for.
@@ -1445,7 +1604,7 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     if (slots > kMaxSlots) slots = kMaxSlots;
     plan->stream_batch = (int32_t)batch;
     plan->stream_slots = slots;
-    plan->scratch_bytes = plan->stream_slots * stream_layout(batch, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
+    plan->scratch_bytes = stream_layout(npoints, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
     return GB_OK;
   }
   plan->n_slabs = 160;
@@ -1516,6 +1675,11 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool cov = d->covariances != nullptr;
   int64_t launches = 0;
+  if (d->plan.mode == GB_MODE_STREAM) {
+    if ((rc = track_streaming(*d, stream, &launches))) return rc;
+    if (launches_out) *launches_out = launches;
+    return GB_OK;
+  }
   // per-time work flags from the host copies (tracker.py:321-347)
   StepParams probe;
   fill_params(*d, 0, probe);

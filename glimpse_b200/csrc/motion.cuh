@@ -37,25 +37,38 @@ struct Philox {
 };
 
 // Three standard normals for (point, time, particle); `stream` separates init (0..1) from steps (2).
+// `need` masks the pairs that are actually used (bit 0: z0/z1, bit 1: z2): a normal that only multiplies a
+// zero sigma is not generated (the stream of the others is unchanged).
 __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t point, uint32_t time, uint32_t particle,
-                                                uint32_t stream, double& z0, double& z1, double& z2) {
+                                                uint32_t stream, double& z0, double& z1, double& z2, int need = 3) {
   Philox g{(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t r[4];
   g.generate(particle, time, (uint32_t)point, ((uint32_t)(point >> 32) << 8) | stream, r);
   const float two_neg32 = 2.3283064365386963e-10f;
-  const float u0 = ((float)r[0] + 0.5f) * two_neg32, u1 = ((float)r[2] + 0.5f) * two_neg32;
-  // u in (0, 1]: clamp the fp32 rounding of values next to 1 and 0
-  const float a0 = fminf(fmaxf(u0, 1.0e-10f), 1.0f), a1 = fminf(fmaxf(u1, 1.0e-10f), 1.0f);
-  // sqrt(x) as x * rsqrt(x) (MUFU.RSQ); x = -2 ln(u) is floored at 1e-30 so that u == 1 gives 0, not NaN
-  const float e0 = fmaxf(-2.0f * __logf(a0), 1.0e-30f), e1 = fmaxf(-2.0f * __logf(a1), 1.0e-30f);
-  const float rad0 = e0 * rsqrtf(e0), rad1 = e1 * rsqrtf(e1);
-  float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * ((float)(r[1] >> 8) * 5.9604644775390625e-08f), &s0, &c0);
-  __sincosf(6.283185307179586f * ((float)(r[3] >> 8) * 5.9604644775390625e-08f), &s1, &c1);
-  z0 = (double)(rad0 * c0);
-  z1 = (double)(rad0 * s0);
-  z2 = (double)(rad1 * c1);
-  (void)s1;
+  z0 = z1 = z2 = 0.0;
+  if (need & 1) {
+    const float u0 = ((float)r[0] + 0.5f) * two_neg32;
+    const float a0 = fminf(fmaxf(u0, 1.0e-10f), 1.0f);  // u in (0, 1]
+    // sqrt(x) as x * rsqrt(x) (MUFU.RSQ); x = -2 ln(u) is floored at 1e-30 so that u == 1 gives 0, not NaN
+    const float e0 = fmaxf(-2.0f * __logf(a0), 1.0e-30f);
+    const float rad0 = e0 * rsqrtf(e0);
+    float s0, c0;
+    __sincosf(6.283185307179586f * ((float)(r[1] >> 8) * 5.9604644775390625e-08f), &s0, &c0);
+    z0 = (double)(rad0 * c0);
+    z1 = (double)(rad0 * s0);
+  }
+  if (need & 2) {
+    const float u1 = ((float)r[2] + 0.5f) * two_neg32;
+    const float a1 = fminf(fmaxf(u1, 1.0e-10f), 1.0f);
+    const float e1 = fmaxf(-2.0f * __logf(a1), 1.0e-30f);
+    const float rad1 = e1 * rsqrtf(e1);
+    z2 = (double)(rad1 * __cosf(6.283185307179586f * ((float)(r[3] >> 8) * 5.9604644775390625e-08f)));
+  }
+}
+
+// Which normals evolve_particle really consumes for this motion model.
+__device__ __forceinline__ int evolve_needs(const gb_motion& m) {
+  return ((m.a_sigma[0] != 0.0 || m.a_sigma[1] != 0.0) ? 1 : 0) | (m.a_sigma[2] != 0.0 ? 2 : 0);
 }
 
 __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t point, uint32_t time) {

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __g
           z1 = zn[3 * (int64_t)i + 1];
           z2 = zn[3 * (int64_t)i + 2];
         } else {
-          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2);
+          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2, evolve_needs(s_motion));
         }
         evolve_particle(s_motion, prm.tau, prm.tau2, z0, z1, z2, s[q]);
       }
@@ -223,7 +223,17 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
   }
   if (prm.s_pflags[p] != 0) return;  // the point failed its particle tests: reference raises before any observer work
   const int N = (int)prm.N;
-  const int* ib = prm.s_ibox + po * 5;
+  // consume the integer cloud box and leave it empty for the next time (one thread reads, all share)
+  __shared__ int s_ib[5];
+  if (tid == 0) {
+    int* gib = prm.s_ibox + po * 5;
+    for (int k = 0; k < 5; ++k) {
+      s_ib[k] = gib[k];
+      gib[k] = (k == 4) ? 0 : 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  const int* ib = s_ib;
   int box_l = ib[0], box_t = ib[1], box_r = -ib[2], box_b = -ib[3];
   const bool nan_any = ib[4] != 0;
   if (!nan_any && ((box_r - box_l) - prm.tile_w < 5 || (box_b - box_t) - prm.tile_h < 5)) {
@@ -512,6 +522,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
     s_pref[3] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
                                                 : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
     s_pref[4] = quo(1.0, (double)N);
+    s_pref[5] = quo(1.0, run);
   }
   const double* wsrc = prm.s_w + (int64_t)p * N;
   const int base = b * prm.s_block;
@@ -537,7 +548,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
     w[q] = tsum;  // inclusive prefix inside the thread
   }
   const double off = block_exclusive_offset(tsum, s_warp);  // contains a __syncthreads(): s_pref is visible
-  const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4];
+  const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4], inv_total = s_pref[5];
   // The last parent of the CTA takes the next CTA's prefix as its cumulative weight, so that child ranges
   // are seamless across CTAs whatever the association of the in-CTA sums.
 #pragma unroll
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
       s_end[k] = count_positions_le(quo(c, total), u01, inv_n, N);
     }
   }
-  if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
+  if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(prefix >= total ? 1.0 : prefix * inv_total, u01, inv_n, N);
   __syncthreads();
   const int J0 = s_j0, J1 = n_here > 0 ? s_end[n_here - 1] : J0;
   const double* ev = prm.s_ev + p * 6 * (int64_t)N + base;
@@ -625,6 +636,325 @@ __global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {
   const double* sin_ = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * N : state_buffer(prm, t - 1) + p * 6 * N;
   double ref[6];
   for (int c = 0; c < 6; ++c) ref[c] = sin_[c * N];
+  double mean[6], sg[6], cv[36];
+  finalize_moments<COV>(a, ref, mean, sg, cv);
+  double* mo = prm.means + ((int64_t)p * prm.T + t) * 6;
+  for (int c = 0; c < 6; ++c) mo[c] = mean[c];
+  if (COV) {
+    double* co = prm.covariances + ((int64_t)p * prm.T + t) * 36;
+    for (int c = 0; c < 36; ++c) co[c] = cv[c];
+  } else {
+    double* so = prm.sigmas + ((int64_t)p * prm.T + t) * 6;
+    for (int c = 0; c < 6; ++c) so[c] = sg[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined flow used by gb_track: the resampling of time t and the motion step to time t + 1 are
+// one kernel (k_s4p), so the resampled state is never written to / read back from HBM between
+// updates: a child thread gathers its parent's evolved particle, and immediately evolves, tests and
+// projects it for the next time.  Per time t and batch:  k_s0p -> k_s2 -> k_s3 -> k_s4p -> k_s5p.
+//   activity bits of (point, t):  ACTIVE    = an update happens at t        (first < t <= last, alive)
+//                                 PROPAGATE = particles are advanced to t+1 (first <= t < last, alive)
+// Evolved particles and the per-point failure flags are double-buffered by time parity
+// (s_ev / s_ev_next, s_pflags / s_pflags_next); the integer cloud box is consumed and reset by k_s2.
+// ---------------------------------------------------------------------------------------------
+#define GB_ACT_PROPAGATE 4
+
+__global__ void k_s0p_activity(const __grid_constant__ StepParams prm) {
+  for (int64_t i = prm.p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.p0 + prm.pb; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool alive = prm.status[i] == 0;
+    const int f = prm.first[i], l = prm.last[i];
+    const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
+    const bool sll = !(sg.z == nullptr && sg.value == 0.0);
+    prm.s_act[i] = (uint8_t)(((alive && f < prm.t && prm.t <= l) ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) |
+                             ((alive && f <= prm.t && prm.t < l) ? GB_ACT_PROPAGATE : 0));
+  }
+}
+
+// Start of a gb_track: empty cloud boxes, no failure flags in either parity.
+__global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
+  const int64_t lo5 = prm.p0 * prm.O * 5, n = prm.pb * prm.O * 5;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    prm.s_ibox[lo5 + i] = (i % 5 == 4) ? 0 : 0x7fffffff;
+  for (int64_t i = prm.p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.p0 + prm.pb; i += (int64_t)gridDim.x * blockDim.x) {
+    prm.s_pflags[i] = 0;
+    prm.s_pflags_next[i] = 0;
+  }
+}
+
+template <bool COV>
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
+                                                                                   const __grid_constant__ NextParams nxt) {
+  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4_PPT, CAP = PPT * GB_SBLOCK_THREADS;
+  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
+  __shared__ double s_pref[6];
+  __shared__ double s_red[GB_SBLOCK_THREADS / 32][KP];
+  __shared__ double s_w[CAP];
+  __shared__ int s_end[CAP];
+  __shared__ int s_j0;
+  __shared__ gb_motion s_motion;
+  __shared__ int s_box[GB_MAX_OBS][5];
+  __shared__ unsigned s_or;
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
+  const int act = prm.s_act[p];
+  const bool update = (act & GB_ACT_ACTIVE) != 0, propagate = (act & GB_ACT_PROPAGATE) != 0;
+  if ((!update && !propagate) || prm.s_pflags[p] != 0) return;  // a point that failed at t is neither resampled nor advanced
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
+  const int N = (int)prm.N, O = prm.O;
+  const int base = b * prm.s_block;
+  const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA (<= CAP)
+  const int k0 = PPT * tid;                                      // first local parent of this thread
+  if (propagate) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
+    for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
+    if (tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
+  }
+  // ---- child ranges of the CTA's parents ----
+  int J0, J1;
+  // source of the particles that are resampled: the evolved particles of time t, or — at a point's first
+  // time — the initial particles, taken one to one
+  const double* src6;
+  if (update) {
+    if (tid == 0) {
+      const double* bs = prm.s_bsum + p * prm.s_nblk;
+      double run = 0.0, pre = 0.0, nx = 0.0;
+      for (int k = 0; k < prm.s_nblk; ++k) {
+        if (k == b) pre = run;
+        run += bs[k];
+        if (k == b) nx = run;
+      }
+      s_pref[0] = pre;
+      s_pref[1] = run;
+      s_pref[2] = nx;
+      s_pref[3] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
+                                                  : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
+      s_pref[4] = quo(1.0, (double)N);
+      s_pref[5] = quo(1.0, run);
+    }
+    const double* wsrc = prm.s_w + (int64_t)p * N;
+    double w[PPT];
+    if ((N & 1) == 0 && k0 + PPT <= n_here) {
+#pragma unroll
+      for (int q = 0; q < PPT; q += 2) {
+        const double2 x = *reinterpret_cast<const double2*>(wsrc + base + k0 + q);
+        w[q] = x.x;
+        w[q + 1] = x.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) w[q] = (k0 + q < n_here) ? wsrc[base + k0 + q] : 0.0;
+    }
+    double tsum = 0.0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      if (k0 + q < CAP) s_w[k0 + q] = w[q];
+      tsum += w[q];
+      w[q] = tsum;  // inclusive prefix inside the thread
+    }
+    const double off = block_exclusive_offset(tsum, s_warp);  // contains a __syncthreads(): s_pref is visible
+    const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4], inv_total = s_pref[5];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int k = k0 + q;
+      if (k < n_here) {
+        const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
+        // normalised cumulative weight: one reciprocal per CTA instead of a division per particle (the total maps to exactly 1)
+        s_end[k] = count_positions_le(c >= total ? 1.0 : c * inv_total, u01, inv_n, N);
+      }
+    }
+    if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(prefix >= total ? 1.0 : prefix * inv_total, u01, inv_n, N);
+    __syncthreads();
+    J0 = s_j0;
+    J1 = n_here > 0 ? s_end[n_here - 1] : J0;
+    src6 = prm.s_ev + p * 6 * (int64_t)N + base;
+  } else {
+    __syncthreads();
+    J0 = base;
+    J1 = base + n_here;
+    src6 = state_buffer(prm, t) + p * 6 * (int64_t)N + base;  // initial particles written by k_init
+  }
+  const double* sin0 = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
+  // ---- moments of the resampled set: parents weighted by (children x weight), coalesced reads ----
+  if (update) {
+    double ref[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ref[c] = prm.s_ref[p * 6 + c];
+    Moments<COV> mom;
+    mom.clear();
+#pragma unroll 2
+    for (int q = 0; q < PPT; ++q) {
+      const int k = k0 + q;
+      if (k >= n_here) break;
+      const int cnt = s_end[k] - (k > 0 ? s_end[k - 1] : J0);
+      if (cnt > 0) {
+        double s[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s[c] = src6[c * (int64_t)N + k];
+        mom.accumulate((double)cnt * s_w[k], s, ref);
+      }
+    }
+    double r[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) r[k] = k < NM ? mom.a[k] : 0.0;
+    warp_reduce_transpose<KP>(r, lane);
+    if (KP == 32 || (lane & 1) == 0) s_red[warp][transposed_index<KP>(lane)] = r[0];
+    __syncthreads();
+    if (tid < NM) {
+      double x = s_red[0][tid];
+      for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) x += s_red[wv][tid];
+      prm.s_pm[(p * prm.s_nblk + b) * 28 + tid] = x;
+    }
+  }
+  (void)sin0;
+  // ---- children: gather, report, and advance to t + 1 ----
+  const bool last_time = !propagate;  // t == last: the resampled particles are the final state
+  double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
+  double* evn = prm.s_ev_next + p * 6 * (int64_t)N;
+  double* wst = prm.weight_state ? prm.weight_state + (int64_t)p * N : nullptr;
+  double* outp = (update && prm.out_particles) ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
+  double* outw = (update && prm.out_weights) ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
+  const int s_idx = (t + 1) - prm.first[p] - 1;
+  const double* zn = (propagate && prm.step_normals) ? prm.step_normals + (((int64_t)p * prm.S + s_idx) * N) * 3 : nullptr;
+  const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
+  uint32_t flags = 0;
+  const int need = propagate ? evolve_needs(s_motion) : 0;
+  int ibx[GB_MAX_OBS > 2 ? 2 : GB_MAX_OBS][5];  // register boxes for the first two observers; others go straight to shared memory
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    ibx[o][0] = ibx[o][1] = ibx[o][2] = ibx[o][3] = 0x7fffffff;
+    ibx[o][4] = 0;
+  }
+  for (int j = J0 + tid; j < J1; j += GB_SBLOCK_THREADS) {
+    int lo;
+    double wj;
+    if (update) {
+      int l2 = 0, hi = n_here - 1;  // smallest parent whose range end exceeds j
+      while (l2 < hi) {
+        const int mid = (l2 + hi) >> 1;
+        if (s_end[mid] > j) hi = mid; else l2 = mid + 1;
+      }
+      lo = l2;
+      wj = s_w[lo];
+    } else {
+      lo = j - base;
+      wj = 1.0;
+    }
+    double s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = src6[c * (int64_t)N + lo];
+    if (update) {
+      if (last_time) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);
+      }
+      if (wst) wst[j] = wj;
+      if (outp) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
+      }
+      if (outw) outw[j] = wj;
+    }
+    if (propagate) {
+      double z0, z1, z2;
+      if (prm.rng_mode == GB_RNG_SUPPLIED) {
+        z0 = zn[3 * (int64_t)j];
+        z1 = zn[3 * (int64_t)j + 1];
+        z2 = zn[3 * (int64_t)j + 2];
+      } else {
+        philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)(t + 1), (uint32_t)j, 2u, z0, z1, z2, need);
+      }
+      evolve_particle(s_motion, nxt.tau, nxt.tau2, z0, z1, z2, s);
+      flags |= test_particle(prm, s);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) evn[c * (int64_t)N + j] = s[c];
+      for (int o = 0; o < O; ++o) {
+        const int64_t po = p * O + o;
+        if (nxt.img[o] < 0 || !prm.mask[po]) continue;  // block-uniform
+        double u, v;
+        project_fast(nxt.cam[o], s[0], s[1], s[2], u, v);
+        double* uv = prm.s_uv + po * 2 * (int64_t)N;
+        uv[j] = u;
+        uv[(int64_t)N + j] = v;
+        const int e0 = __double2int_rd(u - hw), e1 = __double2int_rd(v - hh), e2 = -__double2int_ru(u + hw),
+                  e3 = -__double2int_ru(v + hh), e4 = (isnan(u) | isnan(v)) ? -1 : 0;
+        if (o < 2) {
+          ibx[o][0] = min(ibx[o][0], e0);
+          ibx[o][1] = min(ibx[o][1], e1);
+          ibx[o][2] = min(ibx[o][2], e2);
+          ibx[o][3] = min(ibx[o][3], e3);
+          ibx[o][4] = min(ibx[o][4], e4);
+        } else {
+          atomicMin(&s_box[o][0], e0);
+          atomicMin(&s_box[o][1], e1);
+          atomicMin(&s_box[o][2], e2);
+          atomicMin(&s_box[o][3], e3);
+          atomicMin(&s_box[o][4], e4);
+        }
+      }
+    }
+  }
+  if (propagate) {
+    // cloud boxes of time t + 1: registers -> warp -> shared -> global
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (o >= O) break;
+      int mine = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int x = __reduce_min_sync(0xffffffffu, ibx[o][k]);
+        if (lane == k) mine = x;
+      }
+      if (lane < 5) atomicMin(&s_box[o][lane], mine);
+    }
+    const int any = (int)block_or(flags, &s_or);  // also orders the shared-memory atomics above
+    if (any && tid == 0) atomicOr(&prm.s_pflags_next[p], any);
+    if (tid < O * 5) {
+      const int o = tid / 5, k = tid - o * 5;
+      const int64_t po = p * O + o;
+      if (nxt.img[o] >= 0 && prm.mask[po]) atomicMin(&prm.s_ibox[po * 5 + k], s_box[o][k]);
+    }
+  }
+}
+
+// s5 of the pipelined flow: moments and status of time t, then the failure flags of this parity are cleared
+// for time t + 2.  Also stores the moment origin of the next time (the first resampled particle).
+template <bool COV>
+__global__ void k_s5p_finalize(const __grid_constant__ StepParams prm) {
+  const int64_t p = prm.p0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= prm.p0 + prm.pb) return;
+  const int act = prm.s_act[p];
+  const int t = prm.t;
+  const int f = prm.s_pflags[p];
+  if (lane == 0) prm.s_pflags[p] = 0;
+  if (!(act & GB_ACT_ACTIVE)) {
+    // a point can fail while being advanced from its first time: the failure belongs to time t
+    if (f && lane == 0 && prm.status[p] == 0 && t > prm.first[p] && t <= prm.last[p]) {
+      prm.status[p] = status_from_flags((uint32_t)f);
+      prm.status_time[p] = t;
+    }
+    return;
+  }
+  if (f) {
+    if (lane == 0) {
+      prm.status[p] = status_from_flags((uint32_t)f);
+      prm.status_time[p] = t;
+    }
+    return;
+  }
+  constexpr int NM = Moments<COV>::NM;
+  double x = 0.0;
+  if (lane < NM)
+    for (int b = 0; b < prm.s_nblk; ++b) x += prm.s_pm[(p * prm.s_nblk + b) * 28 + lane];
+  double a[NM];
+#pragma unroll
+  for (int k = 0; k < NM; ++k) a[k] = __shfl_sync(0xffffffffu, x, k);
+  if (lane != 0) return;
+  double ref[6];
+  for (int c = 0; c < 6; ++c) ref[c] = prm.s_ref[p * 6 + c];
   double mean[6], sg[6], cv[36];
   finalize_moments<COV>(a, ref, mean, sg, cv);
   double* mo = prm.means + ((int64_t)p * prm.T + t) * 6;
