@@ -296,13 +296,31 @@ def run_gpu_arm(args):
     if not args.per_step_events:
         kernel_ms /= (T - 1)  # gb_track = init + templates + (T - 1) updates; the updates are > 99 % of it
     status = session.buf["status"].cpu().numpy()
+    # per-kernel durations of one more (untimed) track: CUDA events around every launch on its own stream
+    import ctypes as C
+    lib = _lib.load()
+    KINDS = ["k_s0p_activity", "k_s2_surface", "k_s3_weights", "k_s4p_resample_propagate", "k_s5p_finalize", "k_init", "k_template", "k_s3b_publish"]
+    kernels = {}
+    session.launches = 0
+    if args.mode == "stream" and not args.per_step_events:
+        _lib.check(lib.gb_kernel_timing(1))
+        one_track()
+        torch.cuda.synchronize()
+        k_ms, k_n = (C.c_double * len(KINDS))(), (C.c_int64 * len(KINDS))()
+        _lib.check(lib.gb_kernel_timing_read(k_ms, k_n, len(KINDS)))
+        _lib.check(lib.gb_kernel_timing(0))
+        kernels = {name: {"ms_per_track": float(k_ms[i]), "launches": int(k_n[i]),
+                          "us_per_launch": 1e3 * float(k_ms[i]) / max(1, int(k_n[i]))} for i, name in enumerate(KINDS)}
+    launches_per_track = session.launches
     session.launches = 0
     stats_out = session.fetch()
     failed = int((status != 0).sum())
     value = world * P * N * T / (dev_ms / 1e3)
-    nbatch = -(-P // max(1, session.stats["plan"].get("stream_batch", P) or P)) if args.mode == "stream" else 1
-    per_update = 6 * nbatch if args.mode == "stream" else 1
-    launches_per_step = 2 + per_update * (T - 1)  # k_init + k_template + (T - 1) updates
+    if launches_per_track:
+        launches_per_step = launches_per_track  # counted by gb_track itself
+    else:
+        nbatch = -(-P // max(1, session.stats["plan"].get("stream_batch", P) or P)) if args.mode == "stream" else 1
+        launches_per_step = 2 + (6 * nbatch if args.mode == "stream" else 1) * (T - 1)
     peak, peak_src = hbm_peak()
     achieved = ALGORITHMIC_BYTES_PER_UPDATE * P * N / (kernel_ms / 1e3) / 1e9
     win_w, win_h = session.stats["window_width"], session.stats["window_height"]
@@ -355,8 +373,10 @@ def run_gpu_arm(args):
                 "failed_points": failed, "median_abs_velocity_error_m_per_day": v_err,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_step" if args.mode == "fused" else "update = k_s0..k_s5", "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N},
+                         "traffic": None, "kernel": "k_step" if args.mode == "fused" else "one update of all points = k_s0p + k_s2 + k_s3 + k_s4p + k_s5p (x batches)",
+                         "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N,
+                         "kernels": kernels},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,

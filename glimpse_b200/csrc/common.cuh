@@ -37,6 +37,51 @@ __device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_dow
 __device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_xor(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk asynchronous copies global -> shared (the TMA engine's 1-D mode: `cp.async.bulk`, SASS UBLKCP)
+// completing on an mbarrier.  Sizes are multiples of 16 bytes, both addresses 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(__cvta_generic_to_global(src_global)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Message passing between CTAs without the sequentially consistent fence of __threadfence() (which also
+// invalidates the SM's L1): the producer's atomic carries release semantics at GPU scope, the consumer reads
+// the published data with GPU-scope loads (served by L2).
+__device__ __forceinline__ int atomic_add_release_gpu(int* p, int v) {
+  int old;
+  asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ double load_relaxed_gpu(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += shfl_xor(v, d);

@@ -94,6 +94,7 @@ struct StepParams {
   double* s_w;       // [P][N]      weights
   double* s_bsum;    // [P][nblk]   per-CTA weight totals
   double* s_pm;      // [P][nblk][28] per-CTA moment sums
+  double* s_pre;     // [P][nblk + 4] prefix of the CTA totals (0 .. total), 1 / total, uniform draw, 1 / N (written by k_s3b_publish)
   int* s_ibox;       // [P][O][5]   integer cloud box (left, top, -right, -bottom, -(any NaN))
   int* s_pflags;     // [P]         GB_F_* raised during this update
   uint8_t* s_act;    // [P]         GB_ACT_* bits of this update
@@ -1191,7 +1192,7 @@ static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t 
 }
 
 struct StreamLayout {
-  int64_t ev[2], uv, w, bsum, pm, ibox, pflags[2], act, meta, ref, surf, total;
+  int64_t ev[2], uv, w, bsum, pre, pm, ibox, pflags[2], act, meta, ref, surf, total;
 };
 
 // Scratch of GB_MODE_STREAM for `B` points.
@@ -1208,6 +1209,7 @@ static StreamLayout stream_layout(int64_t B, int64_t N, int64_t O, int64_t nblk,
   L.uv = take(B * O * 2 * N * 8);
   L.w = take(B * N * 8);
   L.bsum = take(B * nblk * 8);
+  L.pre = take(B * (nblk + 4) * 8);  // per point: prefix[0..nblk], 1/total, uniform draw, 1/N
   L.pm = take(B * nblk * 28 * 8);
   L.ibox = take(B * O * 5 * 4);
   L.pflags[0] = take(B * 4);
@@ -1231,6 +1233,7 @@ static void stream_bind(const gb_track_desc& d, StepParams& prm, int par, int64_
   prm.s_uv = reinterpret_cast<double*>(base + L.uv);
   prm.s_w = reinterpret_cast<double*>(base + L.w);
   prm.s_bsum = reinterpret_cast<double*>(base + L.bsum);
+  prm.s_pre = reinterpret_cast<double*>(base + L.pre);
   prm.s_pm = reinterpret_cast<double*>(base + L.pm);
   prm.s_ibox = reinterpret_cast<int*>(base + L.ibox);
   prm.s_pflags = reinterpret_cast<int*>(base + L.pflags[par & 1]);
@@ -1282,7 +1285,7 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   k_s0_reset<<<grid_for(prm.pb * prm.O * 5, 256), 256, 0, stream>>>(prm);
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
-  k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
   k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s5_finalize<COV><<<(unsigned)((prm.pb + 3) / 4), 128, 0, stream>>>(prm);
   GB_CUDA(cudaGetLastError());
@@ -1340,6 +1343,49 @@ static int launch_stream_update(const gb_track_desc& d, StepParams& prm, cudaStr
 static int launch_init(const StepParams& prm, bool cov, cudaStream_t stream);
 static int launch_template(const StepParams& prm, cudaStream_t stream);
 
+// Optional per-kernel timing of the pipelined flow (gb_kernel_timing): every launch is bracketed by CUDA events
+// on the stream it is launched on; durations are accumulated per kernel kind when the track has finished.
+enum { GB_K_ACTIVITY = 0, GB_K_SURFACE, GB_K_WEIGHTS, GB_K_RESAMPLE_PROPAGATE, GB_K_FINALIZE, GB_K_INIT, GB_K_TEMPLATE, GB_K_PUBLISH, GB_K_KINDS };
+struct KernelTimer {
+  std::mutex mu;
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  size_t used = 0;
+  double ms[GB_K_KINDS] = {0};
+  int64_t n[GB_K_KINDS] = {0};
+  cudaEvent_t next() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  void begin(int k, cudaStream_t s) {
+    if (!on) return;
+    kind.push_back(k);
+    cudaEventRecord(next(), s);
+  }
+  void end(cudaStream_t s) {
+    if (!on) return;
+    cudaEventRecord(next(), s);
+  }
+  // after the streams have been synchronised
+  void collect() {
+    for (size_t i = 0; i < kind.size(); ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) {
+        ms[kind[i]] += t;
+        n[kind[i]] += 1;
+      }
+    }
+    kind.clear();
+    used = 0;
+  }
+};
+static KernelTimer g_ktimer;
+
 // gb_track in GB_MODE_STREAM: the pipelined flow of stream.cuh.  Points are cut into `slots` batches that
 // advance on their own side streams without meeting; the caller's stream runs the kernels that need all
 // batches to be at the same time (first-frame initialisation, template construction) between a join and a fork.
@@ -1350,8 +1396,12 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
   cudaError_t aerr = cudaSuccess;
   std::call_once(attr_once[dev & 15], [&]() {
     aerr = cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
   });
-  if (aerr != cudaSuccess) return fail(GB_E_CUDA, "k_s2_surface attributes: %s", cudaGetErrorString(aerr));
+  if (aerr != cudaSuccess) return fail(GB_E_CUDA, "stream kernel attributes: %s", cudaGetErrorString(aerr));
+  if (d.plan.stream_block > GB_S4P_CAP || (d.plan.stream_block & 1)) return fail(GB_E_INVALID, "plan: stream_block must be even and <= 768%s");
+  if (d.plan.stream_batch > 65535) return fail(GB_E_INVALID, "plan: stream_batch must be <= 65535%s");
   const bool cov = d.covariances != nullptr;
   const int slots = d.plan.stream_slots;
   const int64_t batch = d.plan.stream_batch;
@@ -1434,11 +1484,15 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
       stream_bind(d, prm, t, 0, d.P);
       prm.tmpl_from_ev = 1;
       if (has_init[t]) {
+        g_ktimer.begin(GB_K_INIT, stream);
         if ((rc = launch_init(prm, cov, stream))) return rc;
+        g_ktimer.end(stream);
         if (launches) ++*launches;
       }
       if (has_tmpl[t]) {
+        g_ktimer.begin(GB_K_TEMPLATE, stream);
         if ((rc = launch_template(prm, stream))) return rc;
+        g_ktimer.end(stream);
         if (launches) ++*launches;
       }
     }
@@ -1456,23 +1510,43 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
       const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
       stream_bind(d, prm, t, p0, pb);
       const unsigned nb = (unsigned)(pb * prm.s_nblk);
+      KernelTimer& kt = g_ktimer;
+      kt.begin(GB_K_ACTIVITY, ss);
       k_s0p_activity<<<grid_for(pb, 256), 256, 0, ss>>>(prm);
+      kt.end(ss);
       if (has_update[t]) {
+        kt.begin(GB_K_SURFACE, ss);
         k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, kSurfaceSmem);
-        k_s3_weights<<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm);
+        kt.end(ss);
+        kt.begin(GB_K_WEIGHTS, ss);
+        k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);
+        kt.end(ss);
+        kt.begin(GB_K_PUBLISH, ss);
+        k_s3b_publish<<<(unsigned)((pb + 7) / 8), 256, 0, ss>>>(prm);
+        kt.end(ss);
       }
-      if (cov) {
-        k_s4p_resample_propagate<true><<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm, nxt);
+      kt.begin(GB_K_RESAMPLE_PROPAGATE, ss);
+      if (cov)
+        k_s4p_resample_propagate<true><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+      else
+        k_s4p_resample_propagate<false><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+      kt.end(ss);
+      kt.begin(GB_K_FINALIZE, ss);
+      if (cov)
         k_s5p_finalize<true><<<(unsigned)((pb + 3) / 4), 128, 0, ss>>>(prm);
-      } else {
-        k_s4p_resample_propagate<false><<<nb, GB_SBLOCK_THREADS, 0, ss>>>(prm, nxt);
+      else
         k_s5p_finalize<false><<<(unsigned)((pb + 3) / 4), 128, 0, ss>>>(prm);
-      }
+      kt.end(ss);
       GB_CUDA(cudaGetLastError());
-      if (launches) *launches += has_update[t] ? 5 : 3;
+      if (launches) *launches += has_update[t] ? 6 : 3;
     }
   }
-  return join_sides();
+  if ((rc = join_sides())) return rc;
+  if (g_ktimer.on) {
+    GB_CUDA(cudaStreamSynchronize(stream));
+    g_ktimer.collect();
+  }
+  return GB_OK;
 }
 
 // One update for all points in the organisation the plan asks for.
@@ -1507,6 +1581,28 @@ extern "C" {
 
 int gb_version(void) { return GB_VERSION; }
 const char* gb_last_error(void) { return g_error; }
+
+int gb_kernel_timing(int32_t enable) {
+  std::lock_guard<std::mutex> guard(gb::g_ktimer.mu);
+  gb::g_ktimer.on = enable != 0;
+  gb::g_ktimer.kind.clear();
+  gb::g_ktimer.used = 0;
+  for (int k = 0; k < gb::GB_K_KINDS; ++k) {
+    gb::g_ktimer.ms[k] = 0.0;
+    gb::g_ktimer.n[k] = 0;
+  }
+  return GB_OK;
+}
+
+int gb_kernel_timing_read(double* ms, int64_t* launches, int32_t n) {
+  if (!ms || !launches || n < 0) return gb::fail(GB_E_INVALID, "null argument%s");
+  std::lock_guard<std::mutex> guard(gb::g_ktimer.mu);
+  for (int k = 0; k < n; ++k) {
+    ms[k] = k < gb::GB_K_KINDS ? gb::g_ktimer.ms[k] : 0.0;
+    launches[k] = k < gb::GB_K_KINDS ? gb::g_ktimer.n[k] : 0;
+  }
+  return GB_OK;
+}
 
 int gb_camera_from_vector(const double* v, const double* corr, gb_camera* out) {
   if (!v || !out) return fail(GB_E_INVALID, "null argument%s");
@@ -1587,7 +1683,9 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     plan->n_local = (int32_t)n_particles;
     plan->particles_in_smem = 0;
     plan->tile_bytes = kSurfaceSmem;
-    plan->stream_block = GB_S4_PPT * GB_SBLOCK_THREADS;
+    // particles of a point are cut into equal even-sized blocks that fit k_s4p's shared memory (<= 768 parents)
+    plan->stream_nblk = (int32_t)((n_particles + GB_S4P_CAP - 1) / GB_S4P_CAP);
+    plan->stream_block = (int32_t)(((n_particles + plan->stream_nblk - 1) / plan->stream_nblk + 1) / 2 * 2);
     plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
     // surface regions sized for search windows up to 191 px larger than the template
     plan->surf_bytes = (tile_bytes_needed(tile_w + 191, tile_h + 191, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
@@ -1600,6 +1698,7 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     if (const char* e = getenv("GB_STREAM_SLOTS")) slots = atoi(e);
     if (batch < 1) batch = 1;
     if (batch > npoints) batch = npoints;
+    if (batch > 65535) batch = 65535;  // a batch is the y extent of the k_s4p grid
     if (slots < 1) slots = 1;
     if (slots > kMaxSlots) slots = kMaxSlots;
     plan->stream_batch = (int32_t)batch;

@@ -85,9 +85,10 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __g
   const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
   const bool vec = (N & 1) == 0;  // 16-byte aligned pairs
   uint32_t flags = 0;
-  for (int sub = 0; sub < prm.s_block; sub += 2 * GB_SBLOCK_THREADS) {
+  const int blk_end = min(N, (b + 1) * prm.s_block);  // s_block is even: pairs never straddle CTAs
+  for (int sub = 0; sub < prm.s_block; sub += 2 * (int)blockDim.x) {
   const int ia = b * prm.s_block + sub + 2 * tid;  // particles ia, ia + 1
-  const bool va = ia < N, vb = ia + 1 < N;
+  const bool va = ia < blk_end, vb = ia + 1 < blk_end;
   if (va) {
     double s[2][6];
     if (vec) {
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
 
 // Exclusive offsets of one value per thread across the CTA (warp shuffles + one pass over the
 // warp totals).  Returns the offset of the calling thread.
+template <int NWARPS = GB_SBLOCK_THREADS / 32>
 __device__ __forceinline__ double block_exclusive_offset(double v, double* s_warp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double incl = warp_inclusive_scan(v, lane);
@@ -352,7 +354,7 @@ __device__ __forceinline__ double block_exclusive_offset(double v, double* s_war
   __syncthreads();
   double off = 0.0;
 #pragma unroll
-  for (int k = 0; k < GB_SBLOCK_THREADS / 32; ++k) off += k < warp ? s_warp[k] : 0.0;
+  for (int k = 0; k < NWARPS; ++k) off += k < warp ? s_warp[k] : 0.0;
   double excl = shfl_up(incl, 1);
   if (lane == 0) excl = 0.0;
   return off + excl;
@@ -366,13 +368,43 @@ struct SurfaceRef {
   int Mu, Mv, Mp, ok;
 };
 
-// s3: spline sample + surface likelihood -> weight; two consecutive particles per thread.
-__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __grid_constant__ StepParams prm) {
+// s3: spline sample + surface likelihood -> weight; two consecutive particles per thread.  Grid: blocks of a
+// point x points; launched with s3_threads(s_block) threads so that full trips cover the CTA's particle pairs.
+#define GB_S3_MAX_THREADS 256
+__host__ __device__ inline int s3_threads(int s_block) {
+  const int pairs = (s_block + 1) / 2;
+  const int trips = (pairs + GB_S3_MAX_THREADS - 1) / GB_S3_MAX_THREADS;
+  return ((pairs + trips - 1) / trips + 31) / 32 * 32;
+}
+
+// One warp per point (k_s3b_publish): turns the CTA totals of k_s3 into what k_s4p needs — the prefix
+// of the totals (CTA b owns cumulative weights (pre[b], pre[b + 1]]), 1 / total, the uniform draw of this update
+// and 1 / N.  Every k_s4p CTA of the point reads the same record, so child ranges meet exactly at CTA boundaries.
+__device__ __forceinline__ void s3_publish_prefix(const StepParams& prm, int64_t p, int lane) {
+  const int nblk = prm.s_nblk;
+  const double* bs = prm.s_bsum + p * nblk;
+  double* pre = prm.s_pre + p * (nblk + 4);
+  double run = 0.0;
+  for (int c0 = 0; c0 < nblk; c0 += 32) {
+    const double x = c0 + lane < nblk ? bs[c0 + lane] : 0.0;
+    const double incl = run + warp_inclusive_scan(x, lane);
+    if (c0 + lane < nblk) pre[c0 + lane + 1] = incl;
+    run = __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    pre[0] = 0.0;
+    pre[nblk + 1] = quo(1.0, run);
+    pre[nblk + 2] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (prm.t - prm.first[p] - 1)]
+                                                    : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)prm.t);
+    pre[nblk + 3] = quo(1.0, (double)prm.N);
+  }
+}
+__global__ void __launch_bounds__(GB_S3_MAX_THREADS, 4) k_s3_weights(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ SurfaceRef s_ref[GB_MAX_OBS];
-  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
-  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
-  const int b = (int)(blockIdx.x % prm.s_nblk);
+  __shared__ double s_warp[GB_S3_MAX_THREADS / 32];
+  const int64_t p = prm.p0 + blockIdx.y;
+  const int b = (int)blockIdx.x;
   const int act = prm.s_act[p];
   if (!(act & GB_ACT_ACTIVE) || prm.s_pflags[p] != 0) return;
   const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
@@ -414,9 +446,10 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   const bool vec = (N & 1) == 0;
   uint32_t flags = 0;
   double wacc = 0.0;
-  for (int sub = 0; sub < prm.s_block; sub += 2 * GB_SBLOCK_THREADS) {
+  const int blk_end = min(N, (b + 1) * prm.s_block);  // s_block is even: pairs never straddle CTAs
+  for (int sub = 0; sub < prm.s_block; sub += 2 * (int)blockDim.x) {
   const int ia = b * prm.s_block + sub + 2 * tid;
-  const bool va = ia < N, vb = ia + 1 < N;
+  const bool va = ia < blk_end, vb = ia + 1 < blk_end;
   double w[2] = {0.0, 0.0};
   if (va) {
     if (fw) {
@@ -476,7 +509,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
   wacc += w[0] + w[1];
   }
   // CTA total of the weights (fixed association: per thread, warp butterfly, warps in order)
-  double tsum = warp_sum(wacc);
+  const double tsum = warp_sum(wacc);
   if (lane == 0) s_warp[warp] = tsum;
   __shared__ unsigned s_or;
   const int any = (int)block_or(flags, &s_or);
@@ -486,6 +519,14 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s3_weights(const __gri
     prm.s_bsum[p * prm.s_nblk + b] = tot;
     if (any) atomicOr(&prm.s_pflags[p], any);
   }
+}
+
+// s3b (pipelined flow): one warp per point turns the CTA totals of k_s3 into the record k_s4p reads.
+__global__ void k_s3b_publish(const __grid_constant__ StepParams prm) {
+  const int64_t p = prm.p0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (p >= prm.p0 + prm.pb) return;
+  if (!(prm.s_act[p] & GB_ACT_ACTIVE) || prm.s_pflags[p] != 0) return;
+  s3_publish_prefix(prm, p, threadIdx.x & 31);
 }
 
 // s4: prefix of the weights and child ranges (GB_S4_PPT consecutive parents per thread), then one thread
@@ -683,21 +724,48 @@ __global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
   }
 }
 
+// Capacity of one k_s4p CTA: the parents' evolved state (48 B), weight (8 B), child range end (4 B) and the
+// children's parent index (4 B) live in shared memory — 64 B per parent, 48 KB per CTA, four CTAs per SM.
+#ifndef GB_S4P_THREADS
+#define GB_S4P_THREADS 192
+#endif
+#define GB_S4P_CAP 768
+#define GB_S4P_PPT (GB_S4P_CAP / GB_S4P_THREADS)
+constexpr int kS4pSmem = GB_S4P_CAP * 64;
+
+// One projected child: image coordinates of time t + 1 and its contribution to the integer cloud box.
+__device__ __forceinline__ void s4p_project_child(const CamK& cam, const double (&s)[6], double* uv, int64_t N, int j, double hw,
+                                                  double hh, int (&e)[5]) {
+  double u, v;
+  project_fast(cam, s[0], s[1], s[2], u, v);
+  uv[j] = u;
+  uv[N + j] = v;
+  e[0] = __double2int_rd(u - hw);
+  e[1] = __double2int_rd(v - hh);
+  e[2] = -__double2int_ru(u + hw);
+  e[3] = -__double2int_ru(v + hh);
+  e[4] = (isnan(u) | isnan(v)) ? -1 : 0;
+}
+
 template <bool COV>
-__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
+__global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
                                                                                    const __grid_constant__ NextParams nxt) {
-  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4_PPT, CAP = PPT * GB_SBLOCK_THREADS;
-  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
-  __shared__ double s_pref[6];
-  __shared__ double s_red[GB_SBLOCK_THREADS / 32][KP];
-  __shared__ double s_w[CAP];
-  __shared__ int s_end[CAP];
+  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4P_PPT, CAP = GB_S4P_CAP, NW = GB_S4P_THREADS / 32, TH = GB_S4P_THREADS;
+  extern __shared__ __align__(128) unsigned char s4p_raw[];
+  double* s_st = reinterpret_cast<double*>(s4p_raw);  // [6][CAP] parents' state: bulk-copy destination
+  double* s_w = s_st + 6 * CAP;                       // [CAP] parents' weights
+  int* s_end = reinterpret_cast<int*>(s_w + CAP);     // [CAP] child range ends
+  int* s_par = s_end + CAP;                           // [CAP] parent of each child of the current chunk
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ double s_warp[NW];
+  __shared__ double s_red[NW][KP];
+  __shared__ int s_wmax[NW];
   __shared__ int s_j0;
   __shared__ gb_motion s_motion;
   __shared__ int s_box[GB_MAX_OBS][5];
   __shared__ unsigned s_or;
-  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
-  const int b = (int)(blockIdx.x % prm.s_nblk);
+  const int64_t p = prm.p0 + blockIdx.y;  // grid: (blocks of a point, points of the batch)
+  const int b = (int)blockIdx.x;
   const int act = prm.s_act[p];
   const bool update = (act & GB_ACT_ACTIVE) != 0, propagate = (act & GB_ACT_PROPAGATE) != 0;
   if ((!update && !propagate) || prm.s_pflags[p] != 0) return;  // a point that failed at t is neither resampled nor advanced
@@ -705,61 +773,66 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate
   const int N = (int)prm.N, O = prm.O;
   const int base = b * prm.s_block;
   const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA (<= CAP)
-  const int k0 = PPT * tid;                                      // first local parent of this thread
+  // source of the particles that are resampled: the evolved particles of time t, or — at a point's first
+  // time — the initial particles, taken one to one
+  const double* src6 = (update ? prm.s_ev : state_buffer(prm, t)) + p * 6 * (int64_t)N + base;
+  const double* wsrc = prm.s_w + (int64_t)p * N + base;
+  const bool bulk = n_here > 0 && ((N | n_here) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src6) | reinterpret_cast<uintptr_t>(wsrc)) & 15) == 0;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
   if (propagate) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
     for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
     if (tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
   }
+  __syncthreads();
+  if (bulk) {
+    // weights first (the prefix needs them), then the six state rows: all in flight while the prefix is computed
+    if (tid == 0) {
+      const uint32_t row = (uint32_t)n_here * 8u;
+      if (update) {
+        mbar_expect_tx(&s_bar[0], row);
+        bulk_load(s_w, wsrc, row, &s_bar[0]);
+      }
+      mbar_expect_tx(&s_bar[1], 6u * row);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) bulk_load(s_st + c * CAP, src6 + c * (int64_t)N, row, &s_bar[1]);
+    }
+  } else {
+    for (int i = tid; i < n_here; i += TH) {
+      if (update) s_w[i] = wsrc[i];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s_st[c * CAP + i] = src6[c * (int64_t)N + i];
+    }
+  }
   // ---- child ranges of the CTA's parents ----
   int J0, J1;
-  // source of the particles that are resampled: the evolved particles of time t, or — at a point's first
-  // time — the initial particles, taken one to one
-  const double* src6;
   if (update) {
-    if (tid == 0) {
-      const double* bs = prm.s_bsum + p * prm.s_nblk;
-      double run = 0.0, pre = 0.0, nx = 0.0;
-      for (int k = 0; k < prm.s_nblk; ++k) {
-        if (k == b) pre = run;
-        run += bs[k];
-        if (k == b) nx = run;
-      }
-      s_pref[0] = pre;
-      s_pref[1] = run;
-      s_pref[2] = nx;
-      s_pref[3] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
-                                                  : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
-      s_pref[4] = quo(1.0, (double)N);
-      s_pref[5] = quo(1.0, run);
-    }
-    const double* wsrc = prm.s_w + (int64_t)p * N;
+    // written by k_s3b_publish: every thread reads the same few words (one broadcast line)
+    const double* pre = prm.s_pre + p * (prm.s_nblk + 4);
+    const double prefix = pre[b], next_prefix = pre[b + 1], total = pre[prm.s_nblk], inv_total = pre[prm.s_nblk + 1],
+                 u01 = pre[prm.s_nblk + 2], inv_n = pre[prm.s_nblk + 3];
+    if (bulk) mbar_wait(&s_bar[0], 0);
+    else __syncthreads();
+    const int k0 = PPT * tid;  // first local parent of this thread (consecutive parents: in-thread prefix)
     double w[PPT];
-    if ((N & 1) == 0 && k0 + PPT <= n_here) {
-#pragma unroll
-      for (int q = 0; q < PPT; q += 2) {
-        const double2 x = *reinterpret_cast<const double2*>(wsrc + base + k0 + q);
-        w[q] = x.x;
-        w[q + 1] = x.y;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < PPT; ++q) w[q] = (k0 + q < n_here) ? wsrc[base + k0 + q] : 0.0;
-    }
     double tsum = 0.0;
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
-      if (k0 + q < CAP) s_w[k0 + q] = w[q];
-      tsum += w[q];
+      tsum += (k0 + q < n_here) ? s_w[k0 + q] : 0.0;
       w[q] = tsum;  // inclusive prefix inside the thread
     }
-    const double off = block_exclusive_offset(tsum, s_warp);  // contains a __syncthreads(): s_pref is visible
-    const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4], inv_total = s_pref[5];
+    const double off = block_exclusive_offset<NW>(tsum, s_warp);
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       const int k = k0 + q;
       if (k < n_here) {
+        // The last parent of the CTA takes the next CTA's prefix as its cumulative weight: child ranges are seamless
+        // across CTAs whatever the association of the in-CTA sums.
         const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
         // normalised cumulative weight: one reciprocal per CTA instead of a division per particle (the total maps to exactly 1)
         s_end[k] = count_positions_le(c >= total ? 1.0 : c * inv_total, u01, inv_n, N);
@@ -769,31 +842,30 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate
     __syncthreads();
     J0 = s_j0;
     J1 = n_here > 0 ? s_end[n_here - 1] : J0;
-    src6 = prm.s_ev + p * 6 * (int64_t)N + base;
   } else {
-    __syncthreads();
     J0 = base;
     J1 = base + n_here;
-    src6 = state_buffer(prm, t) + p * 6 * (int64_t)N + base;  // initial particles written by k_init
   }
-  const double* sin0 = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
-  // ---- moments of the resampled set: parents weighted by (children x weight), coalesced reads ----
+  if (bulk) mbar_wait(&s_bar[1], 0);
+  else if (!update) __syncthreads();
+  // ---- moments of the resampled set: parents weighted by (children x weight), from shared memory ----
   if (update) {
     double ref[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) ref[c] = prm.s_ref[p * 6 + c];
     Moments<COV> mom;
     mom.clear();
-#pragma unroll 2
-    for (int q = 0; q < PPT; ++q) {
-      const int k = k0 + q;
-      if (k >= n_here) break;
-      const int cnt = s_end[k] - (k > 0 ? s_end[k - 1] : J0);
-      if (cnt > 0) {
-        double s[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) s[c] = src6[c * (int64_t)N + k];
-        mom.accumulate((double)cnt * s_w[k], s, ref);
+    for (int q = 0; q < PPT; ++q) {
+      const int k = tid + q * TH;
+      if (k < n_here) {
+        const int cnt = s_end[k] - (k > 0 ? s_end[k - 1] : J0);
+        if (cnt > 0) {
+          double s[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) s[c] = s_st[c * CAP + k];
+          mom.accumulate((double)cnt * s_w[k], s, ref);
+        }
       }
     }
     double r[KP];
@@ -804,12 +876,11 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate
     __syncthreads();
     if (tid < NM) {
       double x = s_red[0][tid];
-      for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) x += s_red[wv][tid];
+      for (int wv = 1; wv < NW; ++wv) x += s_red[wv][tid];
       prm.s_pm[(p * prm.s_nblk + b) * 28 + tid] = x;
     }
   }
-  (void)sin0;
-  // ---- children: gather, report, and advance to t + 1 ----
+  // ---- children: gather from shared memory, report, and advance to t + 1 ----
   const bool last_time = !propagate;  // t == last: the resampled particles are the final state
   double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
   double* evn = prm.s_ev_next + p * 6 * (int64_t)N;
@@ -821,80 +892,118 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate
   const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
   uint32_t flags = 0;
   const int need = propagate ? evolve_needs(s_motion) : 0;
-  int ibx[GB_MAX_OBS > 2 ? 2 : GB_MAX_OBS][5];  // register boxes for the first two observers; others go straight to shared memory
+  int ibx[2][5];  // register boxes for the first two observers; others go straight to shared memory
 #pragma unroll
   for (int o = 0; o < 2; ++o) {
     ibx[o][0] = ibx[o][1] = ibx[o][2] = ibx[o][3] = 0x7fffffff;
     ibx[o][4] = 0;
   }
-  for (int j = J0 + tid; j < J1; j += GB_SBLOCK_THREADS) {
-    int lo;
-    double wj;
+  unsigned obs_on = 0;  // observers that see this point at t + 1 (block-uniform)
+  if (propagate)
+    for (int o = 0; o < O; ++o)
+      if (nxt.img[o] >= 0 && prm.mask[p * O + o]) obs_on |= 1u << o;
+  int carry = 0;  // parent of the last child of the previous chunk
+  for (int Jc = J0; Jc < J1; Jc += CAP) {
+    const int nch = min(CAP, J1 - Jc);
     if (update) {
-      int l2 = 0, hi = n_here - 1;  // smallest parent whose range end exceeds j
-      while (l2 < hi) {
-        const int mid = (l2 + hi) >> 1;
-        if (s_end[mid] > j) hi = mid; else l2 = mid + 1;
+      // parent of every child of the chunk: each parent marks its first child, a running maximum fills the rest
+      for (int i = tid; i < nch; i += TH) s_par[i] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const int k = tid + q * TH;
+        if (k < n_here) {
+          const int st = k > 0 ? s_end[k - 1] : J0, en = s_end[k];
+          if (en > st && st >= Jc && st - Jc < nch) s_par[st - Jc] = k;
+        }
       }
-      lo = l2;
-      wj = s_w[lo];
-    } else {
-      lo = j - base;
-      wj = 1.0;
+      __syncthreads();
+      int v[PPT], run = 0;
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const int i = PPT * tid + q;
+        run = max(run, i < nch ? s_par[i] : 0);
+        v[q] = run;
+      }
+      int incl = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, x);
+      }
+      if (lane == 31) s_wmax[warp] = incl;
+      __syncthreads();
+      int pre = carry, all = carry;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const int x = s_wmax[k];
+        if (k < warp) pre = max(pre, x);
+        all = max(all, x);
+      }
+      int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0;
+      pre = max(pre, excl);
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const int i = PPT * tid + q;
+        if (i < nch) s_par[i] = max(pre, v[q]);
+      }
+      carry = all;
+      __syncthreads();
     }
-    double s[6];
+    for (int j = Jc + tid; j < Jc + nch; j += TH) {
+      const int lo = update ? s_par[j - Jc] : j - base;
+      double s[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) s[c] = src6[c * (int64_t)N + lo];
-    if (update) {
-      if (last_time) {
+      for (int c = 0; c < 6; ++c) s[c] = s_st[c * CAP + lo];
+      if (update) {
+        const double wj = s_w[lo];
+        if (last_time) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);
+          for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);
+        }
+        if (wst) wst[j] = wj;
+        if (outp) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
+        }
+        if (outw) outw[j] = wj;
       }
-      if (wst) wst[j] = wj;
-      if (outp) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
-      }
-      if (outw) outw[j] = wj;
-    }
-    if (propagate) {
-      double z0, z1, z2;
-      if (prm.rng_mode == GB_RNG_SUPPLIED) {
-        z0 = zn[3 * (int64_t)j];
-        z1 = zn[3 * (int64_t)j + 1];
-        z2 = zn[3 * (int64_t)j + 2];
-      } else {
-        philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)(t + 1), (uint32_t)j, 2u, z0, z1, z2, need);
-      }
-      evolve_particle(s_motion, nxt.tau, nxt.tau2, z0, z1, z2, s);
-      flags |= test_particle(prm, s);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) evn[c * (int64_t)N + j] = s[c];
-      for (int o = 0; o < O; ++o) {
-        const int64_t po = p * O + o;
-        if (nxt.img[o] < 0 || !prm.mask[po]) continue;  // block-uniform
-        double u, v;
-        project_fast(nxt.cam[o], s[0], s[1], s[2], u, v);
-        double* uv = prm.s_uv + po * 2 * (int64_t)N;
-        uv[j] = u;
-        uv[(int64_t)N + j] = v;
-        const int e0 = __double2int_rd(u - hw), e1 = __double2int_rd(v - hh), e2 = -__double2int_ru(u + hw),
-                  e3 = -__double2int_ru(v + hh), e4 = (isnan(u) | isnan(v)) ? -1 : 0;
-        if (o < 2) {
-          ibx[o][0] = min(ibx[o][0], e0);
-          ibx[o][1] = min(ibx[o][1], e1);
-          ibx[o][2] = min(ibx[o][2], e2);
-          ibx[o][3] = min(ibx[o][3], e3);
-          ibx[o][4] = min(ibx[o][4], e4);
+      if (propagate) {
+        double z0, z1, z2;
+        if (prm.rng_mode == GB_RNG_SUPPLIED) {
+          z0 = zn[3 * (int64_t)j];
+          z1 = zn[3 * (int64_t)j + 1];
+          z2 = zn[3 * (int64_t)j + 2];
         } else {
-          atomicMin(&s_box[o][0], e0);
-          atomicMin(&s_box[o][1], e1);
-          atomicMin(&s_box[o][2], e2);
-          atomicMin(&s_box[o][3], e3);
-          atomicMin(&s_box[o][4], e4);
+          philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)(t + 1), (uint32_t)j, 2u, z0, z1, z2, need);
+        }
+        evolve_particle(s_motion, nxt.tau, nxt.tau2, z0, z1, z2, s);
+        flags |= test_particle(prm, s);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) evn[c * (int64_t)N + j] = s[c];
+        // the first two observers are unrolled: their camera operands come straight from the constant bank
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o >= O) break;
+          if (!(obs_on >> o & 1)) continue;
+          const int64_t po = p * O + o;
+          int e[5];
+          s4p_project_child(nxt.cam[o], s, prm.s_uv + po * 2 * (int64_t)N, N, j, hw, hh, e);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) ibx[o][k] = min(ibx[o][k], e[k]);
+        }
+        for (int o = 2; o < O; ++o) {
+          if (!(obs_on >> o & 1)) continue;
+          const int64_t po = p * O + o;
+          int e[5];
+          s4p_project_child(nxt.cam[o], s, prm.s_uv + po * 2 * (int64_t)N, N, j, hw, hh, e);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) atomicMin(&s_box[o][k], e[k]);
         }
       }
     }
+    if (update && Jc + CAP < J1) __syncthreads();  // the next chunk rewrites s_par
   }
   if (propagate) {
     // cloud boxes of time t + 1: registers -> warp -> shared -> global
@@ -914,7 +1023,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4p_resample_propagate
     if (tid < O * 5) {
       const int o = tid / 5, k = tid - o * 5;
       const int64_t po = p * O + o;
-      if (nxt.img[o] >= 0 && prm.mask[po]) atomicMin(&prm.s_ibox[po * 5 + k], s_box[o][k]);
+      if (obs_on >> o & 1) atomicMin(&prm.s_ibox[po * 5 + k], s_box[o][k]);
     }
   }
 }

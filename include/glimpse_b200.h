@@ -111,6 +111,21 @@ typedef struct gb_motion {
  * ------------------------------------------------------------------------------------------ */
 int gb_version(void);
 const char* gb_last_error(void);
+
+/* Measurement aid (no reference counterpart): when enabled, every kernel launch of gb_track's streaming
+ * flow is bracketed by CUDA events on the stream it is launched on; gb_kernel_timing_read returns the
+ * accumulated milliseconds and launch counts per kernel kind, index = GB_KERNEL_*.  Enabling resets the sums. */
+#define GB_KERNEL_ACTIVITY 0            /* k_s0p_activity */
+#define GB_KERNEL_SURFACE 1             /* k_s2_surface */
+#define GB_KERNEL_WEIGHTS 2             /* k_s3_weights */
+#define GB_KERNEL_RESAMPLE_PROPAGATE 3  /* k_s4p_resample_propagate */
+#define GB_KERNEL_FINALIZE 4            /* k_s5p_finalize */
+#define GB_KERNEL_INIT 5                /* k_init */
+#define GB_KERNEL_TEMPLATE 6            /* k_template */
+#define GB_KERNEL_PUBLISH 7            /* k_s3b_publish */
+#define GB_KERNEL_KINDS 8
+int gb_kernel_timing(int32_t enable);
+int gb_kernel_timing_read(double* ms, int64_t* launches, int32_t n);
 /* Build a gb_camera from the reference 20-vector on the host (libm sin/cos).  corr_host = {radius,
  * refraction} or NULL.  Replaces Camera.__init__ + Camera.R (camera.py:74-123, 239-280). */
 int gb_camera_from_vector(const double* vec20_host, const double* corr_host, gb_camera* out_host);
