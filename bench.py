@@ -7,15 +7,20 @@ Workload (``config.workload``): BASELINE.json configs[1] — single nadir observ
 1 000 points x 10 000 particles x 100 frames, full k1-k6/p1/p2 distortion, 15x15 template, synthetic
 translated-texture 4288x2848 uint8 frames.  One "step" = one whole ``track`` of that workload.
 
-* ``value``   device-resident inputs (frames already in HBM), CUDA-event time of the per-time kernel
-              sequence (gb_track_init + gb_track_step for t = 1..T-1, the same launches gb_track makes),
-              plus — for N > 1 — the final NCCL all-gather of the results.  Points x particles x frames
-              of ALL ranks / max-over-ranks time.  Weak scaling: every rank tracks its own 1 000 points.
+* ``value``   device-resident inputs (frames already in HBM), CUDA-event time around ``gb_track`` (every update
+              of every point, batches of points advancing on their own streams) plus — for N > 1 — the final
+              NCCL all-gather of the results.  Points x particles x frames of ALL ranks / max-over-ranks time.
+              Weak scaling: every rank tracks its own 1 000 points.
 * ``e2e``     the same metric through the public ``Tracker.track`` call with the frames in pinned HOST
               memory: per step the H2D copy of all frames + model tables and the D2H read of means /
               sigmas / status are inside the timed region.
-* ``roofline`` for the dominant kernel ``k_step``: algorithmic bytes per launch (96 B x P x N, SURVEY.md
-              §8d) / its mean CUDA-event duration, against MEASURED_PEAKS.json ``hbm_gbs``.
+* ``roofline`` for the dominant kernel ``k_s4p_resample_propagate``: algorithmic bytes per launch (96 B x the
+              particles of a launch) / its mean duration from CUDA events recorded around every
+              launch on the launching stream (``gb_kernel_timing``; one untimed extra track with all points in
+              one batch so that launches do not overlap), against MEASURED_PEAKS.json ``hbm_gbs``.
+              ``whole_update`` is the same figure for a complete update (all kernels) inside the timed region;
+              ``kernels`` / ``kernels_serial`` list every kernel's time per track in the production plan
+              (overlapping streams) and alone.
 * ``cpu_baseline`` the NumPy/SciPy/OpenCV oracle (a port of the Python reference, ``oracle/``) timed on one
               host core on a bounded sub-sample of the same workload (full N, fewer points and frames).
 * ``--impl reference`` times that CPU port with every host core (fork pool over points, the reference's
@@ -38,6 +43,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "particle_updates_per_s"
 UNIT = "particle-updates/s"
+# DRAM bytes per particle of k_s4p_resample_propagate from the ncu --set full capture (profiles/r1_summary.md)
+S4P_DRAM_BYTES_PER_PARTICLE = 99.0
 ALGORITHMIC_BYTES_PER_UPDATE = 96.0  # read 6 x f64 parent state + write 6 x f64 child state
 
 WORKLOAD = dict(n_points=1000, n_particles=10000, n_frames=100, imgsz=(4288, 2848), velocity_sigma=0.2, seed=2,
@@ -300,20 +307,42 @@ def run_gpu_arm(args):
     import ctypes as C
     lib = _lib.load()
     KINDS = ["k_s0p_activity", "k_s2_surface", "k_s3_weights", "k_s4p_resample_propagate", "k_s5p_finalize", "k_init", "k_template", "k_s3b_publish"]
-    kernels = {}
-    session.launches = 0
-    if args.mode == "stream" and not args.per_step_events:
+
+    def kernel_times(sess):
         _lib.check(lib.gb_kernel_timing(1))
-        one_track()
+        sess.buf["status"].zero_()
+        sess.run()
         torch.cuda.synchronize()
         k_ms, k_n = (C.c_double * len(KINDS))(), (C.c_int64 * len(KINDS))()
         _lib.check(lib.gb_kernel_timing_read(k_ms, k_n, len(KINDS)))
         _lib.check(lib.gb_kernel_timing(0))
-        kernels = {name: {"ms_per_track": float(k_ms[i]), "launches": int(k_n[i]),
-                          "us_per_launch": 1e3 * float(k_ms[i]) / max(1, int(k_n[i]))} for i, name in enumerate(KINDS)}
+        return {name: {"ms_per_track": float(k_ms[i]), "launches": int(k_n[i]),
+                       "us_per_launch": 1e3 * float(k_ms[i]) / max(1, int(k_n[i]))} for i, name in enumerate(KINDS)}
+
+    kernels, kernels_serial = {}, {}
+    session.launches = 0
+    if args.mode == "stream" and not args.per_step_events:
+        kernels = kernel_times(session)  # production plan: batches overlap on their streams, durations include sharing
     launches_per_track = session.launches
     session.launches = 0
     stats_out = session.fetch()
+    if kernels and rank == 0:
+        # the same track with all points in one batch on one stream: launches do not overlap, so the per-launch
+        # durations are those of each kernel alone (warm caches) — the figures the per-kernel roofline uses
+        saved = {k: os.environ.get(k) for k in ("GB_STREAM_SLOTS", "GB_STREAM_BATCH")}
+        os.environ["GB_STREAM_SLOTS"], os.environ["GB_STREAM_BATCH"] = "1", str(P)
+        try:
+            serial = Session(tracker, models[lo:hi], image_index, taus, scene.tile_size, mask, point_offset=lo)
+            serial.run()
+            torch.cuda.synchronize()
+            kernels_serial = kernel_times(serial)
+            del serial
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     failed = int((status != 0).sum())
     value = world * P * N * T / (dev_ms / 1e3)
     if launches_per_track:
@@ -324,6 +353,24 @@ def run_gpu_arm(args):
     peak, peak_src = hbm_peak()
     achieved = ALGORITHMIC_BYTES_PER_UPDATE * P * N / (kernel_ms / 1e3) / 1e9
     win_w, win_h = session.stats["window_width"], session.stats["window_height"]
+    update = {"achieved": achieved, "frac": achieved / peak, "ms": kernel_ms,
+              "what": "one update of all points (every kernel and batch), algorithmic bytes / (track time / updates)"}
+    dom = kernels_serial.get("k_s4p_resample_propagate")
+    if dom and dom["launches"]:
+        # dominant kernel: SURVEY.md 8(d)'s 96 B per particle-update x the particles one launch processes
+        dom_bytes = ALGORITHMIC_BYTES_PER_UPDATE * P * N
+        dom_ach = dom_bytes / (dom["us_per_launch"] * 1e-6) / 1e9
+        total_ms = sum(v["ms_per_track"] for v in kernels_serial.values())
+        roofline = {"bound": "hbm", "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak,
+                    "traffic": S4P_DRAM_BYTES_PER_PARTICLE * P * N if not args.small else None,
+                    "kernel": "k_s4p_resample_propagate", "kernel_ms": dom["us_per_launch"] / 1e3, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom_bytes, "share_of_step": dom["ms_per_track"] / total_ms,
+                    "measured": "CUDA events around every launch on the launching stream, all points in one batch (no overlap)",
+                    "whole_update": update, "kernels_serial": kernels_serial, "kernels": kernels}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": "k_step" if args.mode == "fused" else "one update of all points", "kernel_ms": kernel_ms,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N}
 
     # ---------------- e2e: public API, host frames, copies inside the timed region -----------------
     def e2e_once():
@@ -347,7 +394,7 @@ def run_gpu_arm(args):
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sub_points, sub_frames = 12, 12
+        sub_points, sub_frames = 40, 50  # ~12 s on one core
         sub = build_scene(sub_points, sub_frames)
         os.environ.setdefault("OMP_NUM_THREADS", "1")
         rate, dt = cpu_rate(sub, sub_points, 1)
@@ -372,11 +419,7 @@ def run_gpu_arm(args):
                                      "max_h": int(win_h.max()) if len(win_h) else None},
                 "failed_points": failed, "median_abs_velocity_error_m_per_day": v_err,
             },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_step" if args.mode == "fused" else "one update of all points = k_s0p + k_s2 + k_s3 + k_s4p + k_s5p (x batches)",
-                         "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_UPDATE * P * N,
-                         "kernels": kernels},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,

@@ -1249,7 +1249,7 @@ static void stream_bind(const gb_track_desc& d, StepParams& prm, int par, int64_
   prm.pb = pb;
 }
 
-static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2_surface (3 CTAs per SM)
+static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2_surface (windows up to ~66 px; larger ones work in their global region)
 
 // Side streams on which batches of points advance independently (points never interact).  One pool per device.
 struct StreamPool {

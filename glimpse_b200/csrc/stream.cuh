@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
   const int o = (int)(po - p * prm.O);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
   int* meta = prm.s_meta + po * 8;
+  // profiling aid (gb_track_step only): clock64() of thread 0 at the phase boundaries, window size, SM id
+  long long* clk = prm.io.dump_clocks ? reinterpret_cast<long long*>(prm.io.dump_clocks) + po * 16 : nullptr;
+  if (clk && tid == 0) clk[0] = clock64();
   if (tid == 0) meta[7] = 0;
   if (!stream_point_active(prm, p) || prm.io.force_weights) return;
   uint8_t* oflag = prm.obs_flags + ((int64_t)p * prm.T + t) * prm.O + o;
@@ -322,12 +325,22 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
     return;
   }
   const bool in_smem = need <= smem_budget;
+  if (clk && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    clk[1] = clock64();
+    clk[7] = w.Su;
+    clk[8] = w.Sv;
+    clk[9] = smid;
+    clk[10] = in_smem;
+  }
   tile_carve(in_smem ? reinterpret_cast<char*>(smem_raw) : region, w);
   const int64_t ta = (int64_t)w.tw * w.th;
   const int boxv[4] = {box_l, box_t, box_r, box_b};
   tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
                      prm.tmpl_values + po * ta, w, prm.io.dump_search ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
-                     prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap, nullptr);
+                     prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap, clk ? clk + 2 : nullptr);
+  if (clk && tid == 0) clk[5] = clock64();
   if (in_smem) {
     float4* dst = reinterpret_cast<float4*>(region);
     for (int i = tid; i < w.Mv * w.Mp; i += blockDim.x) dst[i] = w.herm[i];
@@ -341,6 +354,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
     meta[5] = w.Mv;
     meta[6] = w.Mp;
     meta[7] = 1;
+    if (clk) clk[6] = clock64();
   }
 }
 
