@@ -283,12 +283,26 @@ class Session:
                 g = out[k]
                 g.pixels = dev.data_ptr()
                 g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
-                g.cam = lower_camera(img.cam)
+                g.cam = self._lower_camera_memo(img.cam)
                 self._pending_events.append((k, event))
         self.images_host = (_lib.gb_image * len(out))(*out)
         images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
         self.h2d += images_dev.numel()
         return images_dev, np.asarray(offsets, dtype=np.int32)
+
+    def _lower_camera_memo(self, cam):
+        """``lower_camera`` once per distinct camera (a sequence of frames usually shares one)."""
+        memo = self.__dict__.setdefault("_camera_memo", {})
+        vec = getattr(cam, "vector", None)
+        if vec is None:
+            return lower_camera(cam)
+        corr = getattr(cam, "correction", None)
+        key = (np.asarray(vec, dtype=float).tobytes(), tuple(int(v) for v in cam.imgsz),
+               tuple(sorted(corr.items())) if isinstance(corr, dict) else None)
+        hit = memo.get(key)
+        if hit is None:
+            hit = memo[key] = lower_camera(cam)
+        return hit
 
     def _lower_models(self, models):
         torch, device = self.torch, self.device
@@ -369,17 +383,26 @@ class Session:
 
     # ---------------------------------------------------------------- results
     def fetch(self) -> dict:
-        b, P, T = self.buf, self.P, self.T
-        out = {"means": b["means"].cpu().numpy()}
-        sig = b["sig"].cpu().numpy()
-        out["sigmas"] = sig.reshape(P, T, 6, 6) if self.return_covariances else sig
-        out["status"], out["status_time"] = b["status"].cpu().numpy(), b["status_time"].cpu().numpy()
-        out["obs_flags"] = b["obs_flags"].cpu().numpy()
+        """Results to host memory: every array is copied into pinned memory on the compute stream without
+        blocking, then one synchronisation covers them all."""
+        torch, b, P, T = self.torch, self.buf, self.P, self.T
+        names = ["means", "sig", "status", "status_time", "obs_flags", "window"]
+        if self.return_particles:
+            names += ["particles", "weights"]
+        host = {}
+        with torch.cuda.device(self.device):
+            for k in names:
+                host[k] = torch.empty(b[k].shape, dtype=b[k].dtype, pin_memory=True)
+                host[k].copy_(b[k], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        h = {k: v.numpy() for k, v in host.items()}
+        out = {"means": h["means"], "sigmas": h["sig"].reshape(P, T, 6, 6) if self.return_covariances else h["sig"],
+               "status": h["status"], "status_time": h["status_time"], "obs_flags": h["obs_flags"]}
         d2h = b["means"].numel() * 8 + b["sig"].numel() * 8 + P * 8 + b["obs_flags"].numel()
         if self.return_particles:
-            out["particles"], out["weights"] = b["particles"].cpu().numpy(), b["weights"].cpu().numpy()
+            out["particles"], out["weights"] = h["particles"], h["weights"]
             d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
-        win = b["window"].cpu().numpy()
+        win = h["window"]
         used = (out["obs_flags"] == 0) & (win[..., 0] > 0)
         self.stats = {
             "plan": {k: getattr(self.plan, k) for k, _ in self.plan._fields_}, "kernel_launches": self.launches,
