@@ -23,7 +23,7 @@ GB_ST_MESSAGES = {
 GB_OBS_OUT_OF_FRAME = 2
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
 GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
-GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL = 0, 1
+GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 
 
 class gb_camera(C.Structure):
@@ -53,7 +53,7 @@ class gb_motion(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("dem", C.c_int32), ("dem_sigma", C.c_int32), ("pad_", C.c_int32),
         ("xy", C.c_double * 2), ("xy_sigma", C.c_double * 2), ("v", C.c_double * 3), ("v_sigma", C.c_double * 3),
-        ("a", C.c_double * 3), ("a_sigma", C.c_double * 3),
+        ("a", C.c_double * 3), ("a_sigma", C.c_double * 3), ("slope_sigma", C.c_double),
     ]
 
 
@@ -75,7 +75,7 @@ class gb_track_desc(C.Structure):
         ("mask_host", C.c_void_p), ("first_host", C.c_void_p), ("last_host", C.c_void_p),
         ("tau_host", C.c_void_p), ("tau2_host", C.c_void_p),
         ("motion", C.c_void_p), ("surfaces", C.c_void_p), ("n_surfaces", C.c_int32), ("viewshed", C.c_int32),
-        ("rng_mode", C.c_int32), ("pad0_", C.c_int32), ("seed", C.c_uint64), ("point_offset", C.c_int64),
+        ("rng_mode", C.c_int32), ("motion_kinds", C.c_int32), ("seed", C.c_uint64), ("point_offset", C.c_int64),
         ("init_normals", C.c_void_p), ("step_normals", C.c_void_p), ("uniforms", C.c_void_p),
         ("state_a", C.c_void_p), ("state_b", C.c_void_p), ("weight_state", C.c_void_p), ("scratch", C.c_void_p),
         ("tmpl_tile", C.c_void_p), ("tmpl_values", C.c_void_p), ("tmpl_quantiles", C.c_void_p),
@@ -110,7 +110,7 @@ SIGNATURES = {
     "gb_track": (C.c_int, [C.POINTER(gb_track_desc), C.c_void_p, C.POINTER(C.c_int64)]),
     "gb_track_step": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.POINTER(gb_stage_io), C.c_void_p]),
     "gb_track_init": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.c_void_p]),
-    "gb_evolve": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gb_evolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gb_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

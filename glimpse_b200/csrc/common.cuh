@@ -23,6 +23,7 @@ namespace cg = cooperative_groups;
 #define GB_F_DEM_OOB 16u
 #define GB_F_WINDOW 32u
 #define GB_F_TEMPLATE 64u
+#define GB_F_EVOLVE_OOB 128u /* a tangent model sampled its DEM out of bounds while evolving (before the particle tests) */
 
 namespace gb {
 

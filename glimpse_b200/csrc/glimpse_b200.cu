@@ -116,6 +116,7 @@ struct NextParams {
 __device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
 
 __device__ __forceinline__ int status_from_flags(uint32_t f) {
+  if (f & GB_F_EVOLVE_OOB) return GB_ST_DEM_BOUNDS;  // raised inside evolve_particles, before the particle tests
   if (f & GB_F_VIEW_OOB) return GB_ST_DEM_BOUNDS;
   if (f & GB_F_NOT_VISIBLE) return GB_ST_NOT_VISIBLE;
   if (f & GB_F_NAN) return GB_ST_NAN;
@@ -249,15 +250,16 @@ __global__ void k_state_to_rows(const double* __restrict__ state, int64_t npoint
 
 // Motion.evolve_particles on SoA state with supplied normals (stage entry point + staggered
 // template path of gb_track, where t/first/last select the points that step at time t).
-__global__ void k_evolve(const gb_motion* __restrict__ motion, int64_t P, int64_t N, double tau, double tau2,
-                         const double* __restrict__ normals, int64_t normals_point_stride, double* __restrict__ state,
-                         const int32_t* first, const int32_t* last, const int32_t* status, int t, int rng_mode,
-                         uint64_t seed, int S, int64_t point_offset) {
+__global__ void k_evolve(const gb_motion* __restrict__ motion, const gb_surface* __restrict__ surfaces, int64_t P, int64_t N,
+                         double tau, double tau2, const double* __restrict__ normals, int64_t normals_point_stride,
+                         double* __restrict__ state, const int32_t* first, const int32_t* last, int32_t* status, int32_t* status_time,
+                         int t, int rng_mode, uint64_t seed, int S, int64_t point_offset) {
   const int64_t p = blockIdx.y;
   if (first && (status[p] != 0 || t <= first[p] || t > last[p])) return;
   const gb_motion m = motion[p];
   const double* zn = normals ? normals + p * normals_point_stride + (first ? (int64_t)(t - first[p] - 1) * N * 3 : 0) : nullptr;
   (void)S;
+  uint32_t flags = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     double s[6];
 #pragma unroll
@@ -270,9 +272,14 @@ __global__ void k_evolve(const gb_motion* __restrict__ motion, int64_t P, int64_
     } else {
       philox_normals3(seed, (uint64_t)(p + point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2);
     }
-    evolve_particle(m, tau, tau2, z0, z1, z2, s);
+    evolve_particle(m, surfaces, tau, tau2, z0, z1, z2, s, flags);
 #pragma unroll
     for (int c = 0; c < 6; ++c) state[(p * 6 + c) * N + i] = s[c];
+  }
+  // (stand-alone call: the failure is reported after the fact; inside gb_track_step the step kernels see the status)
+  if (flags && status) {
+    atomicCAS(&status[p], 0, GB_ST_DEM_BOUNDS);
+    if (status_time) status_time[p] = t;
   }
 }
 
@@ -669,7 +676,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
           } else {
             philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)(i0 + ii[q]), 2u, z0, z1, z2);
           }
-          evolve_particle(hdr->motion, prm.tau, prm.tau2, z0, z1, z2, s[q]);
+          evolve_particle<false>(hdr->motion, prm.surfaces, prm.tau, prm.tau2, z0, z1, z2, s[q], flags);  // fused mode: no tangent models
         }
       }
 #pragma unroll
@@ -1396,13 +1403,17 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
   cudaError_t aerr = cudaSuccess;
   std::call_once(attr_once[dev & 15], [&]() {
     aerr = cudaFuncSetAttribute(k_s2_surface, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurfaceSmem);
-    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
-    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
+    if (aerr == cudaSuccess) aerr = cudaFuncSetAttribute(k_s4p_resample_propagate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS4pSmem);
   });
   if (aerr != cudaSuccess) return fail(GB_E_CUDA, "stream kernel attributes: %s", cudaGetErrorString(aerr));
   if (d.plan.stream_block > GB_S4P_CAP || (d.plan.stream_block & 1)) return fail(GB_E_INVALID, "plan: stream_block must be even and <= 768%s");
   if (d.plan.stream_batch > 65535) return fail(GB_E_INVALID, "plan: stream_batch must be <= 65535%s");
   const bool cov = d.covariances != nullptr;
+  // kernels without the tangent models' DEM gathers when the caller says no point uses them (0 = unknown: assume any kind)
+  const bool tangent = d.motion_kinds == 0 || (d.motion_kinds & ((1 << GB_MOTION_TANGENT_CARTESIAN) | (1 << GB_MOTION_TANGENT_CYLINDRICAL))) != 0;
   const int slots = d.plan.stream_slots;
   const int64_t batch = d.plan.stream_batch;
   const int64_t nbatch = (d.P + batch - 1) / batch;
@@ -1526,10 +1537,17 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
         kt.end(ss);
       }
       kt.begin(GB_K_RESAMPLE_PROPAGATE, ss);
-      if (cov)
-        k_s4p_resample_propagate<true><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
-      else
-        k_s4p_resample_propagate<false><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+      {
+        const dim3 grid((unsigned)prm.s_nblk, (unsigned)pb);
+        if (cov && tangent)
+          k_s4p_resample_propagate<true, true><<<grid, GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+        else if (cov)
+          k_s4p_resample_propagate<true, false><<<grid, GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+        else if (tangent)
+          k_s4p_resample_propagate<false, true><<<grid, GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+        else
+          k_s4p_resample_propagate<false, false><<<grid, GB_S4P_THREADS, kS4pSmem, ss>>>(prm, nxt);
+      }
       kt.end(ss);
       kt.begin(GB_K_FINALIZE, ss);
       if (cov)
@@ -1830,9 +1848,9 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
     if (staggered) {
       if (!d->weight_state) return fail(GB_E_INVALID, "weight_state is required when a template starts after a point's first frame%s");
       dim3 grid((unsigned)grid_for(d->N, 256), (unsigned)d->P, 1);
-      k_evolve<<<grid, 256, 0, stream>>>(d->motion, d->P, d->N, prm.tau, prm.tau2, d->step_normals, (int64_t)(d->T - 1) * d->N * 3,
-                                         ((t - 1) & 1) ? d->state_b : d->state_a, d->first, d->last, d->status, t, d->rng_mode,
-                                         d->seed, d->T - 1, d->point_offset);
+      k_evolve<<<grid, 256, 0, stream>>>(d->motion, d->surfaces, d->P, d->N, prm.tau, prm.tau2, d->step_normals,
+                                         (int64_t)(d->T - 1) * d->N * 3, ((t - 1) & 1) ? d->state_b : d->state_a, d->first, d->last,
+                                         d->status, d->status_time, t, d->rng_mode, d->seed, d->T - 1, d->point_offset);
       GB_CUDA(cudaGetLastError());
       ++launches;
       prm.skip_evolve = 1;
@@ -1856,12 +1874,12 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   return GB_OK;
 }
 
-int gb_evolve(const gb_motion* motion, int64_t P, int64_t N, double tau, double tau2, const double* normals, double* state,
-              void* stream) {
+int gb_evolve(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, double tau, double tau2,
+              const double* normals, double* state, int32_t* status, void* stream) {
   if (!motion || !normals || !state || P <= 0 || N <= 0) return fail(GB_E_INVALID, "bad arguments%s");
   dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
-  k_evolve<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, P, N, tau, tau2, normals, N * 3, state, nullptr, nullptr, nullptr, 0,
-                                                   GB_RNG_SUPPLIED, 0, 0, 0);
+  k_evolve<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, surfaces, P, N, tau, tau2, normals, N * 3, state, nullptr, nullptr, status,
+                                                   nullptr, 0, GB_RNG_SUPPLIED, 0, 0, 0);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

@@ -1,5 +1,6 @@
 // Motion models, surfaces and random draws.
 //   CartesianMotion / CylindricalMotion: reference track/motion.py:92-311
+//   TangentCartesianMotion / TangentCylindricalMotion: reference track/motion.py:314-522
 //   Raster.sample point mode (DEM, DEM sigma, viewshed): reference raster.py:891-1027
 #pragma once
 #include "common.cuh"
@@ -66,9 +67,15 @@ __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t point, u
   }
 }
 
+__device__ __forceinline__ bool motion_is_tangent(const gb_motion& m) { return m.kind >= GB_MOTION_TANGENT_CARTESIAN; }
+__device__ __forceinline__ bool motion_is_cylindrical(const gb_motion& m) {
+  return m.kind == GB_MOTION_CYLINDRICAL || m.kind == GB_MOTION_TANGENT_CYLINDRICAL;
+}
+
 // Which normals evolve_particle really consumes for this motion model.
 __device__ __forceinline__ int evolve_needs(const gb_motion& m) {
-  return ((m.a_sigma[0] != 0.0 || m.a_sigma[1] != 0.0) ? 1 : 0) | (m.a_sigma[2] != 0.0 ? 2 : 0);
+  const double third = motion_is_tangent(m) ? m.slope_sigma : m.a_sigma[2];
+  return ((m.a_sigma[0] != 0.0 || m.a_sigma[1] != 0.0) ? 1 : 0) | (third != 0.0 ? 2 : 0);
 }
 
 __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t point, uint32_t time) {
@@ -109,8 +116,9 @@ __device__ inline double surface_sample(const gb_surface& s, double x, double y,
 // ---------------------------------------------------------------------------------------------
 // Particle initialisation and evolution
 // ---------------------------------------------------------------------------------------------
-// initialize_particles (motion.py:149-163, 260-283).  zn = the six normals of this particle in the
-// reference's draw order: randn(n,2) -> xy, randn(n) -> z, randn(n,3) -> velocity.
+// initialize_particles (motion.py:149-163, 260-283, 378-390, 485-505).  zn = the six normals of this particle
+// in the reference's draw order: randn(n,2) -> xy, randn(n) -> z, randn(n,3) -> velocity (tangent kinds:
+// randn(n,2), zn[5] unused and vz = 0).
 __device__ inline void init_particle(const gb_motion& m, const gb_surface* surfaces, const double (&zn)[6],
                                      double (&s)[6], uint32_t& flags) {
   s[0] = add(m.xy[0], mul(m.xy_sigma[0], zn[0]));
@@ -122,24 +130,38 @@ __device__ inline void init_particle(const gb_motion& m, const gb_surface* surfa
   s[2] = add(z, mul(zs, zn[2]));
   const double v0 = add(m.v[0], mul(m.v_sigma[0], zn[3]));
   const double v1 = add(m.v[1], mul(m.v_sigma[1], zn[4]));
-  const double v2 = add(m.v[2], mul(m.v_sigma[2], zn[5]));
-  if (m.kind == GB_MOTION_CYLINDRICAL) {
+  if (motion_is_cylindrical(m)) {
     s[3] = mul(v0, cos(v1));
     s[4] = mul(v0, sin(v1));
   } else {
     s[3] = v0;
     s[4] = v1;
   }
-  s[5] = v2;
+  s[5] = motion_is_tangent(m) ? 0.0 : add(m.v[2], mul(m.v_sigma[2], zn[5]));
 }
 
-// evolve_particles (motion.py:165-179, 285-311): position uses the old velocity.
-__device__ __forceinline__ void evolve_particle(const gb_motion& m, double tau, double tau2, double z0, double z1,
-                                                double z2, double (&s)[6]) {
+// Height of a tangent-model particle after a horizontal step (dx, dy) from (x, y, z) (motion.py:402-409):
+// its offset above the DEM, widened by slope_sigma * z2 * |dxy|, on top of the DEM at the new position.
+__device__ __forceinline__ double tangent_height(const gb_surface& dem, double slope_sigma, double z2, double x, double y,
+                                              double z, double dx, double dy, uint32_t& flags) {
+  bool oob0, oob1;
+  double zoff = sub(z, surface_sample(dem, x, y, 1, oob0));
+  zoff = add(zoff, mul(mul(slope_sigma, z2), sqrt(add(mul(dx, dx), mul(dy, dy)))));
+  const double znew = add(surface_sample(dem, add(x, dx), add(y, dy), 1, oob1), zoff);
+  if (oob0 | oob1) flags |= GB_F_EVOLVE_OOB;
+  return znew;
+}
+
+// evolve_particles (motion.py:165-179, 285-311): position uses the old velocity.  Tangent kinds
+// (motion.py:392-420, 507-522): the step is horizontal, the particle keeps its offset above the DEM, widened by
+// slope_sigma * z2 * |dxy|; z0, z1 are the randn(n,2) draw and z2 the randn(n) draw.
+// TAN = false compiles the tangent branch out (kernels specialised for tracks without tangent models).
+template <bool TAN = true>
+__device__ __forceinline__ void evolve_particle(const gb_motion& m, const gb_surface* surfaces, double tau, double tau2,
+                                                double z0, double z1, double z2, double (&s)[6], uint32_t& flags) {
   double a0 = add(m.a[0], mul(m.a_sigma[0], z0));
   double a1 = add(m.a[1], mul(m.a_sigma[1], z1));
-  const double a2 = add(m.a[2], mul(m.a_sigma[2], z2));
-  if (m.kind == GB_MOTION_CYLINDRICAL) {
+  if (motion_is_cylindrical(m)) {
     const double vx = s[3], vy = s[4];
     const double vr = sqrt(add(mul(vx, vx), mul(vy, vy)));
     const double ax = sub(mul(a0, quo(vx, vr)), mul(vy, a1));
@@ -147,8 +169,19 @@ __device__ __forceinline__ void evolve_particle(const gb_motion& m, double tau, 
     a0 = ax;
     a1 = ay;
   }
-  s[0] = add(s[0], add(mul(tau, s[3]), mul(mul(0.5, a0), tau2)));
-  s[1] = add(s[1], add(mul(tau, s[4]), mul(mul(0.5, a1), tau2)));
+  const double dx = add(mul(tau, s[3]), mul(mul(0.5, a0), tau2));
+  const double dy = add(mul(tau, s[4]), mul(mul(0.5, a1), tau2));
+  if (TAN && motion_is_tangent(m)) {
+    s[2] = tangent_height(surfaces[m.dem], m.slope_sigma, z2, s[0], s[1], s[2], dx, dy, flags);
+    s[0] = add(s[0], dx);
+    s[1] = add(s[1], dy);
+    s[3] = add(s[3], mul(tau, a0));
+    s[4] = add(s[4], mul(tau, a1));
+    return;
+  }
+  const double a2 = add(m.a[2], mul(m.a_sigma[2], z2));
+  s[0] = add(s[0], dx);
+  s[1] = add(s[1], dy);
   s[2] = add(s[2], add(mul(tau, s[5]), mul(mul(0.5, a2), tau2)));
   s[3] = add(s[3], mul(tau, a0));
   s[4] = add(s[4], mul(tau, a1));

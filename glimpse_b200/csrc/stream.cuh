@@ -18,6 +18,7 @@
 // model has a non-trivial surface likelihood.  One load instead of a chain of dependent ones.
 #define GB_ACT_ACTIVE 1
 #define GB_ACT_SURFACE_LL 2
+#define GB_ACT_NO_MOTION_LL 8 /* the motion model returns no likelihood at all (tangent kinds) */
 __device__ __forceinline__ bool stream_point_active(const StepParams& prm, int64_t p) {
   return (prm.s_act[p] & GB_ACT_ACTIVE) != 0;
 }
@@ -32,8 +33,9 @@ __global__ void k_s0_reset(const __grid_constant__ StepParams prm) {
     prm.s_pflags[i] = 0;
     const bool active = prm.status[i] == 0 && prm.t > prm.first[i] && prm.t <= prm.last[i];
     const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
-    const bool sll = !(sg.z == nullptr && sg.value == 0.0);
-    prm.s_act[i] = (uint8_t)((active ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0));
+    const bool tangent = prm.motion[i].kind >= GB_MOTION_TANGENT_CARTESIAN;  // compute_log_likelihoods is None (motion.py:77-89)
+    const bool sll = !tangent && !(sg.z == nullptr && sg.value == 0.0);
+    prm.s_act[i] = (uint8_t)((active ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) | (tangent ? GB_ACT_NO_MOTION_LL : 0));
   }
 }
 
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __g
         } else {
           philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)i, 2u, z0, z1, z2, evolve_needs(s_motion));
         }
-        evolve_particle(s_motion, prm.tau, prm.tau2, z0, z1, z2, s[q]);
+        evolve_particle(s_motion, prm.surfaces, prm.tau, prm.tau2, z0, z1, z2, s[q], flags);
       }
     }
     flags |= test_particle(prm, s[0]);
@@ -457,6 +459,13 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 4) k_s3_weights(const __gri
   __syncthreads();
   const double* ev = prm.s_ev + p * 6 * (int64_t)N;
   const double* fw = prm.io.force_weights ? prm.io.force_weights + (int64_t)p * N : nullptr;
+  if (!fw && (act & GB_ACT_NO_MOTION_LL)) {
+    // no image likelihood at this time and a motion model without one: the reference leaves the weights of the last
+    // resampling in place (tracker.py:146-149); they live in weight_state (ones after initialisation)
+    bool any_ok = false;
+    for (int o = 0; o < O; ++o) any_ok |= s_ref[o].ok != 0;
+    if (!any_ok && prm.weight_state) fw = prm.weight_state + (int64_t)p * N;
+  }
   const bool vec = (N & 1) == 0;
   uint32_t flags = 0;
   double wacc = 0.0;
@@ -721,8 +730,9 @@ __global__ void k_s0p_activity(const __grid_constant__ StepParams prm) {
     const bool alive = prm.status[i] == 0;
     const int f = prm.first[i], l = prm.last[i];
     const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
-    const bool sll = !(sg.z == nullptr && sg.value == 0.0);
-    prm.s_act[i] = (uint8_t)(((alive && f < prm.t && prm.t <= l) ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) |
+    const bool tangent = prm.motion[i].kind >= GB_MOTION_TANGENT_CARTESIAN;  // compute_log_likelihoods is None (motion.py:77-89)
+    const bool sll = !tangent && !(sg.z == nullptr && sg.value == 0.0);
+    prm.s_act[i] = (uint8_t)(((alive && f < prm.t && prm.t <= l) ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) | (tangent ? GB_ACT_NO_MOTION_LL : 0) |
                              ((alive && f <= prm.t && prm.t < l) ? GB_ACT_PROPAGATE : 0));
   }
 }
@@ -761,7 +771,7 @@ __device__ __forceinline__ void s4p_project_child(const CamK& cam, const double 
   e[4] = (isnan(u) | isnan(v)) ? -1 : 0;
 }
 
-template <bool COV>
+template <bool COV, bool TAN>
 __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
                                                                                    const __grid_constant__ NextParams nxt) {
   constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4P_PPT, CAP = GB_S4P_CAP, NW = GB_S4P_THREADS / 32, TH = GB_S4P_THREADS;
@@ -992,7 +1002,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
         } else {
           philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)(t + 1), (uint32_t)j, 2u, z0, z1, z2, need);
         }
-        evolve_particle(s_motion, nxt.tau, nxt.tau2, z0, z1, z2, s);
+        evolve_particle<TAN>(s_motion, prm.surfaces, nxt.tau, nxt.tau2, z0, z1, z2, s, flags);
         flags |= test_particle(prm, s);
 #pragma unroll
         for (int c = 0; c < 6; ++c) evn[c * (int64_t)N + j] = s[c];

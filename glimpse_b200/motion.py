@@ -1,4 +1,4 @@
-"""Motion models (reference ``track/motion.py:92-311``) as parameter holders that the Tracker lowers
+"""Motion models (reference ``track/motion.py:92-522``) as parameter holders that the Tracker lowers
 to ``gb_motion`` structs; ``evolve_particles`` is also callable on its own (``gb_evolve``)."""
 from __future__ import annotations
 
@@ -55,21 +55,37 @@ class CartesianMotion:
         m.v_sigma[:] = np.asarray(vs, dtype=float).tolist()
         m.a[:] = np.asarray(a, dtype=float).tolist()
         m.a_sigma[:] = np.asarray(as_, dtype=float).tolist()
+        m.slope_sigma = float(getattr(self, "slope_sigma", 0.0))
         return m
 
+    def _draw_step_normals(self, n: int) -> np.ndarray:
+        """The reference's draws of one ``evolve_particles`` call, as (n, 3)."""
+        return np.random.randn(n, 3)
+
     def evolve_particles(self, particles: np.ndarray, dt: _dt.timedelta) -> None:
-        """In-place motion step on (n, 6) particles with draws from ``np.random.randn(n, 3)`` — the
-        reference's call (motion.py:165-179) — evaluated by ``gb_evolve``."""
+        """In-place motion step on (n, 6) particles with draws from the legacy global NumPy generator in the
+        reference's order (motion.py:165-179, 285-311, 392-420, 507-522), evaluated by ``gb_evolve``."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         n = len(particles)
         tau = dt.total_seconds() / self.time_unit.total_seconds()
-        normals = torch.as_tensor(np.random.randn(n, 3)).cuda()
+        normals = torch.as_tensor(np.ascontiguousarray(self._draw_step_normals(n))).cuda()
         state = torch.as_tensor(np.ascontiguousarray(particles.T)).cuda()  # [6][n]
-        motion = torch.frombuffer(bytearray(bytes(self.lower(0, 0))), dtype=torch.uint8).cuda()
+        device = state.device
+        s_dem, t_dem = self.dem.lower(torch, device)
+        s_sig, t_sig = self.dem_sigma.lower(torch, device)
+        surfaces = torch.frombuffer(bytearray(bytes(s_dem) + bytes(s_sig)), dtype=torch.uint8).cuda()
+        motion = torch.frombuffer(bytearray(bytes(self.lower(0, 1))), dtype=torch.uint8).cuda()
+        status = torch.zeros(1, dtype=torch.int32, device=device)
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.gb_evolve(motion.data_ptr(), 1, n, tau, tau ** 2, normals.data_ptr(), state.data_ptr(), stream))
+        _lib.check(lib.gb_evolve(motion.data_ptr(), surfaces.data_ptr(), 1, n, tau, tau ** 2, normals.data_ptr(),
+                                 state.data_ptr(), status.data_ptr(), stream))
+        code = int(status.item())
+        if code:
+            cls, msg = _lib.GB_ST_MESSAGES[code]  # DEM sampled out of bounds: raster.py:961-973
+            raise cls(msg)
         particles[:] = state.cpu().numpy().T
+        del t_dem, t_sig
 
 
 class CylindricalMotion(CartesianMotion):
@@ -92,3 +108,56 @@ class CylindricalMotion(CartesianMotion):
 
     def _velocity(self):
         return self.vrthz, self.vrthz_sigma, self.arthz, self.arthz_sigma
+
+
+class TangentCartesianMotion(CartesianMotion):
+    """Particles move tangent to a mean surface: horizontal random-acceleration model, heights follow the DEM plus
+    a per-particle offset that random-walks with the distance travelled (reference motion.py:314-420)."""
+
+    kind = _lib.GB_MOTION_TANGENT_CARTESIAN
+
+    def __init__(self, xy, time_unit: _dt.timedelta, dem, dem_sigma=0.0, n: int = 1000, xy_sigma=(0, 0),
+                 vxy=(0, 0), vxy_sigma=(0, 0), axy=(0, 0), axy_sigma=(0, 0), slope_sigma: Number = 0) -> None:
+        self.xy = xy
+        self.time_unit = time_unit
+        self.dem = _as_raster(dem)
+        self.dem_sigma = _as_raster(dem_sigma)
+        self.n = n
+        self.xy_sigma = xy_sigma
+        self.vxy = vxy
+        self.vxy_sigma = vxy_sigma
+        self.axy = axy
+        self.axy_sigma = axy_sigma
+        self.slope_sigma = slope_sigma
+
+    def _velocity(self):
+        pad = lambda x: tuple(np.broadcast_to(np.asarray(x, dtype=float), (2,))) + (0.0,)  # noqa: E731
+        return pad(self.vxy), pad(self.vxy_sigma), pad(self.axy), pad(self.axy_sigma)
+
+    def _draw_step_normals(self, n: int) -> np.ndarray:
+        first = np.random.randn(n, 2)  # accelerations
+        return np.column_stack((first, np.random.randn(n)))  # then the slope walk (motion.py:400-407)
+
+
+class TangentCylindricalMotion(TangentCartesianMotion):
+    """``TangentCartesianMotion`` with speed / heading components (reference motion.py:423-522)."""
+
+    kind = _lib.GB_MOTION_TANGENT_CYLINDRICAL
+
+    def __init__(self, xy, time_unit: _dt.timedelta, dem, dem_sigma=0.0, n: int = 1000, xy_sigma=(0, 0),
+                 vrth=(0, 0), vrth_sigma=(0, 0), arth=(0, 0), arth_sigma=(0, 0), slope_sigma: Number = 0) -> None:
+        self.xy = xy
+        self.time_unit = time_unit
+        self.dem = _as_raster(dem)
+        self.dem_sigma = _as_raster(dem_sigma)
+        self.n = n
+        self.xy_sigma = xy_sigma
+        self.vrth = vrth
+        self.vrth_sigma = vrth_sigma
+        self.arth = arth
+        self.arth_sigma = arth_sigma
+        self.slope_sigma = slope_sigma
+
+    def _velocity(self):
+        pad = lambda x: tuple(np.broadcast_to(np.asarray(x, dtype=float), (2,))) + (0.0,)  # noqa: E731
+        return pad(self.vrth), pad(self.vrth_sigma), pad(self.arth), pad(self.arth_sigma)

@@ -40,47 +40,56 @@ def empty_result(P, T, O, return_covariances, return_particles, N=0) -> dict:
     return out
 
 
-def reference_order_draws(P, N, steps_per_point):
+def reference_order_draws(P, N, steps_per_point, tangent=None):
     """Draws from the legacy global NumPy generator in the reference's order: per point
-    randn(N,2), randn(N), randn(N,3); then per update randn(N,3) and one random()."""
+    randn(N,2), randn(N), randn(N,3); then per update randn(N,3) and one random().  Points with a tangent model
+    (``tangent[p]``) draw randn(N,2), randn(N), randn(N,2); then per update randn(N,2), randn(N) and one random()
+    (motion.py:378-420).  Unused slots are 0."""
     S = int(max(steps_per_point)) if len(steps_per_point) else 0
-    init = np.empty((P, N, 6))
+    init = np.zeros((P, N, 6))
     step = np.zeros((P, max(S, 1), N, 3))
     unif = np.zeros((P, max(S, 1)))
     for p in range(P):
+        tan = bool(tangent[p]) if tangent is not None else False
         init[p, :, 0:2] = np.random.randn(N, 2)
         init[p, :, 2] = np.random.randn(N)
-        init[p, :, 3:6] = np.random.randn(N, 3)
+        if tan:
+            init[p, :, 3:5] = np.random.randn(N, 2)
+        else:
+            init[p, :, 3:6] = np.random.randn(N, 3)
         for s in range(int(steps_per_point[p])):
-            step[p, s] = np.random.randn(N, 3)
+            if tan:
+                step[p, s, :, 0:2] = np.random.randn(N, 2)
+                step[p, s, :, 2] = np.random.randn(N)
+            else:
+                step[p, s] = np.random.randn(N, 3)
             unif[p, s] = np.random.random()
     return init, step, unif
 
 
-class _Adopted:
-    """Reference motion-model object (duck-typed by attributes) presented through ``lower``."""
+_REFERENCE_MODELS = {  # class name -> (kind, attribute names of v, v_sigma, a, a_sigma)
+    "CartesianMotion": (_lib.GB_MOTION_CARTESIAN, ("vxyz", "vxyz_sigma", "axyz", "axyz_sigma")),
+    "CylindricalMotion": (_lib.GB_MOTION_CYLINDRICAL, ("vrthz", "vrthz_sigma", "arthz", "arthz_sigma")),
+    "TangentCartesianMotion": (_lib.GB_MOTION_TANGENT_CARTESIAN, ("vxy", "vxy_sigma", "axy", "axy_sigma")),
+    "TangentCylindricalMotion": (_lib.GB_MOTION_TANGENT_CYLINDRICAL, ("vrth", "vrth_sigma", "arth", "arth_sigma")),
+}
 
-    def __init__(self, model, kind):
-        self._m, self._kind = model, kind
-        self.kind = kind
+
+class _Adopted:
+    """Reference motion-model object (duck-typed by attributes) presented like this package's models."""
+
+    def __init__(self, model, kind, names):
+        self._m, self.kind, self._names = model, kind, names
         self.dem, self.dem_sigma, self.n, self.time_unit = model.dem, model.dem_sigma, model.n, model.time_unit
         self.xy, self.xy_sigma = model.xy, model.xy_sigma
+        self.slope_sigma = getattr(model, "slope_sigma", 0.0)
 
     def _velocity(self):
-        m = self._m
-        if self._kind == _lib.GB_MOTION_CARTESIAN:
-            return m.vxyz, m.vxyz_sigma, m.axyz, m.axyz_sigma
-        return m.vrthz, m.vrthz_sigma, m.arthz, m.arthz_sigma
+        def pad(x):
+            x = tuple(np.asarray(x, dtype=float).ravel())
+            return x + (0.0,) * (3 - len(x))
 
-    def lower(self, dem_index, dem_sigma_index):
-        from .motion import CartesianMotion, CylindricalMotion
-
-        m = self._m
-        if self._kind == _lib.GB_MOTION_CARTESIAN:
-            tmp = CartesianMotion(m.xy, m.time_unit, 0.0, 0.0, m.n, m.xy_sigma, m.vxyz, m.vxyz_sigma, m.axyz, m.axyz_sigma)
-        else:
-            tmp = CylindricalMotion(m.xy, m.time_unit, 0.0, 0.0, m.n, m.xy_sigma, m.vrthz, m.vrthz_sigma, m.arthz, m.arthz_sigma)
-        return tmp.lower(dem_index, dem_sigma_index)
+        return tuple(pad(getattr(self._m, n)) for n in self._names)
 
 
 def adopt_model(model):
@@ -89,10 +98,9 @@ def adopt_model(model):
     if hasattr(model, "lower"):
         return model
     name = type(model).__name__
-    if name == "CartesianMotion" and hasattr(model, "vxyz"):
-        return _Adopted(model, _lib.GB_MOTION_CARTESIAN)
-    if name == "CylindricalMotion" and hasattr(model, "vrthz"):
-        return _Adopted(model, _lib.GB_MOTION_CYLINDRICAL)
+    known = _REFERENCE_MODELS.get(name)
+    if known is not None and all(hasattr(model, n) for n in known[1]):
+        return _Adopted(model, *known)
     raise NotImplementedError(f"motion model {name} has no device kernel (no CPU fallback)")
 
 
@@ -126,6 +134,8 @@ class Session:
             self.h2d = 0
             # small tables first: once the frame uploads are queued they keep the copy engine busy for tens of ms
             motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)
+            if mode == _lib.GB_MODE_FUSED and self.tangent.any():
+                raise NotImplementedError("the tangent motion models run in mode='stream' only")
             images_dev, self.offsets = self._upload_frames()
             self.first, self.last = point_span(self.image_index, observer_mask)
             self.tmpl_frame = np.array([int(np.argmax(self.image_index[:, o] >= 0)) if (self.image_index[:, o] >= 0).any() else -1
@@ -142,7 +152,8 @@ class Session:
             b["first"], b["last"] = torch.as_tensor(self.first).to(device), torch.as_tensor(self.last).to(device)
             b["state_a"] = torch.empty((P, 6, N), dtype=f64, **dev)
             b["state_b"] = torch.empty((P, 6, N), dtype=f64, **dev)
-            b["weight_state"] = torch.empty((P, N), dtype=f64, **dev) if (staggered or return_particles) else None
+            # (tangent models keep the weights of the last resampling through updates without any likelihood)
+            b["weight_state"] = torch.empty((P, N), dtype=f64, **dev) if (staggered or return_particles or self.tangent.any()) else None
             b["scratch"] = torch.empty((self.plan.scratch_bytes // 8,), dtype=f64, **dev) if self.plan.scratch_bytes else None
             ta = self.tw * self.th
             b["tmpl_tile"] = torch.zeros((P, O, ta), dtype=f64, **dev)
@@ -175,13 +186,14 @@ class Session:
             d.motion, d.surfaces, d.n_surfaces, d.viewshed = motion_dev.data_ptr(), surf_dev.data_ptr(), n_surf, viewshed
             self.keep += [images_dev, motion_dev, surf_dev]
             d.point_offset = int(point_offset)
+            d.motion_kinds = self.motion_kinds
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED
                 if draws is None:
                     nbytes = P * max(T - 1, 1) * N * 24
                     if nbytes > 8 << 30:
                         raise MemoryError("rng='numpy' would need %.1f GiB of supplied normals; use rng='philox'" % (nbytes / 2 ** 30))
-                    draws = reference_order_draws(P, N, self.last - self.first)
+                    draws = reference_order_draws(P, N, self.last - self.first, self.tangent)
                 init, step, unif = draws
                 S = T - 1
                 step_full = np.zeros((P, S, N, 3))
@@ -338,7 +350,8 @@ class Session:
 
         # gb_motion table as one structured array (field layout of include/glimpse_b200.h)
         dt = np.dtype([("kind", "<i4"), ("dem", "<i4"), ("dem_sigma", "<i4"), ("pad_", "<i4"), ("xy", "<f8", 2),
-                       ("xy_sigma", "<f8", 2), ("v", "<f8", 3), ("v_sigma", "<f8", 3), ("a", "<f8", 3), ("a_sigma", "<f8", 3)])
+                       ("xy_sigma", "<f8", 2), ("v", "<f8", 3), ("v_sigma", "<f8", 3), ("a", "<f8", 3), ("a_sigma", "<f8", 3),
+                       ("slope_sigma", "<f8")])
         assert dt.itemsize == C.sizeof(_lib.gb_motion)
         table_m = np.zeros(len(models), dtype=dt)
         adopted = [adopt_model(m) for m in models]
@@ -351,6 +364,9 @@ class Session:
         table_m["xy_sigma"] = xs if xs.ndim == 2 else xs[:, None]
         for k, name in enumerate(("v", "v_sigma", "a", "a_sigma")):
             table_m[name] = np.array([v[k] for v in vel], dtype=float)
+        table_m["slope_sigma"] = [float(getattr(m, "slope_sigma", 0.0)) for m in adopted]
+        self.tangent = table_m["kind"] >= _lib.GB_MOTION_TANGENT_CARTESIAN
+        self.motion_kinds = int(np.bitwise_or.reduce(1 << table_m["kind"].astype(np.int64))) if len(models) else 0
         viewshed = index_of(self.tracker.viewshed) if self.tracker.viewshed is not None else -1
         motion_dev = torch.from_numpy(table_m.view(np.uint8).reshape(-1)).to(device)
         surf_dev = _struct_array_to_device(torch, table, _lib.gb_surface, device)

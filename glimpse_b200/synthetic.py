@@ -121,6 +121,13 @@ def nadir_scene(
     if kind == "cartesian":
         motion = dict(kind="cartesian", dem=0.0, dem_sigma=0.0, xy_sigma=(0.1, 0.1), vxyz=v_true,
                       vxyz_sigma=(s, s, 0.0), axyz=(0, 0, 0), axyz_sigma=(0.05, 0.05, 0.0))
+    elif kind == "tangent_cartesian":
+        motion = dict(kind=kind, dem=0.0, dem_sigma=0.3, xy_sigma=(0.1, 0.1), vxy=v_true[:2], vxy_sigma=(s, s),
+                      axy=(0, 0), axy_sigma=(0.05, 0.05), slope_sigma=0.1)
+    elif kind == "tangent_cylindrical":
+        motion = dict(kind=kind, dem=0.0, dem_sigma=0.3, xy_sigma=(0.1, 0.1),
+                      vrth=(float(np.hypot(v_true[0], v_true[1])), float(np.arctan2(v_true[1], v_true[0]))),
+                      vrth_sigma=(s, 0.3), arth=(0, 0), arth_sigma=(0.05, 0.02), slope_sigma=0.1)
     else:
         speed = float(np.hypot(v_true[0], v_true[1]))
         theta = float(np.arctan2(v_true[1], v_true[0]))
@@ -149,7 +156,12 @@ def build(scene: Scene, api, points: Optional[Sequence[int]] = None):
         observers.append(api.Observer(images, sigma=obs.sigma))
     params = dict(scene.motion)
     kind = params.pop("kind")
-    cls = api.CartesianMotion if kind == "cartesian" else api.CylindricalMotion
+    cls = {"cartesian": "CartesianMotion", "cylindrical": "CylindricalMotion", "tangent_cartesian": "TangentCartesianMotion",
+           "tangent_cylindrical": "TangentCylindricalMotion"}[kind]
+    cls = getattr(api, cls)
+    for key in ("dem", "dem_sigma"):  # gridded surfaces travel as dict(array=, x=, y=) and become the api's Raster
+        if isinstance(params.get(key), dict):
+            params[key] = api.Raster(params[key]["array"], x=params[key]["x"], y=params[key]["y"])
     sel = range(len(scene.points)) if points is None else points
     models = [cls(xy=scene.points[i], time_unit=scene.time_unit, n=scene.n_particles, **params) for i in sel]
     return observers, models

@@ -50,6 +50,8 @@ extern "C" {
 
 #define GB_MOTION_CARTESIAN 0   /* track/motion.py:92-204 */
 #define GB_MOTION_CYLINDRICAL 1 /* track/motion.py:207-311 */
+#define GB_MOTION_TANGENT_CARTESIAN 2   /* track/motion.py:314-420 */
+#define GB_MOTION_TANGENT_CYLINDRICAL 3 /* track/motion.py:423-522 */
 
 #define GB_RNG_SUPPLIED 0 /* normals / uniforms provided in the reference's draw order */
 #define GB_RNG_PHILOX 1   /* counter-based Philox4x32-10 on device */
@@ -95,8 +97,10 @@ typedef struct gb_surface {
 } gb_surface;
 
 /* Motion-model parameters of one tracked point (CartesianMotion motion.py:122-147 /
- * CylindricalMotion motion.py:239-258).  For the cylindrical kind v/a are (vr, theta, vz) and
- * (ar, dtheta/dt, az).  dem / dem_sigma index the `surfaces` table of the call. */
+ * CylindricalMotion motion.py:239-258 / TangentCartesianMotion motion.py:350-376 /
+ * TangentCylindricalMotion motion.py:457-483).  For the cylindrical kinds v/a are (vr, theta, vz) and
+ * (ar, dtheta/dt, az); the tangent kinds use the first two components of v/a (the third must be 0) and
+ * slope_sigma.  dem / dem_sigma index the `surfaces` table of the call. */
 typedef struct gb_motion {
   int32_t kind;
   int32_t dem, dem_sigma;
@@ -104,6 +108,7 @@ typedef struct gb_motion {
   double xy[2], xy_sigma[2];
   double v[3], v_sigma[3];
   double a[3], a_sigma[3];
+  double slope_sigma; /* tangent kinds: sigma of the slope of small-scale features (motion.py:345-346) */
 } gb_motion;
 
 /* ------------------------------------------------------------------------------------------
@@ -217,7 +222,7 @@ typedef struct gb_track_desc {
 
   /* random draws */
   int32_t rng_mode;                /* GB_RNG_* */
-  int32_t pad0_;
+  int32_t motion_kinds;            /* bit k set = some point has motion kind k; 0 = unspecified (kernels handle every kind) */
   uint64_t seed;                   /* Philox key */
   int64_t point_offset;            /* global index of point 0 (Philox counters use global indices, so results do not depend on sharding) */
   const double* init_normals;      /* supplied: [P][N][6] = randn(N,2) | randn(N) | randn(N,3) per particle */
@@ -293,10 +298,12 @@ int gb_track_step(const gb_track_desc* desc_host, int32_t t, const gb_stage_io* 
  * first time index is `t`, and template construction (tracker.py:536-561) for templates due at t. */
 int gb_track_init(const gb_track_desc* desc_host, int32_t t, void* stream);
 
-/* Motion.evolve_particles as a stand-alone call (motion.py:165-179, 285-311) on SoA state
- * [P][6][N] in place; normals[P][N][3] supplied. */
-int gb_evolve(const gb_motion* motion, int64_t P, int64_t N, double tau, double tau2, const double* normals,
-              double* state, void* stream);
+/* Motion.evolve_particles as a stand-alone call (motion.py:165-179, 285-311, 392-420, 507-522) on SoA
+ * state [P][6][N] in place; normals[P][N][3] supplied (tangent kinds: columns 0-1 = the randn(n,2) draw,
+ * column 2 = the randn(n) draw).  `surfaces` is the table motion[].dem indexes (may be NULL when no model is
+ * tangent); status[P] (may be NULL) receives GB_ST_DEM_BOUNDS where a tangent model sampled its DEM out of bounds. */
+int gb_evolve(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, double tau, double tau2,
+              const double* normals, double* state, int32_t* status, void* stream);
 /* Tracker.particle_mean / compute_particle_sigma / particle_covariance (tracker.py:72-104) on
  * row-major particles[n][6], weights[n]: mean[6], sigma[6] (or NULL), cov[36] (or NULL). */
 int gb_moments(const double* particles, const double* weights, int64_t n, double* mean, double* sigma, double* cov,

@@ -245,9 +245,11 @@ class Surface:
 
 @dataclass
 class MotionSpec:
-    """Parameters of CartesianMotion (kind='cartesian', motion.py:92-204) or
-    CylindricalMotion (kind='cylindrical', motion.py:207-311).  For the cylindrical model
-    ``v``/``a`` hold (d radius/dt, theta, dz/dt) and (d2 radius/dt2, d theta/dt, d2z/dt2)."""
+    """Parameters of CartesianMotion (kind='cartesian', motion.py:92-204), CylindricalMotion
+    (kind='cylindrical', motion.py:207-311), TangentCartesianMotion (kind='tangent_cartesian',
+    motion.py:314-420) or TangentCylindricalMotion (kind='tangent_cylindrical', motion.py:423-522).
+    For the cylindrical models ``v``/``a`` hold (d radius/dt, theta[, dz/dt]) and
+    (d2 radius/dt2, d theta/dt[, d2z/dt2]); the tangent models use the first two components only."""
 
     xy: Sequence[float]
     n: int = 1000
@@ -259,26 +261,60 @@ class MotionSpec:
     v_sigma: Sequence[float] = (0, 0, 0)
     a: Sequence[float] = (0, 0, 0)
     a_sigma: Sequence[float] = (0, 0, 0)
+    slope_sigma: float = 0.0
+
+    @property
+    def tangent(self) -> bool:
+        return self.kind.startswith("tangent")
+
+    @property
+    def cylindrical(self) -> bool:
+        return self.kind.endswith("cylindrical")
 
 
 def init_particles(m: MotionSpec, randn: Callable = np.random.randn) -> np.ndarray:
-    """Draw order: randn(n,2), randn(n), randn(n,3) (motion.py:149-163, 260-283)."""
+    """Draw order: randn(n,2), randn(n), then randn(n,3) (motion.py:149-163, 260-283) or, for the tangent
+    models, randn(n,2) — their vz stays 0 (motion.py:378-390, 485-505)."""
     ps = np.zeros((m.n, 6))
     ps[:, 0:2] = np.asarray(m.xy, float) + np.asarray(m.xy_sigma, float) * randn(m.n, 2)
+    if m.tangent:
+        z_offsets = m.dem_sigma.sample(ps[:, 0:2]) * randn(m.n)
+        ps[:, 2] = m.dem.sample(ps[:, 0:2]) + z_offsets
+        vel = np.asarray(m.v, float)[:2] + np.asarray(m.v_sigma, float)[:2] * randn(m.n, 2)
+        if m.cylindrical:
+            vel = np.column_stack((vel[:, 0] * np.cos(vel[:, 1]), vel[:, 0] * np.sin(vel[:, 1])))
+        ps[:, 3:5] = vel
+        return ps
     ps[:, 2] = m.dem.sample(ps[:, 0:2])
     ps[:, 2] += m.dem_sigma.sample(ps[:, 0:2]) * randn(m.n)
     vel = np.asarray(m.v, float) + np.asarray(m.v_sigma, float) * randn(m.n, 3)
-    if m.kind == "cylindrical":
+    if m.cylindrical:
         vel = np.column_stack((vel[:, 0] * np.cos(vel[:, 1]), vel[:, 0] * np.sin(vel[:, 1]), vel[:, 2]))
     ps[:, 3:6] = vel
     return ps
 
 
 def evolve_particles(m: MotionSpec, ps: np.ndarray, tau: float, randn: Callable = np.random.randn) -> None:
-    """In-place random-acceleration step over ``tau`` time units (motion.py:165-179, 285-311)."""
+    """In-place random-acceleration step over ``tau`` time units (motion.py:165-179, 285-311); the tangent
+    models move in x, y only and carry each particle's offset above the DEM along, widened by a random walk
+    proportional to the distance travelled (motion.py:392-420, 507-522; draws: randn(n,2) then randn(n))."""
     n = len(ps)
+    if m.tangent:
+        acc = np.asarray(m.a, float)[:2] + np.asarray(m.a_sigma, float)[:2] * randn(n, 2)
+        if m.cylindrical:
+            vx, vy = ps[:, 3], ps[:, 4]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                speed = np.sqrt(vx ** 2 + vy ** 2)
+                acc = np.column_stack((acc[:, 0] * (vx / speed) - vy * acc[:, 1], acc[:, 0] * (vy / speed) + vx * acc[:, 1]))
+        dxy = tau * ps[:, 3:5] + 0.5 * acc * tau ** 2
+        z_offsets = ps[:, 2] - m.dem.sample(ps[:, 0:2])
+        z_offsets += m.slope_sigma * randn(n) * (dxy ** 2).sum(axis=1) ** 0.5
+        ps[:, 0:2] += dxy
+        ps[:, 2] = m.dem.sample(ps[:, 0:2]) + z_offsets
+        ps[:, 3:5] += tau * acc
+        return
     acc = np.asarray(m.a, float) + np.asarray(m.a_sigma, float) * randn(n, 3)
-    if m.kind == "cylindrical":
+    if m.cylindrical:
         vx, vy = ps[:, 3], ps[:, 4]
         with np.errstate(invalid="ignore", divide="ignore"):
             speed = np.sqrt(vx ** 2 + vy ** 2)
@@ -289,8 +325,11 @@ def evolve_particles(m: MotionSpec, ps: np.ndarray, tau: float, randn: Callable 
     ps[:, 3:6] += tau * acc
 
 
-def surface_log_likelihood(m: MotionSpec, ps: np.ndarray) -> np.ndarray:
-    """(dem(xy) - z)^2 / (2 sigma^2) where sigma != 0 (motion.py:181-204)."""
+def surface_log_likelihood(m: MotionSpec, ps: np.ndarray) -> Optional[np.ndarray]:
+    """(dem(xy) - z)^2 / (2 sigma^2) where sigma != 0 (motion.py:181-204); the tangent models inherit the
+    base class's ``None`` (motion.py:77-89)."""
+    if m.tangent:
+        return None
     z = m.dem.sample(ps[:, 0:2])
     zs = m.dem_sigma.sample(ps[:, 0:2])
     nz = np.nonzero(zs)[0]
@@ -628,7 +667,9 @@ def track(
                                 "uv": uv, "box": box, "search": search, "sse": sse, "sse_box": sbox, "sampled": sampled,
                             }
                     terms.append(surface_log_likelihood(model, ps))
-                    w = weights_from_log_likelihoods(terms)
+                    terms = [x for x in terms if x is not None]
+                    if terms:  # otherwise the weights of the last resampling stay (tracker.py:146-149)
+                        w = weights_from_log_likelihoods(terms)
                     u = random()
                     idx = systematic_indices(w, u)
                     if trace:

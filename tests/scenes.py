@@ -50,6 +50,20 @@ def add_second_observer(scene):
     return scene
 
 
+def add_gridded_dem(scene):
+    """A gently sloping, bumpy DEM and a spatially varying DEM sigma over the whole footprint (north-up raster:
+    y decreasing), as dict(array, x, y) that ``synthetic.build`` turns into the API's Raster."""
+    rng = np.random.RandomState(11)
+    ny, nx = 14, 18
+    xs = np.linspace(-1, 1, nx)[None, :]
+    ys = np.linspace(-1, 1, ny)[:, None]
+    dem = 0.8 * xs + 0.4 * ys + 0.15 * rng.rand(ny, nx)
+    sig = 0.2 + 0.1 * rng.rand(ny, nx)
+    x, y = (-45.0, 45.0), (35.0, -35.0)
+    scene.motion.update(dem=dict(array=dem, x=x, y=y), dem_sigma=dict(array=sig, x=x, y=y))
+    return scene
+
+
 def track_cases():
     return {
         # config-1 shape, shrunk: 1 observer, Cartesian, full distortion
@@ -62,6 +76,17 @@ def track_cases():
             scene_kwargs=dict(seed=3, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
                               kind="cylindrical", velocity_sigma=0.2),
             seed=303, post=add_second_observer, return_covariances=True,
+        ),
+        # tangent models on a gridded, sloping DEM (two bilinear DEM gathers per particle and step)
+        "track_tangent": dict(
+            scene_kwargs=dict(seed=7, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              kind="tangent_cartesian"),
+            seed=707, post=add_gridded_dem,
+        ),
+        "track_tangent_cyl": dict(
+            scene_kwargs=dict(seed=9, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              kind="tangent_cylindrical", velocity_sigma=0.2),
+            seed=909, post=add_gridded_dem,
         ),
         # map-scale world coordinates + per-frame view-direction jitter
         "track_jitter": dict(

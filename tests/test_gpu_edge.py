@@ -248,3 +248,53 @@ def test_collapsed_weights_give_one_parent_many_children(cuda):
     assert max(uniq) < 100
     same = np.isclose(tracks.particles, ref.particles, rtol=0, atol=1e-9).all(axis=3)
     assert same[:, :2].mean() > 0.99 and same.mean() > 0.95, (same[:, :2].mean(), same.mean())
+
+
+def test_tangent_model_keeps_its_weights_when_no_image_is_usable(cuda):
+    """tracker.py:146-149 with a motion model whose compute_log_likelihoods is None (tangent kinds): when the only
+    observer is skipped (cloud beyond the frame) no likelihood exists at all and the weights of the last resampling
+    stay in place — they are not reset to uniform."""
+    import scenes
+
+    scene = synthetic.nadir_scene(seed=6, n_points=2, n_particles=256, n_frames=6, imgsz=(320, 240), margin_px=100,
+                                  velocity_sigma=0.3, kind="tangent_cartesian")
+    scenes.add_gridded_dem(scene)
+    scene.points[0, 0] = (320 / 2 - 24) * 0.2  # template fits, the growing cloud does not
+    scene.motion["vxy"] = (2.0, 0.0)            # 10 px / day towards the edge
+    tracks, ref, _ = run_both(scene, 21, "stream", return_particles=True)
+    assert tracks.errors[0] is None and tracks.warnings[0] is not None
+    skipped = (ref.skipped[0] == 2).any(axis=1)
+    assert skipped.sum() == len(tracks.warnings[0]) > 0
+    # at a skipped time the reported weights are a resampling of the previous ones: not all equal
+    t_skip = int(np.nonzero(skipped)[0][0])
+    assert np.ptp(ref.weights[0, t_skip]) > 0 and np.ptp(tracks.weights[0, t_skip]) > 0
+    np.testing.assert_allclose(tracks.weights[0, t_skip], ref.weights[0, t_skip], rtol=1e-4)
+    assert_close_to_oracle(tracks, ref)
+
+
+@pytest.mark.parametrize("kind", ["cartesian", "cylindrical", "tangent_cartesian", "tangent_cylindrical"])
+def test_stand_alone_evolve_particles_matches_the_oracle(cuda, kind):
+    """``Motion.evolve_particles`` (gb_evolve) for every built-in model against the oracle's restatement of
+    motion.py:165-179, 285-311, 392-420, 507-522 on the same draws; tangent models on a gridded DEM."""
+    import glimpse_b200 as gb
+    import scenes
+
+    scene = synthetic.nadir_scene(seed=31, n_points=1, n_particles=500, n_frames=2, imgsz=(320, 240), margin_px=100, kind=kind)
+    if kind.startswith("tangent"):
+        scenes.add_gridded_dem(scene)
+    _, models = synthetic.build(scene, gb)
+    _, specs, _, _ = helpers.oracle_inputs(scene)
+    np.random.seed(3)
+    ps = orc.init_particles(specs[0])
+    mine, ref = ps.copy(), ps.copy()
+    dt = datetime.timedelta(days=1.5)
+    np.random.seed(4)
+    models[0].evolve_particles(mine, dt)
+    np.random.seed(4)
+    orc.evolve_particles(specs[0], ref, 1.5)
+    np.testing.assert_allclose(mine, ref, rtol=1e-13, atol=1e-13)
+    if kind.startswith("tangent"):
+        far = ps.copy()
+        far[:, 0] += 1e4  # off the DEM: Raster.sample raises (raster.py:961-973)
+        with pytest.raises(ValueError, match="out of bounds"):
+            models[0].evolve_particles(far, dt)

@@ -37,6 +37,11 @@ def case_scene(name):
     return scene, case
 
 
+CASES = list(scenes.track_cases())
+# the tangent motion models run in the default streaming organisation only
+CASE_MODES = [(n, m) for n in CASES for m in ("stream", "fused") if not (m == "fused" and "tangent" in n)]
+
+
 def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None, mode="stream"):
     import glimpse_b200 as gb
     from glimpse_b200.session import Session, reference_order_draws
@@ -55,7 +60,8 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
 
     first, last = point_span(image_index, mask)
     np.random.seed(int(golden["seed"]))
-    draws = reference_order_draws(P, scene.n_particles, last - first)
+    tangent = np.full(P, scene.motion["kind"].startswith("tangent"))
+    draws = reference_order_draws(P, scene.n_particles, last - first, tangent)
     session = Session(tracker, models, image_index, taus, scene.tile_size, mask,
                       return_covariances=bool(case.get("return_covariances", False)),
                       return_particles=return_particles, draws=draws)
@@ -72,8 +78,7 @@ def golden_steps(g, P, T_steps):
     return per
 
 
-@pytest.mark.parametrize("mode", ["stream", "fused"])
-@pytest.mark.parametrize("name", list(scenes.track_cases()))
+@pytest.mark.parametrize("name,mode", CASE_MODES)
 def test_templates_match_reference(cuda, name, mode):
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
@@ -100,8 +105,7 @@ def test_templates_match_reference(cuda, name, mode):
 
 
 @pytest.mark.parametrize("name,mode,cluster,tile_bytes",
-                         [(n, "stream", 0, None) for n in scenes.track_cases()]
-                         + [(n, "fused", 0, None) for n in scenes.track_cases()]
+                         [(n, m, 0, None) for n, m in CASE_MODES]
                          + [("track_c1", "fused", 2, None), ("track_cyl2", "fused", 4, None), ("track_jitter", "fused", 8, None),
                             ("track_c1", "fused", 4, 2048)])
 def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
@@ -211,8 +215,7 @@ def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
     assert worst["sigma"] <= 1e-7
 
 
-@pytest.mark.parametrize("mode", ["stream", "fused"])
-@pytest.mark.parametrize("name", list(scenes.track_cases()))
+@pytest.mark.parametrize("name,mode", CASE_MODES)
 def test_track_free_running_matches_reference(cuda, name, mode):
     """Whole Tracker.track with the reference's draw sequence (rng='numpy')."""
     import glimpse_b200 as gb
