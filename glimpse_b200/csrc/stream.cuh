@@ -386,7 +386,7 @@ struct SurfaceRef {
 
 // s3: spline sample + surface likelihood -> weight; two consecutive particles per thread.  Grid: blocks of a
 // point x points; launched with s3_threads(s_block) threads so that full trips cover the CTA's particle pairs.
-#define GB_S3_MAX_THREADS 256
+#define GB_S3_MAX_THREADS 64
 __host__ __device__ inline int s3_threads(int s_block) {
   const int pairs = (s_block + 1) / 2;
   const int trips = (pairs + GB_S3_MAX_THREADS - 1) / GB_S3_MAX_THREADS;
@@ -415,7 +415,7 @@ __device__ __forceinline__ void s3_publish_prefix(const StepParams& prm, int64_t
     pre[nblk + 3] = quo(1.0, (double)prm.N);
   }
 }
-__global__ void __launch_bounds__(GB_S3_MAX_THREADS, 4) k_s3_weights(const __grid_constant__ StepParams prm) {
+__global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ SurfaceRef s_ref[GB_MAX_OBS];
   __shared__ double s_warp[GB_S3_MAX_THREADS / 32];
@@ -754,7 +754,7 @@ __global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
 #define GB_S4P_THREADS 192
 #endif
 #define GB_S4P_CAP 768
-#define GB_S4P_PPT (GB_S4P_CAP / GB_S4P_THREADS)
+#define GB_S4P_PPT ((GB_S4P_CAP + GB_S4P_THREADS - 1) / GB_S4P_THREADS)
 constexpr int kS4pSmem = GB_S4P_CAP * 64;
 
 // One projected child: image coordinates of time t + 1 and its contribution to the integer cloud box.
