@@ -22,6 +22,7 @@ GB_ST_MESSAGES = {
 }
 GB_OBS_OUT_OF_FRAME = 2
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
+GB_RESAMPLE = {"systematic": 0, "stratified": 1}
 GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 
@@ -83,6 +84,7 @@ class gb_track_desc(C.Structure):
         ("means", C.c_void_p), ("sigmas", C.c_void_p), ("covariances", C.c_void_p), ("out_particles", C.c_void_p),
         ("out_weights", C.c_void_p), ("status", C.c_void_p), ("status_time", C.c_void_p), ("obs_flags", C.c_void_p),
         ("window_stats", C.c_void_p),
+        ("resample_method", C.c_int32), ("pad1_", C.c_int32),
         ("plan", gb_plan),
     ]
 

@@ -102,7 +102,8 @@ struct StepParams {
   char* s_surf;      // [P][O] surface regions of surf_bytes each (Hermite array first)
   int64_t surf_bytes;
   int s_block, s_nblk;
-  int tmpl_from_ev, pad3_;  // k_template: staggered templates read the evolved particles from s_ev (pipelined flow)
+  int tmpl_from_ev;  // k_template: staggered templates read the evolved particles from s_ev (pipelined flow)
+  int resample_method;  // GB_RESAMPLE_*
   int64_t p0, pb;    // batch of points handled by this launch
 };
 
@@ -559,6 +560,34 @@ __device__ __forceinline__ int count_positions_le(double c, double u, double inv
     while (e < N && resample_position(e, u, inv_n) <= c) ++e;
   }
   return e;
+}
+
+// Stratified resampling (tracker.py:178-186): position j = (j + u_j) / N with one uniform per particle, taken from
+// the supplied draws or from Philox.  Positions still increase with j, so a parent's child range ends at the number
+// of positions <= its normalised cumulative weight: j < floor(c N) always qualify, the stratum containing c decides
+// with its own uniform; the guess is verified against the reference's position formula like the systematic one.
+struct StratifiedDraws {
+  const double* supplied;  // [N] uniforms of this (point, update), or nullptr: Philox
+  uint64_t seed, point;
+  uint32_t time;
+  __device__ __forceinline__ double u(int j) const {
+    return supplied ? supplied[j] : philox_uniform_particle(seed, point, time, (uint32_t)j);
+  }
+};
+__device__ __noinline__ int count_positions_le_stratified(double c, StratifiedDraws d, double inv_n, int N) {
+  int e = __double2int_rd(c * (double)N);
+  e = min(max(e, 0), N);
+  while (e > 0 && resample_position(e - 1, d.u(e - 1), inv_n) > c) --e;
+  while (e < N && resample_position(e, d.u(e), inv_n) <= c) ++e;
+  return e;
+}
+__device__ __forceinline__ StratifiedDraws stratified_draws(const StepParams& prm, int64_t p, int t) {
+  StratifiedDraws d;
+  d.supplied = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms + ((int64_t)p * prm.S + (t - prm.first[p] - 1)) * prm.N : nullptr;
+  d.seed = prm.seed;
+  d.point = (uint64_t)(p + prm.point_offset);
+  d.time = (uint32_t)t;
+  return d;
 }
 
 __device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
@@ -1134,6 +1163,7 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.init_normals = d.init_normals;
   prm.step_normals = d.step_normals;
   prm.uniforms = d.uniforms;
+  prm.resample_method = d.resample_method;
   prm.state_a = d.state_a;
   prm.state_b = d.state_b;
   prm.weight_state = d.weight_state;

@@ -87,6 +87,15 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t point, 
   return (double)bits * (1.0 / 9007199254740992.0);
 }
 
+// One uniform per (point, time, particle): the stratified resampler's per-stratum draw (stream 4).
+__device__ __forceinline__ double philox_uniform_particle(uint64_t seed, uint64_t point, uint32_t time, uint32_t particle) {
+  Philox g{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t r[4];
+  g.generate(particle, time, (uint32_t)point, ((uint32_t)(point >> 32) << 8) | 4u, r);
+  const uint64_t bits = (((uint64_t)r[0] >> 5) << 26) | ((uint64_t)r[1] >> 6);
+  return (double)bits * (1.0 / 9007199254740992.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Surfaces
 // ---------------------------------------------------------------------------------------------

@@ -410,8 +410,9 @@ __device__ __forceinline__ void s3_publish_prefix(const StepParams& prm, int64_t
   if (lane == 0) {
     pre[0] = 0.0;
     pre[nblk + 1] = quo(1.0, run);
-    pre[nblk + 2] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (prm.t - prm.first[p] - 1)]
-                                                    : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)prm.t);
+    pre[nblk + 2] = prm.resample_method != GB_RESAMPLE_SYSTEMATIC ? 0.0
+                    : prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (prm.t - prm.first[p] - 1)]
+                                                      : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)prm.t);
     pre[nblk + 3] = quo(1.0, (double)prm.N);
   }
 }
@@ -583,8 +584,9 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
     s_pref[0] = pre;
     s_pref[1] = run;
     s_pref[2] = nxt;
-    s_pref[3] = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
-                                                : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
+    s_pref[3] = prm.resample_method != GB_RESAMPLE_SYSTEMATIC ? 0.0
+                : prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
+                                                  : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
     s_pref[4] = quo(1.0, (double)N);
     s_pref[5] = quo(1.0, run);
   }
@@ -613,6 +615,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
   }
   const double off = block_exclusive_offset(tsum, s_warp);  // contains a __syncthreads(): s_pref is visible
   const double prefix = s_pref[0], total = s_pref[1], next_prefix = s_pref[2], u01 = s_pref[3], inv_n = s_pref[4], inv_total = s_pref[5];
+  const bool stratified = prm.resample_method == GB_RESAMPLE_STRATIFIED;
   // The last parent of the CTA takes the next CTA's prefix as its cumulative weight, so that child ranges
   // are seamless across CTAs whatever the association of the in-CTA sums.
 #pragma unroll
@@ -620,10 +623,14 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
     const int k = k0 + q;
     if (k < n_here) {
       const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
-      s_end[k] = count_positions_le(quo(c, total), u01, inv_n, N);
+      s_end[k] = stratified ? count_positions_le_stratified(quo(c, total), stratified_draws(prm, p, t), inv_n, N)
+                            : count_positions_le(quo(c, total), u01, inv_n, N);
     }
   }
-  if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(prefix >= total ? 1.0 : prefix * inv_total, u01, inv_n, N);
+  if (tid == 0) {
+    const double c0 = prefix >= total ? 1.0 : prefix * inv_total;
+    s_j0 = b == 0 ? 0 : stratified ? count_positions_le_stratified(c0, stratified_draws(prm, p, t), inv_n, N) : count_positions_le(c0, u01, inv_n, N);
+  }
   __syncthreads();
   const int J0 = s_j0, J1 = n_here > 0 ? s_end[n_here - 1] : J0;
   const double* ev = prm.s_ev + p * 6 * (int64_t)N + base;
@@ -840,6 +847,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
     const double* pre = prm.s_pre + p * (prm.s_nblk + 4);
     const double prefix = pre[b], next_prefix = pre[b + 1], total = pre[prm.s_nblk], inv_total = pre[prm.s_nblk + 1],
                  u01 = pre[prm.s_nblk + 2], inv_n = pre[prm.s_nblk + 3];
+    const bool stratified = prm.resample_method == GB_RESAMPLE_STRATIFIED;
     if (bulk) mbar_wait(&s_bar[0], 0);
     else __syncthreads();
     const int k0 = PPT * tid;  // first local parent of this thread (consecutive parents: in-thread prefix)
@@ -859,10 +867,14 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
         // across CTAs whatever the association of the in-CTA sums.
         const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
         // normalised cumulative weight: one reciprocal per CTA instead of a division per particle (the total maps to exactly 1)
-        s_end[k] = count_positions_le(c >= total ? 1.0 : c * inv_total, u01, inv_n, N);
+        const double cn = c >= total ? 1.0 : c * inv_total;
+        s_end[k] = stratified ? count_positions_le_stratified(cn, stratified_draws(prm, p, t), inv_n, N) : count_positions_le(cn, u01, inv_n, N);
       }
     }
-    if (tid == 0) s_j0 = b == 0 ? 0 : count_positions_le(prefix >= total ? 1.0 : prefix * inv_total, u01, inv_n, N);
+    if (tid == 0) {
+      const double c0 = prefix >= total ? 1.0 : prefix * inv_total;
+      s_j0 = b == 0 ? 0 : stratified ? count_positions_le_stratified(c0, stratified_draws(prm, p, t), inv_n, N) : count_positions_le(c0, u01, inv_n, N);
+    }
     __syncthreads();
     J0 = s_j0;
     J1 = n_here > 0 ? s_end[n_here - 1] : J0;

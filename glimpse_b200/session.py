@@ -40,15 +40,16 @@ def empty_result(P, T, O, return_covariances, return_particles, N=0) -> dict:
     return out
 
 
-def reference_order_draws(P, N, steps_per_point, tangent=None):
+def reference_order_draws(P, N, steps_per_point, tangent=None, stratified=False):
     """Draws from the legacy global NumPy generator in the reference's order: per point
     randn(N,2), randn(N), randn(N,3); then per update randn(N,3) and one random().  Points with a tangent model
     (``tangent[p]``) draw randn(N,2), randn(N), randn(N,2); then per update randn(N,2), randn(N) and one random()
-    (motion.py:378-420).  Unused slots are 0."""
+    (motion.py:378-420).  The stratified resampler draws random(N) instead of random() (tracker.py:183): ``unif`` is
+    then (P, S, N).  Unused slots are 0."""
     S = int(max(steps_per_point)) if len(steps_per_point) else 0
     init = np.zeros((P, N, 6))
     step = np.zeros((P, max(S, 1), N, 3))
-    unif = np.zeros((P, max(S, 1)))
+    unif = np.zeros((P, max(S, 1), N) if stratified else (P, max(S, 1)))
     for p in range(P):
         tan = bool(tangent[p]) if tangent is not None else False
         init[p, :, 0:2] = np.random.randn(N, 2)
@@ -63,7 +64,7 @@ def reference_order_draws(P, N, steps_per_point, tangent=None):
                 step[p, s, :, 2] = np.random.randn(N)
             else:
                 step[p, s] = np.random.randn(N, 3)
-            unif[p, s] = np.random.random()
+            unif[p, s] = np.random.random(N) if stratified else np.random.random()
     return init, step, unif
 
 
@@ -187,17 +188,22 @@ class Session:
             self.keep += [images_dev, motion_dev, surf_dev]
             d.point_offset = int(point_offset)
             d.motion_kinds = self.motion_kinds
+            method = getattr(tracker, "resample_method", "systematic")
+            stratified = method == "stratified"
+            if stratified and mode == _lib.GB_MODE_FUSED:
+                raise NotImplementedError("resample_method='stratified' runs in mode='stream' only")
+            d.resample_method = _lib.GB_RESAMPLE[method]
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED
                 if draws is None:
-                    nbytes = P * max(T - 1, 1) * N * 24
+                    nbytes = P * max(T - 1, 1) * N * (32 if stratified else 24)
                     if nbytes > 8 << 30:
                         raise MemoryError("rng='numpy' would need %.1f GiB of supplied normals; use rng='philox'" % (nbytes / 2 ** 30))
-                    draws = reference_order_draws(P, N, self.last - self.first, self.tangent)
+                    draws = reference_order_draws(P, N, self.last - self.first, self.tangent, stratified)
                 init, step, unif = draws
                 S = T - 1
                 step_full = np.zeros((P, S, N, 3))
-                unif_full = np.zeros((P, S))
+                unif_full = np.zeros((P, S, N) if stratified else (P, S))
                 step_full[:, : step.shape[1]] = step[:, :S]
                 unif_full[:, : unif.shape[1]] = unif[:, :S]
                 b["init_normals"] = torch.as_tensor(np.ascontiguousarray(init)).to(device)

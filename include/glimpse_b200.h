@@ -53,6 +53,9 @@ extern "C" {
 #define GB_MOTION_TANGENT_CARTESIAN 2   /* track/motion.py:314-420 */
 #define GB_MOTION_TANGENT_CYLINDRICAL 3 /* track/motion.py:423-522 */
 
+#define GB_RESAMPLE_SYSTEMATIC 0 /* tracker.py:168-176: one uniform per update */
+#define GB_RESAMPLE_STRATIFIED 1 /* tracker.py:178-186: one uniform per particle and update */
+
 #define GB_RNG_SUPPLIED 0 /* normals / uniforms provided in the reference's draw order */
 #define GB_RNG_PHILOX 1   /* counter-based Philox4x32-10 on device */
 
@@ -227,7 +230,7 @@ typedef struct gb_track_desc {
   int64_t point_offset;            /* global index of point 0 (Philox counters use global indices, so results do not depend on sharding) */
   const double* init_normals;      /* supplied: [P][N][6] = randn(N,2) | randn(N) | randn(N,3) per particle */
   const double* step_normals;      /* supplied: [P][S][N][3] */
-  const double* uniforms;          /* supplied: [P][S] one np.random.random() per update */
+  const double* uniforms;          /* supplied: [P][S] one np.random.random() per update (systematic) or [P][S][N] np.random.random(N) (stratified) */
 
   /* work buffers (caller-allocated) */
   double* state_a;                 /* [P][6][N] */
@@ -253,6 +256,8 @@ typedef struct gb_track_desc {
   uint8_t* obs_flags;              /* [P][T][O] GB_OBS_* */
   int32_t* window_stats;           /* [P][T][O][2] realised search-window (width, height), or NULL */
 
+  int32_t resample_method;         /* GB_RESAMPLE_* (Tracker.resample_method, tracker.py:151-223) */
+  int32_t pad1_;
   gb_plan plan;
 } gb_track_desc;
 

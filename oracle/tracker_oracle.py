@@ -536,6 +536,14 @@ def systematic_indices(weights: np.ndarray, u: float) -> np.ndarray:
     return np.searchsorted(np.cumsum(wn), positions)
 
 
+def stratified_indices(weights: np.ndarray, u: np.ndarray) -> np.ndarray:
+    """(tracker.py:178-186): one uniform per stratum instead of one for all."""
+    n = len(weights)
+    wn = weights / weights.sum()
+    positions = (np.arange(n) + u) * (1 / n)
+    return np.searchsorted(np.cumsum(wn), positions)
+
+
 def weighted_mean(ps: np.ndarray, w: np.ndarray) -> np.ndarray:
     return np.average(ps, weights=w, axis=0)
 
@@ -590,6 +598,7 @@ def track(
     exact: bool = False,
     randn: Callable = None,
     random: Callable = None,
+    resample_method: str = "systematic",
     trace: bool = False,
     raise_errors: bool = False,
 ) -> TrackResult:
@@ -670,8 +679,12 @@ def track(
                     terms = [x for x in terms if x is not None]
                     if terms:  # otherwise the weights of the last resampling stay (tracker.py:146-149)
                         w = weights_from_log_likelihoods(terms)
-                    u = random()
-                    idx = systematic_indices(w, u)
+                    if resample_method == "stratified":
+                        u = random(len(w))
+                        idx = stratified_indices(w, u)
+                    else:
+                        u = random()
+                        idx = systematic_indices(w, u)
                     if trace:
                         step.update({"evolved": ps.copy(), "weights": w.copy(), "u": u, "indices": idx})
                     ps = ps[idx]

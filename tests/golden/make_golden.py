@@ -33,9 +33,9 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def run_reference(scene, seed, points=None, return_covariances=False, observer_mask=None, viewshed=None,
-                  datetimes=None, capture=True):
+                  datetimes=None, capture=True, resample_method="systematic"):
     observers, models = synthetic.build(scene, glimpse, points=points)
-    tracker = glimpse.Tracker(observers, viewshed=viewshed)
+    tracker = glimpse.Tracker(observers, viewshed=viewshed, resample_method=resample_method)
     steps = []  # one dict per resample call (point-major, time-minor)
     templates = []
     current = {"obs": {}}

@@ -88,6 +88,11 @@ def track_cases():
                               kind="tangent_cylindrical", velocity_sigma=0.2),
             seed=909, post=add_gridded_dem,
         ),
+        # stratified resampling, one uniform per particle and update (tracker.py:178-186)
+        "track_stratified": dict(
+            scene_kwargs=dict(seed=13, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=1313, resample_method="stratified",
+        ),
         # map-scale world coordinates + per-frame view-direction jitter
         "track_jitter": dict(
             scene_kwargs=dict(seed=5, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,

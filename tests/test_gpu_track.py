@@ -39,7 +39,8 @@ def case_scene(name):
 
 CASES = list(scenes.track_cases())
 # the tangent motion models run in the default streaming organisation only
-CASE_MODES = [(n, m) for n in CASES for m in ("stream", "fused") if not (m == "fused" and "tangent" in n)]
+# ... and so does stratified resampling (rank 2)
+CASE_MODES = [(n, m) for n in CASES for m in ("stream", "fused") if not (m == "fused" and ("tangent" in n or "stratified" in n))]
 
 
 def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None, mode="stream"):
@@ -47,7 +48,8 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
     from glimpse_b200.session import Session, reference_order_draws
 
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode)
+    method = case.get("resample_method", "systematic")
+    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode, resample_method=method)
     datetimes = tracker.datetimes
     matching = tracker.match_datetimes(datetimes)
     image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
@@ -61,7 +63,7 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
     first, last = point_span(image_index, mask)
     np.random.seed(int(golden["seed"]))
     tangent = np.full(P, scene.motion["kind"].startswith("tangent"))
-    draws = reference_order_draws(P, scene.n_particles, last - first, tangent)
+    draws = reference_order_draws(P, scene.n_particles, last - first, tangent, method == "stratified")
     session = Session(tracker, models, image_index, taus, scene.tile_size, mask,
                       return_covariances=bool(case.get("return_covariances", False)),
                       return_particles=return_particles, draws=draws)
@@ -135,7 +137,7 @@ def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
         t = int(session.first[0]) + 1 + s
         evolved = np.stack([g[f"step{p * per + s}.evolved"] for p in range(P)])  # (P, N, 6)
         weights_ref = np.stack([g[f"step{p * per + s}.weights"] for p in range(P)])
-        u_ref = np.array([float(g[f"step{p * per + s}.u"]) for p in range(P)])
+        u_ref = np.stack([np.asarray(g[f"step{p * per + s}.u"], dtype=float) for p in range(P)])  # (P,) or (P, N)
         session.buf["uniforms"][:, t - 1 - int(session.first[0])] = torch.as_tensor(u_ref).to(dev)
         f_ev = torch.as_tensor(np.ascontiguousarray(evolved.transpose(0, 2, 1))).to(dev)  # (P, 6, N)
         dump = {
@@ -223,7 +225,7 @@ def test_track_free_running_matches_reference(cuda, name, mode):
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, rng="numpy", mode=mode)
+    tracker = gb.Tracker(observers, rng="numpy", mode=mode, resample_method=case.get("resample_method", "systematic"))
     np.random.seed(int(g["seed"]))
     cov = bool(case.get("return_covariances", False))
     tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True, return_covariances=cov)
@@ -242,21 +244,26 @@ def test_track_free_running_matches_reference(cuda, name, mode):
         assert np.nanmax(np.abs(tracks.sigmas[ok] - g["sigmas"][ok]) / g["sigmas"][ok]) < 0.05
 
 
-@pytest.mark.parametrize("mode", ["stream", "fused"])
-def test_philox_run_recovers_velocity(cuda, mode):
-    """Device RNG: the filter recovers the synthetic ground-truth velocity (0.4 m/d along +x)."""
+@pytest.mark.parametrize("mode,kind,method", [("stream", "cartesian", "systematic"), ("fused", "cartesian", "systematic"),
+                                              ("stream", "cartesian", "stratified"), ("stream", "tangent_cartesian", "systematic")])
+def test_philox_run_recovers_velocity(cuda, mode, kind, method):
+    """Device RNG: the filter recovers the synthetic ground-truth velocity (0.4 m/d along +x), for both resamplers and
+    for a tangent motion model on a gridded DEM."""
     import glimpse_b200 as gb
 
-    scene = synthetic.nadir_scene(seed=9, n_points=12, n_particles=2000, n_frames=10, imgsz=(600, 400))
+    scene = synthetic.nadir_scene(seed=9, n_points=12, n_particles=2000, n_frames=10, imgsz=(600, 400), kind=kind)
+    if kind.startswith("tangent"):
+        rng = np.random.RandomState(2)
+        scene.motion.update(dem=dict(array=0.3 * rng.rand(10, 14), x=(-80.0, 80.0), y=(60.0, -60.0)), dem_sigma=0.2)
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, seed=1234, mode=mode)
-    tracks = tracker.track(models, tile_size=scene.tile_size)
+    make = lambda seed: gb.Tracker(observers, seed=seed, mode=mode, resample_method=method)  # noqa: E731
+    tracks = make(1234).track(models, tile_size=scene.tile_size)
     assert all(e is None for e in tracks.errors)
     v = tracks.vxyz[:, -1]
     assert np.all(np.abs(v[:, 0] - scene.truth_velocity[0]) < 0.03), v
     assert np.all(np.abs(v[:, 1] - scene.truth_velocity[1]) < 0.03), v
     # determinism: same seed, same answer; other seed, other answer
-    again = gb.Tracker(observers, seed=1234, mode=mode).track(models, tile_size=scene.tile_size)
+    again = make(1234).track(models, tile_size=scene.tile_size)
     np.testing.assert_array_equal(again.means, tracks.means)
-    other = gb.Tracker(observers, seed=99, mode=mode).track(models, tile_size=scene.tile_size)
+    other = make(99).track(models, tile_size=scene.tile_size)
     assert not np.array_equal(other.means, tracks.means)
