@@ -61,7 +61,8 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons of one GPU sampled every ~10 ms during the timed region, through NVML
+    (``pynvml``) in a thread; falls back to polling ``nvidia-smi`` when NVML cannot be loaded."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,45 +70,76 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.proc = self.path = self.thread = None
+        self.sm, self.smax, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, handle):
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    self.sm.append(float(parts[1]))
+                    self.smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            os.unlink(self.path)
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.smax)), "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def build_scene(n_points, n_frames, pinned=False):
