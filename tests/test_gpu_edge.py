@@ -298,3 +298,29 @@ def test_stand_alone_evolve_particles_matches_the_oracle(cuda, kind):
         far[:, 0] += 1e4  # off the DEM: Raster.sample raises (raster.py:961-973)
         with pytest.raises(ValueError, match="out of bounds"):
             models[0].evolve_particles(far, dt)
+
+
+def test_kernel_timing_reports_every_kernel_of_the_streaming_flow(cuda):
+    """gb_kernel_timing / gb_kernel_timing_read (include/glimpse_b200.h): CUDA-event durations per kernel kind."""
+    import ctypes as C
+
+    import glimpse_b200 as gb
+    from glimpse_b200 import _lib
+
+    scene = synthetic.nadir_scene(seed=2, n_points=8, n_particles=1000, n_frames=6, imgsz=(320, 240), margin_px=90)
+    observers, models = synthetic.build(scene, gb)
+    lib = _lib.load()
+    _lib.check(lib.gb_kernel_timing(1))
+    try:
+        tracks = gb.Tracker(observers, seed=3).track(models, tile_size=scene.tile_size)
+        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        _lib.check(lib.gb_kernel_timing_read(ms, n, 8))
+    finally:
+        _lib.check(lib.gb_kernel_timing(0))
+    assert all(e is None for e in tracks.errors)
+    # activity, surface, weights, resample+propagate, finalize, init, template, publish
+    # per batch of points: one launch per time for the first three, one per update (5 of the 6 times) for the others
+    assert list(n)[5:7] == [1, 1] and n[3] == n[0] == n[4] and n[3] % 6 == 0 and n[1] == n[2] == n[7] == n[3] // 6 * 5
+    assert all(ms[k] > 0 for k in range(8))
+    _lib.check(lib.gb_kernel_timing_read(ms, n, 8))
+    assert sum(n) == 0  # switching the timer off clears it
