@@ -104,6 +104,7 @@ struct StepParams {
   int s_block, s_nblk;
   int tmpl_from_ev;  // k_template: staggered templates read the evolved particles from s_ev (pipelined flow)
   int resample_method;  // GB_RESAMPLE_*
+  int s2_budget;        // shared-memory bytes k_s2_surface may use for one window (negative: planar path forced, tests)
   int64_t p0, pb;    // batch of points handled by this launch
 };
 
@@ -1228,6 +1229,10 @@ static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t 
   return GB_OK;
 }
 
+// dynamic shared memory of k_s2_surface: windows up to ~66 px with the interleaved surface, up to ~80 px on planes;
+// larger ones work in their global region
+static constexpr int kSurfaceSmem = 110 * 1024;
+
 struct StreamLayout {
   int64_t ev[2], uv, w, bsum, pre, pm, ibox, pflags[2], act, meta, ref, surf, total;
 };
@@ -1282,11 +1287,14 @@ static void stream_bind(const gb_track_desc& d, StepParams& prm, int par, int64_
   prm.surf_bytes = pl.surf_bytes;
   prm.s_block = pl.stream_block;
   prm.s_nblk = pl.stream_nblk;
+  {
+    const int mag = pl.tile_bytes < 0 ? -pl.tile_bytes : pl.tile_bytes;
+    prm.s2_budget = (pl.tile_bytes < 0 ? -1 : 1) * (mag < kSurfaceSmem ? mag : kSurfaceSmem);
+  }
   prm.p0 = p0;
   prm.pb = pb;
 }
 
-static constexpr int kSurfaceSmem = 72 * 1024;  // dynamic shared memory of k_s2_surface (windows up to ~66 px; larger ones work in their global region)
 
 // Side streams on which batches of points advance independently (points never interact).  One pool per device.
 struct StreamPool {
@@ -1321,7 +1329,7 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   const unsigned nb = (unsigned)(prm.pb * prm.s_nblk);
   k_s0_reset<<<grid_for(prm.pb * prm.O * 5, 256), 256, 0, stream>>>(prm);
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
-  k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, kSurfaceSmem);
+  k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, prm.s2_budget);
   k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
   k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s5_finalize<COV><<<(unsigned)((prm.pb + 3) / 4), 128, 0, stream>>>(prm);
@@ -1557,7 +1565,7 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
       kt.end(ss);
       if (has_update[t]) {
         kt.begin(GB_K_SURFACE, ss);
-        k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, kSurfaceSmem);
+        k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, prm.s2_budget);
         kt.end(ss);
         kt.begin(GB_K_WEIGHTS, ss);
         k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);

@@ -326,7 +326,14 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
     if (tid == 0) atomicOr(&prm.s_pflags[p], (int)GB_F_WINDOW);
     return;
   }
-  const bool in_smem = need <= smem_budget;
+  // Where the window is worked on: in shared memory with the surface interleaved (small windows), in shared memory
+  // on planes (windows whose 16-byte cells would not fit, up to ~100 px at 110 KB), in shared memory phase by phase
+  // with hand-overs through the global region (up to ~128 px), or entirely in its global region.
+  // (A negative budget skips the interleaved path: parity tests of the other paths.)
+  const int64_t budget = smem_budget < 0 ? -smem_budget : smem_budget;
+  const bool in_smem = smem_budget >= 0 && need <= budget;
+  const bool planar = !in_smem && tile_bytes_needed_planar(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
+  const bool staged = !in_smem && !planar && tile_bytes_needed_staged(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
   if (clk && tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -334,18 +341,33 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
     clk[7] = w.Su;
     clk[8] = w.Sv;
     clk[9] = smid;
-    clk[10] = in_smem;
+    clk[10] = in_smem ? 1 : planar ? 2 : staged ? 3 : 0;
   }
-  tile_carve(in_smem ? reinterpret_cast<char*>(smem_raw) : region, w);
   const int64_t ta = (int64_t)w.tw * w.th;
   const int boxv[4] = {box_l, box_t, box_r, box_b};
-  tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
-                     prm.tmpl_values + po * ta, w, prm.io.dump_search ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
-                     prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap, clk ? clk + 2 : nullptr);
-  if (clk && tid == 0) clk[5] = clock64();
-  if (in_smem) {
-    float4* dst = reinterpret_cast<float4*>(region);
-    for (int i = tid; i < w.Mv * w.Mp; i += blockDim.x) dst[i] = w.herm[i];
+  float* dump_search = prm.io.dump_search ? prm.io.dump_search + po * prm.io.dump_cap : nullptr;
+  float* dump_sse = prm.io.dump_sse ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr;
+  if (planar) {
+    TilePlanes pl;
+    tile_carve_planar(reinterpret_cast<char*>(smem_raw), w, pl);
+    tile_prepare(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+                 prm.tmpl_values + po * ta, w, dump_search, prm.io.dump_cap, clk ? clk + 2 : nullptr);
+    tile_finish_planar(w, pl, reinterpret_cast<float4*>(region), dump_sse, prm.io.dump_cap, clk ? clk + 2 : nullptr);
+    if (clk && tid == 0) clk[5] = clock64();
+  } else if (staged) {
+    tile_build_surface_staged(reinterpret_cast<char*>(smem_raw), region, prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv,
+                              prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta, prm.tmpl_values + po * ta, w, dump_search, dump_sse,
+                              prm.io.dump_cap, clk ? clk + 2 : nullptr);
+    if (clk && tid == 0) clk[5] = clock64();
+  } else {
+    tile_carve(in_smem ? reinterpret_cast<char*>(smem_raw) : region, w);
+    tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
+                       prm.tmpl_values + po * ta, w, dump_search, dump_sse, prm.io.dump_cap, clk ? clk + 2 : nullptr);
+    if (clk && tid == 0) clk[5] = clock64();
+    if (in_smem) {
+      float4* dst = reinterpret_cast<float4*>(region);
+      for (int i = tid; i < w.Mv * w.Mp; i += blockDim.x) dst[i] = w.herm[i];
+    }
   }
   if (tid == 0) {
     meta[0] = box_l;

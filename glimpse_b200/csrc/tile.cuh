@@ -189,14 +189,14 @@ __device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, i
   return b0 * top_f + b2 * bot_f + b1 * top_v + b3 * bot_v;
 }
 
-// Build the Hermite surface for one search window.  All threads of the CTA participate.
-// `box` = (left, top, right, bottom); template data in global memory.  The caller has verified the
-// capacity and carved `w`.
-__device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
-                                          const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
-                                          float* dump_search, float* dump_sse, int64_t dump_cap, long long* clk) {
+// Phases 1-5 of the surface of one search window: raw window -> high-passed, CDF-matched float tile `w.hp`
+// (plus the template in `w.tmpl`).  All threads of the CTA participate.  `box` = (left, top, right, bottom);
+// template data in global memory.  The caller has verified the capacity and carved `w`.
+__device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
+                                    const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
+                                    float* dump_search, int64_t dump_cap, long long* clk) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-  const int Su = w.Su, Sv = w.Sv, Mu = w.Mu, Mv = w.Mv, Mp = w.Mp, Sp = w.Sp, Tp = w.Tp;
+  const int Su = w.Su, Sv = w.Sv, Sp = w.Sp, Tp = w.Tp;
   const int area = Su * Sv;
   // 1. raw window (a warp per row: consecutive lanes read consecutive pixels), template and its
   //    CDF; clear the histogram
@@ -293,6 +293,83 @@ __device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, in
   }
   __syncthreads();
   if (clk && threadIdx.x == 0) clk[1] = clock64();
+}
+
+// SSD of one warp item: output rows r0 .. r0 + kmax - 1 (kmax <= 4), output column c, template columns
+// [jlo, jhi).  Lanes run along the image row (conflict-free loads, template values broadcast) and each lane
+// keeps the four row outputs in registers while the template column slides past.
+__device__ __forceinline__ void ssd_warp_item(const TileWork& w, int r0, int c, int kmax, int jlo, int jhi, float (&acc)[4]) {
+  const int th = w.th, Sp = w.Sp, Tp = w.Tp;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  for (int j = jlo; j < jhi; ++j) {
+    const float* Icol = w.hp + r0 * Sp + c + j;
+    const float* Tcol = w.tmpl + j;
+    const int nrow = th + kmax - 1;
+    if (th >= 4) {
+      // ta, tb, tc = template rows ip-1, ip-2, ip-3; output row k pairs image row ip with template row ip-k
+      float ta, tb, tc;
+      {
+        const float t_0 = Tcol[0], t_1 = Tcol[Tp], t_2 = Tcol[2 * Tp];
+        const float i_0 = Icol[0], i_1 = Icol[Sp], i_2 = Icol[2 * Sp];
+        float d = i_0 - t_0; a0 = fmaf(d, d, a0);
+        d = i_1 - t_1; a0 = fmaf(d, d, a0);
+        d = i_1 - t_0; a1 = fmaf(d, d, a1);
+        d = i_2 - t_2; a0 = fmaf(d, d, a0);
+        d = i_2 - t_1; a1 = fmaf(d, d, a1);
+        d = i_2 - t_0; a2 = fmaf(d, d, a2);
+        ta = t_2; tb = t_1; tc = t_0;
+      }
+#pragma unroll 4
+      for (int ip = 3; ip < th; ++ip) {
+        const float tn = Tcol[ip * Tp];
+        const float iv = Icol[ip * Sp];
+        float d = iv - tn; a0 = fmaf(d, d, a0);
+        d = iv - ta; a1 = fmaf(d, d, a1);
+        d = iv - tb; a2 = fmaf(d, d, a2);
+        d = iv - tc; a3 = fmaf(d, d, a3);
+        tc = tb; tb = ta; ta = tn;
+      }
+      // tail: image rows th .. th + kmax - 2 only feed output rows 1..3
+      if (th < nrow) {
+        const float iv = Icol[th * Sp];
+        float d = iv - ta; a1 = fmaf(d, d, a1);
+        d = iv - tb; a2 = fmaf(d, d, a2);
+        d = iv - tc; a3 = fmaf(d, d, a3);
+      }
+      if (th + 1 < nrow) {
+        const float iv = Icol[(th + 1) * Sp];
+        float d = iv - ta; a2 = fmaf(d, d, a2);
+        d = iv - tb; a3 = fmaf(d, d, a3);
+      }
+      if (th + 2 < nrow) {
+        const float iv = Icol[(th + 2) * Sp];
+        const float d = iv - ta; a3 = fmaf(d, d, a3);
+      }
+    } else {
+      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+      for (int ip = 0; ip < nrow; ++ip) {
+        t3 = t2;
+        t2 = t1;
+        t1 = t0;
+        t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
+        const float iv = Icol[ip * Sp];
+        if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
+        if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
+        if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
+        if (ip >= 3 && ip <= th + 2) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
+      }
+    }
+  }
+  acc[0] = a0;
+  acc[1] = a1;
+  acc[2] = a2;
+  acc[3] = a3;
+}
+
+// Phases 6-7 with the surface in its final interleaved form (F, F_u, F_v, F_uv per cell) in `w.herm`.
+__device__ inline void tile_finish_interleaved(TileWork& w, float* dump_sse, int64_t dump_cap, long long* clk) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int Mu = w.Mu, Mv = w.Mv, Mp = w.Mp;
   // 6. area-normalised sum of squared differences (tracker.py:609-614).  One warp owns a block of
   //    4 output rows x 32 output columns and a slice of the template columns: lanes run along the
   //    image row (conflict-free loads, template values broadcast) and each lane keeps the four row
@@ -312,68 +389,9 @@ __device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, in
       const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
       const int kmax = min(4, Mv - r0);  // valid output rows in this block
       const int jlo = jp * jper, jhi = min(jlo + jper, tw);
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-      for (int j = jlo; j < jhi; ++j) {
-        const float* Icol = w.hp + r0 * Sp + c + j;
-        const float* Tcol = w.tmpl + j;
-        const int nrow = th + kmax - 1;
-        if (th >= 4) {
-          // ta, tb, tc = template rows ip-1, ip-2, ip-3; output row k pairs image row ip with template row ip-k
-          float ta, tb, tc;
-          {
-            const float t_0 = Tcol[0], t_1 = Tcol[Tp], t_2 = Tcol[2 * Tp];
-            const float i_0 = Icol[0], i_1 = Icol[Sp], i_2 = Icol[2 * Sp];
-            float d = i_0 - t_0; a0 = fmaf(d, d, a0);
-            d = i_1 - t_1; a0 = fmaf(d, d, a0);
-            d = i_1 - t_0; a1 = fmaf(d, d, a1);
-            d = i_2 - t_2; a0 = fmaf(d, d, a0);
-            d = i_2 - t_1; a1 = fmaf(d, d, a1);
-            d = i_2 - t_0; a2 = fmaf(d, d, a2);
-            ta = t_2; tb = t_1; tc = t_0;
-          }
-#pragma unroll 4
-          for (int ip = 3; ip < th; ++ip) {
-            const float tn = Tcol[ip * Tp];
-            const float iv = Icol[ip * Sp];
-            float d = iv - tn; a0 = fmaf(d, d, a0);
-            d = iv - ta; a1 = fmaf(d, d, a1);
-            d = iv - tb; a2 = fmaf(d, d, a2);
-            d = iv - tc; a3 = fmaf(d, d, a3);
-            tc = tb; tb = ta; ta = tn;
-          }
-          // tail: image rows th .. th + kmax - 2 only feed output rows 1..3
-          if (th < nrow) {
-            const float iv = Icol[th * Sp];
-            float d = iv - ta; a1 = fmaf(d, d, a1);
-            d = iv - tb; a2 = fmaf(d, d, a2);
-            d = iv - tc; a3 = fmaf(d, d, a3);
-          }
-          if (th + 1 < nrow) {
-            const float iv = Icol[(th + 1) * Sp];
-            float d = iv - ta; a2 = fmaf(d, d, a2);
-            d = iv - tb; a3 = fmaf(d, d, a3);
-          }
-          if (th + 2 < nrow) {
-            const float iv = Icol[(th + 2) * Sp];
-            const float d = iv - ta; a3 = fmaf(d, d, a3);
-          }
-        } else {
-          float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-          for (int ip = 0; ip < nrow; ++ip) {
-            t3 = t2;
-            t2 = t1;
-            t1 = t0;
-            t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
-            const float iv = Icol[ip * Sp];
-            if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
-            if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
-            if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
-            if (ip >= 3 && ip <= th + 2) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
-          }
-        }
-      }
+      float acc[4];
+      ssd_warp_item(w, r0, c, kmax, jlo, jhi, acc);
       if (cb * 32 + lane < Mu) {
-        const float acc[4] = {a0, a1, a2, a3};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k < kmax) hf[((r0 + k) * Mp + c) * 4 + jp] = acc[k];
@@ -408,6 +426,232 @@ __device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, in
     }
     __syncthreads();
     for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mp * 4, Mv);
+  }
+  __syncthreads();
+}
+
+// Build the Hermite surface for one search window in `w.herm` (interleaved layout).
+__device__ inline void tile_build_surface(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
+                                          const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
+                                          float* dump_search, float* dump_sse, int64_t dump_cap, long long* clk) {
+  tile_prepare(pixels, pitch, nchan, box, g_tmpl, g_tq, g_tv, w, dump_search, dump_cap, clk);
+  tile_finish_interleaved(w, dump_sse, dump_cap, clk);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large search windows (k_s2_large): planar work arrays, so that windows up to ~140 px stay in the
+// 200 KB of shared memory one CTA per SM can have.  Regions and lifetimes:
+//   R1 = hp [Sv][Sp] float (median -> SSD); hosts the raw u16 window before and the row slopes F_u after
+//   R2 = packed u32 [(Sv+4)][(Su+4)] (until the median) / F [Mv][Mq] + one scratch plane [Mv][Mq] (from the SSD on)
+// The finished surface is written straight to its global region in the interleaved form k_s3 samples.
+// ---------------------------------------------------------------------------------------------
+struct TilePlanes {
+  float *F, *Fu, *G;  // SSE surface, its row slopes, scratch plane for the column solves
+  int Mq;             // plane pitch in floats (odd: row solves of different rows hit different banks)
+};
+
+__host__ __device__ inline int64_t tile_bytes_needed_planar(int Su, int Sv, int tw, int th, int nbins, int nvals) {
+  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mq = Mu | 1, Sp = (Su + 3) / 4 * 4, Tp = (tw + 3) / 4 * 4;
+  const int64_t r1 = align16((int64_t)Sv * Sp * 4);  // >= Mv * Mq * 4 (F_u) and >= Sv * Su * 2 (raw)
+  const int64_t packed = (int64_t)(Sv + 4) * (Su + 4) * 4, planes = 2 * align16(Mv * Mq * 4);
+  int64_t b = r1 + align16(packed > planes ? packed : planes);
+  b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
+  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)nbins * 4);
+  return b;
+}
+
+__device__ inline void tile_carve_planar(char* base, TileWork& w, TilePlanes& pl) {
+  w.Mp = w.Mu | 1;
+  w.Sp = (w.Su + 3) / 4 * 4;
+  w.Tp = (w.tw + 3) / 4 * 4;
+  pl.Mq = w.Mu | 1;
+  char* p = base;
+  w.hp = reinterpret_cast<float*>(p);
+  w.raw = reinterpret_cast<uint16_t*>(p);
+  pl.Fu = reinterpret_cast<float*>(p);
+  p += align16((int64_t)w.Sv * w.Sp * 4);
+  const int64_t plane = align16((int64_t)w.Mv * pl.Mq * 4), packed = (int64_t)(w.Sv + 4) * (w.Su + 4) * 4;
+  w.packed = reinterpret_cast<uint32_t*>(p);
+  w.herm = nullptr;
+  pl.F = reinterpret_cast<float*>(p);
+  pl.G = reinterpret_cast<float*>(p + plane);
+  p += align16(packed > 2 * plane ? packed : 2 * plane);
+  w.lut = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nbins * 8);
+  w.tq = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nvals * 8);
+  w.tv = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nvals * 8);
+  w.tmpl = reinterpret_cast<float*>(p);
+  p += align16((int64_t)w.th * w.Tp * 4);
+  w.hist = reinterpret_cast<uint32_t*>(p);
+}
+
+// Phases 6-7 on planes; `out` = the surface's global region, float4 [Mv][Mp].  Same arithmetic as
+// tile_finish_interleaved with one template slice (JP = 1): identical results.
+__device__ inline void tile_finish_planar(TileWork& w, const TilePlanes& pl, float4* __restrict__ out, float* dump_sse,
+                                          int64_t dump_cap, long long* clk) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int Mu = w.Mu, Mv = w.Mv, Mp = w.Mp, Mq = pl.Mq;
+  {
+    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    const double inv_area = 1.0 / (double)(w.tw * w.th);
+    for (int item = warp; item < RG * CB; item += nwarp) {
+      const int rg = item / CB, cb = item - rg * CB;
+      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
+      const int kmax = min(4, Mv - r0);
+      float acc[4];
+      ssd_warp_item(w, r0, c, kmax, 0, w.tw, acc);
+      if (cb * 32 + lane < Mu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < kmax) {
+            const float sse = (float)((double)acc[k] * inv_area);
+            pl.F[(r0 + k) * Mq + c] = sse;
+            const int64_t o = (int64_t)(r0 + k) * Mu + c;
+            if (dump_sse && o < dump_cap) dump_sse[o] = sse;
+          }
+      }
+    }
+  }
+  __syncthreads();  // hp is dead from here on: F_u takes its place
+  if (clk && threadIdx.x == 0) clk[2] = clock64();
+  {
+    // rows (F -> F_u) and columns (F -> F_v in the scratch plane) on separate warps
+    const int Mvp = 32 * ((Mv + 31) / 32);
+    for (int line = tid; line < Mvp + Mu; line += nthr) {
+      if (line < Mv) {
+        spline_slopes_line(pl.F + (int64_t)line * Mq, pl.Fu + (int64_t)line * Mq, 1, Mu);
+      } else if (line >= Mvp) {
+        const int c = line - Mvp;
+        spline_slopes_line(pl.F + c, pl.G + c, Mq, Mv);
+      }
+    }
+    __syncthreads();
+    for (int o = tid; o < Mu * Mv; o += nthr) {
+      const int r = o / Mu, c = o - r * Mu;
+      out[r * Mp + c] = make_float4(pl.F[r * Mq + c], pl.Fu[r * Mq + c], pl.G[r * Mq + c], 0.0f);
+    }
+    __syncthreads();
+    // cross derivative: columns of F_u into the scratch plane, then into the fourth component
+    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(pl.Fu + c, pl.G + c, Mq, Mv);
+    __syncthreads();
+    float* outf = reinterpret_cast<float*>(out);
+    for (int o = tid; o < Mu * Mv; o += nthr) {
+      const int r = o / Mu, c = o - r * Mu;
+      outf[((int64_t)r * Mp + c) * 4 + 3] = pl.G[r * Mq + c];
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Largest search windows (up to ~128 px at 110 KB): every phase still runs out of shared memory, but the phases
+// hand their results over through the window's global region, because no two of the big arrays fit at once:
+//   prepare:  raw + packed + tables in shared memory, high-passed tile hp written to the region
+//   SSD:      hp staged back into shared memory (raw / packed are dead), SSE plane F written to the region
+//   Hermite:  two planes in shared memory; F_u, F_v, F_uv are produced one after the other and stored into the
+//             interleaved surface as they appear (F_u is reloaded for the cross derivative)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t tile_bytes_needed_staged(int Su, int Sv, int tw, int th, int nbins, int nvals) {
+  const int64_t Tp = (tw + 3) / 4 * 4;
+  int64_t b = align16((int64_t)Su * Sv * 2) + align16((int64_t)(Sv + 4) * (Su + 4) * 4);
+  b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
+  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)nbins * 4);
+  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, planes = 2 * align16(Mv * (Mu | 1) * 4);
+  return b > planes ? b : planes;
+}
+
+__device__ inline void tile_build_surface_staged(char* smem, char* region, const uint8_t* __restrict__ pixels, int pitch, int nchan,
+                                                 const int* box, const double* __restrict__ g_tmpl, const double* __restrict__ g_tq,
+                                                 const double* __restrict__ g_tv, TileWork& w, float* dump_search, float* dump_sse,
+                                                 int64_t dump_cap, long long* clk) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  w.Mp = w.Mu | 1;
+  w.Sp = (w.Su + 3) / 4 * 4;
+  w.Tp = (w.tw + 3) / 4 * 4;
+  const int Mu = w.Mu, Mv = w.Mv, Mp = w.Mp, Mq = w.Mu | 1;
+  char* p = smem;
+  w.raw = reinterpret_cast<uint16_t*>(p);
+  p += align16((int64_t)w.Su * w.Sv * 2);
+  w.packed = reinterpret_cast<uint32_t*>(p);
+  p += align16((int64_t)(w.Sv + 4) * (w.Su + 4) * 4);
+  w.lut = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nbins * 8);
+  w.tq = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nvals * 8);
+  w.tv = reinterpret_cast<double*>(p);
+  p += align16((int64_t)w.nvals * 8);
+  w.tmpl = reinterpret_cast<float*>(p);
+  p += align16((int64_t)w.th * w.Tp * 4);
+  w.hist = reinterpret_cast<uint32_t*>(p);
+  w.herm = nullptr;
+  float* hp_global = reinterpret_cast<float*>(region);
+  w.hp = hp_global;
+  tile_prepare(pixels, pitch, nchan, box, g_tmpl, g_tq, g_tv, w, dump_search, dump_cap, clk);
+  // hp back into shared memory, over raw / packed (4 Sv Sp <= their 6 S^2 bytes)
+  float* hp_s = reinterpret_cast<float*>(smem);
+  {
+    const int n4 = w.Sv * w.Sp / 4;  // Sp is a multiple of 4
+    const float4* src = reinterpret_cast<const float4*>(hp_global);
+    float4* dst = reinterpret_cast<float4*>(hp_s);
+    for (int i = tid; i < n4; i += nthr) dst[i] = src[i];
+  }
+  __syncthreads();
+  w.hp = hp_s;
+  // SSD plane F -> region (hp's global copy is dead)
+  float* F_global = reinterpret_cast<float*>(region);
+  {
+    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    const double inv_area = 1.0 / (double)(w.tw * w.th);
+    for (int item = warp; item < RG * CB; item += nwarp) {
+      const int rg = item / CB, cb = item - rg * CB;
+      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
+      const int kmax = min(4, Mv - r0);
+      float acc[4];
+      ssd_warp_item(w, r0, c, kmax, 0, w.tw, acc);
+      if (cb * 32 + lane < Mu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < kmax) {
+            const float sse = (float)((double)acc[k] * inv_area);
+            F_global[(r0 + k) * Mq + c] = sse;
+            const int64_t o = (int64_t)(r0 + k) * Mu + c;
+            if (dump_sse && o < dump_cap) dump_sse[o] = sse;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  if (clk && threadIdx.x == 0) clk[2] = clock64();
+  // Hermite on two planes
+  float* P0 = reinterpret_cast<float*>(smem);
+  float* P1 = reinterpret_cast<float*>(smem + align16((int64_t)Mv * Mq * 4));
+  for (int i = tid; i < Mv * Mq; i += nthr) P0[i] = F_global[i];
+  __syncthreads();  // F is in shared memory: the region is free for the final surface
+  float* out = reinterpret_cast<float*>(region);
+  for (int r = tid; r < Mv; r += nthr) spline_slopes_line(P0 + (int64_t)r * Mq, P1 + (int64_t)r * Mq, 1, Mu);  // F -> F_u
+  __syncthreads();
+  for (int o = tid; o < Mu * Mv; o += nthr) {
+    const int r = o / Mu, c = o - r * Mu;
+    *reinterpret_cast<float2*>(out + ((int64_t)r * Mp + c) * 4) = make_float2(P0[r * Mq + c], P1[r * Mq + c]);
+  }
+  __syncthreads();
+  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv);  // F -> F_v
+  __syncthreads();
+  for (int o = tid; o < Mu * Mv; o += nthr) {
+    const int r = o / Mu, c = o - r * Mu;
+    out[((int64_t)r * Mp + c) * 4 + 2] = P1[r * Mq + c];
+    P0[r * Mq + c] = out[((int64_t)r * Mp + c) * 4 + 1];  // F_u back in (written by this CTA before the last barrier)
+  }
+  __syncthreads();
+  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv);  // F_u -> F_uv
+  __syncthreads();
+  for (int o = tid; o < Mu * Mv; o += nthr) {
+    const int r = o / Mu, c = o - r * Mu;
+    out[((int64_t)r * Mp + c) * 4 + 3] = P1[r * Mq + c];
   }
   __syncthreads();
 }

@@ -109,7 +109,11 @@ def test_templates_match_reference(cuda, name, mode):
 @pytest.mark.parametrize("name,mode,cluster,tile_bytes",
                          [(n, m, 0, None) for n, m in CASE_MODES]
                          + [("track_c1", "fused", 2, None), ("track_cyl2", "fused", 4, None), ("track_jitter", "fused", 8, None),
-                            ("track_c1", "fused", 4, 2048)])
+                            ("track_c1", "fused", 4, 2048),
+                            # k_s2_surface's other work-space organisations (negative = no interleaved path): every window on
+                            # planes; a budget that sends windows to the staged, planar or global path depending on their size
+                            ("track_c1", "stream", 0, -112640), ("track_cyl2", "stream", 0, -112640),
+                            ("track_c1", "stream", 0, -18000), ("track_cyl2", "stream", 0, -30000), ("track_jitter", "stream", 0, -16000)])
 def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
     from glimpse_b200 import _lib
 
