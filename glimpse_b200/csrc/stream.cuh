@@ -221,22 +221,26 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
   long long* clk = prm.io.dump_clocks ? reinterpret_cast<long long*>(prm.io.dump_clocks) + po * 16 : nullptr;
   if (clk && tid == 0) clk[0] = clock64();
   if (tid == 0) meta[7] = 0;
-  if (!stream_point_active(prm, p) || prm.io.force_weights) return;
+  // every scalar the CTA branches on is requested before the first branch: one memory round trip instead of five
+  int* gib = prm.s_ibox + po * 5;
+  const int act = prm.s_act[p];
+  const int seen = prm.mask[po];
+  const int failed = prm.s_pflags[p];
+  const int n_values = prm.tmpl_nvalues[po];
+  const int my_ib = tid < 5 ? gib[tid] : 0;
+  if (!(act & GB_ACT_ACTIVE) || prm.io.force_weights) return;
   uint8_t* oflag = prm.obs_flags + ((int64_t)p * prm.T + t) * prm.O + o;
-  if (prm.img[o] < 0 || !prm.mask[po]) {
+  if (prm.img[o] < 0 || !seen) {
     if (tid == 0) *oflag = GB_OBS_NO_IMAGE;
     return;
   }
-  if (prm.s_pflags[p] != 0) return;  // the point failed its particle tests: reference raises before any observer work
+  if (failed != 0) return;  // the point failed its particle tests: reference raises before any observer work
   const int N = (int)prm.N;
-  // consume the integer cloud box and leave it empty for the next time (one thread reads, all share)
+  // consume the integer cloud box and leave it empty for the next time
   __shared__ int s_ib[5];
-  if (tid == 0) {
-    int* gib = prm.s_ibox + po * 5;
-    for (int k = 0; k < 5; ++k) {
-      s_ib[k] = gib[k];
-      gib[k] = (k == 4) ? 0 : 0x7fffffff;
-    }
+  if (tid < 5) {
+    s_ib[tid] = my_ib;
+    gib[tid] = (tid == 4) ? 0 : 0x7fffffff;
   }
   __syncthreads();
   const int* ib = s_ib;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_const
   w.Mu = w.Su - w.tw + 1;
   w.Mv = w.Sv - w.th + 1;
   w.nbins = 255 * prm.nchan[o] + 1;
-  w.nvals = prm.tmpl_nvalues[po];
+  w.nvals = n_values;
   if (tid == 0) {
     *oflag = GB_OBS_USED;
     if (prm.window_stats) {

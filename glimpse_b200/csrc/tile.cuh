@@ -198,30 +198,42 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int Su = w.Su, Sv = w.Sv, Sp = w.Sp, Tp = w.Tp;
   const int area = Su * Sv;
-  // 1. raw window (a warp per row: consecutive lanes read consecutive pixels), template and its
-  //    CDF; clear the histogram
+  // 1. raw window, template and its CDF; clear the histogram.  Every global load a thread needs first is issued
+  //    before anything waits on one (the template words, then four window pixels per trip): the phase costs about
+  //    one memory round trip instead of one per loop.
   {
+    const int ta = w.tw * w.th;
+    const double t_first = tid < ta ? g_tmpl[tid] : 0.0;
+    const double q_first = tid < w.nvals ? g_tq[tid] : 0.0;
+    const double v_first = tid < w.nvals ? g_tv[tid] : 0.0;
     const uint8_t* px = pixels + (int64_t)box[1] * pitch + (int64_t)box[0] * nchan;
-    if (nchan == 1) {
-      for (int r = warp; r < Sv; r += nwarp)
-        for (int c = lane; c < Su; c += 32) w.raw[r * Su + c] = px[(int64_t)r * pitch + c];
-    } else {
-      for (int r = warp; r < Sv; r += nwarp)
-        for (int c = lane; c < Su; c += 32) {
+    for (int e0 = tid; e0 < area; e0 += 4 * nthr) {
+      unsigned v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * nthr;
+        v[k] = 0;
+        if (e < area) {
+          const int r = e / Su, c = e - r * Su;
           const uint8_t* q = px + (int64_t)r * pitch + c * nchan;
-          unsigned sum = 0;
-          for (int k = 0; k < nchan; ++k) sum += q[k];
-          w.raw[r * Su + c] = (uint16_t)sum;
+          v[k] = q[0];
+          for (int ch = 1; ch < nchan; ++ch) v[k] += q[ch];
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * nthr;
+        if (e < area) w.raw[e] = (uint16_t)v[k];
+      }
     }
     for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
-    for (int i = tid; i < w.tw * w.th; i += nthr) {
+    for (int i = tid; i < ta; i += nthr) {
       const int r = i / w.tw, c = i - r * w.tw;
-      w.tmpl[r * Tp + c] = (float)g_tmpl[i];
+      w.tmpl[r * Tp + c] = (float)(i == tid ? t_first : g_tmpl[i]);
     }
     for (int i = tid; i < w.nvals; i += nthr) {
-      w.tq[i] = g_tq[i];
-      w.tv[i] = g_tv[i];
+      w.tq[i] = i == tid ? q_first : g_tq[i];
+      w.tv[i] = i == tid ? v_first : g_tv[i];
     }
   }
   __syncthreads();
