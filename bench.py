@@ -215,7 +215,7 @@ def run_reference_arm(args):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = min(cores, 64)
-    n_points, n_frames = 8 * cores, 12
+    n_points, n_frames = 4 * cores, 50  # half of the workload's frames: search windows grow with time, so do the costs
     scene = build_scene(n_points, n_frames)
     times = []
     for i in range(args.warmup + args.steps):

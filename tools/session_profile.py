@@ -20,4 +20,4 @@ pr = cProfile.Profile()
 pr.enable()
 tracker.track(models, tile_size=scene.tile_size)
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
