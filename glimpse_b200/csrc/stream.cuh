@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __g
 }
 
 #define GB_S2_THREADS 512
-__global__ void __launch_bounds__(GB_S2_THREADS) k_s2_surface(const __grid_constant__ StepParams prm, int smem_budget) {
+__global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_constant__ StepParams prm, int smem_budget) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_mm[GB_S2_THREADS / 32][4];
   __shared__ int s_box[4];

@@ -31,7 +31,7 @@ struct TileWork {
   double* tv;        // [nvals] template values
   float* hp;         // [Sv][Sp] high-passed search tile, Sp = Su rounded up to 4
   uint16_t* raw;     // [Sv][Su] raw window; aliases hp (dead before hp is written)
-  float* tmpl;       // [th][Tp] high-passed template, Tp = tw rounded up to 4
+  float2* tmpl;      // [th][tw] high-passed template, negated and duplicated (-t, -t): the packed FP32 SSD adds it to two pixels
   uint32_t* hist;    // [nbins]
   int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
 };
@@ -44,7 +44,7 @@ __host__ __device__ inline int64_t tile_bytes_needed(int Su, int Sv, int tw, int
   int64_t b = align16(herm > packed ? herm : packed);
   b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
   b += align16((int64_t)Sv * Sp * 4);
-  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)th * tw * 8);
   b += align16((int64_t)nbins * 4);
   return b;
 }
@@ -67,8 +67,8 @@ __device__ inline void tile_carve(char* base, TileWork& w) {
   w.hp = reinterpret_cast<float*>(p);
   w.raw = reinterpret_cast<uint16_t*>(p);
   p += align16((int64_t)w.Sv * w.Sp * 4);
-  w.tmpl = reinterpret_cast<float*>(p);
-  p += align16((int64_t)w.th * w.Tp * 4);
+  w.tmpl = reinterpret_cast<float2*>(p);
+  p += align16((int64_t)w.th * w.tw * 8);
   w.hist = reinterpret_cast<uint32_t*>(p);
 }
 
@@ -228,8 +228,8 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
     }
     for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
     for (int i = tid; i < ta; i += nthr) {
-      const int r = i / w.tw, c = i - r * w.tw;
-      w.tmpl[r * Tp + c] = (float)(i == tid ? t_first : g_tmpl[i]);
+      const float tv = -(float)(i == tid ? t_first : g_tmpl[i]);
+      w.tmpl[i] = make_float2(tv, tv);
     }
     for (int i = tid; i < w.nvals; i += nthr) {
       w.tq[i] = i == tid ? q_first : g_tq[i];
@@ -307,75 +307,106 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   if (clk && threadIdx.x == 0) clk[1] = clock64();
 }
 
-// SSD of one warp item: output rows r0 .. r0 + kmax - 1 (kmax <= 4), output column c, template columns
-// [jlo, jhi).  Lanes run along the image row (conflict-free loads, template values broadcast) and each lane
-// keeps the four row outputs in registers while the template column slides past.
-__device__ __forceinline__ void ssd_warp_item(const TileWork& w, int r0, int c, int kmax, int jlo, int jhi, float (&acc)[4]) {
-  const int th = w.th, Sp = w.Sp, Tp = w.Tp;
-  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-  for (int j = jlo; j < jhi; ++j) {
-    const float* Icol = w.hp + r0 * Sp + c + j;
-    const float* Tcol = w.tmpl + j;
-    const int nrow = th + kmax - 1;
-    if (th >= 4) {
-      // ta, tb, tc = template rows ip-1, ip-2, ip-3; output row k pairs image row ip with template row ip-k
-      float ta, tb, tc;
-      {
-        const float t_0 = Tcol[0], t_1 = Tcol[Tp], t_2 = Tcol[2 * Tp];
-        const float i_0 = Icol[0], i_1 = Icol[Sp], i_2 = Icol[2 * Sp];
-        float d = i_0 - t_0; a0 = fmaf(d, d, a0);
-        d = i_1 - t_1; a0 = fmaf(d, d, a0);
-        d = i_1 - t_0; a1 = fmaf(d, d, a1);
-        d = i_2 - t_2; a0 = fmaf(d, d, a0);
-        d = i_2 - t_1; a1 = fmaf(d, d, a1);
-        d = i_2 - t_0; a2 = fmaf(d, d, a2);
-        ta = t_2; tb = t_1; tc = t_0;
-      }
+// How the 32 lanes of a warp tile the SSD surface: `cw` lanes along the columns, two adjacent output columns each, times
+// 32 / cw groups of four output rows.  Narrow surfaces get more row groups so that lanes are not left idle.
+struct SsdLanes {
+  int cw, rh, RG, CB;  // lanes per row group, row groups per warp, item grid
+  __device__ __forceinline__ SsdLanes(int Mu, int Mv) {
+    cw = Mu > 32 ? 32 : (Mu > 16 ? 16 : 8);
+    rh = 32 / cw;
+    RG = (Mv + 4 * rh - 1) / (4 * rh);
+    CB = (Mu + 2 * cw - 1) / (2 * cw);
+  }
+  // first output row / column of a lane in item (rg, cb)
+  __device__ __forceinline__ int row(int rg, int lane) const { return (rg * rh + lane / cw) * 4; }
+  __device__ __forceinline__ int col(int cb, int lane) const { return 2 * (cb * cw + (lane & (cw - 1))); }
+};
+
+// One pixel pair of the high-passed tile; the pair starts at an even float index when ALIGNED.
+template <bool ALIGNED>
+__device__ __forceinline__ float2 ssd_load(const float* p) {
+  if (ALIGNED) return *reinterpret_cast<const float2*>(p);
+  return make_float2(p[0], p[1]);
+}
+
+// SSD of one lane: output rows r0 .. r0 + kmax - 1 (kmax <= 4), output columns c (even) and c + 1, template columns
+// [jlo, jhi).  Packed FP32 arithmetic (FADD2 / FFMA2, new in sm_100): the two columns share every instruction, each half
+// an ordinary IEEE operation, so the sums are bit-identical to scalar code.  The four row outputs stay in registers
+// while the template column slides past; the template is stored negated (d = pixel + (-t)).
+template <bool ALIGNED>
+__device__ __forceinline__ void ssd_column(const TileWork& w, const float* Icol, const float2* Tcol, int kmax, float2 (&a)[4]) {
+  const int th = w.th, Sp = w.Sp, tw = w.tw;
+  const int nrow = th + kmax - 1;
+  if (th >= 4) {
+    // ta, tb, tc = template rows ip-1, ip-2, ip-3; output row k pairs image row ip with template row ip-k
+    float2 ta, tb, tc, d;
+    {
+      const float2 t_0 = Tcol[0], t_1 = Tcol[tw], t_2 = Tcol[2 * tw];
+      const float2 i_0 = ssd_load<ALIGNED>(Icol), i_1 = ssd_load<ALIGNED>(Icol + Sp), i_2 = ssd_load<ALIGNED>(Icol + 2 * Sp);
+      d = __fadd2_rn(i_0, t_0); a[0] = __ffma2_rn(d, d, a[0]);
+      d = __fadd2_rn(i_1, t_1); a[0] = __ffma2_rn(d, d, a[0]);
+      d = __fadd2_rn(i_1, t_0); a[1] = __ffma2_rn(d, d, a[1]);
+      d = __fadd2_rn(i_2, t_2); a[0] = __ffma2_rn(d, d, a[0]);
+      d = __fadd2_rn(i_2, t_1); a[1] = __ffma2_rn(d, d, a[1]);
+      d = __fadd2_rn(i_2, t_0); a[2] = __ffma2_rn(d, d, a[2]);
+      ta = t_2; tb = t_1; tc = t_0;
+    }
 #pragma unroll 4
-      for (int ip = 3; ip < th; ++ip) {
-        const float tn = Tcol[ip * Tp];
-        const float iv = Icol[ip * Sp];
-        float d = iv - tn; a0 = fmaf(d, d, a0);
-        d = iv - ta; a1 = fmaf(d, d, a1);
-        d = iv - tb; a2 = fmaf(d, d, a2);
-        d = iv - tc; a3 = fmaf(d, d, a3);
-        tc = tb; tb = ta; ta = tn;
-      }
-      // tail: image rows th .. th + kmax - 2 only feed output rows 1..3
-      if (th < nrow) {
-        const float iv = Icol[th * Sp];
-        float d = iv - ta; a1 = fmaf(d, d, a1);
-        d = iv - tb; a2 = fmaf(d, d, a2);
-        d = iv - tc; a3 = fmaf(d, d, a3);
-      }
-      if (th + 1 < nrow) {
-        const float iv = Icol[(th + 1) * Sp];
-        float d = iv - ta; a2 = fmaf(d, d, a2);
-        d = iv - tb; a3 = fmaf(d, d, a3);
-      }
-      if (th + 2 < nrow) {
-        const float iv = Icol[(th + 2) * Sp];
-        const float d = iv - ta; a3 = fmaf(d, d, a3);
-      }
-    } else {
-      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-      for (int ip = 0; ip < nrow; ++ip) {
-        t3 = t2;
-        t2 = t1;
-        t1 = t0;
-        t0 = ip < th ? Tcol[ip * Tp] : 0.0f;
-        const float iv = Icol[ip * Sp];
-        if (ip < th) { const float d = iv - t0; a0 = fmaf(d, d, a0); }
-        if (ip >= 1 && ip <= th) { const float d = iv - t1; a1 = fmaf(d, d, a1); }
-        if (ip >= 2 && ip <= th + 1) { const float d = iv - t2; a2 = fmaf(d, d, a2); }
-        if (ip >= 3 && ip <= th + 2) { const float d = iv - t3; a3 = fmaf(d, d, a3); }
-      }
+    for (int ip = 3; ip < th; ++ip) {
+      const float2 tn = Tcol[ip * tw];
+      const float2 iv = ssd_load<ALIGNED>(Icol + ip * Sp);
+      d = __fadd2_rn(iv, tn); a[0] = __ffma2_rn(d, d, a[0]);
+      d = __fadd2_rn(iv, ta); a[1] = __ffma2_rn(d, d, a[1]);
+      d = __fadd2_rn(iv, tb); a[2] = __ffma2_rn(d, d, a[2]);
+      d = __fadd2_rn(iv, tc); a[3] = __ffma2_rn(d, d, a[3]);
+      tc = tb; tb = ta; ta = tn;
+    }
+    // tail: image rows th .. th + kmax - 2 only feed output rows 1..3
+    if (th < nrow) {
+      const float2 iv = ssd_load<ALIGNED>(Icol + th * Sp);
+      d = __fadd2_rn(iv, ta); a[1] = __ffma2_rn(d, d, a[1]);
+      d = __fadd2_rn(iv, tb); a[2] = __ffma2_rn(d, d, a[2]);
+      d = __fadd2_rn(iv, tc); a[3] = __ffma2_rn(d, d, a[3]);
+    }
+    if (th + 1 < nrow) {
+      const float2 iv = ssd_load<ALIGNED>(Icol + (th + 1) * Sp);
+      d = __fadd2_rn(iv, ta); a[2] = __ffma2_rn(d, d, a[2]);
+      d = __fadd2_rn(iv, tb); a[3] = __ffma2_rn(d, d, a[3]);
+    }
+    if (th + 2 < nrow) {
+      const float2 iv = ssd_load<ALIGNED>(Icol + (th + 2) * Sp);
+      d = __fadd2_rn(iv, ta); a[3] = __ffma2_rn(d, d, a[3]);
+    }
+  } else {
+    const float2 zero = make_float2(0.0f, 0.0f);
+    float2 t0 = zero, t1 = zero, t2 = zero, t3 = zero;
+    for (int ip = 0; ip < nrow; ++ip) {
+      t3 = t2;
+      t2 = t1;
+      t1 = t0;
+      t0 = ip < th ? Tcol[ip * tw] : zero;
+      const float2 iv = ssd_load<ALIGNED>(Icol + ip * Sp);
+      if (ip < th) { const float2 d = __fadd2_rn(iv, t0); a[0] = __ffma2_rn(d, d, a[0]); }
+      if (ip >= 1 && ip <= th) { const float2 d = __fadd2_rn(iv, t1); a[1] = __ffma2_rn(d, d, a[1]); }
+      if (ip >= 2 && ip <= th + 1) { const float2 d = __fadd2_rn(iv, t2); a[2] = __ffma2_rn(d, d, a[2]); }
+      if (ip >= 3 && ip <= th + 2) { const float2 d = __fadd2_rn(iv, t3); a[3] = __ffma2_rn(d, d, a[3]); }
     }
   }
-  acc[0] = a0;
-  acc[1] = a1;
-  acc[2] = a2;
-  acc[3] = a3;
+}
+
+// SSD of one lane of a warp item.  (r0, c) as given by SsdLanes; lanes beyond the surface are clamped onto it (their
+// results are discarded by the caller) so that every load stays inside the tile.
+__device__ __forceinline__ void ssd_warp_item(const TileWork& w, int r0, int c, int jlo, int jhi, float2 (&acc)[4]) {
+  const float2 zero = make_float2(0.0f, 0.0f);
+  acc[0] = acc[1] = acc[2] = acc[3] = zero;
+  const int rc = min(r0, w.Mv - 1), cc = min(c, (w.Mu - 1) & ~1);
+  const int kmax = max(1, min(4, w.Mv - rc));
+  for (int j = jlo; j < jhi; ++j) {
+    const float* Icol = w.hp + rc * w.Sp + cc + j;
+    const float2* Tcol = w.tmpl + j;
+    if (j & 1) ssd_column<false>(w, Icol, Tcol, kmax, acc);  // cc is even and rows start 16-byte aligned: parity of j decides
+    else ssd_column<true>(w, Icol, Tcol, kmax, acc);
+  }
 }
 
 // Phases 6-7 with the surface in its final interleaved form (F, F_u, F_v, F_uv per cell) in `w.herm`.
@@ -389,25 +420,25 @@ __device__ inline void tile_finish_interleaved(TileWork& w, float* dump_sse, int
   //    components of the Hermite cells and are summed in a fixed order (bit-reproducible).
   {
     const int tw = w.tw, th = w.th;
-    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    const SsdLanes L(Mu, Mv);
     int JP = 1;
-    while (JP < 4 && JP * 2 * RG * CB <= nwarp && JP * 2 <= tw) JP *= 2;
+    while (JP < 4 && JP * 2 * L.RG * L.CB <= nwarp && JP * 2 <= tw) JP *= 2;
     const int jper = (tw + JP - 1) / JP;
-    const int items = RG * CB * JP;
+    const int items = L.RG * L.CB * JP;
     float* hf = reinterpret_cast<float*>(w.herm);
     for (int item = warp; item < items; item += nwarp) {
       const int jp = item % JP, blk = item / JP;
-      const int rg = blk / CB, cb = blk - rg * CB;
-      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
-      const int kmax = min(4, Mv - r0);  // valid output rows in this block
+      const int rg = blk / L.CB, cb = blk - rg * L.CB;
+      const int r0 = L.row(rg, lane), c = L.col(cb, lane);
       const int jlo = jp * jper, jhi = min(jlo + jper, tw);
-      float acc[4];
-      ssd_warp_item(w, r0, c, kmax, jlo, jhi, acc);
-      if (cb * 32 + lane < Mu) {
+      float2 acc[4];
+      ssd_warp_item(w, r0, c, jlo, jhi, acc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < kmax) hf[((r0 + k) * Mp + c) * 4 + jp] = acc[k];
-      }
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < Mv) {
+          if (c < Mu) hf[((r0 + k) * Mp + c) * 4 + jp] = acc[k].x;
+          if (c + 1 < Mu) hf[((r0 + k) * Mp + c + 1) * 4 + jp] = acc[k].y;
+        }
     }
     __syncthreads();
     const double inv_area = 1.0 / (double)(tw * th);
@@ -468,7 +499,7 @@ __host__ __device__ inline int64_t tile_bytes_needed_planar(int Su, int Sv, int 
   const int64_t packed = (int64_t)(Sv + 4) * (Su + 4) * 4, planes = 2 * align16(Mv * Mq * 4);
   int64_t b = r1 + align16(packed > planes ? packed : planes);
   b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
-  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)th * tw * 8);
   b += align16((int64_t)nbins * 4);
   return b;
 }
@@ -495,8 +526,8 @@ __device__ inline void tile_carve_planar(char* base, TileWork& w, TilePlanes& pl
   p += align16((int64_t)w.nvals * 8);
   w.tv = reinterpret_cast<double*>(p);
   p += align16((int64_t)w.nvals * 8);
-  w.tmpl = reinterpret_cast<float*>(p);
-  p += align16((int64_t)w.th * w.Tp * 4);
+  w.tmpl = reinterpret_cast<float2*>(p);
+  p += align16((int64_t)w.th * w.tw * 8);
   w.hist = reinterpret_cast<uint32_t*>(p);
 }
 
@@ -507,24 +538,25 @@ __device__ inline void tile_finish_planar(TileWork& w, const TilePlanes& pl, flo
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int Mu = w.Mu, Mv = w.Mv, Mp = w.Mp, Mq = pl.Mq;
   {
-    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    const SsdLanes L(Mu, Mv);
     const double inv_area = 1.0 / (double)(w.tw * w.th);
-    for (int item = warp; item < RG * CB; item += nwarp) {
-      const int rg = item / CB, cb = item - rg * CB;
-      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
-      const int kmax = min(4, Mv - r0);
-      float acc[4];
-      ssd_warp_item(w, r0, c, kmax, 0, w.tw, acc);
-      if (cb * 32 + lane < Mu) {
+    for (int item = warp; item < L.RG * L.CB; item += nwarp) {
+      const int rg = item / L.CB, cb = item - rg * L.CB;
+      const int r0 = L.row(rg, lane), c = L.col(cb, lane);
+      float2 acc[4];
+      ssd_warp_item(w, r0, c, 0, w.tw, acc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < kmax) {
-            const float sse = (float)((double)acc[k] * inv_area);
-            pl.F[(r0 + k) * Mq + c] = sse;
-            const int64_t o = (int64_t)(r0 + k) * Mu + c;
-            if (dump_sse && o < dump_cap) dump_sse[o] = sse;
-          }
-      }
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < Mv) {
+          const float sse[2] = {(float)((double)acc[k].x * inv_area), (float)((double)acc[k].y * inv_area)};
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (c + h < Mu) {
+              pl.F[(r0 + k) * Mq + c + h] = sse[h];
+              const int64_t o = (int64_t)(r0 + k) * Mu + c + h;
+              if (dump_sse && o < dump_cap) dump_sse[o] = sse[h];
+            }
+        }
     }
   }
   __syncthreads();  // hp is dead from here on: F_u takes its place
@@ -570,7 +602,7 @@ __host__ __device__ inline int64_t tile_bytes_needed_staged(int Su, int Sv, int 
   const int64_t Tp = (tw + 3) / 4 * 4;
   int64_t b = align16((int64_t)Su * Sv * 2) + align16((int64_t)(Sv + 4) * (Su + 4) * 4);
   b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
-  b += align16((int64_t)th * Tp * 4);
+  b += align16((int64_t)th * tw * 8);
   b += align16((int64_t)nbins * 4);
   const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, planes = 2 * align16(Mv * (Mu | 1) * 4);
   return b > planes ? b : planes;
@@ -596,8 +628,8 @@ __device__ inline void tile_build_surface_staged(char* smem, char* region, const
   p += align16((int64_t)w.nvals * 8);
   w.tv = reinterpret_cast<double*>(p);
   p += align16((int64_t)w.nvals * 8);
-  w.tmpl = reinterpret_cast<float*>(p);
-  p += align16((int64_t)w.th * w.Tp * 4);
+  w.tmpl = reinterpret_cast<float2*>(p);
+  p += align16((int64_t)w.th * w.tw * 8);
   w.hist = reinterpret_cast<uint32_t*>(p);
   w.herm = nullptr;
   float* hp_global = reinterpret_cast<float*>(region);
@@ -616,24 +648,25 @@ __device__ inline void tile_build_surface_staged(char* smem, char* region, const
   // SSD plane F -> region (hp's global copy is dead)
   float* F_global = reinterpret_cast<float*>(region);
   {
-    const int RG = (Mv + 3) / 4, CB = (Mu + 31) / 32;
+    const SsdLanes L(Mu, Mv);
     const double inv_area = 1.0 / (double)(w.tw * w.th);
-    for (int item = warp; item < RG * CB; item += nwarp) {
-      const int rg = item / CB, cb = item - rg * CB;
-      const int r0 = rg * 4, c = min(cb * 32 + lane, Mu - 1);
-      const int kmax = min(4, Mv - r0);
-      float acc[4];
-      ssd_warp_item(w, r0, c, kmax, 0, w.tw, acc);
-      if (cb * 32 + lane < Mu) {
+    for (int item = warp; item < L.RG * L.CB; item += nwarp) {
+      const int rg = item / L.CB, cb = item - rg * L.CB;
+      const int r0 = L.row(rg, lane), c = L.col(cb, lane);
+      float2 acc[4];
+      ssd_warp_item(w, r0, c, 0, w.tw, acc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < kmax) {
-            const float sse = (float)((double)acc[k] * inv_area);
-            F_global[(r0 + k) * Mq + c] = sse;
-            const int64_t o = (int64_t)(r0 + k) * Mu + c;
-            if (dump_sse && o < dump_cap) dump_sse[o] = sse;
-          }
-      }
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < Mv) {
+          const float sse[2] = {(float)((double)acc[k].x * inv_area), (float)((double)acc[k].y * inv_area)};
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (c + h < Mu) {
+              F_global[(r0 + k) * Mq + c + h] = sse[h];
+              const int64_t o = (int64_t)(r0 + k) * Mu + c + h;
+              if (dump_sse && o < dump_cap) dump_sse[o] = sse[h];
+            }
+        }
     }
   }
   __syncthreads();
