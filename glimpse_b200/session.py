@@ -107,11 +107,12 @@ def adopt_model(model):
 
 class Session:
     def __init__(self, tracker, models, image_index, taus, tile_size, observer_mask, return_covariances=False,
-                 return_particles=False, point_offset=0, draws=None):
+                 return_particles=False, point_offset=0, draws=None, dist=None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
         self.tracker = tracker
+        self.dist = dist  # torch.distributed with an NCCL group spanning the GPUs of the box, or None
         self.device = torch.device(tracker.device) if tracker.device is not None else torch.device("cuda", torch.cuda.current_device())
         self.P, self.T, self.O = len(models), image_index.shape[0], image_index.shape[1]
         P, T, O = self.P, self.T, self.O
@@ -237,11 +238,32 @@ class Session:
 
     def _start_frame_copies(self) -> None:
         """Queue the frame uploads (in time order) on the copy stream, each followed by its event.  Called after
-        every small table is on the device: the big copies keep the copy engine busy for tens of milliseconds."""
-        torch, copy_stream = self.torch, self.tracker._copy_stream
+        every small table is on the device: the big copies keep the copy engine busy for tens of milliseconds.
+        With an NCCL group every rank holds the same frames on its host: rank k uploads every world-th frame and
+        broadcasts it to the others over NVLink instead of all ranks pulling everything through PCIe."""
+        torch, copy_stream, dist = self.torch, self.tracker._copy_stream, self.dist
+        shared = False
+        if dist is not None and self._pending_copies:
+            # all ranks must be about to upload the same list (a rank with cached frames would not take part)
+            sig = torch.tensor([len(self._pending_copies), sum(a.nbytes for _, a, _ in self._pending_copies)], dtype=torch.int64,
+                               device=self.device)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            shared = bool(torch.equal(lo, hi))
+        elif dist is not None:
+            none = torch.zeros(2, dtype=torch.int64, device=self.device)
+            dist.all_reduce(none.clone(), op=dist.ReduceOp.MIN)
+            dist.all_reduce(none, op=dist.ReduceOp.MAX)
+        world, rank = (dist.get_world_size(), dist.get_rank()) if shared else (1, 0)
         with torch.cuda.stream(copy_stream):
-            for dev, arr, event in self._pending_copies:
-                dev.copy_(torch.from_numpy(arr), non_blocking=True)
+            for k, (dev, arr, event) in enumerate(self._pending_copies):
+                if k % world == rank:
+                    dev.copy_(torch.from_numpy(arr), non_blocking=True)
+                else:
+                    self.h2d -= arr.nbytes  # arrives over NVLink
+                if shared:
+                    dist.broadcast(dev, src=k % world)
                 event.record(copy_stream)
         for k, event in self._pending_events:
             self.image_events[k] = event.cuda_event
@@ -404,9 +426,10 @@ class Session:
             _lib.check(self.lib.gb_track_step(C.byref(self.desc), int(t), C.byref(io) if io is not None else None, self.stream))
 
     # ---------------------------------------------------------------- results
-    def fetch(self) -> dict:
+    def fetch(self, gather=None) -> dict:
         """Results to host memory: every array is copied into pinned memory on the compute stream without
-        blocking, then one synchronisation covers them all."""
+        blocking, then one synchronisation covers them all.  ``gather`` = (dist, points per rank, world size): the
+        blocks of all ranks are all-gathered on the devices first (NCCL), so every rank returns every point."""
         torch, b, P, T = self.torch, self.buf, self.P, self.T
         names = ["means", "sig", "status", "status_time", "obs_flags", "window"]
         if self.return_particles:
@@ -414,18 +437,28 @@ class Session:
         host = {}
         with torch.cuda.device(self.device):
             for k in names:
-                host[k] = torch.empty(b[k].shape, dtype=b[k].dtype, pin_memory=True)
-                host[k].copy_(b[k], non_blocking=True)
+                src = b[k]
+                if gather is not None and k != "window":
+                    dist, per, world = gather
+                    mine = torch.zeros((per,) + tuple(src.shape[1:]), dtype=src.dtype, device=self.device)
+                    mine[:P] = src
+                    src = torch.empty((per * world,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=self.device)
+                    dist.all_gather_into_tensor(src, mine)
+                host[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                host[k].copy_(src, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         h = {k: v.numpy() for k, v in host.items()}
-        out = {"means": h["means"], "sigmas": h["sig"].reshape(P, T, 6, 6) if self.return_covariances else h["sig"],
+        n = h["means"].shape[0]
+        out = {"means": h["means"], "sigmas": h["sig"].reshape(n, T, 6, 6) if self.return_covariances else h["sig"],
                "status": h["status"], "status_time": h["status_time"], "obs_flags": h["obs_flags"]}
         d2h = b["means"].numel() * 8 + b["sig"].numel() * 8 + P * 8 + b["obs_flags"].numel()
         if self.return_particles:
             out["particles"], out["weights"] = h["particles"], h["weights"]
             d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
+        if gather is not None:
+            d2h *= gather[2]
         win = h["window"]
-        used = (out["obs_flags"] == 0) & (win[..., 0] > 0)
+        used = (b["obs_flags"].cpu().numpy() == 0) & (win[..., 0] > 0) if gather is not None else (out["obs_flags"] == 0) & (win[..., 0] > 0)
         self.stats = {
             "plan": {k: getattr(self.plan, k) for k, _ in self.plan._fields_}, "kernel_launches": self.launches,
             "h2d_bytes": int(self.h2d), "d2h_bytes": int(d2h),

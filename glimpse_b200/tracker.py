@@ -195,9 +195,16 @@ class Tracker:
                     lo, hi = shard_bounds(ntracks, world, rank)
             except ImportError:
                 pass
+        # NCCL: frames are uploaded once per box (each rank a share, broadcast over NVLink) and the result blocks are
+        # gathered on the devices; other backends (gloo in the CPU tests) gather the host arrays
+        per_rank = -(-ntracks // world)
+        on_device = dist is not None and dist.get_backend() == "nccl" and (world - 1) * per_rank < ntracks  # no idle rank
+        extra = {"gather": (dist, per_rank, world)} if on_device else {}
         local = self._track_local(motion_models[lo:hi], image_index, taus, tuple(int(v) for v in tile_size),
-                                  observer_mask[lo:hi], return_covariances, return_particles, point_offset=lo)
-        if dist is not None:
+                                  observer_mask[lo:hi], return_covariances, return_particles, point_offset=lo, **extra)
+        if on_device:
+            local = {k: v[:ntracks] for k, v in local.items()}
+        elif dist is not None:
             local = self._gather(dist, local, ntracks, world)
 
         # materialise errors / warnings the way the reference reports them (tracker.py:358-368)
@@ -235,16 +242,17 @@ class Tracker:
 
     # ------------------------------------------------------------------ device plumbing
     def _track_local(self, models, image_index, taus, tile_size, observer_mask, return_covariances, return_particles,
-                     point_offset=0) -> dict:
-        """Run the filter for ``models`` on this process's GPU; returns host arrays."""
+                     point_offset=0, gather=None) -> dict:
+        """Run the filter for ``models`` on this process's GPU; returns host arrays.  ``gather`` = (dist, points per
+        rank, world size): frames are shared between the ranks and the returned arrays hold every rank's block."""
         from .session import Session, empty_result
 
         if len(models) == 0:
             return empty_result(0, image_index.shape[0], image_index.shape[1], return_covariances, return_particles)
         session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
-                          return_particles, point_offset=point_offset)
+                          return_particles, point_offset=point_offset, dist=gather[0] if gather else None)
         session.run()
-        out = session.fetch()
+        out = session.fetch(gather)
         self.last_run = session.stats
         self.particles, self.weights, self.templates = session.final_state()
         return out
