@@ -130,7 +130,7 @@ const char* gb_last_error(void);
 #define GB_KERNEL_FINALIZE 4            /* k_s5p_finalize */
 #define GB_KERNEL_INIT 5                /* k_init */
 #define GB_KERNEL_TEMPLATE 6            /* k_template */
-#define GB_KERNEL_PUBLISH 7            /* k_s3b_publish */
+#define GB_KERNEL_PUBLISH 7             /* k_s3b_publish */
 #define GB_KERNEL_KINDS 8
 int gb_kernel_timing(int32_t enable);
 int gb_kernel_timing_read(double* ms, int64_t* launches, int32_t n);
@@ -160,8 +160,10 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
 /* Two device organisations of the same update (identical results up to floating-point association):
  *  GB_MODE_FUSED  one thread-block cluster owns a point for a whole update; particle intermediates
  *                 stay in (distributed) shared memory, state streams through HBM once (96 B/update).
- *  GB_MODE_STREAM five massively parallel kernels per update over all points (propagate, surface,
- *                 weights, resample, finalise); intermediates go through global memory / L2. */
+ *  GB_MODE_STREAM kernels over all points (default).  gb_track pipelines them: per update and batch of points
+ *                 k_s0p_activity -> k_s2_surface -> k_s3_weights -> k_s3b_publish -> k_s4p_resample_propagate (the
+ *                 resampling of time t fused with the motion step to t + 1) -> k_s5p_finalize, batches on their own
+ *                 streams; gb_track_step runs the same stages unfused so that intermediates can be forced / dumped. */
 #define GB_MODE_FUSED 0
 #define GB_MODE_STREAM 1
 
@@ -173,18 +175,19 @@ typedef struct gb_plan {
   int32_t n_local;          /* particles per CTA */
   int32_t particles_in_smem; /* 1: evolved state / uv / weights live in shared memory; 0: in `scratch` */
   int32_t smem_bytes;       /* dynamic shared memory per CTA */
-  int32_t tile_bytes;       /* bytes of it available to the tile pipeline */
+  int32_t tile_bytes;       /* bytes of it available to the tile pipeline (GB_MODE_STREAM: shared memory one search window may use
+                             * in k_s2_surface; negative = skip the interleaved organisation, parity tests) */
   int32_t max_template;     /* template pixels the plan was sized for */
   int32_t n_slabs;          /* per-SM overflow slabs for search windows that do not fit tile_bytes */
   int64_t slab_bytes;       /* bytes per slab (windows up to 256 + template - 1 pixels a side) */
   int64_t particle_scratch_bytes; /* global particle arrays when !particles_in_smem */
   int64_t scratch_bytes;    /* total global scratch the caller must provide */
   int32_t mode;             /* GB_MODE_* */
-  int32_t stream_block;     /* GB_MODE_STREAM: particles per CTA of the per-particle kernels */
+  int32_t stream_block;     /* GB_MODE_STREAM: particles per CTA of the per-particle kernels (even, <= 768) */
   int32_t stream_nblk;      /* GB_MODE_STREAM: CTAs per point */
   int32_t n_observers;
   int64_t surf_bytes;       /* GB_MODE_STREAM: bytes of the per-(point, observer) surface region */
-  int32_t stream_batch;     /* GB_MODE_STREAM: points per batch (intermediates of one batch stay L2-resident) */
+  int32_t stream_batch;     /* GB_MODE_STREAM: points per batch (<= 65535) */
   int32_t stream_slots;     /* GB_MODE_STREAM: batches in flight (side streams / scratch slots) */
 } gb_plan;
 
