@@ -297,6 +297,8 @@ class Session:
             copy_stream = tracker._copy_stream = torch.cuda.Stream(device=device)
         compute_stream = torch.cuda.current_stream(device)
         copy_stream.wait_stream(compute_stream)
+        fresh, placed = [], []
+        order_of = {k: n for n, (_, k) in enumerate(sorted(order))}
         with torch.cuda.stream(copy_stream):
             for _, k in sorted(order):
                 o, i, img, _used = structs[k]
@@ -309,14 +311,29 @@ class Session:
                     if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
                         raise NotImplementedError("device frames must be uint8 with 1-4 bands")
                     arr = array if array.flags.c_contiguous else np.ascontiguousarray(array)
-                    dev = torch.empty(arr.shape, dtype=torch.uint8, device=device)  # allocated on the copy stream
-                    event = torch.cuda.Event()
+                    fresh.append((k, key, use_cache, arr))
+                    continue
+                placed.append((k, cached))
+            # frames not on the device yet: one allocation (on the copy stream) carved into 256-byte aligned slices
+            if fresh:
+                offsets_b, total = [], 0
+                for _, _, _, arr in fresh:
+                    offsets_b.append(total)
+                    total += (arr.nbytes + 255) // 256 * 256
+                arena = torch.empty(total, dtype=torch.uint8, device=device)
+                arena.record_stream(compute_stream)
+                free = tracker.__dict__.setdefault("_event_free", [])  # events handed back by clear_device_cache()
+                for (k, key, use_cache, arr), off in zip(fresh, offsets_b):
+                    dev = arena[off:off + arr.nbytes].view(arr.shape)
+                    event = free.pop() if free else torch.cuda.Event()
                     self._pending_copies.append((dev, arr, event))
-                    dev.record_stream(compute_stream)
                     self.h2d += arr.nbytes
                     cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
                     if use_cache:
                         tracker._frame_cache[key] = cached
+                    placed.append((k, cached))
+            for k, cached in sorted(placed, key=lambda kc: order_of[kc[0]]):
+                o, i, img, _used = structs[k]
                 dev, w, h, pitch, nchan, event = cached
                 self.keep.append(dev)
                 self.keep_events.append(event)

@@ -104,6 +104,9 @@ class Tracker:
         self.templates = None
 
     def clear_device_cache(self) -> None:
+        """Forget the frames kept on the device (their upload events are recycled)."""
+        free = self.__dict__.setdefault("_event_free", [])
+        free.extend(entry[5] for entry in self._frame_cache.values())
         self._frame_cache.clear()
 
     # ------------------------------------------------------------------ host-side time logic
