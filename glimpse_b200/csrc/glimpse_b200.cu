@@ -1510,8 +1510,12 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
     GB_CUDA(cudaGetLastError());
     if (launches) ++*launches;
   }
+  bool have_activity = false;
   for (int t = 0; t < T; ++t) {
-    if (!has_init[t] && !has_update[t] && !has_prop[t]) continue;
+    if (!has_init[t] && !has_update[t] && !has_prop[t]) {
+      have_activity = false;  // a gap: the last k_s5p wrote the activity of a time that is not processed
+      continue;
+    }
     StepParams prm;
     fill_params(d, t, prm);
     NextParams nxt;
@@ -1554,15 +1558,20 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
     if (has_update[t])
       for (int k = 0; k < used; ++k)
         if ((rc = wait_images(pool->side[k], prm))) return rc;
+    // activity of time t: written by k_s5p of the previous processed time unless statuses may have changed since
+    const bool need_activity = !have_activity || has_init[t] || has_tmpl[t];
+    have_activity = true;
     for (int64_t b = 0; b < nbatch; ++b) {
       cudaStream_t ss = pool->side[b % slots];
       const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
       stream_bind(d, prm, t, p0, pb);
       const unsigned nb = (unsigned)(pb * prm.s_nblk);
       KernelTimer& kt = g_ktimer;
-      kt.begin(GB_K_ACTIVITY, ss);
-      k_s0p_activity<<<grid_for(pb, 256), 256, 0, ss>>>(prm);
-      kt.end(ss);
+      if (need_activity) {
+        kt.begin(GB_K_ACTIVITY, ss);
+        k_s0p_activity<<<grid_for(pb, 256), 256, 0, ss>>>(prm);
+        kt.end(ss);
+      }
       if (has_update[t]) {
         kt.begin(GB_K_SURFACE, ss);
         k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, prm.s2_budget);
@@ -1594,7 +1603,7 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
         k_s5p_finalize<false><<<(unsigned)((pb + 3) / 4), 128, 0, ss>>>(prm);
       kt.end(ss);
       GB_CUDA(cudaGetLastError());
-      if (launches) *launches += has_update[t] ? 6 : 3;
+      if (launches) *launches += (has_update[t] ? 5 : 2) + (need_activity ? 1 : 0);
     }
   }
   if ((rc = join_sides())) return rc;

@@ -758,16 +758,20 @@ __global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {
 // ---------------------------------------------------------------------------------------------
 #define GB_ACT_PROPAGATE 4
 
+__device__ __forceinline__ uint8_t activity_bits(const StepParams& prm, int64_t i, int t, bool alive) {
+  const int f = prm.first[i], l = prm.last[i];
+  const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
+  const bool tangent = prm.motion[i].kind >= GB_MOTION_TANGENT_CARTESIAN;  // compute_log_likelihoods is None (motion.py:77-89)
+  const bool sll = !tangent && !(sg.z == nullptr && sg.value == 0.0);
+  return (uint8_t)(((alive && f < t && t <= l) ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) | (tangent ? GB_ACT_NO_MOTION_LL : 0) |
+                   ((alive && f <= t && t < l) ? GB_ACT_PROPAGATE : 0));
+}
+
+// Activity of time prm.t.  Launched at a track's first time and after the kernels that can change a point's status
+// outside the update (initialisation, templates); otherwise k_s5p_finalize of time t - 1 has already written it.
 __global__ void k_s0p_activity(const __grid_constant__ StepParams prm) {
-  for (int64_t i = prm.p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.p0 + prm.pb; i += (int64_t)gridDim.x * blockDim.x) {
-    const bool alive = prm.status[i] == 0;
-    const int f = prm.first[i], l = prm.last[i];
-    const gb_surface& sg = prm.surfaces[prm.motion[i].dem_sigma];
-    const bool tangent = prm.motion[i].kind >= GB_MOTION_TANGENT_CARTESIAN;  // compute_log_likelihoods is None (motion.py:77-89)
-    const bool sll = !tangent && !(sg.z == nullptr && sg.value == 0.0);
-    prm.s_act[i] = (uint8_t)(((alive && f < prm.t && prm.t <= l) ? GB_ACT_ACTIVE : 0) | (sll ? GB_ACT_SURFACE_LL : 0) | (tangent ? GB_ACT_NO_MOTION_LL : 0) |
-                             ((alive && f <= prm.t && prm.t < l) ? GB_ACT_PROPAGATE : 0));
-  }
+  for (int64_t i = prm.p0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < prm.p0 + prm.pb; i += (int64_t)gridDim.x * blockDim.x)
+    prm.s_act[i] = activity_bits(prm, i, prm.t, prm.status[i] == 0);
 }
 
 // Start of a gb_track: empty cloud boxes, no failure flags in either parity.
@@ -1101,11 +1105,17 @@ __global__ void k_s5p_finalize(const __grid_constant__ StepParams prm) {
   const int t = prm.t;
   const int f = prm.s_pflags[p];
   if (lane == 0) prm.s_pflags[p] = 0;
+  // (every exit also writes the activity of time t + 1: the next update needs no launch of its own for it)
   if (!(act & GB_ACT_ACTIVE)) {
-    // a point can fail while being advanced from its first time: the failure belongs to time t
-    if (f && lane == 0 && prm.status[p] == 0 && t > prm.first[p] && t <= prm.last[p]) {
-      prm.status[p] = status_from_flags((uint32_t)f);
-      prm.status_time[p] = t;
+    if (lane == 0) {
+      bool alive = prm.status[p] == 0;
+      // a point can fail while being advanced from its first time: the failure belongs to time t
+      if (f && alive && t > prm.first[p] && t <= prm.last[p]) {
+        prm.status[p] = status_from_flags((uint32_t)f);
+        prm.status_time[p] = t;
+        alive = false;
+      }
+      prm.s_act[p] = activity_bits(prm, p, t + 1, alive);
     }
     return;
   }
@@ -1113,6 +1123,7 @@ __global__ void k_s5p_finalize(const __grid_constant__ StepParams prm) {
     if (lane == 0) {
       prm.status[p] = status_from_flags((uint32_t)f);
       prm.status_time[p] = t;
+      prm.s_act[p] = activity_bits(prm, p, t + 1, false);
     }
     return;
   }
@@ -1124,6 +1135,7 @@ __global__ void k_s5p_finalize(const __grid_constant__ StepParams prm) {
 #pragma unroll
   for (int k = 0; k < NM; ++k) a[k] = __shfl_sync(0xffffffffu, x, k);
   if (lane != 0) return;
+  prm.s_act[p] = activity_bits(prm, p, t + 1, true);
   double ref[6];
   for (int c = 0; c < 6; ++c) ref[c] = prm.s_ref[p * 6 + c];
   double mean[6], sg[6], cv[36];

@@ -320,7 +320,7 @@ def test_kernel_timing_reports_every_kernel_of_the_streaming_flow(cuda):
     assert all(e is None for e in tracks.errors)
     # activity, surface, weights, resample+propagate, finalize, init, template, publish
     # per batch of points: one launch per time for the first three, one per update (5 of the 6 times) for the others
-    assert list(n)[5:7] == [1, 1] and n[3] == n[0] == n[4] and n[3] % 6 == 0 and n[1] == n[2] == n[7] == n[3] // 6 * 5
+    assert list(n)[5:7] == [1, 1] and n[3] == n[4] and n[3] % 6 == 0 and n[1] == n[2] == n[7] == n[3] // 6 * 5 and 0 < n[0] <= n[3]
     assert all(ms[k] > 0 for k in range(8))
     _lib.check(lib.gb_kernel_timing_read(ms, n, 8))
     assert sum(n) == 0  # switching the timer off clears it
