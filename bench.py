@@ -409,18 +409,22 @@ def run_gpu_arm(args):
         tracker.clear_device_cache()
         return tracker.track(models, tile_size=scene.tile_size)
 
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1 if args.warmup else 0):
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 2)):
         e2e_once()
     barrier()
     t0 = time.perf_counter()
+    e2e_each = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         tracks = e2e_once()
+        e2e_each.append(1e3 * (time.perf_counter() - t1))  # track() returns host arrays: the device is idle again
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = world * P * N * T / e2e_s
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tracker.last_run["h2d_bytes"]),
-           "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps}
+           "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+           "ms_each": e2e_each}
     v_err = float(np.nanmedian(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0])))
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------
