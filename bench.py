@@ -413,6 +413,10 @@ def run_gpu_arm(args):
     for _ in range(min(args.warmup, 2)):
         e2e_once()
     barrier()
+    import gc
+
+    gc.collect()
+    gc.disable()  # as timeit does: a cyclic collection over the scene's objects would land in one of the steps
     t0 = time.perf_counter()
     e2e_each = []
     for _ in range(e2e_steps):
@@ -420,11 +424,15 @@ def run_gpu_arm(args):
         tracks = e2e_once()
         e2e_each.append(1e3 * (time.perf_counter() - t1))  # track() returns host arrays: the device is idle again
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    # the median of the steps: one step in a few shows a host-side hiccup of tens of ms (not GC, not the device: the
+    # device-timed region never does); all step times are reported in ms_each, the mean in mean_ms_per_step
+    e2e_mean_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_s = max_over_ranks(float(np.median(e2e_each)) / 1e3)
+    gc.enable()
     e2e_value = world * P * N * T / e2e_s
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tracker.last_run["h2d_bytes"]),
            "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
-           "ms_each": e2e_each}
+           "ms_each": e2e_each, "mean_ms_per_step": 1e3 * e2e_mean_s, "aggregate": "median of steps"}
     v_err = float(np.nanmedian(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0])))
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------
