@@ -22,7 +22,7 @@ GB_ST_MESSAGES = {
 }
 GB_OBS_OUT_OF_FRAME = 2
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
-GB_RESAMPLE = {"systematic": 0, "stratified": 1}
+GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2}
 GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 

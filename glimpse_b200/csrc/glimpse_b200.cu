@@ -1331,7 +1331,12 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, prm.s2_budget);
   k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
-  k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  if (prm.resample_method == GB_RESAMPLE_CHOICE) {
+    k_s4c_scan<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+    k_s4c_gather<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  } else {
+    k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  }
   k_s5_finalize<COV><<<(unsigned)((prm.pb + 3) / 4), 128, 0, stream>>>(prm);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
@@ -1839,7 +1844,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool cov = d->covariances != nullptr;
   int64_t launches = 0;
-  if (d->plan.mode == GB_MODE_STREAM) {
+  if (d->plan.mode == GB_MODE_STREAM && d->resample_method != GB_RESAMPLE_CHOICE) {  // (choice: step-by-step flow below)
     if ((rc = track_streaming(*d, stream, &launches))) return rc;
     if (launches_out) *launches_out = launches;
     return GB_OK;

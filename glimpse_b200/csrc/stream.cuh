@@ -706,6 +706,111 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
   }
 }
 
+// Random choice with replacement (Tracker(resample_method='choice'), tracker.py:205-209 = the legacy generator's inverse-CDF
+// sampling).  Children are not sorted by parent, so every child searches the point's whole cumulative distribution:
+// k_s4c_scan writes it (normalised cumulative weights, last entry exactly 1) into the point's projected-coordinate scratch,
+// which is dead after k_s3; k_s4c_gather draws one uniform per child, finds #{i : cdf[i] <= u} and copies that parent.
+// Used by the step-by-step flow only (gb_track falls back to it for this method).
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_scan(const __grid_constant__ StepParams prm) {
+  constexpr int PPT = GB_S4_PPT;
+  __shared__ double s_warp[GB_SBLOCK_THREADS / 32];
+  __shared__ double s_pref[2];
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
+  if (!stream_point_active(prm, p) || prm.s_pflags[p] != 0) return;
+  const int tid = threadIdx.x;
+  const int N = (int)prm.N;
+  if (tid == 0) {
+    const double* bs = prm.s_bsum + p * prm.s_nblk;
+    double run = 0.0, pre = 0.0;
+    for (int k = 0; k < prm.s_nblk; ++k) {
+      if (k == b) pre = run;
+      run += bs[k];
+    }
+    s_pref[0] = pre;
+    s_pref[1] = run;
+  }
+  const double* wsrc = prm.s_w + (int64_t)p * N;
+  const int base = b * prm.s_block;
+  const int n_here = max(0, min(N, base + prm.s_block) - base);
+  const int k0 = PPT * tid;
+  double w[PPT], tsum = 0.0;
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    tsum += (k0 + q < n_here) ? wsrc[base + k0 + q] : 0.0;
+    w[q] = tsum;
+  }
+  const double off = block_exclusive_offset(tsum, s_warp);
+  const double prefix = s_pref[0], total = s_pref[1];
+  double* cdf = prm.s_uv + p * prm.O * 2 * (int64_t)N;
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int k = k0 + q;
+    if (k < n_here) cdf[base + k] = (base + k == N - 1) ? 1.0 : quo(prefix + (off + w[q]), total);
+  }
+}
+
+template <bool COV>
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_gather(const __grid_constant__ StepParams prm) {
+  constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16;
+  __shared__ double s_red[GB_SBLOCK_THREADS / 32][KP];
+  const int64_t p = prm.p0 + blockIdx.x / prm.s_nblk;
+  const int b = (int)(blockIdx.x % prm.s_nblk);
+  if (!stream_point_active(prm, p) || prm.s_pflags[p] != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
+  const int N = (int)prm.N;
+  const int base = b * prm.s_block, end = min(N, base + prm.s_block);
+  const double* cdf = prm.s_uv + p * prm.O * 2 * (int64_t)N;
+  const double* ev = prm.s_ev + p * 6 * (int64_t)N;
+  const double* wsrc = prm.s_w + (int64_t)p * N;
+  const StratifiedDraws draws = stratified_draws(prm, p, t);  // one uniform per child, like the stratified resampler
+  const double* sin0 = prm.io.force_evolved ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
+  double ref[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) ref[c] = sin0[c * (int64_t)N];
+  double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
+  double* wst = prm.weight_state ? prm.weight_state + (int64_t)p * N : nullptr;
+  double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
+  double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
+  int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
+  Moments<COV> mom;
+  mom.clear();
+  for (int j = base + tid; j < end; j += GB_SBLOCK_THREADS) {
+    const double u = draws.u(j);
+    int lo = 0, hi = N;  // number of entries <= u (np.searchsorted side='right')
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int idx = min(lo, N - 1);
+    double s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = ev[c * (int64_t)N + idx];
+    const double wj = wsrc[idx];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
+    mom.accumulate(wj, s, ref);
+    if (wst) wst[j] = wj;
+    if (outp) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
+    }
+    if (outw) outw[j] = wj;
+    if (outi) outi[j] = idx;
+  }
+  double r[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) r[k] = k < NM ? mom.a[k] : 0.0;
+  warp_reduce_transpose<KP>(r, lane);
+  if (KP == 32 || (lane & 1) == 0) s_red[warp][transposed_index<KP>(lane)] = r[0];
+  __syncthreads();
+  if (tid < NM) {
+    double x = s_red[0][tid];
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) x += s_red[wv][tid];
+    prm.s_pm[(p * prm.s_nblk + b) * 28 + tid] = x;
+  }
+}
+
 // s5: one warp per point: lane k sums moment k over the CTAs in order, lane 0 finalises.
 template <bool COV>
 __global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {

@@ -190,9 +190,9 @@ class Session:
             d.point_offset = int(point_offset)
             d.motion_kinds = self.motion_kinds
             method = getattr(tracker, "resample_method", "systematic")
-            stratified = method == "stratified"
+            stratified = method in ("stratified", "choice")  # one uniform per particle and update
             if stratified and mode == _lib.GB_MODE_FUSED:
-                raise NotImplementedError("resample_method='stratified' runs in mode='stream' only")
+                raise NotImplementedError(f"resample_method='{method}' runs in mode='stream' only")
             d.resample_method = _lib.GB_RESAMPLE[method]
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED

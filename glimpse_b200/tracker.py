@@ -15,7 +15,7 @@ Differences a user can see (all documented in DESIGN.md):
   (``cluster`` = CTAs per point, 0 = automatic).  Same results up to floating-point association.
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
-* ``resample_method`` 'systematic' and 'stratified' and the default ``highpass`` / ``interpolation`` have kernels; other values
+* ``resample_method`` 'systematic', 'stratified' and 'choice' and the default ``highpass`` / ``interpolation`` have kernels; other values
   raise ``NotImplementedError`` (no CPU fallback).
 """
 from __future__ import annotations
@@ -165,7 +165,7 @@ class Tracker:
             if model.time_unit != time_unit:
                 raise ValueError("Motion models must have equal time units")
         if self.resample_method not in _lib.GB_RESAMPLE:
-            raise NotImplementedError("only resample_method='systematic' and 'stratified' have device kernels")
+            raise NotImplementedError("only resample_method='systematic', 'stratified' and 'choice' have device kernels")
         if tuple(self.highpass.get("size", ())) != (5, 5) or set(self.highpass) - {"size"}:
             raise NotImplementedError("only highpass={'size': (5, 5)} has a device kernel")
         if self.interpolation.get("kx", 3) != 3 or self.interpolation.get("ky", 3) != 3 or set(self.interpolation) - {"kx", "ky"}:

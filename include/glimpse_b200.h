@@ -55,6 +55,7 @@ extern "C" {
 
 #define GB_RESAMPLE_SYSTEMATIC 0 /* tracker.py:168-176: one uniform per update */
 #define GB_RESAMPLE_STRATIFIED 1 /* tracker.py:178-186: one uniform per particle and update */
+#define GB_RESAMPLE_CHOICE 2     /* tracker.py:205-209: np.random.choice with replacement = inverse-CDF sampling, one uniform per particle */
 
 #define GB_RNG_SUPPLIED 0 /* normals / uniforms provided in the reference's draw order */
 #define GB_RNG_PHILOX 1   /* counter-based Philox4x32-10 on device */
@@ -233,7 +234,7 @@ typedef struct gb_track_desc {
   int64_t point_offset;            /* global index of point 0 (Philox counters use global indices, so results do not depend on sharding) */
   const double* init_normals;      /* supplied: [P][N][6] = randn(N,2) | randn(N) | randn(N,3) per particle */
   const double* step_normals;      /* supplied: [P][S][N][3] */
-  const double* uniforms;          /* supplied: [P][S] one np.random.random() per update (systematic) or [P][S][N] np.random.random(N) (stratified) */
+  const double* uniforms;          /* supplied: [P][S] one np.random.random() per update (systematic) or [P][S][N] np.random.random(N) (stratified, choice) */
 
   /* work buffers (caller-allocated) */
   double* state_a;                 /* [P][6][N] */

@@ -544,6 +544,14 @@ def stratified_indices(weights: np.ndarray, u: np.ndarray) -> np.ndarray:
     return np.searchsorted(np.cumsum(wn), positions)
 
 
+def choice_indices(weights: np.ndarray, u: np.ndarray) -> np.ndarray:
+    """(tracker.py:205-209): ``np.random.choice(arange(n), n, replace=True, p=w / w.sum())`` of the legacy generator =
+    inverse-CDF sampling with ``random_sample(n)`` (numpy/random/mtrand.pyx, ``RandomState.choice``)."""
+    cdf = (weights / weights.sum()).cumsum()
+    cdf /= cdf[-1]
+    return cdf.searchsorted(u, side="right")
+
+
 def weighted_mean(ps: np.ndarray, w: np.ndarray) -> np.ndarray:
     return np.average(ps, weights=w, axis=0)
 
@@ -682,6 +690,9 @@ def track(
                     if resample_method == "stratified":
                         u = random(len(w))
                         idx = stratified_indices(w, u)
+                    elif resample_method == "choice":
+                        u = random(len(w))
+                        idx = choice_indices(w, u)
                     else:
                         u = random()
                         idx = systematic_indices(w, u)

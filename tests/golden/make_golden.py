@@ -81,11 +81,22 @@ def run_reference(scene, seed, points=None, return_covariances=False, observer_m
             rec["indices"] = np.array(out)
             return out
 
-        np.random.random, np.searchsorted = random, searchsorted
+        orig_choice = np.random.choice
+
+        def choice(a, size=None, replace=True, p=None):
+            state = np.random.get_state()
+            out = orig_choice(a, size=size, replace=replace, p=p)
+            replay = np.random.RandomState()
+            replay.set_state(state)
+            rec["u"] = replay.random_sample(size)  # what RandomState.choice drew (mtrand.pyx)
+            rec["indices"] = np.array(out)
+            return out
+
+        np.random.random, np.searchsorted, np.random.choice = random, searchsorted, choice
         try:
             orig_resample(method)
         finally:
-            np.random.random, np.searchsorted = orig_random, orig_search
+            np.random.random, np.searchsorted, np.random.choice = orig_random, orig_search, orig_choice
         steps.append(rec)
         current["obs"] = {}
 

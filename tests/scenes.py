@@ -93,6 +93,10 @@ def track_cases():
             scene_kwargs=dict(seed=13, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1313, resample_method="stratified",
         ),
+        "track_choice": dict(
+            scene_kwargs=dict(seed=15, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=1515, resample_method="choice",
+        ),
         # map-scale world coordinates + per-frame view-direction jitter
         "track_jitter": dict(
             scene_kwargs=dict(seed=5, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,

@@ -40,7 +40,7 @@ def case_scene(name):
 CASES = list(scenes.track_cases())
 # the tangent motion models run in the default streaming organisation only
 # ... and so does stratified resampling (rank 2)
-CASE_MODES = [(n, m) for n in CASES for m in ("stream", "fused") if not (m == "fused" and ("tangent" in n or "stratified" in n))]
+CASE_MODES = [(n, m) for n in CASES for m in ("stream", "fused") if not (m == "fused" and ("tangent" in n or "stratified" in n or "choice" in n))]
 
 
 def make_session(scene, case, golden, return_particles=False, cluster=0, tile_bytes=None, mode="stream"):
@@ -63,7 +63,7 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
     first, last = point_span(image_index, mask)
     np.random.seed(int(golden["seed"]))
     tangent = np.full(P, scene.motion["kind"].startswith("tangent"))
-    draws = reference_order_draws(P, scene.n_particles, last - first, tangent, method == "stratified")
+    draws = reference_order_draws(P, scene.n_particles, last - first, tangent, method in ("stratified", "choice"))
     session = Session(tracker, models, image_index, taus, scene.tile_size, mask,
                       return_covariances=bool(case.get("return_covariances", False)),
                       return_particles=return_particles, draws=draws)
@@ -249,7 +249,8 @@ def test_track_free_running_matches_reference(cuda, name, mode):
 
 
 @pytest.mark.parametrize("mode,kind,method", [("stream", "cartesian", "systematic"), ("fused", "cartesian", "systematic"),
-                                              ("stream", "cartesian", "stratified"), ("stream", "tangent_cartesian", "systematic")])
+                                              ("stream", "cartesian", "stratified"), ("stream", "cartesian", "choice"),
+                                              ("stream", "tangent_cartesian", "systematic")])
 def test_philox_run_recovers_velocity(cuda, mode, kind, method):
     """Device RNG: the filter recovers the synthetic ground-truth velocity (0.4 m/d along +x), for both resamplers and
     for a tangent motion model on a gridded DEM."""

@@ -14,7 +14,7 @@ def wrap(name):
     setattr(S.Session, name, f)
 for n in ("_lower_models", "_upload_frames", "_start_frame_copies", "__init__", "run", "fetch", "final_state"):
     wrap(n)
-for rep in range(4):
+for rep in range(10):
     tracker.clear_device_cache(); torch.cuda.synchronize(); acc.clear()
     t0 = time.perf_counter(); tracker.track(models, tile_size=scene.tile_size); tot = time.perf_counter() - t0
     print(rep, f"total {tot*1e3:.1f}", {k: round(v*1e3, 2) for k, v in acc.items()})
