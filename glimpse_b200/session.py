@@ -134,11 +134,13 @@ class Session:
             mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[getattr(tracker, "mode", "stream")]
             _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, O, int(tracker.cluster), mode, C.byref(self.plan)))
             self.h2d = 0
-            # small tables first: once the frame uploads are queued they keep the copy engine busy for tens of ms
+            # the first two frames' uploads start right away (the first kernels wait for them); the other big copies are
+            # queued after the small tables, which they would otherwise hold up on the copy engine for tens of ms
+            images_dev, self.offsets = self._upload_frames()
+            self._start_frame_copies(limit=2)
             motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)
             if mode == _lib.GB_MODE_FUSED and self.tangent.any():
                 raise NotImplementedError("the tangent motion models run in mode='stream' only")
-            images_dev, self.offsets = self._upload_frames()
             self.first, self.last = point_span(self.image_index, observer_mask)
             self.tmpl_frame = np.array([int(np.argmax(self.image_index[:, o] >= 0)) if (self.image_index[:, o] >= 0).any() else -1
                                         for o in range(O)])
@@ -236,14 +238,16 @@ class Session:
         self.launches = 0
         self.stats: dict = {}
 
-    def _start_frame_copies(self) -> None:
-        """Queue the frame uploads (in time order) on the copy stream, each followed by its event.  Called after
-        every small table is on the device: the big copies keep the copy engine busy for tens of milliseconds.
-        With an NCCL group every rank holds the same frames on its host: rank k uploads every world-th frame and
-        broadcasts it to the others over NVLink instead of all ranks pulling everything through PCIe."""
+    def _start_frame_copies(self, limit=None) -> None:
+        """Queue the frame uploads (in time order) on the copy stream, each followed by its event; ``limit`` = only
+        the first so many (the rest on the next call).  With an NCCL group every rank holds the same frames on its
+        host: rank k uploads every world-th frame and broadcasts it to the others over NVLink instead of all ranks
+        pulling everything through PCIe."""
         torch, copy_stream, dist = self.torch, self.tracker._copy_stream, self.dist
-        shared = False
-        if dist is not None and self._pending_copies:
+        shared = getattr(self, "_shared_upload", None)
+        if shared is not None:
+            pass  # decided on the first call
+        elif dist is not None and self._pending_copies:
             # all ranks must be about to upload the same list (a rank with cached frames would not take part)
             sig = torch.tensor([len(self._pending_copies), sum(a.nbytes for _, a, _ in self._pending_copies)], dtype=torch.int64,
                                device=self.device)
@@ -255,9 +259,15 @@ class Session:
             none = torch.zeros(2, dtype=torch.int64, device=self.device)
             dist.all_reduce(none.clone(), op=dist.ReduceOp.MIN)
             dist.all_reduce(none, op=dist.ReduceOp.MAX)
+            shared = False
+        else:
+            shared = False
+        if self.__dict__.get("_shared_upload") is None:
+            self._shared_upload, self._copies_done = shared, 0
         world, rank = (dist.get_world_size(), dist.get_rank()) if shared else (1, 0)
+        todo = self._pending_copies if limit is None else self._pending_copies[:limit]
         with torch.cuda.stream(copy_stream):
-            for k, (dev, arr, event) in enumerate(self._pending_copies):
+            for k, (dev, arr, event) in enumerate(todo, start=self._copies_done):
                 if k % world == rank:
                     dev.copy_(torch.from_numpy(arr), non_blocking=True)
                 else:
@@ -267,7 +277,8 @@ class Session:
                 event.record(copy_stream)
         for k, event in self._pending_events:
             self.image_events[k] = event.cuda_event
-        self._pending_copies = []
+        self._copies_done += len(todo)
+        self._pending_copies = self._pending_copies[len(todo):]
 
     # ---------------------------------------------------------------- uploads
     def _upload_frames(self):
