@@ -3,14 +3,16 @@
 // (already inside namespace gb)
 
 // ---------------------------------------------------------------------------------------------
-// GB_MODE_STREAM: the same update as five kernels over all points.  Intermediates (evolved
-// particles, projected coordinates, weights, spline surfaces) go through global memory / L2; every
-// kernel is embarrassingly parallel with full occupancy and no intra-kernel serial stage.
-//   s1 propagate  evolve + test + project + integer cloud box        (per particle)
-//   s2 surface    search window + tile pipeline -> Hermite surface    (one CTA per point-observer)
-//   s3 weights    spline sample + surface likelihood -> weights, CTA totals (per particle)
-//   s4 resample   prefix of the weights, child ranges, child writes, moment partials (per particle)
-//   s5 finalise   moments, status                                      (per point)
+// GB_MODE_STREAM: one update as kernels over all points of a batch.  Intermediates (evolved particles, projected
+// coordinates, weights, spline surfaces) go through global memory / L2; no kernel has a serial stage across CTAs.
+// Step-by-step flow (gb_track_step: every intermediate can be forced / dumped; also gb_track with the 'choice' resampler):
+//   s0 reset      activity byte, empty cloud boxes and flags                 (per point)
+//   s1 propagate  evolve + test + project + integer cloud box                (per particle)
+//   s2 surface    search window + tile pipeline -> Hermite surface           (one CTA per point-observer)
+//   s3 weights    spline sample + surface likelihood -> weights, block totals (per particle)
+//   s4 resample   prefix of the weights, child ranges, child writes, moment partials (per particle; s4c_* for 'choice')
+//   s5 finalise   moments, status                                            (per point)
+// Pipelined flow (gb_track; further down): s2, s3 as above, s4 of time t fused with s1 of time t + 1.
 // ---------------------------------------------------------------------------------------------
 #define GB_SBLOCK_THREADS 256
 
@@ -855,7 +857,8 @@ __global__ void k_s5_finalize(const __grid_constant__ StepParams prm) {
 // Pipelined flow used by gb_track: the resampling of time t and the motion step to time t + 1 are
 // one kernel (k_s4p), so the resampled state is never written to / read back from HBM between
 // updates: a child thread gathers its parent's evolved particle, and immediately evolves, tests and
-// projects it for the next time.  Per time t and batch:  k_s0p -> k_s2 -> k_s3 -> k_s4p -> k_s5p.
+// projects it for the next time.  Per time t and batch:  [k_s0p ->] k_s2 -> k_s3 -> k_s3b -> k_s4p -> k_s5p
+// (k_s0p only at a track's first time and after initialisation / template kernels).
 //   activity bits of (point, t):  ACTIVE    = an update happens at t        (first < t <= last, alive)
 //                                 PROPAGATE = particles are advanced to t+1 (first <= t < last, alive)
 // Evolved particles and the per-point failure flags are double-buffered by time parity
