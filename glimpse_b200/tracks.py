@@ -75,3 +75,46 @@ class Tracks:
                 setattr(self, name, value[:, ::-1])
         if self.images is not None:
             self.images = self.images[::-1]
+
+    # ------------------------------------------------------------------ merging (reference tracks.py:151-203)
+    @staticmethod
+    def _combine(means: np.ndarray, sigmas: np.ndarray, axis: int, correlated: bool, ignore_nan: bool):
+        """Inverse-variance weighted average of normal distributions along ``axis`` (reference
+        ``helpers.sum_normals(weights=sigmas**-2, normalize=True)``, helpers.py:523-610): mean = sum w mu,
+        variance = sum (w sigma)^2 for uncorrelated terms, (sum w sigma)^2 for fully correlated ones.
+        Missing terms are skipped; the result is NaN where any term (``ignore_nan=False``) or every term is missing."""
+        missing = np.isnan(means)
+        if np.any(missing != np.isnan(sigmas)):
+            raise ValueError("Means and sigmas have missing values at different indices")
+        if np.any(sigmas == 0):
+            raise ValueError("Sigmas cannot be zero")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = np.where(missing, 0.0, sigmas ** -2.0)
+            w = w * (1 / w.sum(axis=axis, keepdims=True))
+            mu = np.where(missing, 0.0, w * means).sum(axis=axis)
+            ws = np.where(missing, 0.0, w * sigmas)
+            var = ws.sum(axis=axis) ** 2 if correlated else (ws ** 2).sum(axis=axis)
+        blank = missing.all(axis=axis) if ignore_nan else missing.any(axis=axis)
+        mu[blank] = np.nan
+        var[blank] = np.nan
+        return mu, np.sqrt(var)
+
+    @classmethod
+    def from_multiple(cls, runs, ignore_nan: bool = False) -> "Tracks":
+        """Merge tracks with identical time steps (for example a forward and a backward run): the inverse-variance
+        weighted average of their distributions at every time, assumed uncorrelated (reference tracks.py:151-189)."""
+        runs = list(runs)
+        if len({tuple(run.datetimes) for run in runs}) != 1:
+            raise ValueError("Datetimes are not equal for all runs")
+        units = {run.time_unit for run in runs}
+        if len(units) != 1:
+            raise ValueError(f"Time units are not equal for all runs: {units}")
+        means = np.stack([run.means for run in runs], axis=3)
+        sigmas = np.stack([run.sigmas for run in runs], axis=3)
+        mu, sg = cls._combine(means, sigmas, axis=3, correlated=False, ignore_nan=ignore_nan)
+        return cls(datetimes=runs[0].datetimes, time_unit=units.pop(), means=mu, sigmas=sg)
+
+    def average(self, ignore_nan: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """Time-averaged mean and sigma of every track: inverse-variance weights, time steps assumed fully
+        correlated (reference tracks.py:191-203)."""
+        return self._combine(self.means, self.sigmas, axis=1, correlated=True, ignore_nan=ignore_nan)

@@ -238,3 +238,26 @@ def test_points_shard_across_ranks_and_gather_over_gloo():
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, out
         assert f"rank {r} ok" in out
+
+
+def test_tracks_from_multiple_and_average_match_the_reference():
+    """Tracks.from_multiple / Tracks.average (reference tracks.py:151-203, helpers.sum_normals) against vectors produced
+    by the unmodified reference (tests/golden/make_tracks_golden.py), with missing values in one or both runs."""
+    import glimpse_b200 as gb
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tracks_merge.npz"))
+    day = datetime.timedelta(days=1)
+    dts = [datetime.datetime(2020, 1, 1) + i * day for i in range(g["m1"].shape[1])]
+    a = gb.Tracks(datetimes=dts, time_unit=day, means=g["m1"], sigmas=g["s1"])
+    b = gb.Tracks(datetimes=dts, time_unit=day, means=g["m2"], sigmas=g["s2"])
+    for ign in (0, 1):
+        merged = gb.Tracks.from_multiple([a, b], ignore_nan=bool(ign))
+        np.testing.assert_allclose(merged.means, g[f"merged_means_{ign}"], rtol=1e-13, atol=0, equal_nan=True)
+        np.testing.assert_allclose(merged.sigmas, g[f"merged_sigmas_{ign}"], rtol=1e-13, atol=0, equal_nan=True)
+        am, asg = a.average(ignore_nan=bool(ign))
+        np.testing.assert_allclose(am, g[f"avg_means_{ign}"], rtol=1e-13, atol=0, equal_nan=True)
+        np.testing.assert_allclose(asg, g[f"avg_sigmas_{ign}"], rtol=1e-12, atol=0, equal_nan=True)
+    with pytest.raises(ValueError, match="Datetimes are not equal"):
+        gb.Tracks.from_multiple([a, gb.Tracks(datetimes=dts[::-1], time_unit=day, means=g["m2"], sigmas=g["s2"])])
+    with pytest.raises(ValueError, match="Time units are not equal"):
+        gb.Tracks.from_multiple([a, gb.Tracks(datetimes=dts, time_unit=2 * day, means=g["m2"], sigmas=g["s2"])])
