@@ -84,7 +84,7 @@ class gb_track_desc(C.Structure):
         ("means", C.c_void_p), ("sigmas", C.c_void_p), ("covariances", C.c_void_p), ("out_particles", C.c_void_p),
         ("out_weights", C.c_void_p), ("status", C.c_void_p), ("status_time", C.c_void_p), ("obs_flags", C.c_void_p),
         ("window_stats", C.c_void_p),
-        ("resample_method", C.c_int32), ("pad1_", C.c_int32),
+        ("resample_method", C.c_int32), ("highpass_size", C.c_int32),
         ("plan", gb_plan),
     ]
 

@@ -21,6 +21,7 @@
 
 #define GB_THREADS 512
 #define GB_MAX_TEMPLATE 1024 /* template pixels handled by k_template */
+#define GB_MAX_HIGHPASS 31   /* rows / columns of the median high-pass */
 
 namespace gb {
 
@@ -44,9 +45,9 @@ struct StepParams {
   int T, O, S, t;
   int tile_w, tile_h;
   int cluster, n_local, particles_in_smem, tile_bytes;
-  int n_slabs, pad2_;
+  int n_slabs, hp_rows;       // hp_rows x hp_cols: size of the median high-pass (Tracker.highpass['size'], tracker.py:59, 530)
   int64_t slab_bytes, particle_scratch_bytes;
-  int skip_evolve, viewshed, rng_mode, pad_;
+  int skip_evolve, viewshed, rng_mode, hp_cols;
   uint64_t seed;
   int64_t point_offset;
   double tau, tau2;
@@ -527,11 +528,13 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
     }
     prm.tmpl_nvalues[p * prm.O + o] = n;
   }
-  // high-pass (tracker.py:530-531): value minus the 5x5 reflected median, taken on grey levels
+  // high-pass (tracker.py:530-531): value minus the reflected median (5x5 unless Tracker.highpass says otherwise), taken
+  // on grey levels
   double* tile = prm.tmpl_tile + (p * prm.O + o) * (int64_t)(tw * th);
+  const bool hp5 = prm.hp_rows == 5 && prm.hp_cols == 5;
   for (int i = tid; i < area; i += blockDim.x) {
     const int r = i / bw, c = i - r * bw;
-    const int med = median5x5(s_raw, bw, bh, r, c);
+    const int med = hp5 ? median5x5(s_raw, bw, bh, r, c) : median_window(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols);
     const double vn = mul(sub(quo((double)s_raw[i], (double)nchan), mean), inv_std);
     const double vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
     tile[i] = sub(vn, vm);
@@ -848,6 +851,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       w.Su = box_r - box_l;
       w.Sv = box_b - box_t;
       w.tw = prm.tile_w;
+      w.mh = prm.hp_rows;
+      w.mw = prm.hp_cols;
       w.th = prm.tile_h;
       w.Mu = w.Su - w.tw + 1;
       w.Mv = w.Sv - w.th + 1;
@@ -1121,6 +1126,8 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.t = t;
   prm.tile_w = d.tile_w;
   prm.tile_h = d.tile_h;
+  prm.hp_rows = d.highpass_size ? (d.highpass_size & 0xffff) : 5;
+  prm.hp_cols = d.highpass_size ? (d.highpass_size >> 16 & 0xffff) : 5;
   prm.cluster = d.plan.cluster;
   prm.n_local = d.plan.n_local;
   prm.particles_in_smem = d.plan.particles_in_smem;
@@ -1191,6 +1198,9 @@ static int check_desc(const gb_track_desc& d) {
   if (d.O < 1 || d.O > GB_MAX_OBS) return fail(GB_E_INVALID, "between 1 and 8 observers are supported%s");
   if (d.tile_w < 1 || d.tile_h < 1 || (int64_t)d.tile_w * d.tile_h > GB_MAX_TEMPLATE)
     return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
+  if (d.highpass_size != 0 && ((d.highpass_size & 0xffff) < 1 || (d.highpass_size & 0xffff) > GB_MAX_HIGHPASS ||
+                               (d.highpass_size >> 16 & 0xffff) < 1 || (d.highpass_size >> 16 & 0xffff) > GB_MAX_HIGHPASS))
+    return fail(GB_E_INVALID, "highpass_size: rows and columns must be between 1 and 31%s");
   if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");
   if (!d.images_host) return fail(GB_E_INVALID, "images_host is required%s");
   if (!d.images || !d.mask || !d.first || !d.last || !d.motion || !d.surfaces || !d.state_a || !d.state_b || !d.means ||

@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   w.Su = box_r - box_l;
   w.Sv = box_b - box_t;
   w.tw = prm.tile_w;
+  w.mh = prm.hp_rows;
+  w.mw = prm.hp_cols;
   w.th = prm.tile_h;
   w.Mu = w.Su - w.tw + 1;
   w.Mv = w.Sv - w.th + 1;

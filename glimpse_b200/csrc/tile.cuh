@@ -34,6 +34,7 @@ struct TileWork {
   float2* tmpl;      // [th][tw] high-passed template, negated and duplicated (-t, -t): the packed FP32 SSD adds it to two pixels
   uint32_t* hist;    // [nbins]
   int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
+  int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
 };
 
 __host__ __device__ inline int64_t align16(int64_t b) { return (b + 15) / 16 * 16; }
@@ -109,6 +110,39 @@ __device__ __forceinline__ int median5x5(const uint16_t* raw, int Su, int Sv, in
     for (int j = 0; j < 5; ++j) v[i * 5 + j] = row[cols[j]];
   }
   return gb_median25(v);
+}
+
+// scipy.ndimage 'reflect' for an offset of any length (the pattern has period 2 n).
+__device__ __forceinline__ int reflect_index_any(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+  return i;
+}
+
+// Median of an mh x mw neighbourhood with reflected borders, any size: scipy.ndimage.median_filter(size=(mh, mw))
+// places the window at offsets -(m / 2) .. m - 1 - m / 2 along each axis and returns the element of rank
+// (mh * mw) / 2.  Grey levels are integers below 1024 (band sums of uint8), so the element is found bit by bit:
+// it is >= L exactly when at most `rank` neighbours are < L.  (The 5x5 default never comes here.)
+__device__ inline int median_window(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw) {
+  const int rank = (mh * mw) >> 1, r0 = r - (mh >> 1), c0 = c - (mw >> 1);
+  const bool inside = r0 >= 0 && r0 + mh <= Sv && c0 >= 0 && c0 + mw <= Su;
+  int level = 0;
+  for (int bit = 512; bit; bit >>= 1) {
+    const int cand = level | bit;
+    int below = 0;
+    if (inside) {
+      for (int a = 0; a < mh; ++a) {
+        const uint16_t* row = raw + (r0 + a) * Su + c0;
+        for (int b = 0; b < mw; ++b) below += (int)row[b] < cand;
+      }
+    } else {
+      for (int a = 0; a < mh; ++a) {
+        const uint16_t* row = raw + reflect_index_any(r0 + a, Sv) * Su;
+        for (int b = 0; b < mw; ++b) below += (int)row[reflect_index_any(c0 + b, Su)] < cand;
+      }
+    }
+    if (below <= rank) level = cand;
+  }
+  return level;
 }
 
 // Solve the not-a-knot slope system along one line of the Hermite array (stride in floats).
@@ -239,7 +273,12 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   __syncthreads();
   // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
   for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
-  {
+  const bool hp5 = w.mh == 5 && w.mw == 5;
+  if (!hp5) {
+    // other median sizes (Tracker.highpass): a plain copy of the window, since hp overwrites raw
+    uint16_t* copy = reinterpret_cast<uint16_t*>(w.packed);
+    for (int i = tid; i < area; i += nthr) copy[i] = w.raw[i];
+  } else {
     const int PW = Su + 4, PH = Sv + 4;
     for (int i = tid; i < PW * PH; i += nthr) {
       const int pr = i / PW, pc = i - pr * PW;
@@ -278,7 +317,16 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   if (clk && threadIdx.x == 0) clk[0] = clock64();
   // 5. high-pass: matched value minus the matched 5x5 median (tracker.py:530-531), cast to float32
   //    as the reference does for matchTemplate (tracker.py:610).  One thread = pixels (r, c), (r+1, c).
-  {
+  if (!hp5) {
+    const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
+    for (int i = tid; i < area; i += nthr) {
+      const int r = i / Su, c = i - r * Su;
+      const int med = median_window(copy, Su, Sv, r, c, w.mh, w.mw);
+      const float o = (float)sub(w.lut[copy[i]], w.lut[med]);
+      w.hp[r * Sp + c] = o;
+      if (dump_search && i < dump_cap) dump_search[i] = o;
+    }
+  } else {
     const int PW = Su + 4, pairs = ((Sv + 1) / 2) * Su;
     for (int i = tid; i < pairs; i += nthr) {
       const int rp = i / Su, c = i - rp * Su, r = 2 * rp;

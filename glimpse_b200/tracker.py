@@ -15,8 +15,9 @@ Differences a user can see (all documented in DESIGN.md):
   (``cluster`` = CTAs per point, 0 = automatic).  Same results up to floating-point association.
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
-* ``resample_method`` 'systematic', 'stratified' and 'choice' and the default ``highpass`` / ``interpolation`` have kernels; other values
-  raise ``NotImplementedError`` (no CPU fallback).
+* ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass={'size': ...}`` of any size up to 31 x 31 (the
+  default 5 x 5 has the fast kernel) and the default ``interpolation`` have kernels; other values raise
+  ``NotImplementedError`` (no CPU fallback).
 """
 from __future__ import annotations
 
@@ -41,6 +42,21 @@ def pairwise_distance_datetimes(x, y) -> np.ndarray:
 
 
 from .session import point_span  # noqa: E402,F401  (re-exported)
+
+
+def highpass_size(highpass: dict):
+    """(rows, columns) of ``scipy.ndimage.median_filter(tile, **highpass)`` (reference tracker.py:59, 530).
+
+    The device kernels implement ``size`` (one integer or a pair, 1..31 each) with the default ``mode='reflect'``
+    and ``origin=0``; anything else has no kernel and raises ``NotImplementedError`` (there is no CPU fallback)."""
+    extra = set(highpass) - {"size", "mode", "origin"}
+    if extra or "size" not in highpass or highpass.get("mode", "reflect") != "reflect" or np.any(np.asarray(highpass.get("origin", 0)) != 0):
+        raise NotImplementedError("highpass: only {'size': int or (rows, columns)} with mode='reflect', origin=0 has a device kernel")
+    size = highpass["size"]
+    rows, cols = (size, size) if np.ndim(size) == 0 else tuple(size)
+    if int(rows) != rows or int(cols) != cols or not (1 <= rows <= 31 and 1 <= cols <= 31):
+        raise NotImplementedError("highpass: 'size' must be integers between 1 and 31")
+    return int(rows), int(cols)
 
 
 def shard_bounds(n_items: int, world_size: int, rank: int):
@@ -166,8 +182,7 @@ class Tracker:
                 raise ValueError("Motion models must have equal time units")
         if self.resample_method not in _lib.GB_RESAMPLE:
             raise NotImplementedError("only resample_method='systematic', 'stratified' and 'choice' have device kernels")
-        if tuple(self.highpass.get("size", ())) != (5, 5) or set(self.highpass) - {"size"}:
-            raise NotImplementedError("only highpass={'size': (5, 5)} has a device kernel")
+        highpass_size(self.highpass)  # raises for what has no device kernel
         if self.interpolation.get("kx", 3) != 3 or self.interpolation.get("ky", 3) != 3 or set(self.interpolation) - {"kx", "ky"}:
             raise NotImplementedError("only interpolation={'kx': 3, 'ky': 3} has a device kernel")
         self.reset()

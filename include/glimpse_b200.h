@@ -261,7 +261,8 @@ typedef struct gb_track_desc {
   int32_t* window_stats;           /* [P][T][O][2] realised search-window (width, height), or NULL */
 
   int32_t resample_method;         /* GB_RESAMPLE_* (Tracker.resample_method, tracker.py:151-223) */
-  int32_t pad1_;
+  int32_t highpass_size;           /* rows | columns << 16 of the median high-pass (Tracker.highpass['size'], tracker.py:59, 530:
+                                    * scipy.ndimage.median_filter(tile, size=(rows, columns)), 1..31 each); 0 = the default 5 x 5 */
   gb_plan plan;
 } gb_track_desc;
 

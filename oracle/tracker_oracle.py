@@ -609,6 +609,7 @@ def track(
     resample_method: str = "systematic",
     trace: bool = False,
     raise_errors: bool = False,
+    highpass_size=(5, 5),
 ) -> TrackResult:
     """Run the filter for every model (tracker.py:225-417, inner ``process`` 305-374).
 
@@ -616,7 +617,11 @@ def track(
     observer ``o`` matched to time ``t`` or -1 (tracker.py:466-492).  Draws come from the legacy
     global NumPy generator in the reference's order unless ``randn`` / ``random`` are supplied.
     ``exact`` switches the three library kernels to their closed-form restatements.
+    ``highpass_size`` = ``Tracker.highpass["size"]`` as (rows, columns) or one integer (tracker.py:59, 530).
     """
+    if np.ndim(highpass_size) == 0:
+        highpass_size = (int(highpass_size),) * 2
+    highpass_size = tuple(int(v) for v in highpass_size)
     randn = randn or np.random.randn
     random = random or np.random.random
     T, O = image_index.shape
@@ -655,7 +660,7 @@ def track(
                     uv0 = project(cam, weighted_mean(ps, w)[None, 0:3], obs.correction(img)).ravel()
                     box = snap_tile_box(uv0, tile_size, cam[6:8].astype(int))
                     pixels = obs.frames[img][box[1]:box[3], box[0]:box[2]]
-                    tile, cdf = prepare_tile(pixels, exact_median=exact)
+                    tile, cdf = prepare_tile(pixels, size=highpass_size, exact_median=exact)
                     templates[o] = {"tile": tile, "cdf": cdf, "box": box, "duv": uv0 - box.reshape(2, -1).mean(axis=0)}
                 step = {"p": p, "t": t} if trace else None
                 if t > first:
@@ -674,7 +679,7 @@ def track(
                             skipped[p, t, o] = 2
                             continue
                         pixels = obs.frames[img][box[1]:box[3], box[0]:box[2]]
-                        search, _ = prepare_tile(pixels, histogram=tpl["cdf"], exact_median=exact)
+                        search, _ = prepare_tile(pixels, histogram=tpl["cdf"], size=highpass_size, exact_median=exact)
                         sse = ssd_surface(search, tpl["tile"], exact=exact)
                         sbox = surface_box(box, size, tpl["duv"])
                         sampled = spline_sample(uv, sse, sbox, exact=exact)

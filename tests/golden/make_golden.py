@@ -33,9 +33,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def run_reference(scene, seed, points=None, return_covariances=False, observer_mask=None, viewshed=None,
-                  datetimes=None, capture=True, resample_method="systematic"):
+                  datetimes=None, capture=True, resample_method="systematic", highpass=None):
     observers, models = synthetic.build(scene, glimpse, points=points)
-    tracker = glimpse.Tracker(observers, viewshed=viewshed, resample_method=resample_method)
+    extra = {} if highpass is None else {"highpass": highpass}
+    tracker = glimpse.Tracker(observers, viewshed=viewshed, resample_method=resample_method, **extra)
     steps = []  # one dict per resample call (point-major, time-minor)
     templates = []
     current = {"obs": {}}
@@ -187,6 +188,9 @@ def camera_vectors():
 
 
 if __name__ == "__main__":
-    camera_vectors()
+    only = sys.argv[1:]  # optional: names of the track cases to (re)generate
+    if not only:
+        camera_vectors()
     for name, case in scenes.track_cases().items():
-        save_track_case(name, **case)
+        if not only or name in only:
+            save_track_case(name, **case)

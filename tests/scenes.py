@@ -97,6 +97,16 @@ def track_cases():
             scene_kwargs=dict(seed=15, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1515, resample_method="choice",
         ),
+        # other sizes of the median high-pass (Tracker.highpass, tracker.py:59, 530):
+        # rows != columns, and an even size given as one integer (window offsets -2 .. 1)
+        "track_hp37": dict(
+            scene_kwargs=dict(seed=17, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=1717, highpass={"size": (3, 7)},
+        ),
+        "track_hp4": dict(
+            scene_kwargs=dict(seed=19, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=1919, post=add_second_observer, highpass={"size": 4},
+        ),
         # map-scale world coordinates + per-frame view-direction jitter
         "track_jitter": dict(
             scene_kwargs=dict(seed=5, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,

@@ -49,7 +49,8 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
 
     observers, models = synthetic.build(scene, gb)
     method = case.get("resample_method", "systematic")
-    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode, resample_method=method)
+    tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode, resample_method=method,
+                         highpass=case.get("highpass", {"size": (5, 5)}))
     datetimes = tracker.datetimes
     matching = tracker.match_datetimes(datetimes)
     image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
@@ -113,7 +114,9 @@ def test_templates_match_reference(cuda, name, mode):
                             # k_s2_surface's other work-space organisations (negative = no interleaved path): every window on
                             # planes; a budget that sends windows to the staged, planar or global path depending on their size
                             ("track_c1", "stream", 0, -112640), ("track_cyl2", "stream", 0, -112640),
-                            ("track_c1", "stream", 0, -18000), ("track_cyl2", "stream", 0, -30000), ("track_jitter", "stream", 0, -16000)])
+                            ("track_c1", "stream", 0, -18000), ("track_cyl2", "stream", 0, -30000), ("track_jitter", "stream", 0, -16000),
+                            # other median sizes on the planar / staged / global organisations
+                            ("track_hp37", "stream", 0, -112640), ("track_hp4", "stream", 0, -30000), ("track_hp37", "stream", 0, -16000)])
 def test_step_teacher_forced(cuda, name, mode, cluster, tile_bytes):
     from glimpse_b200 import _lib
 
@@ -229,7 +232,8 @@ def test_track_free_running_matches_reference(cuda, name, mode):
     scene, case = case_scene(name)
     g = helpers.load_golden(name)
     observers, models = synthetic.build(scene, gb)
-    tracker = gb.Tracker(observers, rng="numpy", mode=mode, resample_method=case.get("resample_method", "systematic"))
+    tracker = gb.Tracker(observers, rng="numpy", mode=mode, resample_method=case.get("resample_method", "systematic"),
+                         highpass=case.get("highpass", {"size": (5, 5)}))
     np.random.seed(int(g["seed"]))
     cov = bool(case.get("return_covariances", False))
     tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True, return_covariances=cov)

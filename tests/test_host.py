@@ -155,11 +155,17 @@ def test_unsupported_options_raise_instead_of_falling_back():
     obs = _observers(3)
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
-    for kw in (dict(resample_method="residual"), dict(highpass={"size": (3, 3)}), dict(interpolation={"kx": 1, "ky": 1})):
+    for kw in (dict(resample_method="residual"), dict(highpass={"size": (5, 5), "mode": "nearest"}),
+               dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 1, "ky": 1})):
         with pytest.raises(NotImplementedError):
             gb.Tracker([obs], **kw).track(models)
     with pytest.raises(ValueError, match="equal time units"):
         gb.Tracker([obs]).track(models + [gb.CartesianMotion(xy=(0, 0), time_unit=2 * day, dem=0.0, n=10)])
+
+    from glimpse_b200.tracker import highpass_size
+
+    assert highpass_size({"size": (3, 7)}) == (3, 7)  # (rows, columns), as scipy.ndimage.median_filter reads it
+    assert highpass_size({"size": 4, "mode": "reflect", "origin": 0}) == (4, 4)
 
     class Custom:
         n, time_unit = 10, day
