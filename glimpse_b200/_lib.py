@@ -85,6 +85,7 @@ class gb_track_desc(C.Structure):
         ("out_weights", C.c_void_p), ("status", C.c_void_p), ("status_time", C.c_void_p), ("obs_flags", C.c_void_p),
         ("window_stats", C.c_void_p),
         ("resample_method", C.c_int32), ("highpass_size", C.c_int32),
+        ("interp_rows", C.c_int32), ("interp_cols", C.c_int32),
         ("plan", gb_plan),
     ]
 
@@ -97,10 +98,14 @@ class gb_stage_io(C.Structure):
     ]
 
 
+# order of gb_struct_size(which)
+STRUCTS = (gb_camera, gb_image, gb_surface, gb_motion, gb_plan, gb_track_desc, gb_stage_io)
+
 # name -> (restype, argtypes); every symbol include/glimpse_b200.h declares
 SIGNATURES = {
     "gb_version": (C.c_int, []),
     "gb_last_error": (C.c_char_p, []),
+    "gb_struct_size": (C.c_int64, [C.c_int32]),
     "gb_kernel_timing": (C.c_int, [C.c_int32]),
     "gb_kernel_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "gb_camera_from_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(gb_camera)]),

@@ -107,6 +107,7 @@ struct StepParams {
   int resample_method;  // GB_RESAMPLE_*
   int s2_budget;        // shared-memory bytes k_s2_surface may use for one window (negative: planar path forced, tests)
   int64_t p0, pb;    // batch of points handled by this launch
+  int interp_rows, interp_cols;  // spline degree along the rows (kx) / columns (ky) of the SSE surface: 3 or 1 (Tracker.interpolation)
 };
 
 // What k_s4p needs to know about the NEXT time to advance the particles to it.
@@ -817,12 +818,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
         hi_v = -hi_v;
         const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
         double bl = sub(lo_u, hw), bt = sub(lo_v, hh), br = add(hi_u, hw), bb = add(hi_v, hh);
-        const double ncols = sub(3.0, sub(sub(br, bl), tw));
+        const double ncols = sub((double)prm.interp_cols, sub(sub(br, bl), tw));
         if (ncols > 0.0) {
           bl = add(bl, mul(-ncols, 0.5));
           br = add(br, mul(ncols, 0.5));
         }
-        const double nrows = sub(3.0, sub(sub(bb, bt), th));
+        const double nrows = sub((double)prm.interp_rows, sub(sub(bb, bt), th));
         if (nrows > 0.0) {
           bt = add(bt, mul(-nrows, 0.5));
           bb = add(bb, mul(nrows, 0.5));
@@ -853,6 +854,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
       w.tw = prm.tile_w;
       w.mh = prm.hp_rows;
       w.mw = prm.hp_cols;
+      w.cub_u = prm.interp_cols != 1;
+      w.cub_v = prm.interp_rows != 1;
       w.th = prm.tile_h;
       w.Mu = w.Su - w.tw + 1;
       w.Mv = w.Sv - w.th + 1;
@@ -912,7 +915,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ 
         if (!((u >= sl) & (u <= sr) & (v >= st) & (v <= sb))) flags |= GB_F_SAMPLE_OUTSIDE;
         // FITPACK evaluates at the argument clamped to the first/last data site
         const double x = fmin(fmax(u, cu0), cu1) - cu0, y = fmin(fmax(v, cv0), cv1) - cv0;
-        const double val = (double)hermite_eval(w.herm, w.Mp, w.Mu, w.Mv, x, y);
+        const double val = (double)hermite_eval(w.herm, w.Mp, w.Mu, w.Mv, x, y, prm.interp_cols == 1, prm.interp_rows == 1);
         llb[i] = add(llb[i], mul(val, scale));
         if (prm.io.dump_sampled) prm.io.dump_sampled[po * N + i0 + i] = val;
       }
@@ -1126,6 +1129,8 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.t = t;
   prm.tile_w = d.tile_w;
   prm.tile_h = d.tile_h;
+  prm.interp_rows = d.interp_rows ? d.interp_rows : 3;
+  prm.interp_cols = d.interp_cols ? d.interp_cols : 3;
   prm.hp_rows = d.highpass_size ? (d.highpass_size & 0xffff) : 5;
   prm.hp_cols = d.highpass_size ? (d.highpass_size >> 16 & 0xffff) : 5;
   prm.cluster = d.plan.cluster;
@@ -1201,6 +1206,8 @@ static int check_desc(const gb_track_desc& d) {
   if (d.highpass_size != 0 && ((d.highpass_size & 0xffff) < 1 || (d.highpass_size & 0xffff) > GB_MAX_HIGHPASS ||
                                (d.highpass_size >> 16 & 0xffff) < 1 || (d.highpass_size >> 16 & 0xffff) > GB_MAX_HIGHPASS))
     return fail(GB_E_INVALID, "highpass_size: rows and columns must be between 1 and 31%s");
+  if ((d.interp_rows != 0 && d.interp_rows != 1 && d.interp_rows != 3) || (d.interp_cols != 0 && d.interp_cols != 1 && d.interp_cols != 3))
+    return fail(GB_E_INVALID, "interp_rows / interp_cols: spline degrees 1 and 3 are supported%s");
   if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");
   if (!d.images_host) return fail(GB_E_INVALID, "images_host is required%s");
   if (!d.images || !d.mask || !d.first || !d.last || !d.motion || !d.surfaces || !d.state_a || !d.state_b || !d.means ||
@@ -1661,6 +1668,18 @@ extern "C" {
 
 int gb_version(void) { return GB_VERSION; }
 const char* gb_last_error(void) { return g_error; }
+int64_t gb_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(gb_camera);
+    case 1: return sizeof(gb_image);
+    case 2: return sizeof(gb_surface);
+    case 3: return sizeof(gb_motion);
+    case 4: return sizeof(gb_plan);
+    case 5: return sizeof(gb_track_desc);
+    case 6: return sizeof(gb_stage_io);
+    default: return -1;
+  }
+}
 
 int gb_kernel_timing(int32_t enable) {
   std::lock_guard<std::mutex> guard(gb::g_ktimer.mu);

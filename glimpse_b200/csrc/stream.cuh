@@ -274,12 +274,12 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
       const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
       const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
       double bl = sub(e[0], hw), bt = sub(e[1], hh), br = add(-e[2], hw), bb = add(-e[3], hh);
-      const double ncols = sub(3.0, sub(sub(br, bl), tw));
+      const double ncols = sub((double)prm.interp_cols, sub(sub(br, bl), tw));
       if (ncols > 0.0) {
         bl = add(bl, mul(-ncols, 0.5));
         br = add(br, mul(ncols, 0.5));
       }
-      const double nrows = sub(3.0, sub(sub(bb, bt), th));
+      const double nrows = sub((double)prm.interp_rows, sub(sub(bb, bt), th));
       if (nrows > 0.0) {
         bt = add(bt, mul(-nrows, 0.5));
         bb = add(bb, mul(nrows, 0.5));
@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   w.tw = prm.tile_w;
   w.mh = prm.hp_rows;
   w.mw = prm.hp_cols;
+  w.cub_u = prm.interp_cols != 1;
+  w.cub_v = prm.interp_rows != 1;
   w.th = prm.tile_h;
   w.Mu = w.Su - w.tw + 1;
   w.Mv = w.Sv - w.th + 1;
@@ -498,6 +500,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
     if (!any_ok && prm.weight_state) fw = prm.weight_state + (int64_t)p * N;
   }
   const bool vec = (N & 1) == 0;
+  const bool lin_u = prm.interp_cols == 1, lin_v = prm.interp_rows == 1;  // Tracker.interpolation: degree 1 along an axis
   uint32_t flags = 0;
   double wacc = 0.0;
   const int blk_end = min(N, (b + 1) * prm.s_block);  // s_block is even: pairs never straddle CTAs
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
           if (!((u[q] >= r.sl) & (u[q] <= r.sr) & (v[q] >= r.st) & (v[q] <= r.sb))) flags |= GB_F_SAMPLE_OUTSIDE;
           // FITPACK evaluates at the argument clamped to the first/last data site
           const double x = fmin(fmax(u[q], r.cu0), r.cu1) - r.cu0, y = fmin(fmax(v[q], r.cv0), r.cv1) - r.cv0;
-          const double val = (double)hermite_eval(r.herm, r.Mp, r.Mu, r.Mv, x, y);
+          const double val = (double)hermite_eval(r.herm, r.Mp, r.Mu, r.Mv, x, y, lin_u, lin_v);
           ll[q] = add(ll[q], mul(val, r.scale));
           if (prm.io.dump_sampled && (q == 0 || vb)) prm.io.dump_sampled[(p * O + o) * N + ia + q] = val;
         }

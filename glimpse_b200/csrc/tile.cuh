@@ -35,6 +35,7 @@ struct TileWork {
   uint32_t* hist;    // [nbins]
   int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
   int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
+  bool cub_u = true, cub_v = true;  // cubic (default) or piecewise-linear interpolation along the columns / rows (Tracker.interpolation)
 };
 
 __host__ __device__ inline int64_t align16(int64_t b) { return (b + 15) / 16 * 16; }
@@ -148,7 +149,13 @@ __device__ inline int median_window(const uint16_t* raw, int Su, int Sv, int r, 
 // Solve the not-a-knot slope system along one line of the Hermite array (stride in floats).
 // `in` holds the samples, `out` receives the slopes; the forward-sweep values pass through `out`
 // as floats.  The loop-carried chain is one DFMA per element in each direction.
-__device__ __forceinline__ void spline_slopes_line(const float* __restrict__ in, float* __restrict__ out, int stride, int m) {
+// `cubic` = false (degree-1 interpolation along this axis, Tracker.interpolation): the slopes are never used by the
+// evaluation; zeros keep the unused Hermite terms finite (the line may then be shorter than the four samples a cubic needs).
+__device__ __forceinline__ void spline_slopes_line(const float* __restrict__ in, float* __restrict__ out, int stride, int m, bool cubic = true) {
+  if (!cubic) {
+    for (int i = 0; i < m; ++i) out[i * stride] = 0.0f;
+    return;
+  }
   const double f0 = in[0], f1 = in[stride], f2 = in[2 * stride];
   double d = 0.5 * (5.0 * (f1 - f0) + (f2 - f1));
   out[0] = (float)d;
@@ -205,14 +212,17 @@ __device__ __forceinline__ void spline_slopes_line(const float* __restrict__ in,
 // Bicubic Hermite evaluation at (x, y) measured from the first cell centre, in cell units.  The cell
 // index and the in-cell offset are taken in double; the 16-term patch is evaluated in float (the
 // data are float32: the SSE surface is cv2.matchTemplate's float32 output in the reference).
-__device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, int Mp, int Mu, int Mv, double x, double y) {
+// `lin_u` / `lin_v`: degree-1 interpolation along that axis (Tracker.interpolation ky / kx = 1): the value weights become
+// (1 - t, t) and the slope weights vanish — FITPACK's interpolating linear spline has a knot at every data site.
+__device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, int Mp, int Mu, int Mv, double x, double y, bool lin_u = false,
+                                              bool lin_v = false) {
   int j = min((int)x, Mu - 2), i = min((int)y, Mv - 2);  // x, y >= 0
   j = max(j, 0);
   i = max(i, 0);
   const float tx = (float)(x - (double)j), ty = (float)(y - (double)i);
   const float tx2 = tx * tx, tx3 = tx2 * tx, ty2 = ty * ty, ty3 = ty2 * ty;
-  const float a2 = 3.0f * tx2 - 2.0f * tx3, a0 = 1.0f - a2, a3 = tx3 - tx2, a1 = a3 - tx2 + tx;
-  const float b2 = 3.0f * ty2 - 2.0f * ty3, b0 = 1.0f - b2, b3 = ty3 - ty2, b1 = b3 - ty2 + ty;
+  const float a2 = lin_u ? tx : 3.0f * tx2 - 2.0f * tx3, a0 = 1.0f - a2, a3 = lin_u ? 0.0f : tx3 - tx2, a1 = lin_u ? 0.0f : a3 - tx2 + tx;
+  const float b2 = lin_v ? ty : 3.0f * ty2 - 2.0f * ty3, b0 = 1.0f - b2, b3 = lin_v ? 0.0f : ty3 - ty2, b1 = lin_v ? 0.0f : b3 - ty2 + ty;
   const float4* row0 = herm + i * Mp + j;
   const float4 h00 = row0[0], h01 = row0[1], h10 = row0[Mp], h11 = row0[Mp + 1];
   // rows of the patch: value and u-slope interpolated along u, for f and for df/dv
@@ -509,14 +519,14 @@ __device__ inline void tile_finish_interleaved(TileWork& w, float* dump_sse, int
     const int Mvp = 32 * ((Mv + 31) / 32);  // rows and columns on separate warps
     for (int line = tid; line < Mvp + Mu; line += nthr) {
       if (line < Mv) {
-        spline_slopes_line(base + (int64_t)line * Mp * 4, base + (int64_t)line * Mp * 4 + 1, 4, Mu);
+        spline_slopes_line(base + (int64_t)line * Mp * 4, base + (int64_t)line * Mp * 4 + 1, 4, Mu, w.cub_u);
       } else if (line >= Mvp) {
         const int c = line - Mvp;
-        spline_slopes_line(base + (int64_t)c * 4, base + (int64_t)c * 4 + 2, Mp * 4, Mv);
+        spline_slopes_line(base + (int64_t)c * 4, base + (int64_t)c * 4 + 2, Mp * 4, Mv, w.cub_v);
       }
     }
     __syncthreads();
-    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mp * 4, Mv);
+    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mp * 4, Mv, w.cub_v);
   }
   __syncthreads();
 }
@@ -614,10 +624,10 @@ __device__ inline void tile_finish_planar(TileWork& w, const TilePlanes& pl, flo
     const int Mvp = 32 * ((Mv + 31) / 32);
     for (int line = tid; line < Mvp + Mu; line += nthr) {
       if (line < Mv) {
-        spline_slopes_line(pl.F + (int64_t)line * Mq, pl.Fu + (int64_t)line * Mq, 1, Mu);
+        spline_slopes_line(pl.F + (int64_t)line * Mq, pl.Fu + (int64_t)line * Mq, 1, Mu, w.cub_u);
       } else if (line >= Mvp) {
         const int c = line - Mvp;
-        spline_slopes_line(pl.F + c, pl.G + c, Mq, Mv);
+        spline_slopes_line(pl.F + c, pl.G + c, Mq, Mv, w.cub_v);
       }
     }
     __syncthreads();
@@ -627,7 +637,7 @@ __device__ inline void tile_finish_planar(TileWork& w, const TilePlanes& pl, flo
     }
     __syncthreads();
     // cross derivative: columns of F_u into the scratch plane, then into the fourth component
-    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(pl.Fu + c, pl.G + c, Mq, Mv);
+    for (int c = tid; c < Mu; c += nthr) spline_slopes_line(pl.Fu + c, pl.G + c, Mq, Mv, w.cub_v);
     __syncthreads();
     float* outf = reinterpret_cast<float*>(out);
     for (int o = tid; o < Mu * Mv; o += nthr) {
@@ -725,14 +735,14 @@ __device__ inline void tile_build_surface_staged(char* smem, char* region, const
   for (int i = tid; i < Mv * Mq; i += nthr) P0[i] = F_global[i];
   __syncthreads();  // F is in shared memory: the region is free for the final surface
   float* out = reinterpret_cast<float*>(region);
-  for (int r = tid; r < Mv; r += nthr) spline_slopes_line(P0 + (int64_t)r * Mq, P1 + (int64_t)r * Mq, 1, Mu);  // F -> F_u
+  for (int r = tid; r < Mv; r += nthr) spline_slopes_line(P0 + (int64_t)r * Mq, P1 + (int64_t)r * Mq, 1, Mu, w.cub_u);  // F -> F_u
   __syncthreads();
   for (int o = tid; o < Mu * Mv; o += nthr) {
     const int r = o / Mu, c = o - r * Mu;
     *reinterpret_cast<float2*>(out + ((int64_t)r * Mp + c) * 4) = make_float2(P0[r * Mq + c], P1[r * Mq + c]);
   }
   __syncthreads();
-  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv);  // F -> F_v
+  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv, w.cub_v);  // F -> F_v
   __syncthreads();
   for (int o = tid; o < Mu * Mv; o += nthr) {
     const int r = o / Mu, c = o - r * Mu;
@@ -740,7 +750,7 @@ __device__ inline void tile_build_surface_staged(char* smem, char* region, const
     P0[r * Mq + c] = out[((int64_t)r * Mp + c) * 4 + 1];  // F_u back in (written by this CTA before the last barrier)
   }
   __syncthreads();
-  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv);  // F_u -> F_uv
+  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(P0 + c, P1 + c, Mq, Mv, w.cub_v);  // F_u -> F_uv
   __syncthreads();
   for (int o = tid; o < Mu * Mv; o += nthr) {
     const int r = o / Mu, c = o - r * Mu;

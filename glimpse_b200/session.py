@@ -196,10 +196,11 @@ class Session:
             if stratified and mode == _lib.GB_MODE_FUSED:
                 raise NotImplementedError(f"resample_method='{method}' runs in mode='stream' only")
             d.resample_method = _lib.GB_RESAMPLE[method]
-            from .tracker import highpass_size
+            from .tracker import highpass_size, interpolation_degrees
 
             rows, cols = highpass_size(getattr(tracker, "highpass", {"size": (5, 5)}))
             d.highpass_size = 0 if (rows, cols) == (5, 5) else rows | cols << 16
+            d.interp_rows, d.interp_cols = interpolation_degrees(getattr(tracker, "interpolation", {}))
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED
                 if draws is None:

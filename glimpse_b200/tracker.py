@@ -16,8 +16,8 @@ Differences a user can see (all documented in DESIGN.md):
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
 * ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass={'size': ...}`` of any size up to 31 x 31 (the
-  default 5 x 5 has the fast kernel) and the default ``interpolation`` have kernels; other values raise
-  ``NotImplementedError`` (no CPU fallback).
+  default 5 x 5 has the fast kernel) and ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values
+  raise ``NotImplementedError`` (no CPU fallback).
 """
 from __future__ import annotations
 
@@ -57,6 +57,16 @@ def highpass_size(highpass: dict):
     if int(rows) != rows or int(cols) != cols or not (1 <= rows <= 31 and 1 <= cols <= 31):
         raise NotImplementedError("highpass: 'size' must be integers between 1 and 31")
     return int(rows), int(cols)
+
+
+def interpolation_degrees(interpolation: dict):
+    """(kx, ky) of ``RectBivariateSpline(rows, columns, sse, **interpolation)`` (reference tracker.py:60, 584-594,
+    observer.py:210): spline degree along the rows / columns of the SSE surface.  Degrees 3 (default) and 1 have device
+    kernels; 2, 4, 5 and the smoothing / bbox arguments raise ``NotImplementedError`` (there is no CPU fallback)."""
+    kx, ky = interpolation.get("kx", 3), interpolation.get("ky", 3)
+    if set(interpolation) - {"kx", "ky"} or kx not in (1, 3) or ky not in (1, 3):
+        raise NotImplementedError("interpolation: only {'kx': 1 or 3, 'ky': 1 or 3} has a device kernel")
+    return int(kx), int(ky)
 
 
 def shard_bounds(n_items: int, world_size: int, rank: int):
@@ -183,8 +193,7 @@ class Tracker:
         if self.resample_method not in _lib.GB_RESAMPLE:
             raise NotImplementedError("only resample_method='systematic', 'stratified' and 'choice' have device kernels")
         highpass_size(self.highpass)  # raises for what has no device kernel
-        if self.interpolation.get("kx", 3) != 3 or self.interpolation.get("ky", 3) != 3 or set(self.interpolation) - {"kx", "ky"}:
-            raise NotImplementedError("only interpolation={'kx': 3, 'ky': 3} has a device kernel")
+        interpolation_degrees(self.interpolation)
         self.reset()
         ntracks = len(motion_models)
         raise_errors = ntracks < 2

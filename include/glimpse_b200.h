@@ -120,6 +120,9 @@ typedef struct gb_motion {
  * ------------------------------------------------------------------------------------------ */
 int gb_version(void);
 const char* gb_last_error(void);
+/* sizeof() of the public structs as this library was compiled, so that a binding can verify its mirror of the layouts:
+ * which = 0 gb_camera, 1 gb_image, 2 gb_surface, 3 gb_motion, 4 gb_plan, 5 gb_track_desc, 6 gb_stage_io; -1 for anything else. */
+int64_t gb_struct_size(int32_t which);
 
 /* Measurement aid (no reference counterpart): when enabled, every kernel launch of gb_track's streaming
  * flow is bracketed by CUDA events on the stream it is launched on; gb_kernel_timing_read returns the
@@ -263,6 +266,9 @@ typedef struct gb_track_desc {
   int32_t resample_method;         /* GB_RESAMPLE_* (Tracker.resample_method, tracker.py:151-223) */
   int32_t highpass_size;           /* rows | columns << 16 of the median high-pass (Tracker.highpass['size'], tracker.py:59, 530:
                                     * scipy.ndimage.median_filter(tile, size=(rows, columns)), 1..31 each); 0 = the default 5 x 5 */
+  int32_t interp_rows, interp_cols; /* Tracker.interpolation (tracker.py:60, observer.py:210): degree of the interpolating spline along the rows
+                                    * (kx) and the columns (ky) of the SSE surface, which also sets the minimum surface size (tracker.py:584-594).
+                                    * 3 (cubic, not-a-knot) or 1 (piecewise linear); 0 = the default 3 */
   gb_plan plan;
 } gb_track_desc;
 

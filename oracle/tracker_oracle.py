@@ -469,10 +469,12 @@ def notaknot_slopes(y: np.ndarray) -> np.ndarray:
     return np.linalg.solve(A, rhs.reshape(m, -1)).reshape(y.shape)
 
 
-def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: bool = False) -> np.ndarray:
-    """Sample ``surface`` (cell centres inside ``box``) at ``uv`` with the interpolating bicubic
-    spline (observer.py:178-214).  ``exact=False``: FITPACK via RectBivariateSpline(kx=ky=3, s=0).
-    ``exact=True``: tensor not-a-knot cubic in Hermite form with FITPACK's clamped evaluation."""
+def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: bool = False, kx: int = 3, ky: int = 3) -> np.ndarray:
+    """Sample ``surface`` (cell centres inside ``box``) at ``uv`` with the interpolating spline of degree ``kx``
+    along the rows (v) and ``ky`` along the columns (u) (observer.py:178-214; ``Tracker.interpolation``).
+    ``exact=False``: FITPACK via RectBivariateSpline(s=0).
+    ``exact=True`` (degrees 1 and 3 only): tensor product of not-a-knot cubics (Hermite form) and / or piecewise-linear
+    interpolants — FITPACK's degree-1 interpolating spline has a knot at every data site — with FITPACK's clamped evaluation."""
     lo, hi = box[0:2], box[2:4]
     if not np.all((uv >= lo) & (uv <= hi)):
         raise ValueError("Some sampling points are outside box")
@@ -483,12 +485,15 @@ def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: b
     if not exact:
         import scipy.interpolate
 
-        f = scipy.interpolate.RectBivariateSpline(cv, cu, surface, kx=3, ky=3)
+        f = scipy.interpolate.RectBivariateSpline(cv, cu, surface, kx=kx, ky=ky)
         return f(uv[:, 1], uv[:, 0], grid=False)
+    if kx not in (1, 3) or ky not in (1, 3):
+        raise NotImplementedError("closed-form restatement for degrees 1 and 3 only")
     F = surface.astype(float)
-    Fv = notaknot_slopes(F)  # d/dv along rows axis
-    Fu = notaknot_slopes(F.T).T
-    Fuv = notaknot_slopes(Fu)
+    zero = np.zeros_like(F)
+    Fv = notaknot_slopes(F) if kx == 3 else zero  # d/dv along rows axis
+    Fu = notaknot_slopes(F.T).T if ky == 3 else zero
+    Fuv = notaknot_slopes(Fu) if kx == 3 and ky == 3 else zero
     mv, mu = F.shape
     x = np.clip(uv[:, 0], cu[0], cu[-1]) - cu[0]
     y = np.clip(uv[:, 1], cv[0], cv[-1]) - cv[0]
@@ -496,12 +501,14 @@ def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: b
     i = np.minimum(np.floor(y).astype(int), mv - 2)
     tx, ty = x - j, y - i
 
-    def basis(t):
+    def basis(t, k):
+        if k == 1:
+            return 1 - t, 0 * t, t, 0 * t
         t2, t3 = t * t, t * t * t
         return 2 * t3 - 3 * t2 + 1, t3 - 2 * t2 + t, -2 * t3 + 3 * t2, t3 - t2
 
-    a0, a1, a2, a3 = basis(tx)  # value0, slope0, value1, slope1 along u
-    b0, b1, b2, b3 = basis(ty)
+    a0, a1, a2, a3 = basis(tx, ky)  # value0, slope0, value1, slope1 along u
+    b0, b1, b2, b3 = basis(ty, kx)
     out = np.zeros(len(uv))
     for bi, di in ((b0, 0), (b2, 1)):
         for aj, dj in ((a0, 0), (a2, 1)):
@@ -610,6 +617,8 @@ def track(
     trace: bool = False,
     raise_errors: bool = False,
     highpass_size=(5, 5),
+    kx: int = 3,
+    ky: int = 3,
 ) -> TrackResult:
     """Run the filter for every model (tracker.py:225-417, inner ``process`` 305-374).
 
@@ -618,6 +627,7 @@ def track(
     global NumPy generator in the reference's order unless ``randn`` / ``random`` are supplied.
     ``exact`` switches the three library kernels to their closed-form restatements.
     ``highpass_size`` = ``Tracker.highpass["size"]`` as (rows, columns) or one integer (tracker.py:59, 530).
+    ``kx``, ``ky`` = ``Tracker.interpolation`` (tracker.py:60): spline degree along the rows / columns of the SSE surface.
     """
     if np.ndim(highpass_size) == 0:
         highpass_size = (int(highpass_size),) * 2
@@ -674,7 +684,7 @@ def track(
                         cam = obs.cams[img]
                         size = tpl["tile"].shape[::-1]
                         uv = project(cam, ps[:, 0:3], obs.correction(img))
-                        box = search_window(uv, size, cam[6:8].astype(int))
+                        box = search_window(uv, size, cam[6:8].astype(int), kx=kx, ky=ky)
                         if box is None:
                             skipped[p, t, o] = 2
                             continue
@@ -682,7 +692,7 @@ def track(
                         search, _ = prepare_tile(pixels, histogram=tpl["cdf"], size=highpass_size, exact_median=exact)
                         sse = ssd_surface(search, tpl["tile"], exact=exact)
                         sbox = surface_box(box, size, tpl["duv"])
-                        sampled = spline_sample(uv, sse, sbox, exact=exact)
+                        sampled = spline_sample(uv, sse, sbox, exact=exact, kx=kx, ky=ky)
                         terms.append(sampled * (1 / (2 * obs.sigma ** 2)))
                         if trace:
                             step.setdefault("obs", {})[o] = {

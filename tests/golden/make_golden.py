@@ -33,9 +33,11 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def run_reference(scene, seed, points=None, return_covariances=False, observer_mask=None, viewshed=None,
-                  datetimes=None, capture=True, resample_method="systematic", highpass=None):
+                  datetimes=None, capture=True, resample_method="systematic", highpass=None, interpolation=None):
     observers, models = synthetic.build(scene, glimpse, points=points)
     extra = {} if highpass is None else {"highpass": highpass}
+    if interpolation is not None:
+        extra["interpolation"] = interpolation
     tracker = glimpse.Tracker(observers, viewshed=viewshed, resample_method=resample_method, **extra)
     steps = []  # one dict per resample call (point-major, time-minor)
     templates = []

@@ -64,6 +64,13 @@ def add_gridded_dem(scene):
     return scene
 
 
+def narrow_cloud(scene):
+    """Particles that stay within a fraction of a pixel: the search window is widened to the minimum the spline degree
+    needs (tracker.py:584-594), so the SSE surface has only degree + 1 cells per axis."""
+    scene.motion.update(xy_sigma=(0.01, 0.01), vxyz_sigma=(0.01, 0.01, 0.0), axyz_sigma=(0.002, 0.002, 0.0))
+    return scene
+
+
 def track_cases():
     return {
         # config-1 shape, shrunk: 1 observer, Cartesian, full distortion
@@ -106,6 +113,24 @@ def track_cases():
         "track_hp4": dict(
             scene_kwargs=dict(seed=19, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1919, post=add_second_observer, highpass={"size": 4},
+        ),
+        # ... and other spline degrees (Tracker.interpolation, tracker.py:60): bilinear; a 2 x 2 .. 3 x 3 surface (bilinear,
+        # window widened to the minimum); cubic along the rows with linear along the columns, two observers
+        "track_lin": dict(
+            scene_kwargs=dict(seed=21, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=2121, interpolation={"kx": 1, "ky": 1},
+        ),
+        "track_lin_narrow": dict(
+            scene_kwargs=dict(seed=23, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=2323, post=narrow_cloud, interpolation={"kx": 1, "ky": 1},
+        ),
+        "track_k31": dict(
+            scene_kwargs=dict(seed=25, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=2525, post=add_second_observer, interpolation={"kx": 3, "ky": 1},
+        ),
+        "track_narrow": dict(  # the default cubic on a widened 4 x 4 surface
+            scene_kwargs=dict(seed=27, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=2727, post=narrow_cloud,
         ),
         # map-scale world coordinates + per-frame view-direction jitter
         "track_jitter": dict(

@@ -50,7 +50,7 @@ def make_session(scene, case, golden, return_particles=False, cluster=0, tile_by
     observers, models = synthetic.build(scene, gb)
     method = case.get("resample_method", "systematic")
     tracker = gb.Tracker(observers, rng="numpy", cluster=cluster, mode=mode, resample_method=method,
-                         highpass=case.get("highpass", {"size": (5, 5)}))
+                         highpass=case.get("highpass", {"size": (5, 5)}), interpolation=case.get("interpolation", {"kx": 3, "ky": 3}))
     datetimes = tracker.datetimes
     matching = tracker.match_datetimes(datetimes)
     image_index = np.array([[-1 if v is None else int(v) for v in row] for row in matching], dtype=np.int32)
@@ -233,7 +233,7 @@ def test_track_free_running_matches_reference(cuda, name, mode):
     g = helpers.load_golden(name)
     observers, models = synthetic.build(scene, gb)
     tracker = gb.Tracker(observers, rng="numpy", mode=mode, resample_method=case.get("resample_method", "systematic"),
-                         highpass=case.get("highpass", {"size": (5, 5)}))
+                         highpass=case.get("highpass", {"size": (5, 5)}), interpolation=case.get("interpolation", {"kx": 3, "ky": 3}))
     np.random.seed(int(g["seed"]))
     cov = bool(case.get("return_covariances", False))
     tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True, return_covariances=cov)

@@ -22,12 +22,16 @@ def test_library_exports_every_declared_symbol():
     build.build()
     lib = _lib.load()
     text = open(HEADER).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(gb_\w+)\s*\(", text, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(gb_\w+)\s*\(", text, flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.gb_version() == 1
+    # the library was compiled with the layouts the ctypes mirror declares
+    for which, struct in enumerate(_lib.STRUCTS):
+        assert lib.gb_struct_size(which) == C.sizeof(struct), struct.__name__
+    assert lib.gb_struct_size(len(_lib.STRUCTS)) == -1
 
 
 def test_ctypes_layout_matches_header():
@@ -156,13 +160,16 @@ def test_unsupported_options_raise_instead_of_falling_back():
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
     for kw in (dict(resample_method="residual"), dict(highpass={"size": (5, 5), "mode": "nearest"}),
-               dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 1, "ky": 1})):
+               dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
+               dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
         with pytest.raises(NotImplementedError):
             gb.Tracker([obs], **kw).track(models)
     with pytest.raises(ValueError, match="equal time units"):
         gb.Tracker([obs]).track(models + [gb.CartesianMotion(xy=(0, 0), time_unit=2 * day, dem=0.0, n=10)])
 
-    from glimpse_b200.tracker import highpass_size
+    from glimpse_b200.tracker import highpass_size, interpolation_degrees
+
+    assert interpolation_degrees({}) == (3, 3) and interpolation_degrees({"kx": 1}) == (1, 3)
 
     assert highpass_size({"size": (3, 7)}) == (3, 7)  # (rows, columns), as scipy.ndimage.median_filter reads it
     assert highpass_size({"size": 4, "mode": "reflect", "origin": 0}) == (4, 4)
