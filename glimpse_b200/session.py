@@ -105,6 +105,35 @@ def adopt_model(model):
     raise NotImplementedError(f"motion model {name} has no device kernel (no CPU fallback)")
 
 
+def session_bytes(lib, mode: int, cluster: int, P: int, N: int, T: int, O: int, tw: int, th: int, return_covariances: bool,
+                  return_particles: bool) -> int:
+    """Device memory one :class:`Session` of ``P`` points allocates (the frames excluded): two particle-state buffers,
+    the weights, the launch plan's scratch, templates and result blocks."""
+    plan = _lib.gb_plan()
+    _lib.check(lib.gb_step_plan(N, tw, th, P, O, int(cluster), mode, C.byref(plan)))
+    per_point = 2 * 48 * N + 8 * N                      # state_a, state_b, weight_state
+    per_point += 3 * O * tw * th * 8 + O * 40           # templates
+    per_point += T * ((36 if return_covariances else 6) + 6) * 8 + T * O * 9 + 16  # moments, flags, window sizes, status
+    if return_particles:
+        per_point += T * N * 56
+    return int(plan.scratch_bytes) + P * per_point
+
+
+def points_per_session(lib, mode: int, cluster: int, P: int, budget: int, **shape) -> int:
+    """Largest number of points (<= P) whose session fits ``budget`` bytes (at least 1): points are independent, so a
+    track that does not fit the device runs as consecutive sessions of this many points."""
+    if session_bytes(lib, mode, cluster, P, **shape) <= budget:
+        return P
+    lo, hi = 1, P  # session_bytes grows with the number of points
+    while hi - lo > 1:
+        mid = (lo + hi) // 2
+        if session_bytes(lib, mode, cluster, mid, **shape) <= budget:
+            lo = mid
+        else:
+            hi = mid
+    return lo
+
+
 class Session:
     def __init__(self, tracker, models, image_index, taus, tile_size, observer_mask, return_covariances=False,
                  return_particles=False, point_offset=0, draws=None, dist=None):

@@ -13,6 +13,9 @@ Differences a user can see (all documented in DESIGN.md):
 * ``mode="stream"`` (default) runs each update as five massively parallel kernels; ``mode="fused"`` runs
   it as one thread-block-cluster kernel per update with the particle intermediates kept on chip
   (``cluster`` = CTAs per point, 0 = automatic).  Same results up to floating-point association.
+* A track whose work buffers do not fit the device memory that is free runs as consecutive blocks of points (points are
+  independent and the device draws are keyed by the global point index, so the results do not depend on the blocks);
+  ``max_points`` caps the block size by hand.
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
 * ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass={'size': ...}`` of any size up to 31 x 31 (the
@@ -93,6 +96,7 @@ class Tracker:
         mode: str = "stream",
         device=None,
         distributed: bool = True,
+        max_points: Optional[int] = None,
     ) -> None:
         self.observers = list(observers)
         self.viewshed = viewshed
@@ -105,6 +109,7 @@ class Tracker:
         self.mode = mode
         self.device = device
         self.distributed = distributed
+        self.max_points = max_points
         self.particles = None
         self.weights = None
         self.templates = None
@@ -276,13 +281,67 @@ class Tracker:
 
         if len(models) == 0:
             return empty_result(0, image_index.shape[0], image_index.shape[1], return_covariances, return_particles)
-        session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
-                          return_particles, point_offset=point_offset, dist=gather[0] if gather else None)
-        session.run()
-        out = session.fetch(gather)
-        self.last_run = session.stats
-        self.particles, self.weights, self.templates = session.final_state()
+        block = self._points_per_session(models, image_index, tile_size, return_covariances, return_particles)
+        if block >= len(models):
+            session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
+                              return_particles, point_offset=point_offset, dist=gather[0] if gather else None)
+            session.run()
+            out = session.fetch(gather)
+            self.last_run = session.stats
+            self.particles, self.weights, self.templates = session.final_state()
+            return out
+        # consecutive blocks of points; the frames stay on the device between them (only the first block takes part in the
+        # shared upload of a multi-GPU box), every block's buffers are released before the next one is planned
+        parts, stats = [], None
+        for lo in range(0, len(models), block):
+            session = Session(self, models[lo:lo + block], image_index, taus, tile_size, observer_mask[lo:lo + block],
+                              return_covariances, return_particles, point_offset=point_offset + lo,
+                              dist=gather[0] if (gather and lo == 0) else None)
+            session.run()
+            parts.append(session.fetch(None))
+            st = session.stats
+            if stats is None:
+                stats = dict(st, sessions=1)
+            else:
+                stats["sessions"] += 1
+                for k in ("kernel_launches", "h2d_bytes", "d2h_bytes"):
+                    stats[k] += st[k]
+                for k in ("window_width", "window_height"):
+                    stats[k] = np.concatenate((stats[k], st[k]))
+            if lo + block >= len(models):
+                self.particles, self.weights, self.templates = session.final_state()
+            del session
+        self.last_run = stats
+        out = {k: np.concatenate([part[k] for part in parts], axis=0) for k in parts[0]}
+        if gather:
+            dist, per_rank, world = gather
+            out = self._gather(dist, out, per_rank * world, world)
         return out
+
+    def _points_per_session(self, models, image_index, tile_size, return_covariances, return_particles) -> int:
+        """How many points one device session may hold: all of them if their buffers fit 90 % of the device memory that is
+        free (counting what the caching allocator can reuse, less the frames still to be uploaded), else the largest block
+        that does."""
+        from . import session as _session
+
+        torch = _lib.require_cuda()
+        P = len(models)
+        cap = P if self.max_points is None else max(1, min(P, int(self.max_points)))
+        device = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        free, _total = torch.cuda.mem_get_info(device)
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        if not self._frame_cache:
+            for o, obs in enumerate(self.observers):
+                for i in {int(v) for v in image_index[:, o] if v >= 0}:
+                    array = getattr(obs.images[i], "array", None)
+                    try:
+                        free -= int(array.nbytes) if array is not None else 3 * int(np.prod(obs.images[i].size))
+                    except (AttributeError, TypeError):
+                        pass  # size unknown before the frame is read: the 10 % margin has to cover it
+        mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[self.mode]
+        shape = dict(N=int(models[0].n), T=image_index.shape[0], O=image_index.shape[1], tw=tile_size[0], th=tile_size[1],
+                     return_covariances=return_covariances, return_particles=return_particles)
+        return _session.points_per_session(_lib.load(), mode, self.cluster, cap, int(0.9 * max(free, 0)), **shape)
 
     # ------------------------------------------------------------------ multi-GPU: one final gather
     @staticmethod

@@ -324,3 +324,28 @@ def test_kernel_timing_reports_every_kernel_of_the_streaming_flow(cuda):
     assert all(ms[k] > 0 for k in range(8))
     _lib.check(lib.gb_kernel_timing_read(ms, n, 8))
     assert sum(n) == 0  # switching the timer off clears it
+
+
+@pytest.mark.parametrize("rng", ["philox", "numpy"])
+def test_blocks_of_points_give_the_same_track(cuda, rng):
+    """A track that does not fit the device runs as consecutive blocks of points (Tracker.max_points forces it here):
+    same results bit for bit, with the device draws (keyed by the global point index) and with the reference's draw
+    sequence (consumed block after block in the reference's order)."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=31, n_points=11, n_particles=500, n_frames=6, imgsz=(400, 300), margin_px=100)
+    observers, models = synthetic.build(scene, gb)
+    runs = []
+    for max_points in (None, 4, 1):
+        np.random.seed(77)
+        tracker = gb.Tracker(observers, seed=5, rng=rng, max_points=max_points)
+        tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=(max_points != 1))
+        assert all(e is None for e in tracks.errors)
+        assert tracker.last_run.get("sessions", 1) == {None: 1, 4: 3, 1: 11}[max_points]
+        runs.append((tracks, tracker))
+    for tracks, tracker in runs[1:]:
+        np.testing.assert_array_equal(tracks.means, runs[0][0].means)
+        np.testing.assert_array_equal(tracks.sigmas, runs[0][0].sigmas)
+        np.testing.assert_array_equal(tracker.particles, runs[0][1].particles)  # state of the last point, as the reference leaves it
+    np.testing.assert_array_equal(runs[1][0].particles, runs[0][0].particles)
+    assert len(runs[1][1].last_run["window_width"]) == len(runs[0][1].last_run["window_width"])

@@ -30,6 +30,12 @@ WORKER = textwrap.dedent('''
     np.testing.assert_array_equal(sharded.means, alone.means)          # Philox counters use global point indices
     np.testing.assert_array_equal(sharded.covariances, alone.covariances)
     assert h2d_sharded < 0.7 * alone.tracker.last_run["h2d_bytes"]     # half of the frames came over NVLink
+    # blocks of points inside every rank (a track too large for the device memory): same answer again
+    blocked = gb.Tracker(observers, seed=11, max_points=2)
+    tracks = blocked.track(models, tile_size=scene.tile_size, return_covariances=True)
+    assert blocked.last_run["sessions"] == 2
+    np.testing.assert_array_equal(tracks.means, alone.means)
+    np.testing.assert_array_equal(tracks.covariances, alone.covariances)
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 ''')

@@ -274,3 +274,22 @@ def test_tracks_from_multiple_and_average_match_the_reference():
         gb.Tracks.from_multiple([a, gb.Tracks(datetimes=dts[::-1], time_unit=day, means=g["m2"], sigmas=g["s2"])])
     with pytest.raises(ValueError, match="Time units are not equal"):
         gb.Tracks.from_multiple([a, gb.Tracks(datetimes=dts, time_unit=2 * day, means=g["m2"], sigmas=g["s2"])])
+
+
+def test_points_are_blocked_by_device_memory():
+    """BASELINE.json config 5 (100 000 points x 10 000 particles x 365 frames) needs ~300 GB of work buffers: more than one
+    B200 has, so a one- or two-GPU run advances consecutive blocks of points; 12 500 points (one of eight ranks) fit."""
+    from glimpse_b200 import _lib, build
+    from glimpse_b200.session import points_per_session, session_bytes
+
+    build.build()
+    lib = _lib.load()
+    shape = dict(N=10000, T=365, O=1, tw=15, th=15, return_covariances=False, return_particles=False)
+    whole = session_bytes(lib, _lib.GB_MODE_STREAM, 0, 100000, **shape)
+    assert 250e9 < whole < 350e9
+    assert session_bytes(lib, _lib.GB_MODE_STREAM, 0, 12500, **shape) < 45e9
+    block = points_per_session(lib, _lib.GB_MODE_STREAM, 0, 100000, int(160e9), **shape)
+    assert 45000 < block < 65000
+    assert session_bytes(lib, _lib.GB_MODE_STREAM, 0, block, **shape) <= 160e9 < session_bytes(lib, _lib.GB_MODE_STREAM, 0, block + 1, **shape)
+    assert points_per_session(lib, _lib.GB_MODE_STREAM, 0, 1000, int(160e9), **shape) == 1000
+    assert points_per_session(lib, _lib.GB_MODE_STREAM, 0, 1000, 1, **shape) == 1  # never less than one point
