@@ -18,7 +18,8 @@ GB_ST_MESSAGES = {
     3: (ValueError, "Some of the sampling coordinates are out of bounds"),
     4: (ValueError, "Some sampling points are outside box"),
     5: (IndexError, "Box extends beyond grid bounds"),
-    6: (MemoryError, "Search window exceeds the on-chip tile capacity of the launch plan (raise Tracker.cluster)"),
+    6: (MemoryError, "Search window larger than the launch plan's surface capacity (template + 191 px per axis in mode='stream'; "
+                     "the particle cloud has dispersed)"),
 }
 GB_OBS_OUT_OF_FRAME = 2
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
