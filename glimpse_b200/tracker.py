@@ -328,20 +328,27 @@ class Tracker:
         P = len(models)
         cap = P if self.max_points is None else max(1, min(P, int(self.max_points)))
         device = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
-        free, _total = torch.cuda.mem_get_info(device)
-        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        frames = 0
         if not self._frame_cache:
             for o, obs in enumerate(self.observers):
                 for i in {int(v) for v in image_index[:, o] if v >= 0}:
                     array = getattr(obs.images[i], "array", None)
                     try:
-                        free -= int(array.nbytes) if array is not None else 3 * int(np.prod(obs.images[i].size))
+                        frames += int(array.nbytes) if array is not None else 3 * int(np.prod(obs.images[i].size))
                     except (AttributeError, TypeError):
                         pass  # size unknown before the frame is read: the 10 % margin has to cover it
         mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[self.mode]
         shape = dict(N=int(models[0].n), T=image_index.shape[0], O=image_index.shape[1], tw=tile_size[0], th=tile_size[1],
                      return_covariances=return_covariances, return_particles=return_particles)
-        return _session.points_per_session(_lib.load(), mode, self.cluster, cap, int(0.9 * max(free, 0)), **shape)
+        lib = _lib.load()
+        # the common case costs no driver call: a track needing less than a quarter of the device is not measured against
+        # the free memory (cudaMemGetInfo takes from a fraction of a millisecond to several)
+        total = torch.cuda.get_device_properties(device).total_memory
+        if _session.session_bytes(lib, mode, self.cluster, cap, **shape) + frames <= total // 4:
+            return cap
+        free, _total = torch.cuda.mem_get_info(device)
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        return _session.points_per_session(lib, mode, self.cluster, cap, int(0.9 * max(free - frames, 0)), **shape)
 
     # ------------------------------------------------------------------ multi-GPU: one final gather
     @staticmethod
