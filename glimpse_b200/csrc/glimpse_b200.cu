@@ -1660,6 +1660,37 @@ static int launch_template(const StepParams& prm, cudaStream_t stream) {
   return GB_OK;
 }
 
+// Motion.initialize_particles as a stand-alone call (motion.py:149-163, 260-283, 378-390, 485-505): one thread per particle,
+// normals[p][i][6] in the reference's draw order (see init_particle).  Grid: (blocks over N, P).
+__global__ void k_init_particles(const gb_motion* __restrict__ motion, const gb_surface* __restrict__ surfaces, int64_t N,
+                                 const double* __restrict__ normals, double* __restrict__ state, int32_t* status) {
+  const int64_t p = blockIdx.y;
+  const gb_motion m = motion[p];
+  uint32_t flags = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    double zn[6], s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) zn[c] = normals[(p * N + i) * 6 + c];
+    init_particle(m, surfaces, zn, s, flags);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) state[(p * 6 + c) * N + i] = s[c];
+  }
+  if (flags && status) atomicCAS(&status[p], 0, GB_ST_DEM_BOUNDS);
+}
+
+// Motion.compute_log_likelihoods as a stand-alone call (motion.py:181-204) on SoA state [P][6][N] -> ll[P][N].
+__global__ void k_motion_log_likelihoods(const gb_motion* __restrict__ motion, const gb_surface* __restrict__ surfaces, int64_t N,
+                                         const double* __restrict__ state, double* __restrict__ ll, int32_t* status) {
+  const int64_t p = blockIdx.y;
+  const gb_motion m = motion[p];
+  uint32_t flags = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const double* s = state + p * 6 * N;
+    ll[p * N + i] = surface_log_likelihood(m, surfaces, s[i], s[N + i], s[2 * N + i], flags);
+  }
+  if (flags && status) atomicCAS(&status[p], 0, GB_ST_DEM_BOUNDS);
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -1961,6 +1992,24 @@ int gb_evolve(const gb_motion* motion, const gb_surface* surfaces, int64_t P, in
   dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
   k_evolve<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, surfaces, P, N, tau, tau2, normals, N * 3, state, nullptr, nullptr, status,
                                                    nullptr, 0, GB_RNG_SUPPLIED, 0, 0, 0);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_init_particles(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* normals, double* state,
+                      int32_t* status, void* stream) {
+  if (!motion || !surfaces || !normals || !state || P <= 0 || N <= 0 || P > 65535) return fail(GB_E_INVALID, "bad arguments%s");
+  dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
+  k_init_particles<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, surfaces, N, normals, state, status);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* state, double* ll,
+                              int32_t* status, void* stream) {
+  if (!motion || !surfaces || !state || !ll || P <= 0 || N <= 0 || P > 65535) return fail(GB_E_INVALID, "bad arguments%s");
+  dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
+  k_motion_log_likelihoods<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, surfaces, N, state, ll, status);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

@@ -320,6 +320,16 @@ int gb_track_init(const gb_track_desc* desc_host, int32_t t, void* stream);
  * tangent); status[P] (may be NULL) receives GB_ST_DEM_BOUNDS where a tangent model sampled its DEM out of bounds. */
 int gb_evolve(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, double tau, double tau2,
               const double* normals, double* state, int32_t* status, void* stream);
+/* Motion.initialize_particles as a stand-alone call (motion.py:149-163, 260-283, 378-390, 485-505): state [P][6][N] from
+ * normals[P][N][6] in the reference's draw order — randn(n,2) -> columns 0-1 (xy), randn(n) -> column 2 (z), randn(n,3) -> columns
+ * 3-5 (velocity; tangent kinds: randn(n,2) in columns 3-4, column 5 unused).  status[P] (may be NULL, zero on entry) receives
+ * GB_ST_DEM_BOUNDS where the DEM or its sigma was sampled out of bounds (raster.py:961-973). */
+int gb_init_particles(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* normals, double* state,
+                      int32_t* status, void* stream);
+/* Motion.compute_log_likelihoods as a stand-alone call (motion.py:181-204): ll[P][N] = (dem(xy) - z)^2 / (2 sigma(xy)^2), 0 where
+ * sigma is 0, for SoA state [P][6][N].  (The tangent kinds return None in the reference, motion.py:77-89: the caller does not ask.) */
+int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* state, double* ll,
+                              int32_t* status, void* stream);
 /* Tracker.particle_mean / compute_particle_sigma / particle_covariance (tracker.py:72-104) on
  * row-major particles[n][6], weights[n]: mean[6], sigma[6] (or NULL), cov[36] (or NULL). */
 int gb_moments(const double* particles, const double* weights, int64_t n, double* mean, double* sigma, double* cov,

@@ -349,3 +349,37 @@ def test_blocks_of_points_give_the_same_track(cuda, rng):
         np.testing.assert_array_equal(tracker.particles, runs[0][1].particles)  # state of the last point, as the reference leaves it
     np.testing.assert_array_equal(runs[1][0].particles, runs[0][0].particles)
     assert len(runs[1][1].last_run["window_width"]) == len(runs[0][1].last_run["window_width"])
+
+
+@pytest.mark.parametrize("kind", ["cartesian", "cylindrical", "tangent_cartesian", "tangent_cylindrical"])
+def test_stand_alone_initialize_and_log_likelihoods_match_the_oracle(cuda, kind):
+    """The rest of the Motion protocol (motion.py:13-89) as stand-alone calls: ``initialize_particles``
+    (gb_init_particles) and ``compute_log_likelihoods`` (gb_motion_log_likelihoods) against the oracle's restatements of
+    motion.py:149-163, 260-283, 378-390, 485-505 and 181-204 on the same draws, on a gridded DEM with a gridded sigma."""
+    import glimpse_b200 as gb
+    import scenes
+
+    scene = synthetic.nadir_scene(seed=33, n_points=1, n_particles=700, n_frames=2, imgsz=(320, 240), margin_px=100, kind=kind)
+    scenes.add_gridded_dem(scene)
+    _, models = synthetic.build(scene, gb)
+    _, specs, _, _ = helpers.oracle_inputs(scene)
+    np.random.seed(5)
+    mine = models[0].initialize_particles()
+    np.random.seed(5)
+    ref = orc.init_particles(specs[0])
+    assert mine.shape == ref.shape == (700, 6)
+    np.testing.assert_allclose(mine, ref, rtol=1e-13, atol=1e-13)
+    ll, ll_ref = models[0].compute_log_likelihoods(ref), orc.surface_log_likelihood(specs[0], ref)
+    if kind.startswith("tangent"):
+        assert ll is None and ll_ref is None
+    else:
+        assert ll.shape == (700,) and (ll_ref > 0).any()
+        np.testing.assert_allclose(ll, ll_ref, rtol=1e-12, atol=1e-300)
+    far = ref.copy()
+    far[:, 0] += 1e4  # off the DEM: Raster.sample raises (raster.py:961-973)
+    if not kind.startswith("tangent"):
+        with pytest.raises(ValueError, match="out of bounds"):
+            models[0].compute_log_likelihoods(far)
+    models[0].xy = (1e4, 0.0)
+    with pytest.raises(ValueError, match="out of bounds"):
+        models[0].initialize_particles()
