@@ -22,6 +22,8 @@ GB_ST_MESSAGES = {
                      "the particle cloud has dispersed)"),
 }
 GB_OBS_OUT_OF_FRAME = 2
+GB_ST_WINDOW_TOO_LARGE = 6
+GB_WINDOW_MARGIN, GB_WINDOW_MARGIN_MAX = 191, 1000  # default / retry capacity of the search windows beyond the template, px
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
 GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2}
 GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
@@ -115,6 +117,7 @@ SIGNATURES = {
     "gb_state_from_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_state_to_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_step_plan": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(gb_plan)]),
+    "gb_step_plan_ex": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(gb_plan)]),
     "gb_track": (C.c_int, [C.POINTER(gb_track_desc), C.c_void_p, C.POINTER(C.c_int64)]),
     "gb_track_step": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.POINTER(gb_stage_io), C.c_void_p]),
     "gb_track_init": (C.c_int, [C.POINTER(gb_track_desc), C.c_int32, C.c_void_p]),

@@ -1094,10 +1094,10 @@ static int ensure_tables() {
   if (dev < 0 || dev >= 16) return fail(GB_E_INVALID, "device index out of range%s");
   cudaError_t err = cudaSuccess;
   std::call_once(g_tables_once[dev], [&]() {
-    double cp[256], inv[256];
+    static double cp[GB_MAX_SURFACE], inv[GB_MAX_SURFACE];
     cp[0] = 2.0;
     inv[0] = 1.0;
-    for (int i = 1; i < 256; ++i) {
+    for (int i = 1; i < GB_MAX_SURFACE; ++i) {
       inv[i] = 1.0 / (4.0 - cp[i - 1]);
       cp[i] = inv[i];
     }
@@ -1795,6 +1795,12 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
 
 int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
                  int32_t prefer_cluster, int32_t mode, gb_plan* plan) {
+  return gb_step_plan_ex(n_particles, tile_w, tile_h, npoints, n_observers, prefer_cluster, mode, 191, plan);
+}
+
+int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
+                    int32_t prefer_cluster, int32_t mode, int32_t window_margin, gb_plan* plan) {
+  if (window_margin < 4 || window_margin > GB_MAX_SURFACE - 1) return fail(GB_E_INVALID, "window_margin must be between 4 and 1023%s");
   if (!plan || n_particles <= 0 || tile_w < 1 || tile_h < 1) return fail(GB_E_INVALID, "bad plan arguments%s");
   if ((int64_t)tile_w * tile_h > GB_MAX_TEMPLATE) return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
   if (prefer_cluster != 0 && prefer_cluster != 1 && prefer_cluster != 2 && prefer_cluster != 4 && prefer_cluster != 8)
@@ -1817,8 +1823,8 @@ int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t np
     plan->stream_nblk = (int32_t)((n_particles + GB_S4P_CAP - 1) / GB_S4P_CAP);
     plan->stream_block = (int32_t)(((n_particles + plan->stream_nblk - 1) / plan->stream_nblk + 1) / 2 * 2);
     plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
-    // surface regions sized for search windows up to 191 px larger than the template
-    plan->surf_bytes = (tile_bytes_needed(tile_w + 191, tile_h + 191, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
+    // surface regions sized for search windows up to `window_margin` (191 by default) px larger than the template
+    plan->surf_bytes = (tile_bytes_needed(tile_w + window_margin, tile_h + window_margin, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
     // Points are independent: they are cut into `slots` batches that advance on their own side streams, so the
     // low-occupancy tails of one batch's kernels (a few very large search windows) overlap the other batches' work.
     // (Batches small enough to keep the intermediates L2-resident were measured slower: launch-bound.)

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   }
   char* region = prm.s_surf + po * prm.surf_bytes;
   const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
-  if (need > prm.surf_bytes || w.Mu > 256 || w.Mv > 256) {
+  if (need > prm.surf_bytes || w.Mu > GB_MAX_SURFACE || w.Mv > GB_MAX_SURFACE) {
     if (tid == 0) atomicOr(&prm.s_pflags[p], (int)GB_F_WINDOW);
     return;
   }

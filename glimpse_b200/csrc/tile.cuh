@@ -20,8 +20,9 @@ namespace gb {
 
 // Thomas-algorithm factors of the not-a-knot slope system (rows [1 2], [1 4 1]..., [2 1]); they
 // depend only on the row index, not on the system size.  Filled once per device by the host.
-__constant__ double c_spline_cp[256];
-__constant__ double c_spline_inv[256];
+#define GB_MAX_SURFACE 1024 /* cells per axis of an SSE surface (the factors below converge after ~30 rows) */
+__constant__ double c_spline_cp[GB_MAX_SURFACE];
+__constant__ double c_spline_inv[GB_MAX_SURFACE];
 
 struct TileWork {
   float4* herm;      // [Mv][Mp] (F, dF/du, dF/dv, d2F/dudv); Mp odd keeps row solves off the same banks

@@ -106,11 +106,11 @@ def adopt_model(model):
 
 
 def session_bytes(lib, mode: int, cluster: int, P: int, N: int, T: int, O: int, tw: int, th: int, return_covariances: bool,
-                  return_particles: bool) -> int:
+                  return_particles: bool, window_margin: int = _lib.GB_WINDOW_MARGIN) -> int:
     """Device memory one :class:`Session` of ``P`` points allocates (the frames excluded): two particle-state buffers,
     the weights, the launch plan's scratch, templates and result blocks."""
     plan = _lib.gb_plan()
-    _lib.check(lib.gb_step_plan(N, tw, th, P, O, int(cluster), mode, C.byref(plan)))
+    _lib.check(lib.gb_step_plan_ex(N, tw, th, P, O, int(cluster), mode, int(window_margin), C.byref(plan)))
     per_point = 2 * 48 * N + 8 * N                      # state_a, state_b, weight_state
     per_point += 3 * O * tw * th * 8 + O * 40           # templates
     per_point += T * ((36 if return_covariances else 6) + 6) * 8 + T * O * 9 + 16  # moments, flags, window sizes, status
@@ -136,7 +136,7 @@ def points_per_session(lib, mode: int, cluster: int, P: int, budget: int, **shap
 
 class Session:
     def __init__(self, tracker, models, image_index, taus, tile_size, observer_mask, return_covariances=False,
-                 return_particles=False, point_offset=0, draws=None, dist=None):
+                 return_particles=False, point_offset=0, draws=None, dist=None, window_margin=None, seed=None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
@@ -161,7 +161,10 @@ class Session:
             self.stream = torch.cuda.current_stream().cuda_stream
             self.plan = _lib.gb_plan()
             mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[getattr(tracker, "mode", "stream")]
-            _lib.check(self.lib.gb_step_plan(N, self.tw, self.th, P, O, int(tracker.cluster), mode, C.byref(self.plan)))
+            if window_margin is None:
+                window_margin = getattr(tracker, "window_margin", _lib.GB_WINDOW_MARGIN)
+            _lib.check(self.lib.gb_step_plan_ex(N, self.tw, self.th, P, O, int(tracker.cluster), mode, int(window_margin),
+                                                C.byref(self.plan)))
             self.h2d = 0
             # the first two frames' uploads start right away (the first kernels wait for them); the other big copies are
             # queued after the small tables, which they would otherwise hold up on the copy engine for tens of ms
@@ -250,7 +253,9 @@ class Session:
                 self.h2d += (init.size + step_full.size + unif_full.size) * 8
             elif tracker.rng == "philox":
                 d.rng_mode = _lib.GB_RNG_PHILOX
-                seed = tracker.seed if tracker.seed is not None else int(np.random.randint(0, 2 ** 62))
+                if seed is None:
+                    seed = tracker.seed if tracker.seed is not None else int(np.random.randint(0, 2 ** 62))
+                self.seed_used = int(seed)
                 d.seed = int(seed) % (1 << 64)
             else:
                 raise ValueError("rng must be 'philox' or 'numpy'")

@@ -16,6 +16,10 @@ Differences a user can see (all documented in DESIGN.md):
 * A track whose work buffers do not fit the device memory that is free runs as consecutive blocks of points (points are
   independent and the device draws are keyed by the global point index, so the results do not depend on the blocks);
   ``max_points`` caps the block size by hand.
+* Search windows: every point owns a surface region for windows up to ``window_margin`` (191) px larger than the template.  A
+  point whose particle cloud outgrows it (loss of lock after hundreds of frames) is run again on its own with a capacity of 1000 px —
+  the device draws are counter-based, so the second run retraces the first one exactly and carries on where it stopped
+  (``rng="numpy"`` cannot replay its draws: such a point keeps its ``MemoryError`` in ``Tracks.errors``).
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
 * ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass={'size': ...}`` of any size up to 31 x 31 (the
@@ -97,6 +101,7 @@ class Tracker:
         device=None,
         distributed: bool = True,
         max_points: Optional[int] = None,
+        window_margin: int = _lib.GB_WINDOW_MARGIN,
     ) -> None:
         self.observers = list(observers)
         self.viewshed = viewshed
@@ -110,6 +115,7 @@ class Tracker:
         self.device = device
         self.distributed = distributed
         self.max_points = max_points
+        self.window_margin = window_margin
         self.particles = None
         self.weights = None
         self.templates = None
@@ -286,7 +292,21 @@ class Tracker:
             session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
                               return_particles, point_offset=point_offset, dist=gather[0] if gather else None)
             session.run()
-            out = session.fetch(gather)
+            rerun = (getattr(session, "seed_used", None), models, image_index, taus, tile_size, observer_mask, return_covariances,
+                     return_particles, point_offset)
+            if gather is None:
+                out = self._rerun_large_windows(session.fetch(None), *rerun)
+            else:
+                # the ranks agree on whether any point needs its second run (then the blocks are patched on the hosts and
+                # gathered from there); normally none does and the blocks are gathered on the devices
+                dist, per_rank, world = gather
+                failed = (session.buf["status"] == _lib.GB_ST_WINDOW_TOO_LARGE).sum()
+                dist.all_reduce(failed)
+                if int(failed) == 0:
+                    out = session.fetch(gather)
+                else:
+                    out = self._rerun_large_windows(session.fetch(None), *rerun)
+                    out = self._gather(dist, out, per_rank * world, world)
             self.last_run = session.stats
             self.particles, self.weights, self.templates = session.final_state()
             return out
@@ -298,7 +318,10 @@ class Tracker:
                               return_covariances, return_particles, point_offset=point_offset + lo,
                               dist=gather[0] if (gather and lo == 0) else None)
             session.run()
-            parts.append(session.fetch(None))
+            parts.append(self._rerun_large_windows(session.fetch(None), getattr(session, "seed_used", None), models[lo:lo + block],
+                                                   image_index, taus, tile_size,
+                                                   observer_mask[lo:lo + block], return_covariances, return_particles,
+                                                   point_offset + lo))
             st = session.stats
             if stats is None:
                 stats = dict(st, sessions=1)
@@ -316,6 +339,28 @@ class Tracker:
         if gather:
             dist, per_rank, world = gather
             out = self._gather(dist, out, per_rank * world, world)
+        return out
+
+    def _rerun_large_windows(self, out, seed, models, image_index, taus, tile_size, observer_mask, return_covariances,
+                             return_particles, point_offset) -> dict:
+        """Points that ended with GB_ST_WINDOW_TOO_LARGE (their particle cloud outgrew the plan's surface regions) are tracked
+        again, one by one, with the largest window capacity; the counter-based device draws make the second run identical to the
+        first up to the time it stopped (``seed`` = the Philox key of the first run).  The rows of ``out`` are replaced in place."""
+        from .session import Session
+
+        failed = np.nonzero(out["status"] == _lib.GB_ST_WINDOW_TOO_LARGE)[0]
+        if len(failed) == 0 or self.rng != "philox" or seed is None or self.window_margin >= _lib.GB_WINDOW_MARGIN_MAX or len(failed) > 1024:
+            return out
+        for p in failed:
+            p = int(p)
+            session = Session(self, models[p:p + 1], image_index, taus, tile_size, observer_mask[p:p + 1], return_covariances,
+                              return_particles, point_offset=point_offset + p, window_margin=_lib.GB_WINDOW_MARGIN_MAX, seed=seed)
+            session.run()
+            one = session.fetch(None)
+            for key, rows in out.items():
+                rows[p] = one[key][0]
+            del session
+        self.__dict__.setdefault("_rerun_points", []).extend(int(point_offset + p) for p in failed)
         return out
 
     def _points_per_session(self, models, image_index, tile_size, return_covariances, return_particles) -> int:

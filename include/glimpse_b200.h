@@ -199,6 +199,11 @@ typedef struct gb_plan {
  * `prefer_cluster` = 0 lets the library choose the cluster size of GB_MODE_FUSED; otherwise forces 1/2/4/8. */
 int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
                  int32_t prefer_cluster, int32_t mode, gb_plan* plan_host);
+/* The same with the capacity of the search windows chosen by the caller: in GB_MODE_STREAM every (point, observer) owns a surface
+ * region sized for windows up to `window_margin` px larger than the template per axis (gb_step_plan: 191; 4..1023).  A point whose
+ * particle cloud outgrows it ends with GB_ST_WINDOW_TOO_LARGE; the Tracker then re-runs that point with the largest margin. */
+int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
+                    int32_t prefer_cluster, int32_t mode, int32_t window_margin, gb_plan* plan_host);
 
 /* Everything one Tracker.track call needs (track/tracker.py:225-417).  Shapes use P points,
  * N particles, T times, O observers, S = T - 1 update steps, w x h template. */

@@ -383,3 +383,60 @@ def test_stand_alone_initialize_and_log_likelihoods_match_the_oracle(cuda, kind)
     models[0].xy = (1e4, 0.0)
     with pytest.raises(ValueError, match="out of bounds"):
         models[0].initialize_particles()
+
+
+def _dispersing_scene(n_points, n_particles):
+    """A weakly informative observer (sigma = 5) and a wide velocity prior (2 m/d = 10 px/d): the particle cloud, and with it
+    the search window, grows by ~60 px per frame — far beyond the default capacity of template + 191 px."""
+    scene = synthetic.nadir_scene(seed=41, n_points=n_points, n_particles=n_particles, n_frames=9, imgsz=(1400, 1000), margin_px=560)
+    scene.observers[0].sigma = 5.0
+    scene.motion.update(vxyz_sigma=(2.0, 2.0, 0.0))
+    return scene
+
+
+def test_search_windows_of_several_hundred_pixels_match_the_oracle(cuda):
+    """Windows up to ~500 px (SSE surfaces beyond 256 cells per axis, worked on in global memory) with the reference's draws
+    against the oracle, which calls OpenCV / FITPACK on the same windows."""
+    import glimpse_b200 as gb
+
+    scene = _dispersing_scene(1, 400)
+    observers, models = synthetic.build(scene, gb)
+    tracker = gb.Tracker(observers, rng="numpy", window_margin=1000)
+    np.random.seed(12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True)
+    assert tracks.errors[0] is None, tracks.errors
+    assert tracker.last_run["window_width"].max() > 300
+    obs, specs, taus, index = helpers.oracle_inputs(scene)
+    np.random.seed(12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = orc.track(obs, specs, taus, index, tile_size=scene.tile_size, return_particles=True, raise_errors=True)
+    same = np.isclose(tracks.particles, ref.particles, rtol=0, atol=1e-9).all(axis=3)
+    assert 1.0 - same.mean() < 0.02
+    assert np.nanmax(np.abs(tracks.means - ref.means) / np.maximum(ref.sigmas, 1e-12)) < 0.05
+
+
+def test_points_that_outgrow_the_window_capacity_are_run_again(cuda):
+    """Default capacity (template + 191 px): the dispersing points stop with GB_ST_WINDOW_TOO_LARGE and are tracked again with
+    the largest capacity; the counter-based draws make the result identical to a run planned with that capacity from the
+    start.  With the reference's draw sequence (not replayable) the error is reported."""
+    import glimpse_b200 as gb
+
+    scene = _dispersing_scene(3, 400)
+    observers, models = synthetic.build(scene, gb)
+    wide = gb.Tracker(observers, seed=3, window_margin=1000).track(models, tile_size=scene.tile_size)
+    assert all(e is None for e in wide.errors)
+    tracker = gb.Tracker(observers, seed=3)
+    tracks = tracker.track(models, tile_size=scene.tile_size)
+    assert all(e is None for e in tracks.errors), tracks.errors
+    assert tracker._rerun_points == [0, 1, 2]
+    np.testing.assert_array_equal(tracks.means, wide.means)
+    np.testing.assert_array_equal(tracks.sigmas, wide.sigmas)
+    blocked = gb.Tracker(observers, seed=3, max_points=2).track(models, tile_size=scene.tile_size)
+    np.testing.assert_array_equal(blocked.means, wide.means)
+    np.random.seed(1)
+    kept = gb.Tracker(observers, rng="numpy").track(models, tile_size=scene.tile_size)
+    assert all(isinstance(e, MemoryError) for e in kept.errors)
+    assert np.isfinite(kept.means[:, 1]).all() and np.isnan(kept.means[:, -1]).all()
