@@ -400,7 +400,6 @@ __global__ void __launch_bounds__(GB_THREADS) k_init(const __grid_constant__ Ste
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepParams prm) {
   __shared__ double s_red[8][8];
-  __shared__ double s_mean[4];
   __shared__ int s_box[4];
   __shared__ int s_ok;
   __shared__ double s_stats[2];
@@ -1587,7 +1586,6 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
       cudaStream_t ss = pool->side[b % slots];
       const int64_t p0 = b * batch, pb = (p0 + batch <= d.P) ? batch : d.P - p0;
       stream_bind(d, prm, t, p0, pb);
-      const unsigned nb = (unsigned)(pb * prm.s_nblk);
       KernelTimer& kt = g_ktimer;
       if (need_activity) {
         kt.begin(GB_K_ACTIVITY, ss);

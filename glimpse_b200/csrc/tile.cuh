@@ -42,7 +42,7 @@ struct TileWork {
 __host__ __device__ inline int64_t align16(int64_t b) { return (b + 15) / 16 * 16; }
 
 __host__ __device__ inline int64_t tile_bytes_needed(int Su, int Sv, int tw, int th, int nbins, int nvals) {
-  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mp = Mu | 1, Sp = (Su + 3) / 4 * 4, Tp = (tw + 3) / 4 * 4;
+  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mp = Mu | 1, Sp = (Su + 3) / 4 * 4;
   const int64_t herm = Mv * Mp * 16, packed = (int64_t)(Sv + 4) * (Su + 4) * 4;
   int64_t b = align16(herm > packed ? herm : packed);
   b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
@@ -240,8 +240,8 @@ __device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, i
 __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
                                     const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
                                     float* dump_search, int64_t dump_cap, long long* clk) {
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-  const int Su = w.Su, Sv = w.Sv, Sp = w.Sp, Tp = w.Tp;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int Su = w.Su, Sv = w.Sv, Sp = w.Sp;
   const int area = Su * Sv;
   // 1. raw window, template and its CDF; clear the histogram.  Every global load a thread needs first is issued
   //    before anything waits on one (the template words, then four window pixels per trip): the phase costs about
@@ -553,7 +553,7 @@ struct TilePlanes {
 };
 
 __host__ __device__ inline int64_t tile_bytes_needed_planar(int Su, int Sv, int tw, int th, int nbins, int nvals) {
-  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mq = Mu | 1, Sp = (Su + 3) / 4 * 4, Tp = (tw + 3) / 4 * 4;
+  const int64_t Mu = Su - tw + 1, Mv = Sv - th + 1, Mq = Mu | 1, Sp = (Su + 3) / 4 * 4;
   const int64_t r1 = align16((int64_t)Sv * Sp * 4);  // >= Mv * Mq * 4 (F_u) and >= Sv * Su * 2 (raw)
   const int64_t packed = (int64_t)(Sv + 4) * (Su + 4) * 4, planes = 2 * align16(Mv * Mq * 4);
   int64_t b = r1 + align16(packed > planes ? packed : planes);
@@ -658,7 +658,6 @@ __device__ inline void tile_finish_planar(TileWork& w, const TilePlanes& pl, flo
 //             interleaved surface as they appear (F_u is reloaded for the cross derivative)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int64_t tile_bytes_needed_staged(int Su, int Sv, int tw, int th, int nbins, int nvals) {
-  const int64_t Tp = (tw + 3) / 4 * 4;
   int64_t b = align16((int64_t)Su * Sv * 2) + align16((int64_t)(Sv + 4) * (Su + 4) * 4);
   b += align16((int64_t)nbins * 8) + align16((int64_t)nvals * 8) * 2;
   b += align16((int64_t)th * tw * 8);
