@@ -293,3 +293,67 @@ def test_points_are_blocked_by_device_memory():
     assert session_bytes(lib, _lib.GB_MODE_STREAM, 0, block, **shape) <= 160e9 < session_bytes(lib, _lib.GB_MODE_STREAM, 0, block + 1, **shape)
     assert points_per_session(lib, _lib.GB_MODE_STREAM, 0, 1000, int(160e9), **shape) == 1000
     assert points_per_session(lib, _lib.GB_MODE_STREAM, 0, 1000, 1, **shape) == 1  # never less than one point
+
+
+def test_blocks_and_second_runs_are_assembled_on_the_host(monkeypatch):
+    """Host logic of Tracker._track_local with the device session stubbed (it has no CPU path): consecutive blocks of
+    points, the second run of points that outgrew the window capacity (same Philox key, own global index, largest
+    capacity), and what is reported in Tracker.last_run."""
+    import glimpse_b200 as gb
+    from glimpse_b200 import _lib, session as session_mod
+
+    created = []
+
+    class FakeSession:
+        def __init__(self, tracker, models, image_index, taus, tile_size, observer_mask, return_covariances=False,
+                     return_particles=False, point_offset=0, draws=None, dist=None, window_margin=None, seed=None):
+            self.models, self.offset, self.margin = models, point_offset, window_margin
+            self.T, self.O = image_index.shape
+            self.seed_used = 4242 if seed is None else seed
+            assert len(observer_mask) == len(models)
+            created.append(self)
+
+        def run(self):
+            pass
+
+        def fetch(self, gather):
+            assert gather is None
+            P = len(self.models)
+            out = session_mod.empty_result(P, self.T, self.O, False, False)
+            for i, m in enumerate(self.models):
+                g = self.offset + i
+                out["means"][i] = g
+                # global points 1 and 4 outgrow the default window capacity; the second run (largest capacity) succeeds
+                if g in (1, 4) and self.margin is None:
+                    out["status"][i], out["status_time"][i] = _lib.GB_ST_WINDOW_TOO_LARGE, 2
+                    out["means"][i] = np.nan
+            self.stats = {"plan": {}, "kernel_launches": 10, "h2d_bytes": 100, "d2h_bytes": 7,
+                          "window_width": np.arange(P), "window_height": np.arange(P)}
+            return out
+
+        def final_state(self):
+            return "particles", "weights", self.offset
+
+    monkeypatch.setattr(session_mod, "Session", FakeSession)
+    obs = _observers(4)
+    day = datetime.timedelta(days=1)
+    models = [gb.CartesianMotion(xy=(float(i), 0), time_unit=day, dem=0.0, n=8) for i in range(5)]
+    tracker = gb.Tracker([obs])
+    tracker._points_per_session = lambda *a, **k: 2
+    tracks = tracker.track(models)
+    blocks = [(s.offset, len(s.models), s.margin) for s in created]
+    # blocks of 2, 2, 1 points; after block 0 point 1 is run again, after block 2 point 4
+    assert blocks == [(0, 2, None), (1, 1, _lib.GB_WINDOW_MARGIN_MAX), (2, 2, None), (4, 1, None), (4, 1, _lib.GB_WINDOW_MARGIN_MAX)]
+    assert all(s.seed_used == 4242 for s in created)
+    assert all(e is None for e in tracks.errors)
+    np.testing.assert_array_equal(tracks.means[:, 0, 0], np.arange(5.0))
+    assert tracker.last_run["sessions"] == 3 and tracker.last_run["kernel_launches"] == 30
+    assert len(tracker.last_run["window_width"]) == 5 and tracker._rerun_points == [1, 4]
+    assert tracker.templates == 4  # the state the last block left, as the reference keeps the last track's
+    # the reference's draw sequence cannot be replayed: the error stays
+    created.clear()
+    tracker = gb.Tracker([obs], rng="numpy")
+    tracker._points_per_session = lambda *a, **k: 5
+    tracks = tracker.track(models)
+    assert [isinstance(e, MemoryError) for e in tracks.errors] == [False, True, False, False, True]
+    assert len(created) == 1
