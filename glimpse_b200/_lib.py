@@ -138,10 +138,11 @@ def load() -> C.CDLL:
     """Load the CUDA library (built in-tree by ``__graft_entry__.build()`` / ``glimpse_b200.build``)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("GLIMPSE_B200_LIB", LIB_PATH)  # (tuning: a variant built with other -D flags, tools/variants.sh)
+        if not os.path.exists(path):
             raise LibraryMissing(
-                f"{LIB_PATH} not found: build it with `python -m glimpse_b200.build` (there is no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
+                f"{path} not found: build it with `python -m glimpse_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(path)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = restype

@@ -19,11 +19,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > built for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """``defines`` / ``out``: a tuning variant (``-DNAME=VALUE`` flags) written next to the library under another name."""
+    if not force and out == OUT and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -34,4 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="--quiet" not in sys.argv, defines=defs,
+                out=os.path.join(HERE, outs[0]) if outs else OUT))

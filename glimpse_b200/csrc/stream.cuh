@@ -408,6 +408,52 @@ __device__ __forceinline__ double block_exclusive_offset(double v, double* s_war
   return off + excl;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cheaper forms of three per-particle operations (same results within the stated bounds)
+// ---------------------------------------------------------------------------------------------
+// exp(-l) as 2^(n + f): the integer part goes into the exponent field, the fraction through MUFU.EX2.
+// Relative error < 3e-7 — below the float32 rounding of the SSE surface the exponent is sampled from (the reference's
+// own cv2.matchTemplate differs from an exact sum by 4e-6).  Underflows to 0 like exp(); NaN stays NaN.
+__device__ __forceinline__ double exp_neg_fast(double l) {
+  const double t = l * -1.4426950408889634074;
+  if (!(t > -1074.0)) return (t != t) ? t : 0.0;
+  const int n = min(__double2int_rd(t), 1023);
+  const float f = (float)(t - (double)n);
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+  const double rd = (double)r;  // [1, 2]
+  if (n >= -1020) return __hiloint2double(__double2hiint(rd) + (n << 20), __double2loint(rd));
+  return __hiloint2double(__double2hiint(rd) + ((n + 1000) << 20), __double2loint(rd)) * 9.33263618503218878990e-302;  // 2^-1000
+}
+
+// Bicubic Hermite patch at (x, y) measured from the first cell centre in cell units, NOT yet clamped: the clamp of
+// FITPACK's evaluation (argument limited to the first / last data site) is the saturation of the in-cell offset.
+__device__ __forceinline__ float hermite_eval_sat(const float4* __restrict__ herm, int Mp, int Mu, int Mv, double x, double y, bool lin_u,
+                                                  bool lin_v) {
+  const int j = max(min(__double2int_rz(x), Mu - 2), 0), i = max(min(__double2int_rz(y), Mv - 2), 0);
+  const float tx = __saturatef((float)(x - (double)j)), ty = __saturatef((float)(y - (double)i));
+  const float tx2 = tx * tx, tx3 = tx2 * tx, ty2 = ty * ty, ty3 = ty2 * ty;
+  const float a2 = lin_u ? tx : 3.0f * tx2 - 2.0f * tx3, a0 = 1.0f - a2, a3 = lin_u ? 0.0f : tx3 - tx2, a1 = lin_u ? 0.0f : a3 - tx2 + tx;
+  const float b2 = lin_v ? ty : 3.0f * ty2 - 2.0f * ty3, b0 = 1.0f - b2, b3 = lin_v ? 0.0f : ty3 - ty2, b1 = lin_v ? 0.0f : b3 - ty2 + ty;
+  const float4* row0 = herm + i * Mp + j;
+  const float4 h00 = row0[0], h01 = row0[1], h10 = row0[Mp], h11 = row0[Mp + 1];
+  const float top_f = a0 * h00.x + a2 * h01.x + a1 * h00.y + a3 * h01.y;
+  const float bot_f = a0 * h10.x + a2 * h11.x + a1 * h10.y + a3 * h11.y;
+  const float top_v = a0 * h00.z + a2 * h01.z + a1 * h00.w + a3 * h01.w;
+  const float bot_v = a0 * h10.z + a2 * h11.z + a1 * h10.w + a3 * h11.w;
+  return b0 * top_f + b2 * bot_f + b1 * top_v + b3 * bot_v;
+}
+
+// Child range end with the verification only where it can matter: floor(c N - u) + 1 is the answer unless c N - u lies
+// within 1e-6 of an integer (its rounding error is ~1e-12), where the reference's own position formula decides.
+__device__ __forceinline__ int count_positions_le_fast(double c, double u, double inv_n, int N, double dN) {
+  const double x = fma(c, dN, -u);
+  const double fl = floor(x);
+  if (x - fl > 1e-6 && x - fl < 1.0 - 1e-6) return min(max((int)fl + 1, 0), N);
+  return count_positions_le(c, u, inv_n, N);
+}
+
 // Per-(CTA, observer) constants of the spline surface: geo-reference (tracker.py:615-620) and cell
 // centres (observer.py:203-208).
 struct SurfaceRef {
@@ -534,9 +580,8 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (!((u[q] >= r.sl) & (u[q] <= r.sr) & (v[q] >= r.st) & (v[q] <= r.sb))) flags |= GB_F_SAMPLE_OUTSIDE;
-          // FITPACK evaluates at the argument clamped to the first/last data site
-          const double x = fmin(fmax(u[q], r.cu0), r.cu1) - r.cu0, y = fmin(fmax(v[q], r.cv0), r.cv1) - r.cv0;
-          const double val = (double)hermite_eval(r.herm, r.Mp, r.Mu, r.Mv, x, y, lin_u, lin_v);
+          // FITPACK evaluates at the argument clamped to the first/last data site: the saturation inside hermite_eval_sat
+          const double val = (double)hermite_eval_sat(r.herm, r.Mp, r.Mu, r.Mv, u[q] - r.cu0, v[q] - r.cv0, lin_u, lin_v);
           ll[q] = add(ll[q], mul(val, r.scale));
           if (prm.io.dump_sampled && (q == 0 || vb)) prm.io.dump_sampled[(p * O + o) * N + ia + q] = val;
         }
@@ -548,7 +593,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
         double l = ll[q];
         if (surface_ll) l = add(l, surface_log_likelihood(s_motion, prm.surfaces, ev[i], ev[(int64_t)N + i], ev[2 * (int64_t)N + i], flags));
         else l = add(l, 0.0);
-        w[q] = add(exp(-l), 1e-300);
+        w[q] = add(exp_neg_fast(l), 1e-300);
       }
     }
     double* wd = prm.s_w + (int64_t)p * N;
@@ -991,6 +1036,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
     const double prefix = pre[b], next_prefix = pre[b + 1], total = pre[prm.s_nblk], inv_total = pre[prm.s_nblk + 1],
                  u01 = pre[prm.s_nblk + 2], inv_n = pre[prm.s_nblk + 3];
     const bool stratified = prm.resample_method == GB_RESAMPLE_STRATIFIED;
+    const double dN = (double)N;
     if (bulk) mbar_wait(&s_bar[0], 0);
     else __syncthreads();
     const int k0 = PPT * tid;  // first local parent of this thread (consecutive parents: in-thread prefix)
@@ -1011,12 +1057,12 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
         const double c = (k == n_here - 1) ? next_prefix : prefix + (off + w[q]);
         // normalised cumulative weight: one reciprocal per CTA instead of a division per particle (the total maps to exactly 1)
         const double cn = c >= total ? 1.0 : c * inv_total;
-        s_end[k] = stratified ? count_positions_le_stratified(cn, stratified_draws(prm, p, t), inv_n, N) : count_positions_le(cn, u01, inv_n, N);
+        s_end[k] = stratified ? count_positions_le_stratified(cn, stratified_draws(prm, p, t), inv_n, N) : count_positions_le_fast(cn, u01, inv_n, N, dN);
       }
     }
     if (tid == 0) {
       const double c0 = prefix >= total ? 1.0 : prefix * inv_total;
-      s_j0 = b == 0 ? 0 : stratified ? count_positions_le_stratified(c0, stratified_draws(prm, p, t), inv_n, N) : count_positions_le(c0, u01, inv_n, N);
+      s_j0 = b == 0 ? 0 : stratified ? count_positions_le_stratified(c0, stratified_draws(prm, p, t), inv_n, N) : count_positions_le_fast(c0, u01, inv_n, N, dN);
     }
     __syncthreads();
     J0 = s_j0;

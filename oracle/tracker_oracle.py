@@ -598,6 +598,7 @@ class TrackResult:
     particles: Optional[np.ndarray] = None
     weights: Optional[np.ndarray] = None
     trace: Optional[List[Dict]] = None
+    templates: Optional[List[Dict]] = None  # with trace=True: every template in creation order (point-major)
 
 
 def track(
@@ -646,6 +647,7 @@ def track(
     all_w = np.full((P, T, models[0].n), np.nan) if return_particles else None
     errors: List[Optional[BaseException]] = [None] * P
     log: List[Dict] = []
+    made: List[Dict] = []
     for p, (model, mask) in enumerate(zip(models, observer_mask)):
         try:
             observed = (image_index[:, mask] >= 0).any(axis=1)
@@ -672,6 +674,8 @@ def track(
                     pixels = obs.frames[img][box[1]:box[3], box[0]:box[2]]
                     tile, cdf = prepare_tile(pixels, size=highpass_size, exact_median=exact)
                     templates[o] = {"tile": tile, "cdf": cdf, "box": box, "duv": uv0 - box.reshape(2, -1).mean(axis=0)}
+                    if trace:
+                        made.append({"p": p, "obs": int(o), "img": img, "box": box, "tile": tile, "values": cdf[0], "quantiles": cdf[1]})
                 step = {"p": p, "t": t} if trace else None
                 if t > first:
                     terms = []
@@ -729,4 +733,4 @@ def track(
             if raise_errors or P < 2:
                 raise
             errors[p] = exc
-    return TrackResult(means, sigmas, errors, skipped, all_ps, all_w, log if trace else None)
+    return TrackResult(means, sigmas, errors, skipped, all_ps, all_w, log if trace else None, made if trace else None)

@@ -158,6 +158,43 @@ def save_track_case(name, scene_kwargs, seed, builder=synthetic.nadir_scene, pos
     return scene, tracks
 
 
+def save_shape_case(name, scene_kwargs, seed, builder=synthetic.nadir_scene, post=None, **run_kwargs):
+    """Compact fixture of a run at one of BASELINE.json's shapes: the reference's means / sigmas, every update's ancestor
+    indices (int32) and uniform draw, checksums of its evolved particles and weights (enough to pin the oracle bit for bit;
+    the tests regenerate the full intermediates with the oracle), and the SSE surface of point 0's last update."""
+    scene = builder(**scene_kwargs)
+    if post is not None:
+        scene = post(scene)
+    tracks, steps, templates, tracker = run_reference(scene, seed, **run_kwargs)
+    out = {
+        "seed": seed, "means": tracks.means, "n_steps": len(steps), "n_templates": len(templates),
+        "error_types": np.array([type(e).__name__ if e is not None else "" for e in np.atleast_1d(tracks.errors)]),
+        "images": np.array([[(-1 if v is None else v) for v in row] for row in tracks.images]),
+        "frame_crc": np.array([int(np.asarray(f, dtype=np.int64).sum()) for o in scene.observers for f in o.frames]),
+        "final_particles_sum": np.nansum(tracks.particles[:, -1], axis=1),
+        "indices": np.stack([s["indices"] for s in steps]).astype(np.int32),
+        "u": np.array([s["u"] for s in steps], dtype=float),
+        "evolved_sum": np.stack([s["evolved"].sum(axis=0) for s in steps]),
+        "weights_sum": np.array([s["weights"].sum() for s in steps]),
+        "weights_max": np.array([s["weights"].max() for s in steps]),
+    }
+    if tracks.sigmas is not None:
+        out["sigmas"] = tracks.sigmas
+    if tracks.covariances is not None:
+        out["covariances"] = tracks.covariances
+    P = len(scene.points)
+    per = len(steps) // P
+    last = steps[per - 1]
+    for o, rec in last["obs"].items():
+        for key in ("box", "sse", "sse_box"):
+            out[f"last0.obs.{o}.{key}"] = np.asarray(rec[key])
+    for i, t in enumerate(templates):
+        out[f"template{i}.obs"], out[f"template{i}.box"] = np.asarray(t["obs"]), np.asarray(t["box"])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "steps", len(steps), "errors", out["error_types"], os.path.getsize(path) // 1024, "KiB")
+
+
 # ---- scene definitions shared with tests/scenes.py (the tests rebuild the same scenes) ----
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import scenes  # noqa: E402
@@ -196,3 +233,6 @@ if __name__ == "__main__":
     for name, case in scenes.track_cases().items():
         if not only or name in only:
             save_track_case(name, **case)
+    for name, case in scenes.shape_cases().items():
+        if not only or name in only:
+            save_shape_case(name, **case)

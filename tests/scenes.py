@@ -139,3 +139,35 @@ def track_cases():
             seed=505,
         ),
     }
+
+
+def shape_cases():
+    """Parity fixtures at the shapes BASELINE.json names (full particle counts, tile sizes, frame sizes and distortion; fewer
+    points / frames for configs 2-4 so that the CPU reference finishes in seconds).  Their goldens are compact: means, sigmas,
+    every update's ancestor indices, uniform draw and checksums of the evolved particles / weights, one SSE surface."""
+    return {
+        # config 1 exactly: 10 points x 1 000 particles x 20 frames, 15 x 15 template, 600 x 400 frames
+        "shape_c1": dict(
+            scene_kwargs=dict(seed=41, n_points=10, n_particles=1000, n_frames=20, imgsz=(600, 400)),
+            seed=4141,
+        ),
+        # config 2: N = 10 000, 4288 x 2848 nadir camera with the full k1-k6 / p1 / p2 distortion
+        "shape_c2": dict(
+            scene_kwargs=dict(seed=42, n_points=3, n_particles=10000, n_frames=8, imgsz=(4288, 2848), velocity_sigma=0.2,
+                              margin_px=200),
+            seed=4242,
+        ),
+        # config 3: CylindricalMotion with an uncertain elevation (dem_sigma = 1), two observers (the second rolled by 180 deg,
+        # RGB, radial-only distortion, starting one frame later), N = 10 000
+        "shape_c3": dict(
+            scene_kwargs=dict(seed=43, n_points=2, n_particles=10000, n_frames=6, imgsz=(1200, 800), kind="cylindrical",
+                              velocity_sigma=0.2, margin_px=200),
+            seed=4343, post=add_second_observer,
+        ),
+        # config 4: 31 x 31 template, N = 100 000 (search windows of ~100 px)
+        "shape_c4": dict(
+            scene_kwargs=dict(seed=44, n_points=2, n_particles=100000, n_frames=5, imgsz=(1200, 800), tile_size=(31, 31),
+                              velocity_sigma=0.3, margin_px=250),
+            seed=4444,
+        ),
+    }

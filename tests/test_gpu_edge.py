@@ -34,12 +34,17 @@ def run_both(scene, seed, mode, points=None, viewshed=None, oracle_viewshed=None
     return tracks, ref, tracker
 
 
-def assert_close_to_oracle(tracks, ref, sig_tol=0.05):
+def assert_close_to_oracle(tracks, ref, sig_tol=1e-5):
+    """Free-running agreement of the means in units of the reference's sigma.  The default asks for identical ancestors
+    everywhere (achieved: <= 1e-7 sigma); tests with thousands of particles per point, where one flipped ancestor turns the
+    rest of the track into another realisation of the filter (tests/test_gpu_track.py), pass their own bound."""
     sig = ref.sigmas if ref.sigmas.ndim == 3 else np.sqrt(np.einsum("ptii->pti", ref.sigmas))
     both = ~np.isnan(ref.means[..., 0])
     assert np.array_equal(~np.isnan(tracks.means[..., 0]), both)
     d = np.abs(tracks.means - ref.means) / np.maximum(sig, 1e-9)
-    assert np.nanmax(d[..., [0, 1, 3, 4]]) < sig_tol
+    worst = float(np.nanmax(d[..., [0, 1, 3, 4]]))
+    assert worst < sig_tol, f"max |dmean| = {worst:.3g} sigma"
+
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -134,7 +139,7 @@ def test_large_template_many_particles_and_mask(cuda, mode):
     tracks, ref, tracker = run_both(scene, 9, mode, return_covariances=True, observer_mask=mask)
     assert all(e is None for e in tracks.errors)
     assert tracks.covariances.shape == (3, 4, 6, 6) and tracks.sigmas is None
-    assert_close_to_oracle(tracks, ref)
+    assert_close_to_oracle(tracks, ref, sig_tol=5e-3)  # 20 000 particles: one ancestor may flip (5e-4 sigma measured)
     c_ref, c = ref.sigmas, tracks.covariances
     scale = np.sqrt(np.einsum("ptii,ptjj->ptij", c_ref, c_ref))
     ok = scale > 0
