@@ -26,7 +26,7 @@ GB_ST_WINDOW_TOO_LARGE = 6
 GB_WINDOW_MARGIN, GB_WINDOW_MARGIN_MAX = 191, 1000  # default / retry capacity of the search windows beyond the template, px
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
 GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2}
-GB_MODE_FUSED, GB_MODE_STREAM = 0, 1
+GB_MODE_STREAM = 1
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 
 
@@ -89,6 +89,7 @@ class gb_track_desc(C.Structure):
         ("window_stats", C.c_void_p),
         ("resample_method", C.c_int32), ("highpass_size", C.c_int32),
         ("interp_rows", C.c_int32), ("interp_cols", C.c_int32),
+        ("final_weights", C.c_void_p),
         ("plan", gb_plan),
     ]
 

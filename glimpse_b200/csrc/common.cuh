@@ -1,17 +1,13 @@
-// Shared device helpers: unfused IEEE arithmetic, warp/block reductions, cluster all-gather.
+// Shared device helpers: unfused IEEE arithmetic, bulk asynchronous copies, warp/block reductions.
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
 
 #include "../../include/glimpse_b200.h"
 
-namespace cg = cooperative_groups;
-
 #define GB_MAX_OBS 8
-#define GB_MAX_CLUSTER 8
-#define GB_XCH 36 /* doubles per CTA slot in the cluster exchange buffer */
+#define GB_XCH 36 /* doubles per slot of a block reduction (28 moment sums at most) */
 #define GB_MAX_BINS 1024
 
 // particle flag bits, in the order the reference would raise (tracker.py:106-119, observer.py:201,
@@ -99,25 +95,11 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// Fixed header at the start of dynamic shared memory.
+// Work area of the block reductions of k_init / k_moments (dynamic shared memory).
 struct SmemHeader {
-  double xch[2][GB_MAX_CLUSTER][GB_XCH];  // cluster all-gather, double buffered by round parity
-  double red[32][GB_XCH];                 // per-warp partials of a block reduction
-  double bcast[GB_XCH];                   // block-wide broadcast values
-  double scan_tot[256];                   // per-(chunk, warp) totals of the block scan, then their exclusive prefix
-  double scan_carry;
-  double ref[6];                          // origin for the moment sums (parent particle 0)
-  int ibox[4];
+  double red[32][GB_XCH];  // per-warp partials of a block reduction
+  double bcast[GB_XCH];    // block-wide broadcast values
   int iflags[4];
-  gb_camera cam;
-  gb_motion motion;
-};
-
-struct ClusterCtx {
-  int rank;      // CTA rank within the cluster
-  int size;      // CTAs per point
-  int round;     // all-gather round counter (selects the exchange buffer)
-  SmemHeader* hdr;
 };
 
 // Bitwise OR of one word per thread across the CTA (__syncthreads_or only tells whether any is non-zero).
@@ -151,28 +133,6 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], SmemHeader* hdr) {
     if (lane == 0) hdr->bcast[k] = x;
   }
   __syncthreads();
-}
-
-// All-gather of hdr->bcast[0..K) across the CTAs of the cluster.  Returns the buffer
-// xch[buf][rank][k]; valid until the next-but-one all-gather.
-template <int K>
-__device__ __forceinline__ double (*cluster_allgather(ClusterCtx& cc))[GB_XCH] {
-  SmemHeader* hdr = cc.hdr;
-  const int buf = cc.round & 1;
-  cc.round++;
-  if (cc.size == 1) {
-    if (threadIdx.x < K) hdr->xch[buf][0][threadIdx.x] = hdr->bcast[threadIdx.x];
-    __syncthreads();
-    return hdr->xch[buf];
-  }
-  cg::cluster_group cluster = cg::this_cluster();
-  for (int idx = threadIdx.x; idx < K * cc.size; idx += blockDim.x) {
-    const int r = idx / K, k = idx - r * K;
-    double* remote = cluster.map_shared_rank(&hdr->xch[buf][cc.rank][k], r);
-    *remote = hdr->bcast[k];
-  }
-  cluster.sync();
-  return hdr->xch[buf];
 }
 
 }  // namespace gb

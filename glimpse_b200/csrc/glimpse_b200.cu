@@ -1,10 +1,8 @@
 // glimpse_b200 — kernels and C ABI of the Tracker hot path (see include/glimpse_b200.h).
 //
-// One tracked point is owned by one thread-block cluster for one time step (k_step): the
-// cluster's CTAs split the point's particles, keep the evolved state, projected coordinates and
-// weights in shared memory, exchange the few cross-CTA scalars (bounding box, weight totals,
-// moments) through distributed shared memory, and stream the particle state in and out of HBM
-// exactly once (96 B per particle update).
+// The per-update kernels are in stream.cuh (one update = kernels over all points of a batch; batches of points advance
+// on their own streams); this file holds the kernel parameters, the first-frame / template kernels, the stand-alone
+// stage entry points and the host side of the C ABI.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -85,6 +83,7 @@ struct StepParams {
   int32_t* status_time;
   uint8_t* obs_flags;
   int32_t* window_stats;
+  double* final_weights;  // [N] weights of the last point's resampled particles at its last time, or NULL
   gb_stage_io io;
   // GB_MODE_STREAM buffers (carved from `scratch` by the host)
   double* s_ev;      // [P][6][N]   particles after the motion step (this time's parity)
@@ -542,10 +541,7 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
 }
 
 // ---------------------------------------------------------------------------------------------
-// The fused update step (tracker.py:331-357 for one point and one time):
-//   evolve -> test -> per observer [project, search window, tile pipeline, spline sample]
-//   -> surface likelihood -> weights -> systematic resampling -> moments.
-// grid.x = P * cluster; one cluster per point.
+// Resampling positions (tracker.py:168-186), shared by the kernels of stream.cuh
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double resample_position(int j, double u, double inv_n) {
   // (np.arange(n) + u) * (1 / n)  (tracker.py:173)
@@ -601,483 +597,6 @@ __device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
     if (lane >= d) v += o;
   }
   return v;
-}
-
-// Block-wide integer min of K values (maxima as minima of negatives): REDUX inside the warp,
-// then one warp over the per-warp partials.  Result in hdr->bcast[0..K) as doubles.
-template <int K>
-__device__ __forceinline__ void block_min_int(const int (&v)[K], SmemHeader* hdr) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  int* red = reinterpret_cast<int*>(hdr->red);
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int x = __reduce_min_sync(0xffffffffu, v[k]);
-    if (lane == 0) red[warp * K + k] = x;
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      int x = lane < nwarp ? red[lane * K + k] : 0x7fffffff;
-      x = __reduce_min_sync(0xffffffffu, x);
-      if (lane == 0) hdr->bcast[k] = (double)x;
-    }
-  }
-  __syncthreads();
-}
-
-template <bool COV>
-__global__ void __launch_bounds__(GB_THREADS, 1) k_step(const __grid_constant__ StepParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
-  constexpr int HDR = (int)((sizeof(SmemHeader) + 15) / 16 * 16);
-  const int cs = prm.cluster;
-  const int rank = (int)(blockIdx.x % cs);
-  const int64_t p = blockIdx.x / cs;
-  const int t = prm.t, tid = threadIdx.x, B = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = B >> 5;
-  const int N = (int)prm.N, O = prm.O;
-  const bool forced = prm.io.force_evolved != nullptr;
-  if (prm.status[p] != 0 || t <= prm.first[p] || t > prm.last[p]) return;
-  long long* clk = (prm.io.dump_clocks && rank == 0) ? reinterpret_cast<long long*>(prm.io.dump_clocks) + p * 16 : nullptr;
-#define GB_CLK(i) do { if (clk && tid == 0) clk[i] = clock64(); } while (0)
-  GB_CLK(0);
-
-  ClusterCtx cc{rank, cs, 0, hdr};
-  const int nl = prm.n_local;
-  const int i0 = rank * nl;
-  const int nv = max(0, min(nl, N - i0));
-
-  double *ev, *uvb, *llb;
-  char* tile_base;
-  if (prm.particles_in_smem) {
-    ev = reinterpret_cast<double*>(smem_raw + HDR);
-    uvb = ev + 6 * nl;
-    llb = uvb + 2 * nl;
-    tile_base = reinterpret_cast<char*>(llb + nl);
-  } else {
-    ev = prm.scratch + (p * cs + rank) * 9 * (int64_t)nl;
-    uvb = ev + 6 * (int64_t)nl;
-    llb = uvb + 2 * (int64_t)nl;
-    tile_base = reinterpret_cast<char*>(smem_raw + HDR);
-  }
-  // motion parameters and the moment origin to shared memory
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&hdr->motion);
-    for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += B) dst[k] = src[k];
-  }
-  const double* sin_ = forced ? prm.io.force_evolved + p * 6 * (int64_t)N : state_buffer(prm, t - 1) + p * 6 * (int64_t)N;
-  if (tid < 6) hdr->ref[tid] = sin_[tid * (int64_t)N];
-  // observers that have an image for this point at this time (block-uniform)
-  int first_obs = -1;
-  for (int o = O - 1; o >= 0; --o)
-    if (prm.img[o] >= 0 && prm.mask[p * O + o]) first_obs = o;
-  const bool use_obs = !prm.io.force_weights;
-  __syncthreads();
-  const bool surface_ll = !(prm.surfaces[hdr->motion.dem_sigma].z == nullptr && prm.surfaces[hdr->motion.dem_sigma].value == 0.0);
-  const double hw = (double)prm.tile_w * 0.5, hh = (double)prm.tile_h * 0.5;
-
-  uint32_t flags = 0;
-  // integer bounding box of the cloud: floor(min - half) = min floor(u - half) (monotone rounding)
-  int ib[5] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff, 0};  // left, top, -right, -bottom, -(any NaN)
-  // ---- phase A: motion step, particle tests and (fused) projection into the first observer ----
-  {
-    const int s_idx = t - prm.first[p] - 1;
-    const double* zn = prm.step_normals ? prm.step_normals + (((int64_t)p * prm.S + s_idx) * N + i0) * 3 : nullptr;
-    const bool evolve = !forced && !prm.skip_evolve;
-    const bool proj = use_obs && first_obs >= 0;
-    const int fo = proj ? first_obs : 0;
-    const double* src = sin_ + i0;
-    // two particles per trip: two independent dependency chains in flight per thread
-    for (int ia = tid; ia < nv; ia += 2 * B) {
-      const int ibx = ia + B;
-      const bool vb = ibx < nv;
-      const int ii[2] = {ia, vb ? ibx : ia};
-      double s[2][6];
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) s[q][c] = src[c * (int64_t)N + ii[q]];
-      if (evolve) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          double z0, z1, z2;
-          if (prm.rng_mode == GB_RNG_SUPPLIED) {
-            z0 = zn[3 * ii[q]];
-            z1 = zn[3 * ii[q] + 1];
-            z2 = zn[3 * ii[q] + 2];
-          } else {
-            philox_normals3(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t, (uint32_t)(i0 + ii[q]), 2u, z0, z1, z2);
-          }
-          evolve_particle<false>(hdr->motion, prm.surfaces, prm.tau, prm.tau2, z0, z1, z2, s[q], flags);  // fused mode: no tangent models
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 1 && !vb) break;
-        const int i = ii[q];
-        flags |= test_particle(prm, s[q]);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ev[c * nl + i] = s[q][c];
-        llb[i] = 0.0;
-        if (prm.io.dump_evolved) {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) prm.io.dump_evolved[((int64_t)p * 6 + c) * N + i0 + i] = s[q][c];
-        }
-      }
-      if (proj) {
-        double u[2], v[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) project_fast(prm.cam[fo], s[q][0], s[q][1], s[q][2], u[q], v[q]);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q == 1 && !vb) break;
-          const int i = ii[q];
-          uvb[i] = u[q];
-          uvb[nl + i] = v[q];
-          if (isnan(u[q]) | isnan(v[q])) ib[4] = -1;
-          ib[0] = min(ib[0], __double2int_rd(u[q] - hw));
-          ib[1] = min(ib[1], __double2int_rd(v[q] - hh));
-          ib[2] = min(ib[2], -__double2int_ru(u[q] + hw));
-          ib[3] = min(ib[3], -__double2int_ru(v[q] + hh));
-          if (prm.io.dump_uv) {
-            double* d = prm.io.dump_uv + (((int64_t)p * O + first_obs) * N + i0 + i) * 2;
-            d[0] = u[q];
-            d[1] = v[q];
-          }
-        }
-      }
-    }
-  }
-  GB_CLK(1);
-
-  // ---- phase B: observers ----
-  bool fatal = false;
-  if (use_obs) {
-    for (int o = 0; o < O && !fatal; ++o) {
-      const int64_t po = p * O + o;
-      uint8_t* oflag = prm.obs_flags + ((int64_t)p * prm.T + t) * O + o;
-      if (prm.img[o] < 0 || !prm.mask[po]) {
-        if (rank == 0 && tid == 0) *oflag = GB_OBS_NO_IMAGE;
-        continue;
-      }
-      if (o != first_obs) {
-        __syncthreads();  // everyone is done with the previous observer's tile buffers
-        ib[0] = ib[1] = ib[2] = ib[3] = 0x7fffffff;
-        ib[4] = 0;
-        for (int i = tid; i < nv; i += B) {
-          double u, v;
-          project_fast(prm.cam[o], ev[i], ev[nl + i], ev[2 * nl + i], u, v);
-          uvb[i] = u;
-          uvb[nl + i] = v;
-          if (isnan(u) | isnan(v)) ib[4] = -1;
-          ib[0] = min(ib[0], __double2int_rd(u - hw));
-          ib[1] = min(ib[1], __double2int_rd(v - hh));
-          ib[2] = min(ib[2], -__double2int_ru(u + hw));
-          ib[3] = min(ib[3], -__double2int_ru(v + hh));
-          if (prm.io.dump_uv) {
-            double* d = prm.io.dump_uv + ((po * N) + i0 + i) * 2;
-            d[0] = u;
-            d[1] = v;
-          }
-        }
-      }
-      block_min_int<5>(ib, hdr);
-      double(*xg)[GB_XCH] = cluster_allgather<5>(cc);
-      int bx[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        double x = xg[0][k];
-        for (int r = 1; r < cs; ++r) x = fmin(x, xg[r][k]);
-        bx[k] = (int)x;
-      }
-      int box_l = bx[0], box_t = bx[1], box_r = -bx[2], box_b = -bx[3];
-      bool nan_any = bx[4] != 0;
-      // The reference widens the box when the cloud spans less than 3 px (tracker.py:584-594); that needs
-      // the exact extents.  Rare: take the exact double-precision route only then (cluster-uniform test).
-      if (!nan_any && ((box_r - box_l) - prm.tile_w < 5 || (box_b - box_t) - prm.tile_h < 5)) {
-        double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
-        for (int i = tid; i < nv; i += B) {
-          const double u = uvb[i], v = uvb[nl + i];
-          mm[0] = fmin(mm[0], u);
-          mm[1] = fmin(mm[1], v);
-          mm[2] = fmin(mm[2], -u);
-          mm[3] = fmin(mm[3], -v);
-        }
-        block_reduce<4, 1>(mm, hdr);
-        double(*xm)[GB_XCH] = cluster_allgather<4>(cc);
-        double lo_u = xm[0][0], lo_v = xm[0][1], hi_u = xm[0][2], hi_v = xm[0][3];
-        for (int r = 1; r < cs; ++r) {
-          lo_u = fmin(lo_u, xm[r][0]);
-          lo_v = fmin(lo_v, xm[r][1]);
-          hi_u = fmin(hi_u, xm[r][2]);
-          hi_v = fmin(hi_v, xm[r][3]);
-        }
-        hi_u = -hi_u;
-        hi_v = -hi_v;
-        const double tw = (double)prm.tile_w, th = (double)prm.tile_h;
-        double bl = sub(lo_u, hw), bt = sub(lo_v, hh), br = add(hi_u, hw), bb = add(hi_v, hh);
-        const double ncols = sub((double)prm.interp_cols, sub(sub(br, bl), tw));
-        if (ncols > 0.0) {
-          bl = add(bl, mul(-ncols, 0.5));
-          br = add(br, mul(ncols, 0.5));
-        }
-        const double nrows = sub((double)prm.interp_rows, sub(sub(bb, bt), th));
-        if (nrows > 0.0) {
-          bt = add(bt, mul(-nrows, 0.5));
-          bb = add(bb, mul(nrows, 0.5));
-        }
-        box_l = __double2int_rd(bl);
-        box_t = __double2int_rd(bt);
-        box_r = __double2int_ru(br);
-        box_b = __double2int_ru(bb);
-      }
-      GB_CLK(2);
-      // Camera.inframe on both corners (camera.py:700-718); NaN fails every comparison
-      const int W = prm.cam[o].c.imgsz[0], H = prm.cam[o].c.imgsz[1];
-      const bool inframe = !nan_any && box_l >= 0 && box_l <= W && box_t >= 0 && box_t <= H && box_r >= 0 && box_r <= W &&
-                           box_b >= 0 && box_b <= H;
-      if (!inframe) {
-        if (rank == 0 && tid == 0) *oflag = GB_OBS_OUT_OF_FRAME;
-        continue;
-      }
-      if (tid == 0) {
-        hdr->ibox[0] = box_l;
-        hdr->ibox[1] = box_t;
-        hdr->ibox[2] = box_r;
-        hdr->ibox[3] = box_b;
-      }
-      TileWork w;
-      w.Su = box_r - box_l;
-      w.Sv = box_b - box_t;
-      w.tw = prm.tile_w;
-      w.mh = prm.hp_rows;
-      w.mw = prm.hp_cols;
-      w.cub_u = prm.interp_cols != 1;
-      w.cub_v = prm.interp_rows != 1;
-      w.th = prm.tile_h;
-      w.Mu = w.Su - w.tw + 1;
-      w.Mv = w.Sv - w.th + 1;
-      w.nbins = 255 * prm.nchan[o] + 1;
-      w.nvals = prm.tmpl_nvalues[po];
-      if (rank == 0 && tid == 0) {
-        *oflag = GB_OBS_USED;
-        if (prm.window_stats) {
-          int32_t* ws = prm.window_stats + (((int64_t)p * prm.T + t) * O + o) * 2;
-          ws[0] = w.Su;
-          ws[1] = w.Sv;
-        }
-        if (prm.io.dump_box) {
-          int32_t* d = prm.io.dump_box + po * 4;
-          d[0] = box_l;
-          d[1] = box_t;
-          d[2] = box_r;
-          d[3] = box_b;
-        }
-      }
-      char* tbase = tile_base;
-      {
-        const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
-        if (need > prm.tile_bytes) {
-          // overflow: this CTA's tile buffers go to its SM's slab in global memory (L2-resident)
-          unsigned smid;
-          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-          if (need > prm.slab_bytes || w.Mu > 256 || w.Mv > 256 || (int)smid >= prm.n_slabs) {
-            flags |= GB_F_WINDOW;
-            fatal = true;
-            break;
-          }
-          tbase = reinterpret_cast<char*>(prm.scratch) + prm.particle_scratch_bytes + (int64_t)smid * prm.slab_bytes;
-        }
-      }
-      tile_carve(tbase, w);
-      const int64_t ta = (int64_t)w.tw * w.th;
-      const bool dumper = rank == 0;
-      const int boxv[4] = {box_l, box_t, box_r, box_b};
-      tile_build_surface(prm.pixels[o], prm.pitch[o], prm.nchan[o], boxv, prm.tmpl_tile + po * ta, prm.tmpl_quantiles + po * ta,
-                         prm.tmpl_values + po * ta, w,
-                         (dumper && prm.io.dump_search) ? prm.io.dump_search + po * prm.io.dump_cap : nullptr,
-                         (dumper && prm.io.dump_sse) ? prm.io.dump_sse + po * prm.io.dump_cap : nullptr, prm.io.dump_cap,
-                         clk ? clk + 3 : nullptr);
-      GB_CLK(6);
-      // geo-reference of the surface (tracker.py:615-620) and cell centres (observer.py:203-208)
-      const double eu = sub(mul((double)w.tw, 0.5), 0.5), evv = sub(mul((double)w.th, 0.5), 0.5);
-      const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
-      const double sl = add(add((double)box_l, eu), du_t), st = add(add((double)box_t, evv), dv_t);
-      const double sr = add(add((double)box_r, -eu), du_t), sb = add(add((double)box_b, -evv), dv_t);
-      const double cu0 = add(sl, mul(quo(sub(sr, sl), (double)w.Mu), 0.5));
-      const double cv0 = add(st, mul(quo(sub(sb, st), (double)w.Mv), 0.5));
-      const double cu1 = add(cu0, (double)(w.Mu - 1)), cv1 = add(cv0, (double)(w.Mv - 1));
-      const double scale = prm.obs_scale[o];
-      for (int i = tid; i < nv; i += B) {
-        const double u = uvb[i], v = uvb[nl + i];
-        if (!((u >= sl) & (u <= sr) & (v >= st) & (v <= sb))) flags |= GB_F_SAMPLE_OUTSIDE;
-        // FITPACK evaluates at the argument clamped to the first/last data site
-        const double x = fmin(fmax(u, cu0), cu1) - cu0, y = fmin(fmax(v, cv0), cv1) - cv0;
-        const double val = (double)hermite_eval(w.herm, w.Mp, w.Mu, w.Mv, x, y, prm.interp_cols == 1, prm.interp_rows == 1);
-        llb[i] = add(llb[i], mul(val, scale));
-        if (prm.io.dump_sampled) prm.io.dump_sampled[po * N + i0 + i] = val;
-      }
-    }
-  }
-  GB_CLK(7);
-
-  // ---- phase C: weights (tracker.py:143-149) and their inclusive prefix within the CTA ----
-  // Particle i = k * B + tid: chunk k is contiguous across the block.  Warp scans first, then one
-  // warp turns the per-(chunk, warp) totals into offsets: two block barriers per 8 chunks.
-  {
-    const double* fw = prm.io.force_weights ? prm.io.force_weights + (int64_t)p * N + i0 : nullptr;
-    double carry = 0.0;
-    for (int base = 0; base < nv; base += 8 * B) {
-      const int nchunk = min(8, (nv - base + B - 1) / B);
-      for (int k = 0; k < nchunk; ++k) {
-        const int i = base + k * B + tid;
-        double w = 0.0;
-        if (i < nv) {
-          if (fw) {
-            w = fw[i];
-          } else {
-            double ll = llb[i];
-            if (surface_ll) ll = add(ll, surface_log_likelihood(hdr->motion, prm.surfaces, ev[i], ev[nl + i], ev[2 * nl + i], flags));
-            else ll = add(ll, 0.0);
-            w = add(exp(-ll), 1e-300);
-          }
-          llb[i] = w;
-          if (prm.io.dump_weights) prm.io.dump_weights[(int64_t)p * N + i0 + i] = w;
-        }
-        const double incl = warp_inclusive_scan(w, lane);
-        if (i < nv) uvb[i] = incl;
-        if (lane == 31) hdr->scan_tot[k * nwarp + warp] = incl;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        double run = carry;
-        for (int b0 = 0; b0 < nchunk * nwarp; b0 += 32) {
-          const double v = (b0 + lane < nchunk * nwarp) ? hdr->scan_tot[b0 + lane] : 0.0;
-          const double incl = warp_inclusive_scan(v, lane);
-          double excl = shfl_up(incl, 1);
-          if (lane == 0) excl = 0.0;
-          if (b0 + lane < nchunk * nwarp) hdr->scan_tot[b0 + lane] = run + excl;
-          run = run + __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) hdr->scan_carry = run;
-      }
-      __syncthreads();
-      for (int k = 0; k < nchunk; ++k) {
-        const int i = base + k * B + tid;
-        if (i < nv) uvb[i] = hdr->scan_tot[k * nwarp + warp] + uvb[i];
-      }
-      carry = hdr->scan_carry;
-      __syncthreads();
-    }
-  }
-  GB_CLK(8);
-  const int blockflags = (int)block_or(flags, reinterpret_cast<unsigned*>(&hdr->iflags[1]));
-  // the CTA total is, by definition, the prefix of its last particle (keeps child ranges seamless)
-  if (tid == 0) {
-    hdr->bcast[0] = nv > 0 ? uvb[nv - 1] : 0.0;
-    hdr->bcast[1] = (double)blockflags;
-  }
-  __syncthreads();
-  double prefix = 0.0, total = 0.0;
-  {
-    double(*xg)[GB_XCH] = cluster_allgather<2>(cc);
-    uint32_t allflags = 0;
-    for (int r = 0; r < cs; ++r) {
-      if (r == rank) prefix = total;
-      total += xg[r][0];
-      allflags |= (uint32_t)xg[r][1];
-    }
-    if (allflags) {
-      if (rank == 0 && tid == 0) {
-        prm.status[p] = status_from_flags(allflags);
-        prm.status_time[p] = t;
-      }
-      return;
-    }
-  }
-  GB_CLK(9);
-
-  // ---- phase D: systematic resampling (tracker.py:168-176): child range [E[i-1], E[i]) of every parent ----
-  const double u01 = prm.rng_mode == GB_RNG_SUPPLIED ? prm.uniforms[(int64_t)p * prm.S + (t - prm.first[p] - 1)]
-                                                      : philox_uniform(prm.seed, (uint64_t)(p + prm.point_offset), (uint32_t)t);
-  const double inv_n = quo(1.0, (double)N);
-  int* E = reinterpret_cast<int*>(uvb + nl);
-  for (int i = tid; i < nv; i += B) E[i] = count_positions_le(quo(prefix + uvb[i], total), u01, inv_n, N);
-  const int J0 = rank == 0 ? 0 : count_positions_le(quo(prefix, total), u01, inv_n, N);
-  __syncthreads();
-  GB_CLK(10);
-
-  // ---- phase E: moments of the resampled set = parents weighted by (children x weight) ----
-  // (before the child stores, so that no global store is in flight at the cluster barrier)
-  Moments<COV> mom;
-  mom.clear();
-  for (int i = tid; i < nv; i += B) {
-    const int cnt = E[i] - (i > 0 ? E[i - 1] : J0);
-    if (cnt > 0) {
-      double s[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + i];
-      mom.accumulate((double)cnt * llb[i], s, hdr->ref);
-    }
-  }
-  block_reduce<Moments<COV>::NM, 0>(mom.a, hdr);
-  {
-    double(*xg)[GB_XCH] = cluster_allgather<Moments<COV>::NM>(cc);
-    if (rank == 0 && tid < Moments<COV>::NM) {
-      double x = xg[0][tid];
-      for (int r = 1; r < cs; ++r) x += xg[r][tid];
-      hdr->bcast[tid] = x;
-    }
-    if (rank == 0) {
-      __syncthreads();
-      if (tid == 0) {
-        double mean[6], sg[6], cv[36];
-        finalize_moments<COV>(hdr->bcast, hdr->ref, mean, sg, cv);
-        double* mo = prm.means + ((int64_t)p * prm.T + t) * 6;
-        for (int c = 0; c < 6; ++c) mo[c] = mean[c];
-        if (COV) {
-          double* co = prm.covariances + ((int64_t)p * prm.T + t) * 36;
-          for (int c = 0; c < 36; ++c) co[c] = cv[c];
-        } else {
-          double* so = prm.sigmas + ((int64_t)p * prm.T + t) * 6;
-          for (int c = 0; c < 6; ++c) so[c] = sg[c];
-        }
-      }
-    }
-  }
-  GB_CLK(11);
-
-  // ---- phase F: every parent writes its children (tracker.py:222-223); no search, no further barrier ----
-  {
-    double* sout = state_buffer(prm, t) + p * 6 * (int64_t)N;
-    double* wst = prm.weight_state ? prm.weight_state + (int64_t)p * N : nullptr;
-    double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
-    double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
-    int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
-    for (int i = tid; i < nv; i += B) {
-      const int j1 = E[i];
-      int j = i > 0 ? E[i - 1] : J0;
-      if (j >= j1) continue;
-      double s[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s[c] = ev[c * nl + i];
-      const double w = llb[i];
-      for (; j < j1; ++j) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
-        if (wst) wst[j] = w;
-        if (outp) {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
-        }
-        if (outw) outw[j] = w;
-        if (outi) outi[j] = i0 + i;
-      }
-    }
-  }
-  GB_CLK(12);
-#undef GB_CLK
 }
 
 #include "stream.cuh"
@@ -1195,6 +714,7 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.status_time = d.status_time;
   prm.obs_flags = d.obs_flags;
   prm.window_stats = d.window_stats;
+  prm.final_weights = d.final_weights;
 }
 
 static int check_desc(const gb_track_desc& d) {
@@ -1215,33 +735,13 @@ static int check_desc(const gb_track_desc& d) {
     return fail(GB_E_INVALID, "missing required buffer%s");
   if (d.rng_mode == GB_RNG_SUPPLIED && (!d.init_normals || !d.step_normals || !d.uniforms))
     return fail(GB_E_INVALID, "supplied-draw mode needs init_normals, step_normals and uniforms%s");
-  if (d.plan.cluster < 1 || d.plan.cluster > GB_MAX_CLUSTER || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
+  if (d.plan.mode != GB_MODE_STREAM || d.plan.threads != GB_THREADS || d.plan.n_local < 1)
     return fail(GB_E_INVALID, "invalid launch plan (use gb_step_plan)%s");
-  if (d.plan.mode == GB_MODE_STREAM && (d.plan.n_observers != d.O || d.plan.stream_nblk < 1 || d.plan.surf_bytes <= 0 ||
+  if ((d.plan.n_observers != d.O || d.plan.stream_nblk < 1 || d.plan.surf_bytes <= 0 ||
                                         d.plan.stream_batch < 1 || d.plan.stream_slots < 1 || d.plan.stream_slots > kMaxSlots))
     return fail(GB_E_INVALID, "streaming plan does not match the descriptor (use gb_step_plan)%s");
   if (d.plan.scratch_bytes > 0 && !d.scratch) return fail(GB_E_INVALID, "plan needs a scratch buffer%s");
-  if ((int64_t)d.plan.cluster * d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
-  return GB_OK;
-}
-
-template <bool COV>
-static int launch_step(const StepParams& prm, const gb_plan& plan, cudaStream_t stream) {
-  GB_CUDA(cudaFuncSetAttribute(k_step<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(prm.P * plan.cluster), 1, 1);
-  cfg.blockDim = dim3(GB_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = plan.smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = plan.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GB_CUDA(cudaLaunchKernelEx(&cfg, k_step<COV>, prm));
+  if ((int64_t)d.plan.n_local < d.N) return fail(GB_E_INVALID, "plan does not cover N particles%s");
   return GB_OK;
 }
 
@@ -1636,10 +1136,7 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
 
 // One update for all points in the organisation the plan asks for.
 static int launch_update(const gb_track_desc& d, StepParams& prm, cudaStream_t stream, bool fork, bool join, int64_t* launches) {
-  if (d.plan.mode == GB_MODE_STREAM) return launch_stream_update(d, prm, stream, fork, join, launches);
-  const bool cov = d.covariances != nullptr;
-  if (launches) *launches += 1;
-  return cov ? launch_step<true>(prm, d.plan, stream) : launch_step<false>(prm, d.plan, stream);
+  return launch_stream_update(d, prm, stream, fork, join, launches);
 }
 
 static int launch_init(const StepParams& prm, bool cov, cudaStream_t stream) {
@@ -1801,10 +1298,9 @@ int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t
   if (window_margin < 4 || window_margin > GB_MAX_SURFACE - 1) return fail(GB_E_INVALID, "window_margin must be between 4 and 1023%s");
   if (!plan || n_particles <= 0 || tile_w < 1 || tile_h < 1) return fail(GB_E_INVALID, "bad plan arguments%s");
   if ((int64_t)tile_w * tile_h > GB_MAX_TEMPLATE) return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
-  if (prefer_cluster != 0 && prefer_cluster != 1 && prefer_cluster != 2 && prefer_cluster != 4 && prefer_cluster != 8)
-    return fail(GB_E_INVALID, "cluster size must be 0 (auto), 1, 2, 4 or 8%s");
+  (void)prefer_cluster;
   if (n_observers < 1 || n_observers > GB_MAX_OBS) return fail(GB_E_INVALID, "between 1 and 8 observers are supported%s");
-  if (mode != GB_MODE_FUSED && mode != GB_MODE_STREAM) return fail(GB_E_INVALID, "unknown mode%s");
+  if (mode != GB_MODE_STREAM) return fail(GB_E_INVALID, "unknown mode (the cluster-per-point organisation of round 1 was removed)%s");
   memset(plan, 0, sizeof(*plan));
   plan->mode = mode;
   plan->n_observers = n_observers;
@@ -1840,39 +1336,7 @@ int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t
     plan->scratch_bytes = stream_layout(npoints, n_particles, n_observers, plan->stream_nblk, plan->surf_bytes).total;
     return GB_OK;
   }
-  plan->n_slabs = 160;
-  plan->slab_bytes = (tile_bytes_needed(tile_w + 255, tile_h + 255, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
-  // on-chip tile capacity we insist on: a search window 24 px larger than the template each way;
-  // bigger windows spill to the per-SM slabs
-  const int64_t want = tile_bytes_needed(tile_w + 24, tile_h + 24, tile_w, tile_h, 256, tile_w * tile_h);
-  const int avail = kMaxSmem - kHeaderBytes;
-  bool chosen = false;
-  for (int cs = 1; cs <= GB_MAX_CLUSTER && !chosen; cs *= 2) {
-    if (prefer_cluster && cs != prefer_cluster) continue;
-    int64_t nl = (n_particles + cs - 1) / cs;
-    nl = (nl + 1) / 2 * 2;
-    const int64_t pbytes = nl * 72;
-    if (pbytes + want <= avail) {
-      chosen = true;
-      plan->cluster = cs;
-      plan->n_local = (int32_t)nl;
-      plan->particles_in_smem = 1;
-      plan->tile_bytes = (int32_t)(avail - pbytes);
-    }
-  }
-  if (!chosen) {
-    const int cs = prefer_cluster ? prefer_cluster : GB_MAX_CLUSTER;
-    int64_t nl = (n_particles + cs - 1) / cs;
-    nl = (nl + 1) / 2 * 2;
-    if (nl > 0x7fffffff / 16) return fail(GB_E_RESOURCE, "too many particles per point%s");
-    plan->cluster = cs;
-    plan->n_local = (int32_t)nl;
-    plan->particles_in_smem = 0;
-    plan->tile_bytes = avail;
-    plan->particle_scratch_bytes = npoints * cs * 9 * nl * (int64_t)sizeof(double);
-  }
-  plan->scratch_bytes = plan->particle_scratch_bytes + plan->n_slabs * plan->slab_bytes;
-  return GB_OK;
+  return fail(GB_E_INVALID, "unknown mode%s");
 }
 
 int gb_track_init(const gb_track_desc* d, int32_t t, void* stream) {
@@ -1908,7 +1372,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool cov = d->covariances != nullptr;
   int64_t launches = 0;
-  if (d->plan.mode == GB_MODE_STREAM && d->resample_method != GB_RESAMPLE_CHOICE) {  // (choice: step-by-step flow below)
+  if (d->resample_method != GB_RESAMPLE_CHOICE) {  // (choice: step-by-step flow below)
     if ((rc = track_streaming(*d, stream, &launches))) return rc;
     if (launches_out) *launches_out = launches;
     return GB_OK;
@@ -1920,7 +1384,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   // caller's stream forks them after its own kernels (init, templates, in-place evolve) and joins them
   // before the next such kernel and at the end.
   bool forked = false, need_fork = true;
-  const bool streaming = d->plan.mode == GB_MODE_STREAM;
+  const bool streaming = true;
   auto join_sides = [&]() -> int {
     if (!streaming || !forked) return GB_OK;
     StreamPool* pool = nullptr;

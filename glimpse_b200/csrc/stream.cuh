@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
   double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
   double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
   int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
+  double* fin = (prm.final_weights && p == prm.P - 1 && t == prm.last[p]) ? prm.final_weights : nullptr;
   Moments<COV> mom;
   mom.clear();
   for (int j = J0 + tid; j < J1; j += GB_SBLOCK_THREADS) {
@@ -737,6 +738,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4_resample(const __gr
     for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);  // next read is a whole update away
     mom.accumulate(wj, s, ref);
     if (wst) wst[j] = wj;
+    if (fin) fin[j] = wj;
     if (outp) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
@@ -825,6 +827,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_gather(const __gri
   double* outp = prm.out_particles ? prm.out_particles + ((int64_t)p * prm.T + t) * N * 6 : nullptr;
   double* outw = prm.out_weights ? prm.out_weights + ((int64_t)p * prm.T + t) * N : nullptr;
   int* outi = prm.io.dump_indices ? prm.io.dump_indices + (int64_t)p * N : nullptr;
+  double* fin = (prm.final_weights && p == prm.P - 1 && t == prm.last[p]) ? prm.final_weights : nullptr;
   Moments<COV> mom;
   mom.clear();
   for (int j = base + tid; j < end; j += GB_SBLOCK_THREADS) {
@@ -843,6 +846,7 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_gather(const __gri
     for (int c = 0; c < 6; ++c) sout[c * (int64_t)N + j] = s[c];
     mom.accumulate(wj, s, ref);
     if (wst) wst[j] = wj;
+    if (fin) fin[j] = wj;
     if (outp) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) outp[(int64_t)j * 6 + c] = s[c];
@@ -1186,6 +1190,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(co
         if (last_time) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) __stcs(&sout[c * (int64_t)N + j], s[c]);
+          if (prm.final_weights && p == prm.P - 1) prm.final_weights[j] = wj;
         }
         if (wst) wst[j] = wj;
         if (outp) {

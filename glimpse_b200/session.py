@@ -160,10 +160,10 @@ class Session:
         with torch.cuda.device(device):
             self.stream = torch.cuda.current_stream().cuda_stream
             self.plan = _lib.gb_plan()
-            mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[getattr(tracker, "mode", "stream")]
+            mode = _lib.GB_MODE_STREAM
             if window_margin is None:
                 window_margin = getattr(tracker, "window_margin", _lib.GB_WINDOW_MARGIN)
-            _lib.check(self.lib.gb_step_plan_ex(N, self.tw, self.th, P, O, int(tracker.cluster), mode, int(window_margin),
+            _lib.check(self.lib.gb_step_plan_ex(N, self.tw, self.th, P, O, 0, mode, int(window_margin),
                                                 C.byref(self.plan)))
             self.h2d = 0
             # the first two frames' uploads start right away (the first kernels wait for them); the other big copies are
@@ -171,8 +171,6 @@ class Session:
             images_dev, self.offsets = self._upload_frames()
             self._start_frame_copies(limit=2)
             motion_dev, surf_dev, n_surf, viewshed = self._lower_models(models)
-            if mode == _lib.GB_MODE_FUSED and self.tangent.any():
-                raise NotImplementedError("the tangent motion models run in mode='stream' only")
             self.first, self.last = point_span(self.image_index, observer_mask)
             self.tmpl_frame = np.array([int(np.argmax(self.image_index[:, o] >= 0)) if (self.image_index[:, o] >= 0).any() else -1
                                         for o in range(O)])
@@ -191,6 +189,8 @@ class Session:
             # (tangent models keep the weights of the last resampling through updates without any likelihood)
             b["weight_state"] = torch.empty((P, N), dtype=f64, **dev) if (staggered or return_particles or self.tangent.any()) else None
             b["scratch"] = torch.empty((self.plan.scratch_bytes // 8,), dtype=f64, **dev) if self.plan.scratch_bytes else None
+            # weights the last point's particles carry when the track ends (Tracker.weights): written at that point's last time only
+            b["final_weights"] = torch.ones((N,), dtype=f64, **dev)
             ta = self.tw * self.th
             b["tmpl_tile"] = torch.zeros((P, O, ta), dtype=f64, **dev)
             b["tmpl_values"] = torch.zeros((P, O, ta), dtype=f64, **dev)
@@ -225,8 +225,6 @@ class Session:
             d.motion_kinds = self.motion_kinds
             method = getattr(tracker, "resample_method", "systematic")
             stratified = method in ("stratified", "choice")  # one uniform per particle and update
-            if stratified and mode == _lib.GB_MODE_FUSED:
-                raise NotImplementedError(f"resample_method='{method}' runs in mode='stream' only")
             d.resample_method = _lib.GB_RESAMPLE[method]
             from .tracker import highpass_size, interpolation_degrees
 
@@ -262,6 +260,7 @@ class Session:
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
             d.state_a, d.state_b = ptr(b["state_a"]), ptr(b["state_b"])
             d.weight_state, d.scratch = ptr(b["weight_state"]), ptr(b["scratch"])
+            d.final_weights = ptr(b["final_weights"])
             d.tmpl_tile, d.tmpl_values, d.tmpl_quantiles = ptr(b["tmpl_tile"]), ptr(b["tmpl_values"]), ptr(b["tmpl_quantiles"])
             d.tmpl_nvalues, d.tmpl_box, d.tmpl_duv = ptr(b["tmpl_nvalues"]), ptr(b["tmpl_box"]), ptr(b["tmpl_duv"])
             d.means = ptr(b["means"])
@@ -279,45 +278,47 @@ class Session:
 
     def _start_frame_copies(self, limit=None) -> None:
         """Queue the frame uploads (in time order) on the copy stream, each followed by its event; ``limit`` = only
-        the first so many (the rest on the next call).  With an NCCL group every rank holds the same frames on its
-        host: rank k uploads every world-th frame and broadcasts it to the others over NVLink instead of all ranks
-        pulling everything through PCIe."""
-        torch, copy_stream, dist = self.torch, self.tracker._copy_stream, self.dist
-        shared = getattr(self, "_shared_upload", None)
-        if shared is not None:
-            pass  # decided on the first call
-        elif dist is not None and self._pending_copies:
-            # all ranks must be about to upload the same list (a rank with cached frames would not take part)
-            sig = torch.tensor([len(self._pending_copies), sum(a.nbytes for _, a, _ in self._pending_copies)], dtype=torch.int64,
-                               device=self.device)
-            lo, hi = sig.clone(), sig.clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            shared = bool(torch.equal(lo, hi))
-        elif dist is not None:
-            none = torch.zeros(2, dtype=torch.int64, device=self.device)
-            dist.all_reduce(none.clone(), op=dist.ReduceOp.MIN)
-            dist.all_reduce(none, op=dist.ReduceOp.MAX)
-            shared = False
-        else:
-            shared = False
-        if self.__dict__.get("_shared_upload") is None:
-            self._shared_upload, self._copies_done = shared, 0
-        world, rank = (dist.get_world_size(), dist.get_rank()) if shared else (1, 0)
-        todo = self._pending_copies if limit is None else self._pending_copies[:limit]
-        with torch.cuda.stream(copy_stream):
-            for k, (dev, arr, event) in enumerate(todo, start=self._copies_done):
-                if k % world == rank:
+        the first so many (the rest on the next call).
+
+        With an NCCL group every rank holds the same frames on its host, so they cross PCIe once per box instead of once per
+        GPU: the frames lie in a few time-ordered groups of the device arena (``_upload_frames``); of every group each rank
+        uploads its 1 / world slice into a staging buffer and ONE ``all_gather_into_tensor`` over NVLink fills the group on
+        every GPU (a handful of collectives per track instead of one broadcast per frame).  The first group is small, so
+        tracking starts while the later groups are still in flight."""
+        torch, copy_stream = self.torch, self.tracker._copy_stream
+        if not self._shared_upload:
+            todo = self._pending_copies if limit is None else self._pending_copies[:limit]
+            with torch.cuda.stream(copy_stream):
+                for dev, arr, event in todo:
                     dev.copy_(torch.from_numpy(arr), non_blocking=True)
-                else:
-                    self.h2d -= arr.nbytes  # arrives over NVLink
-                if shared:
-                    dist.broadcast(dev, src=k % world)
-                event.record(copy_stream)
+                    event.record(copy_stream)
+            for k, event in self._pending_events:
+                self.image_events[k] = event.cuda_event
+            self._pending_copies = self._pending_copies[len(todo):]
+            return
         for k, event in self._pending_events:
             self.image_events[k] = event.cuda_event
-        self._copies_done += len(todo)
-        self._pending_copies = self._pending_copies[len(todo):]
+        if limit is not None or not self._pending_copies:
+            return  # the bulk groups go out once the small tables are queued (second call)
+        dist = self.dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        arena = self._arena
+        flat = {id(arr): torch.from_numpy(arr).view(torch.uint8).reshape(-1) for _, arr, _ in self._pending_copies}
+        with torch.cuda.stream(copy_stream):
+            for g0, span, members in self._upload_groups:
+                chunk = span // world
+                lo, hi = g0 + rank * chunk, g0 + (rank + 1) * chunk
+                staging = torch.empty(chunk, dtype=torch.uint8, device=self.device)
+                staging.record_stream(copy_stream)
+                for off, (dev, arr, event) in members:
+                    a, b = max(off, lo), min(off + arr.nbytes, hi)
+                    if a < b:  # the part of this frame that lies in this rank's slice of the group
+                        staging[a - lo:b - lo].copy_(flat[id(arr)][a - off:b - off], non_blocking=True)
+                        self.h2d += b - a
+                dist.all_gather_into_tensor(arena[g0:g0 + span], staging)
+                for _, (dev, arr, event) in members:
+                    event.record(copy_stream)
+        self._pending_copies = []
 
     # ---------------------------------------------------------------- uploads
     def _upload_frames(self):
@@ -364,20 +365,40 @@ class Session:
                     fresh.append((k, key, use_cache, arr))
                     continue
                 placed.append((k, cached))
-            # frames not on the device yet: one allocation (on the copy stream) carved into 256-byte aligned slices
+            # frames not on the device yet: one allocation (on the copy stream) carved into 256-byte aligned slices.
+            # Shared upload (NCCL group): the frames form a few time-ordered groups, each padded to a multiple of
+            # world x 256 bytes so that every rank contributes an equal slice to the group's all-gather.
+            self._shared_upload = self._agree_on_shared_upload(len(fresh), sum(arr.nbytes for _, _, _, arr in fresh))
+            self._upload_groups = []
             if fresh:
+                world = self.dist.get_world_size() if self._shared_upload else 1
+                n = len(fresh)
+                first = min(n, 4)
+                rest = -(-(n - first) // 3) if n > first else 0
+                bounds = [0, first] + [min(n, first + rest * k) for k in (1, 2, 3) if rest]
+                bounds = sorted(set(bounds))
                 offsets_b, total = [], 0
-                for _, _, _, arr in fresh:
-                    offsets_b.append(total)
-                    total += (arr.nbytes + 255) // 256 * 256
+                for lo_g, hi_g in zip(bounds[:-1], bounds[1:]):
+                    g0 = total
+                    for _, _, _, arr in fresh[lo_g:hi_g]:
+                        offsets_b.append(total)
+                        total += (arr.nbytes + 255) // 256 * 256
+                    if self._shared_upload:
+                        total = g0 + -(-(total - g0) // (world * 256)) * (world * 256)
+                        self._upload_groups.append([g0, total - g0, []])
                 arena = torch.empty(total, dtype=torch.uint8, device=device)
                 arena.record_stream(compute_stream)
+                self._arena = arena
                 free = tracker.__dict__.setdefault("_event_free", [])  # events handed back by clear_device_cache()
-                for (k, key, use_cache, arr), off in zip(fresh, offsets_b):
+                for n_f, ((k, key, use_cache, arr), off) in enumerate(zip(fresh, offsets_b)):
                     dev = arena[off:off + arr.nbytes].view(arr.shape)
                     event = free.pop() if free else torch.cuda.Event()
                     self._pending_copies.append((dev, arr, event))
-                    self.h2d += arr.nbytes
+                    if self._shared_upload:
+                        group = max(g for g in range(len(self._upload_groups)) if self._upload_groups[g][0] <= off)
+                        self._upload_groups[group][2].append((off, (dev, arr, event)))
+                    else:
+                        self.h2d += arr.nbytes
                     cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
                     if use_cache:
                         tracker._frame_cache[key] = cached
@@ -397,10 +418,30 @@ class Session:
         self.h2d += images_dev.numel()
         return images_dev, np.asarray(offsets, dtype=np.int32)
 
+    def _agree_on_shared_upload(self, n_frames: int, n_bytes: int) -> bool:
+        """Whether this session's frames are uploaded once per box and shared over NVLink.  All ranks must be about to upload
+        the same list (a rank whose frames are still cached would not take part): agreed with one ``all_reduce`` the first
+        time a Tracker sees an upload of this size, remembered afterwards — ``track()`` is a collective call under
+        ``torch.distributed`` (same arguments, same cache state on every rank), so later sessions need no agreement."""
+        dist = self.dist
+        if dist is None or dist.get_backend() != "nccl":
+            return False
+        agreed = self.tracker.__dict__.setdefault("_shared_upload_agreed", {})
+        key = (int(n_frames), int(n_bytes))
+        if key not in agreed:
+            torch = self.torch
+            sig = torch.tensor([key[0], key[1], -key[0], -key[1]], dtype=torch.int64, device=self.device)
+            dist.all_reduce(sig, op=dist.ReduceOp.MIN)  # min and (negated) max in one call
+            sig = sig.tolist()
+            agreed[key] = bool(sig[0] == -sig[2] and sig[1] == -sig[3])
+        return agreed[key] and n_frames > 0
+
     def _lower_camera_memo(self, cam):
         """``lower_camera`` once per distinct camera (a sequence of frames usually shares one)."""
         memo = self.__dict__.setdefault("_camera_memo", {})
         vec = getattr(cam, "vector", None)
+        if vec is None:
+            vec = getattr(cam, "_vector", None)  # the reference's Camera keeps its 20-vector here
         if vec is None:
             return lower_camera(cam)
         corr = getattr(cam, "correction", None)
@@ -493,10 +534,9 @@ class Session:
             _lib.check(self.lib.gb_track_step(C.byref(self.desc), int(t), C.byref(io) if io is not None else None, self.stream))
 
     # ---------------------------------------------------------------- results
-    def fetch(self, gather=None) -> dict:
+    def fetch(self) -> dict:
         """Results to host memory: every array is copied into pinned memory on the compute stream without
-        blocking, then one synchronisation covers them all.  ``gather`` = (dist, points per rank, world size): the
-        blocks of all ranks are all-gathered on the devices first (NCCL), so every rank returns every point."""
+        blocking, then one synchronisation covers them all."""
         torch, b, P, T = self.torch, self.buf, self.P, self.T
         names = ["means", "sig", "status", "status_time", "obs_flags", "window"]
         if self.return_particles:
@@ -505,12 +545,6 @@ class Session:
         with torch.cuda.device(self.device):
             for k in names:
                 src = b[k]
-                if gather is not None and k != "window":
-                    dist, per, world = gather
-                    mine = torch.zeros((per,) + tuple(src.shape[1:]), dtype=src.dtype, device=self.device)
-                    mine[:P] = src
-                    src = torch.empty((per * world,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=self.device)
-                    dist.all_gather_into_tensor(src, mine)
                 host[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
                 host[k].copy_(src, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
@@ -522,10 +556,8 @@ class Session:
         if self.return_particles:
             out["particles"], out["weights"] = h["particles"], h["weights"]
             d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
-        if gather is not None:
-            d2h *= gather[2]
         win = h["window"]
-        used = (b["obs_flags"].cpu().numpy() == 0) & (win[..., 0] > 0) if gather is not None else (out["obs_flags"] == 0) & (win[..., 0] > 0)
+        used = (out["obs_flags"] == 0) & (win[..., 0] > 0)
         self.stats = {
             "plan": {k: getattr(self.plan, k) for k, _ in self.plan._fields_}, "kernel_launches": self.launches,
             "h2d_bytes": int(self.h2d), "d2h_bytes": int(d2h),
@@ -536,9 +568,14 @@ class Session:
     def final_state(self):
         """What the reference leaves on the Tracker: particles / weights / templates of the last track."""
         b = self.buf
+        if int(b["status"][-1]) != 0:  # the last point failed: its buffers stopped at the time of the error
+            return None, None, self.templates(self.P - 1)
         final = b["state_b"] if (int(self.last[-1]) & 1) else b["state_a"]
         particles = final[-1].T.contiguous().cpu().numpy()
-        weights = b["weight_state"][-1].cpu().numpy() if b["weight_state"] is not None else np.ones(self.N)
+        if b["final_weights"] is not None:
+            weights = b["final_weights"].cpu().numpy()
+        else:
+            weights = b["weight_state"][-1].cpu().numpy() if b["weight_state"] is not None else np.ones(self.N)
         return particles, weights, self.templates(self.P - 1)
 
     def templates(self, p: int):

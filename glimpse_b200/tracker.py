@@ -10,9 +10,8 @@ Differences a user can see (all documented in DESIGN.md):
 * ``rng="philox"`` (default) draws on the device from Philox4x32-10, keyed by ``seed`` (or by one
   ``np.random.randint`` draw, so ``np.random.seed`` still makes runs reproducible).  ``rng="numpy"``
   supplies the reference's exact legacy-MT19937 draw sequence (parity runs; ~2.5e7 normals/s).
-* ``mode="stream"`` (default) runs each update as five massively parallel kernels; ``mode="fused"`` runs
-  it as one thread-block-cluster kernel per update with the particle intermediates kept on chip
-  (``cluster`` = CTAs per point, 0 = automatic).  Same results up to floating-point association.
+* ``mode`` is kept for compatibility and must be ``"stream"`` (kernels over all points, batches of points on their own
+  streams); round 1's cluster-per-point kernel was removed.
 * A track whose work buffers do not fit the device memory that is free runs as consecutive blocks of points (points are
   independent and the device draws are keyed by the global point index, so the results do not depend on the blocks);
   ``max_points`` caps the block size by hand.
@@ -96,7 +95,6 @@ class Tracker:
         *,
         rng: str = "philox",
         seed: Optional[int] = None,
-        cluster: int = 0,
         mode: str = "stream",
         device=None,
         distributed: bool = True,
@@ -110,7 +108,8 @@ class Tracker:
         self.interpolation = interpolation
         self.rng = rng
         self.seed = seed
-        self.cluster = cluster
+        if mode != "stream":
+            raise ValueError("mode must be 'stream' (the cluster-per-point kernel of round 1 was removed)")
         self.mode = mode
         self.device = device
         self.distributed = distributed
@@ -233,17 +232,39 @@ class Tracker:
                     lo, hi = shard_bounds(ntracks, world, rank)
             except ImportError:
                 pass
-        # NCCL: frames are uploaded once per box (each rank a share, broadcast over NVLink) and the result blocks are
-        # gathered on the devices; other backends (gloo in the CPU tests) gather the host arrays
+        # One Philox key per track() call, whatever the sharding: blocks of points and ranks draw from the same key, indexed
+        # by the global point number (``seed=None``: one draw from the legacy generator, so np.random.seed still reproduces a
+        # run; rank 0's draw is used on every rank).
+        seed = None
+        if self.rng == "philox":
+            seed = self.seed if self.seed is not None else int(np.random.randint(0, 2 ** 62))
+            if dist is not None and self.seed is None:
+                import torch
+
+                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+                box = torch.tensor([seed], dtype=torch.int64, device=dev)
+                dist.broadcast(box, src=0)
+                seed = int(box.item())
+        n_particles = int(motion_models[0].n) if ntracks else 0
+        tile = tuple(int(v) for v in tile_size)
+        args = (image_index, taus, tile)
+        # (frames are shared between the ranks only if every rank has points: an idle rank opens no session)
         per_rank = -(-ntracks // world)
-        on_device = dist is not None and dist.get_backend() == "nccl" and (world - 1) * per_rank < ntracks  # no idle rank
-        extra = {"gather": (dist, per_rank, world)} if on_device else {}
-        local = self._track_local(motion_models[lo:hi], image_index, taus, tuple(int(v) for v in tile_size),
-                                  observer_mask[lo:hi], return_covariances, return_particles, point_offset=lo, **extra)
-        if on_device:
-            local = {k: v[:ntracks] for k, v in local.items()}
-        elif dist is not None:
-            local = self._gather(dist, local, ntracks, world)
+        share = dist if (dist is not None and (world - 1) * per_rank < ntracks) else None
+        local = self._track_local(motion_models[lo:hi], *args, observer_mask[lo:hi], return_covariances, return_particles,
+                                  point_offset=lo, dist=share, seed=seed, n_particles=n_particles)
+        rerun = (seed, motion_models[lo:hi], *args, observer_mask[lo:hi], return_covariances, return_particles, lo)
+        if dist is None:
+            local = self._rerun_large_windows(local, *rerun)
+        else:
+            # points are independent: the only collective of the data path is this gather of the result blocks (one call).
+            # Every rank then sees every status, so all ranks agree without another collective on whether some points need
+            # their second run (a search window that outgrew the plan's capacity) and a second gather.
+            merged = self._gather(dist, local, ntracks, world)
+            if self._can_rerun(seed) and (merged["status"] == _lib.GB_ST_WINDOW_TOO_LARGE).any():
+                local = self._rerun_large_windows(local, *rerun)
+                merged = self._gather(dist, local, ntracks, world)
+            local = merged
 
         # materialise errors / warnings the way the reference reports them (tracker.py:358-368)
         errors: List[Optional[BaseException]] = [None] * ntracks
@@ -280,51 +301,27 @@ class Tracker:
 
     # ------------------------------------------------------------------ device plumbing
     def _track_local(self, models, image_index, taus, tile_size, observer_mask, return_covariances, return_particles,
-                     point_offset=0, gather=None) -> dict:
-        """Run the filter for ``models`` on this process's GPU; returns host arrays.  ``gather`` = (dist, points per
-        rank, world size): frames are shared between the ranks and the returned arrays hold every rank's block."""
+                     point_offset=0, dist=None, seed=None, n_particles=0) -> dict:
+        """Run the filter for ``models`` on this process's GPU; returns host arrays for these points.  ``dist`` = the NCCL
+        group the frames are shared over (only the first session of a call takes part in the shared upload).  Ranks may
+        split their points into different numbers of sessions: no collective depends on it."""
         from .session import Session, empty_result
 
         if len(models) == 0:
-            return empty_result(0, image_index.shape[0], image_index.shape[1], return_covariances, return_particles)
+            return empty_result(0, image_index.shape[0], image_index.shape[1], return_covariances, return_particles, N=n_particles)
         block = self._points_per_session(models, image_index, tile_size, return_covariances, return_particles)
-        if block >= len(models):
-            session = Session(self, models, image_index, taus, tile_size, observer_mask, return_covariances,
-                              return_particles, point_offset=point_offset, dist=gather[0] if gather else None)
-            session.run()
-            rerun = (getattr(session, "seed_used", None), models, image_index, taus, tile_size, observer_mask, return_covariances,
-                     return_particles, point_offset)
-            if gather is None:
-                out = self._rerun_large_windows(session.fetch(None), *rerun)
-            else:
-                # the ranks agree on whether any point needs its second run (then the blocks are patched on the hosts and
-                # gathered from there); normally none does and the blocks are gathered on the devices
-                dist, per_rank, world = gather
-                failed = (session.buf["status"] == _lib.GB_ST_WINDOW_TOO_LARGE).sum()
-                dist.all_reduce(failed)
-                if int(failed) == 0:
-                    out = session.fetch(gather)
-                else:
-                    out = self._rerun_large_windows(session.fetch(None), *rerun)
-                    out = self._gather(dist, out, per_rank * world, world)
-            self.last_run = session.stats
-            self.particles, self.weights, self.templates = session.final_state()
-            return out
-        # consecutive blocks of points; the frames stay on the device between them (only the first block takes part in the
-        # shared upload of a multi-GPU box), every block's buffers are released before the next one is planned
+        # consecutive blocks of points (normally one); the frames stay on the device between them, every block's buffers are
+        # released before the next one is planned
         parts, stats = [], None
         for lo in range(0, len(models), block):
             session = Session(self, models[lo:lo + block], image_index, taus, tile_size, observer_mask[lo:lo + block],
                               return_covariances, return_particles, point_offset=point_offset + lo,
-                              dist=gather[0] if (gather and lo == 0) else None)
+                              dist=dist if lo == 0 else None, seed=seed)
             session.run()
-            parts.append(self._rerun_large_windows(session.fetch(None), getattr(session, "seed_used", None), models[lo:lo + block],
-                                                   image_index, taus, tile_size,
-                                                   observer_mask[lo:lo + block], return_covariances, return_particles,
-                                                   point_offset + lo))
+            parts.append(session.fetch())
             st = session.stats
             if stats is None:
-                stats = dict(st, sessions=1)
+                stats = dict(st, sessions=1) if block < len(models) else st
             else:
                 stats["sessions"] += 1
                 for k in ("kernel_launches", "h2d_bytes", "d2h_bytes"):
@@ -335,30 +332,37 @@ class Tracker:
                 self.particles, self.weights, self.templates = session.final_state()
             del session
         self.last_run = stats
-        out = {k: np.concatenate([part[k] for part in parts], axis=0) for k in parts[0]}
-        if gather:
-            dist, per_rank, world = gather
-            out = self._gather(dist, out, per_rank * world, world)
-        return out
+        if len(parts) == 1:
+            return parts[0]
+        return {k: np.concatenate([part[k] for part in parts], axis=0) for k in parts[0]}
+
+    def _can_rerun(self, seed) -> bool:
+        return self.rng == "philox" and seed is not None and self.window_margin < _lib.GB_WINDOW_MARGIN_MAX
 
     def _rerun_large_windows(self, out, seed, models, image_index, taus, tile_size, observer_mask, return_covariances,
                              return_particles, point_offset) -> dict:
         """Points that ended with GB_ST_WINDOW_TOO_LARGE (their particle cloud outgrew the plan's surface regions) are tracked
-        again, one by one, with the largest window capacity; the counter-based device draws make the second run identical to the
-        first up to the time it stopped (``seed`` = the Philox key of the first run).  The rows of ``out`` are replaced in place."""
+        again with the largest window capacity; the counter-based device draws make the second run identical to the first up
+        to the time it stopped (``seed`` = the Philox key of the first run).  Runs of consecutive failed points share a
+        session (the draws are keyed by the global point number, which a session derives from its first point).  The rows of
+        ``out`` are replaced in place."""
         from .session import Session
 
         failed = np.nonzero(out["status"] == _lib.GB_ST_WINDOW_TOO_LARGE)[0]
-        if len(failed) == 0 or self.rng != "philox" or seed is None or self.window_margin >= _lib.GB_WINDOW_MARGIN_MAX or len(failed) > 1024:
+        if len(failed) == 0 or not self._can_rerun(seed):
             return out
-        for p in failed:
-            p = int(p)
-            session = Session(self, models[p:p + 1], image_index, taus, tile_size, observer_mask[p:p + 1], return_covariances,
-                              return_particles, point_offset=point_offset + p, window_margin=_lib.GB_WINDOW_MARGIN_MAX, seed=seed)
+        runs, start = [], int(failed[0])
+        for a, b in zip(failed, list(failed[1:]) + [None]):
+            if b is None or int(b) != int(a) + 1:
+                runs.append((start, int(a) + 1))
+                start = int(b) if b is not None else 0
+        for lo, hi in runs:
+            session = Session(self, models[lo:hi], image_index, taus, tile_size, observer_mask[lo:hi], return_covariances,
+                              return_particles, point_offset=point_offset + lo, window_margin=_lib.GB_WINDOW_MARGIN_MAX, seed=seed)
             session.run()
-            one = session.fetch(None)
+            part = session.fetch()
             for key, rows in out.items():
-                rows[p] = one[key][0]
+                rows[lo:hi] = part[key]
             del session
         self.__dict__.setdefault("_rerun_points", []).extend(int(point_offset + p) for p in failed)
         return out
@@ -382,35 +386,50 @@ class Tracker:
                         frames += int(array.nbytes) if array is not None else 3 * int(np.prod(obs.images[i].size))
                     except (AttributeError, TypeError):
                         pass  # size unknown before the frame is read: the 10 % margin has to cover it
-        mode = {"fused": _lib.GB_MODE_FUSED, "stream": _lib.GB_MODE_STREAM}[self.mode]
+        mode = _lib.GB_MODE_STREAM
         shape = dict(N=int(models[0].n), T=image_index.shape[0], O=image_index.shape[1], tw=tile_size[0], th=tile_size[1],
-                     return_covariances=return_covariances, return_particles=return_particles)
+                     return_covariances=return_covariances, return_particles=return_particles, window_margin=int(self.window_margin))
         lib = _lib.load()
         # the common case costs no driver call: a track needing less than a quarter of the device is not measured against
         # the free memory (cudaMemGetInfo takes from a fraction of a millisecond to several)
         total = torch.cuda.get_device_properties(device).total_memory
-        if _session.session_bytes(lib, mode, self.cluster, cap, **shape) + frames <= total // 4:
+        if _session.session_bytes(lib, mode, 0, cap, **shape) + frames <= total // 4:
             return cap
         free, _total = torch.cuda.mem_get_info(device)
         free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-        return _session.points_per_session(lib, mode, self.cluster, cap, int(0.9 * max(free - frames, 0)), **shape)
+        return _session.points_per_session(lib, mode, 0, cap, int(0.9 * max(free - frames, 0)), **shape)
 
     # ------------------------------------------------------------------ multi-GPU: one final gather
     @staticmethod
     def _gather(dist, local: dict, ntracks: int, world: int) -> dict:
-        """All-gather the per-rank result blocks (points are independent: no per-step collective)."""
+        """All-gather the per-rank result blocks in ONE collective (points are independent: no per-step collective): every
+        array is padded to the block size ceil(ntracks / world), the blocks are packed into one byte buffer per rank, and the
+        gathered buffers are unpacked on the host.  A rank without points contributes arrays of zero rows."""
         import torch
 
         backend = dist.get_backend()
         device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         per = -(-ntracks // world)
-        merged = {}
-        for key, value in local.items():
-            arr = np.ascontiguousarray(value)
+        keys = sorted(local)
+        layout, chunks = [], []
+        for key in keys:
+            arr = np.ascontiguousarray(local[key])
             pad = np.zeros((per,) + arr.shape[1:], dtype=arr.dtype)
             pad[: arr.shape[0]] = arr
-            mine = torch.as_tensor(pad).to(device)
+            layout.append((key, pad.shape, pad.dtype, pad.nbytes))
+            chunks.append(pad.view(np.uint8).reshape(-1))
+        mine = torch.from_numpy(np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)).to(device)
+        if backend == "nccl":
+            everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(everyone, mine)
+            everyone = everyone.cpu().numpy().reshape(world, -1)
+        else:
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine)
-            merged[key] = np.concatenate([p.cpu().numpy() for p in parts], axis=0)[:ntracks]
+            everyone = np.stack([p.cpu().numpy() for p in parts])
+        merged, at = {}, 0
+        for key, shape, dtype, nbytes in layout:
+            block = np.ascontiguousarray(everyone[:, at:at + nbytes]).view(dtype).reshape((world * per,) + shape[1:])
+            merged[key] = block[:ntracks]
+            at += nbytes
         return merged

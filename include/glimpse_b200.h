@@ -161,14 +161,12 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
 /* ------------------------------------------------------------------------------------------
  * The filter
  * ------------------------------------------------------------------------------------------ */
-/* Two device organisations of the same update (identical results up to floating-point association):
- *  GB_MODE_FUSED  one thread-block cluster owns a point for a whole update; particle intermediates
- *                 stay in (distributed) shared memory, state streams through HBM once (96 B/update).
- *  GB_MODE_STREAM kernels over all points (default).  gb_track pipelines them: per update and batch of points
- *                 k_s0p_activity -> k_s2_surface -> k_s3_weights -> k_s3b_publish -> k_s4p_resample_propagate (the
- *                 resampling of time t fused with the motion step to t + 1) -> k_s5p_finalize, batches on their own
- *                 streams; gb_track_step runs the same stages unfused so that intermediates can be forced / dumped. */
-#define GB_MODE_FUSED 0
+/* Device organisation of an update: kernels over all points.  gb_track pipelines them: per update and batch of points
+ *   [k_s0p_activity ->] k_s2_surface -> k_s3_weights -> k_s3b_publish -> k_s4p_resample_propagate (the resampling of
+ *   time t fused with the motion step to t + 1) -> k_s5p_finalize, batches on their own streams; gb_track_step runs the
+ *   same stages unfused so that intermediates can be forced / dumped.
+ * (Mode 0 was round 1's cluster-per-point kernel, which kept a point's particles in distributed shared memory; it ran at
+ *  a third of this organisation's rate and was removed.  gb_step_plan rejects it.) */
 #define GB_MODE_STREAM 1
 
 /* Launch plan chosen by gb_step_plan: cluster size (CTAs per tracked point), threads per CTA,
@@ -196,7 +194,8 @@ typedef struct gb_plan {
 } gb_plan;
 
 /* Size a launch plan for N particles per point, a w x h template, P points and O observers.
- * `prefer_cluster` = 0 lets the library choose the cluster size of GB_MODE_FUSED; otherwise forces 1/2/4/8. */
+ * `prefer_cluster` is ignored (it sized the removed cluster-per-point organisation); `mode` must be GB_MODE_STREAM.
+ * Plan fields that only that organisation used (cluster, particles_in_smem, n_slabs, slab_bytes, particle_scratch_bytes) are 1 / 0. */
 int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
                  int32_t prefer_cluster, int32_t mode, gb_plan* plan_host);
 /* The same with the capacity of the search windows chosen by the caller: in GB_MODE_STREAM every (point, observer) owns a surface
@@ -274,6 +273,9 @@ typedef struct gb_track_desc {
   int32_t interp_rows, interp_cols; /* Tracker.interpolation (tracker.py:60, observer.py:210): degree of the interpolating spline along the rows
                                     * (kx) and the columns (ky) of the SSE surface, which also sets the minimum surface size (tracker.py:584-594).
                                     * 3 (cubic, not-a-knot) or 1 (piecewise linear); 0 = the default 3 */
+  double* final_weights;           /* [N] or NULL: weights of point P - 1's resampled particles at its last time — what Tracker.weights holds
+                                    * after track() in the reference (tracker.py:62-70, 216-223: the state of the last processed track);
+                                    * the caller pre-fills it with ones (a point that is never updated keeps its initial weights) */
   gb_plan plan;
 } gb_track_desc;
 

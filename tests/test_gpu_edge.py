@@ -11,7 +11,7 @@ from glimpse_b200 import synthetic
 from oracle import tracker_oracle as orc
 
 pytestmark = pytest.mark.gpu
-MODES = ["stream", "fused"]
+MODES = ["stream"]
 
 
 def run_both(scene, seed, mode, points=None, viewshed=None, oracle_viewshed=None, exact=True, **track_kw):

@@ -31,11 +31,20 @@ WORKER = textwrap.dedent('''
     np.testing.assert_array_equal(sharded.covariances, alone.covariances)
     assert h2d_sharded < 0.7 * alone.tracker.last_run["h2d_bytes"]     # half of the frames came over NVLink
     # blocks of points inside every rank (a track too large for the device memory): same answer again
-    blocked = gb.Tracker(observers, seed=11, max_points=2)
+    # (uneven: rank 0 holds 4 points = two sessions of <= 3, rank 1 holds 3 = one session; no collective depends on it)
+    blocked = gb.Tracker(observers, seed=11, max_points=3)
     tracks = blocked.track(models, tile_size=scene.tile_size, return_covariances=True)
-    assert blocked.last_run["sessions"] == 2
+    assert blocked.last_run.get("sessions", 1) == (2 if rank == 0 else 1)
     np.testing.assert_array_equal(tracks.means, alone.means)
     np.testing.assert_array_equal(tracks.covariances, alone.covariances)
+    # seed=None: one key for the whole call, rank 0's draw on every rank; particles returned through the packed gather
+    np.random.seed(100 + rank)
+    free = gb.Tracker(observers).track(models, tile_size=scene.tile_size, return_particles=True)
+    ref = gb.Tracker(observers, distributed=False, seed=None)
+    np.random.seed(100)
+    alone2 = ref.track(models, tile_size=scene.tile_size, return_particles=True)
+    np.testing.assert_array_equal(free.means, alone2.means)
+    np.testing.assert_array_equal(free.particles, alone2.particles)
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 ''')

@@ -78,18 +78,18 @@ def test_plan_sizes():
 
     lib = _lib.load()
     plan = _lib.gb_plan()
-    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 0, 0, C.byref(plan)) == 0
-    assert plan.cluster == 1 and plan.particles_in_smem == 1 and plan.n_local >= 1000
-    assert lib.gb_step_plan(10000, 15, 15, 1000, 1, 0, 0, C.byref(plan)) == 0
-    assert plan.particles_in_smem == 1 and plan.cluster * plan.n_local >= 10000 and plan.smem_bytes <= 232448
-    assert plan.cluster == 4 and plan.tile_bytes >= 24 * 1024  # 39 x 39 windows on chip, larger ones spill to slabs
-    assert plan.scratch_bytes == plan.n_slabs * plan.slab_bytes and plan.slab_bytes > 1 << 20
-    assert lib.gb_step_plan(100000, 31, 31, 1000, 1, 0, 0, C.byref(plan)) == 0
-    assert plan.particles_in_smem == 0 and plan.particle_scratch_bytes == 1000 * plan.cluster * 9 * plan.n_local * 8
-    assert plan.scratch_bytes == plan.particle_scratch_bytes + plan.n_slabs * plan.slab_bytes
-    assert lib.gb_step_plan(1000, 40, 40, 10, 1, 0, 0, C.byref(plan)) == -3  # template > 1024 px
-    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 3, 0, C.byref(plan)) == -1
-    assert b"cluster" in lib.gb_last_error()
+    S = _lib.GB_MODE_STREAM
+    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 0, S, C.byref(plan)) == 0
+    assert plan.stream_nblk == 2 and plan.stream_block == 500 and plan.n_local == 1000 and plan.mode == S
+    assert lib.gb_step_plan(10000, 15, 15, 1000, 1, 0, S, C.byref(plan)) == 0
+    # particles of a point in equal even blocks of <= 768 (k_s4p's shared memory), 4 batches of points on 4 streams
+    assert plan.stream_nblk == 14 and plan.stream_block == 716 and plan.stream_batch == 250 and plan.stream_slots == 4
+    assert plan.surf_bytes > 700 * 1024 and plan.scratch_bytes > 1000 * (2 * 48 + 16 + 8) * 10000 + 1000 * plan.surf_bytes
+    assert lib.gb_step_plan(100000, 31, 31, 1000, 1, 0, S, C.byref(plan)) == 0
+    assert plan.stream_nblk == 131 and plan.stream_block * plan.stream_nblk >= 100000 and plan.stream_block % 2 == 0
+    assert lib.gb_step_plan(1000, 40, 40, 10, 1, 0, S, C.byref(plan)) == -3  # template > 1024 px
+    assert lib.gb_step_plan(1000, 15, 15, 10, 1, 0, 0, C.byref(plan)) == -1    # mode 0: round 1's cluster-per-point kernel, removed
+    assert b"removed" in lib.gb_last_error()
 
 
 def test_point_span_and_shards():
@@ -212,7 +212,7 @@ day = datetime.timedelta(days=1)
 models = [gb.CartesianMotion(xy=(float(i), 0), time_unit=day, dem=0.0, n=8) for i in range(5)]
 tracker = gb.Tracker([obs])
 seen = {}
-def fake_local(models, image_index, taus, tile_size, mask, cov, parts, point_offset=0):
+def fake_local(models, image_index, taus, tile_size, mask, cov, parts, point_offset=0, dist=None, seed=None, n_particles=0):
     # stands in for the GPU compute: encodes (global point index, time) so the gather can be checked
     from glimpse_b200.session import empty_result
     P, T, O = len(models), image_index.shape[0], image_index.shape[1]
@@ -232,6 +232,18 @@ assert tracks.means.shape == (5, 4, 6)
 for i in range(5):
     assert np.all(tracks.means[i] == i * 100 + np.arange(4)[:, None]) and np.all(tracks.sigmas[i] == i)
 assert isinstance(tracks.errors[2], IndexError) and all(tracks.errors[i] is None for i in (0, 1, 3, 4))
+# three points on two ranks with the particles returned: rank 1 holds one point; then one point: rank 1 is idle and
+# contributes blocks of zero rows with the right particle count (shapes must agree across ranks)
+for n in (3, 1):
+    seen.clear()
+    tracks = tracker.track(models[:n] if n > 1 else models[:1] * 1, return_particles=True) if n > 1 else None
+    if n > 1:
+        assert tracks.particles.shape == (3, 4, 8, 6) and tracks.weights.shape == (3, 4, 8)
+        assert seen["block"] == ((0, 2) if dist.get_rank() == 0 else (2, 1)), seen
+local = fake_local(models[:1] if dist.get_rank() == 0 else [], np.zeros((4, 1), dtype=np.int32), None, None, None, False, True,
+                   point_offset=dist.get_rank(), n_particles=8)
+merged = gb.Tracker._gather(dist, local, 1, 2)
+assert merged["particles"].shape == (1, 4, 8, 6) and merged["means"].shape == (1, 4, 6) and merged["status"].shape == (1,)
 dist.barrier(); dist.destroy_process_group()
 print("rank", sys.argv[3], "ok")
 """
@@ -316,8 +328,7 @@ def test_blocks_and_second_runs_are_assembled_on_the_host(monkeypatch):
         def run(self):
             pass
 
-        def fetch(self, gather):
-            assert gather is None
+        def fetch(self):
             P = len(self.models)
             out = session_mod.empty_result(P, self.T, self.O, False, False)
             for i, m in enumerate(self.models):
@@ -342,9 +353,9 @@ def test_blocks_and_second_runs_are_assembled_on_the_host(monkeypatch):
     tracker._points_per_session = lambda *a, **k: 2
     tracks = tracker.track(models)
     blocks = [(s.offset, len(s.models), s.margin) for s in created]
-    # blocks of 2, 2, 1 points; after block 0 point 1 is run again, after block 2 point 4
-    assert blocks == [(0, 2, None), (1, 1, _lib.GB_WINDOW_MARGIN_MAX), (2, 2, None), (4, 1, None), (4, 1, _lib.GB_WINDOW_MARGIN_MAX)]
-    assert all(s.seed_used == 4242 for s in created)
+    # blocks of 2, 2, 1 points; then points 1 and 4 are run again
+    assert blocks == [(0, 2, None), (2, 2, None), (4, 1, None), (1, 1, _lib.GB_WINDOW_MARGIN_MAX), (4, 1, _lib.GB_WINDOW_MARGIN_MAX)]
+    assert len({s.seed_used for s in created}) == 1 and created[0].seed_used != 4242  # one key per track() call, drawn by the Tracker
     assert all(e is None for e in tracks.errors)
     np.testing.assert_array_equal(tracks.means[:, 0, 0], np.arange(5.0))
     assert tracker.last_run["sessions"] == 3 and tracker.last_run["kernel_launches"] == 30
