@@ -481,7 +481,8 @@ def run_gpu_arm(args):
     e2e_value = world * P * N * T / e2e_mean_s
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tracker.last_run["h2d_bytes"]),
            "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_mean_s, "steps": e2e_steps,
-           "ms_each": e2e_each, "median_ms_per_step": 1e3 * e2e_median_s, "aggregate": "mean of steps (max over ranks)"}
+           "ms_each": e2e_each, "median_ms_per_step": 1e3 * e2e_median_s, "aggregate": "mean of steps (max over ranks)",
+           "host_ms_last_step": {k: round(v, 2) for k, v in tracker.last_run.get("host_ms", {}).items()}}
     v_err = float(np.nanmedian(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0])))
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------

@@ -40,6 +40,33 @@ def empty_result(P, T, O, return_covariances, return_particles, N=0) -> dict:
     return out
 
 
+def result_layout(per: int, T: int, O: int, N: int, return_covariances: bool, return_particles: bool):
+    """Byte layout of one rank's block of results in the gather of a multi-GPU track: ``per`` points per rank (the last
+    rank's block is zero-padded), one 16-byte aligned section per array, keys in sorted order.  Returns
+    ([(key, shape after the point axis, dtype, offset, bytes)], total bytes)."""
+    tails = {"means": ((T, 6), np.float64), "sigmas": ((T, 6, 6) if return_covariances else (T, 6), np.float64),
+             "status": ((), np.int32), "status_time": ((), np.int32), "obs_flags": ((T, O), np.uint8)}
+    if return_particles:
+        tails["particles"], tails["weights"] = ((T, N, 6), np.float64), ((T, N), np.float64)
+    layout, at = [], 0
+    for key in sorted(tails):
+        tail, dtype = tails[key]
+        nbytes = per * int(np.prod(tail, dtype=np.int64)) * np.dtype(dtype).itemsize
+        layout.append((key, tail, np.dtype(dtype), at, nbytes))
+        at += -(-nbytes // 16) * 16
+    return layout, at
+
+
+def unpack_results(everyone: np.ndarray, layout, per: int, ntracks: int) -> dict:
+    """``everyone`` = (world, bytes per rank) gathered blocks -> arrays over all points."""
+    world = everyone.shape[0]
+    merged = {}
+    for key, tail, dtype, at, nbytes in layout:
+        block = np.ascontiguousarray(everyone[:, at:at + nbytes]).view(dtype).reshape((world * per,) + tuple(tail))
+        merged[key] = block[:ntracks]
+    return merged
+
+
 def reference_order_draws(P, N, steps_per_point, tangent=None, stratified=False):
     """Draws from the legacy global NumPy generator in the reference's order: per point
     randn(N,2), randn(N), randn(N,3); then per update randn(N,3) and one random().  Points with a tangent model
@@ -283,7 +310,7 @@ class Session:
         With an NCCL group every rank holds the same frames on its host, so they cross PCIe once per box instead of once per
         GPU: the frames lie in a few time-ordered groups of the device arena (``_upload_frames``); of every group each rank
         uploads its 1 / world slice into a staging buffer and ONE ``all_gather_into_tensor`` over NVLink fills the group on
-        every GPU (a handful of collectives per track instead of one broadcast per frame).  The first group is small, so
+        every GPU (one collective per eight frames instead of one broadcast per frame).  The first group is small, so
         tracking starts while the later groups are still in flight."""
         torch, copy_stream = self.torch, self.tracker._copy_stream
         if not self._shared_upload:
@@ -373,10 +400,9 @@ class Session:
             if fresh:
                 world = self.dist.get_world_size() if self._shared_upload else 1
                 n = len(fresh)
-                first = min(n, 4)
-                rest = -(-(n - first) // 3) if n > first else 0
-                bounds = [0, first] + [min(n, first + rest * k) for k in (1, 2, 3) if rest]
-                bounds = sorted(set(bounds))
+                # groups in time order: two frames first (tracking starts as soon as they are there), then eight at a time —
+                # small enough that the uploads stay ahead of the tracking, large enough that a track needs ~n / 8 collectives
+                bounds = sorted(set([0, min(n, 2)] + list(range(min(n, 2), n, 8)) + [n]))
                 offsets_b, total = [], 0
                 for lo_g, hi_g in zip(bounds[:-1], bounds[1:]):
                     g0 = total
@@ -534,30 +560,49 @@ class Session:
             _lib.check(self.lib.gb_track_step(C.byref(self.desc), int(t), C.byref(io) if io is not None else None, self.stream))
 
     # ---------------------------------------------------------------- results
-    def fetch(self) -> dict:
+    def fetch(self, gather=None) -> dict:
         """Results to host memory: every array is copied into pinned memory on the compute stream without
-        blocking, then one synchronisation covers them all."""
+        blocking, then one synchronisation covers them all.  ``gather`` = (dist, points per rank, world size, points in
+        all): this session holds all of this rank's points, so its result blocks are packed into one byte buffer ON THE
+        DEVICE (``result_layout``), all-gathered in one NCCL call, and the returned arrays hold every rank's points."""
         torch, b, P, T = self.torch, self.buf, self.P, self.T
         names = ["means", "sig", "status", "status_time", "obs_flags", "window"]
         if self.return_particles:
             names += ["particles", "weights"]
         host = {}
         with torch.cuda.device(self.device):
+            if gather is not None:
+                dist, per, world, ntracks = gather
+                layout, nbytes = result_layout(per, T, self.O, self.N, self.return_covariances, self.return_particles)
+                mine = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+                for key, tail, dtype, at, _ in layout:
+                    src = b["sig" if key == "sigmas" else key].reshape(-1).view(torch.uint8)
+                    mine[at:at + src.numel()].copy_(src)
+                everyone = torch.empty(world * nbytes, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(everyone, mine)
+                host["everyone"] = torch.empty(everyone.shape, dtype=torch.uint8, pin_memory=True)
+                host["everyone"].copy_(everyone, non_blocking=True)
+                names = ["obs_flags", "window"]
             for k in names:
                 src = b[k]
                 host[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
                 host[k].copy_(src, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         h = {k: v.numpy() for k, v in host.items()}
-        n = h["means"].shape[0]
-        out = {"means": h["means"], "sigmas": h["sig"].reshape(n, T, 6, 6) if self.return_covariances else h["sig"],
-               "status": h["status"], "status_time": h["status_time"], "obs_flags": h["obs_flags"]}
         d2h = b["means"].numel() * 8 + b["sig"].numel() * 8 + P * 8 + b["obs_flags"].numel()
         if self.return_particles:
-            out["particles"], out["weights"] = h["particles"], h["weights"]
             d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
+        if gather is not None:
+            out = unpack_results(h["everyone"].reshape(world, nbytes), layout, per, ntracks)
+            d2h *= world
+        else:
+            n = h["means"].shape[0]
+            out = {"means": h["means"], "sigmas": h["sig"].reshape(n, T, 6, 6) if self.return_covariances else h["sig"],
+                   "status": h["status"], "status_time": h["status_time"], "obs_flags": h["obs_flags"]}
+            if self.return_particles:
+                out["particles"], out["weights"] = h["particles"], h["weights"]
         win = h["window"]
-        used = (out["obs_flags"] == 0) & (win[..., 0] > 0)
+        used = (h["obs_flags"] == 0) & (win[..., 0] > 0)
         self.stats = {
             "plan": {k: getattr(self.plan, k) for k, _ in self.plan._fields_}, "kernel_launches": self.launches,
             "h2d_bytes": int(self.h2d), "d2h_bytes": int(d2h),

@@ -190,6 +190,17 @@ class Tracker:
         parallel: Union[bool, int] = False,
     ) -> Tracks:
         """Track particles through time (reference ``tracker.py:225-417``)."""
+        import time as _time
+
+        clock = [_time.perf_counter()]
+        host_ms = {}
+
+        def lap(name):
+            now = _time.perf_counter()
+            host_ms[name] = host_ms.get(name, 0.0) + 1e3 * (now - clock[0])
+            clock[0] = now
+
+        self._lap = lap
         if reduce_particles:
             return_particles = True
         params = dict(motion_models=motion_models, datetimes=datetimes, maxdt=maxdt, tile_size=tile_size,
@@ -245,14 +256,18 @@ class Tracker:
                 box = torch.tensor([seed], dtype=torch.int64, device=dev)
                 dist.broadcast(box, src=0)
                 seed = int(box.item())
+        lap("prepare")
         n_particles = int(motion_models[0].n) if ntracks else 0
         tile = tuple(int(v) for v in tile_size)
         args = (image_index, taus, tile)
         # (frames are shared between the ranks only if every rank has points: an idle rank opens no session)
         per_rank = -(-ntracks // world)
         share = dist if (dist is not None and (world - 1) * per_rank < ntracks) else None
+        # (a rank whose points fit one device session gathers on the devices while it fetches; the same collective as _gather's)
+        on_device = (dist, per_rank, world, ntracks) if (dist is not None and dist.get_backend() == "nccl") else None
+        self._gathered = False
         local = self._track_local(motion_models[lo:hi], *args, observer_mask[lo:hi], return_covariances, return_particles,
-                                  point_offset=lo, dist=share, seed=seed, n_particles=n_particles)
+                                  point_offset=lo, dist=share, seed=seed, n_particles=n_particles, gather=on_device)
         rerun = (seed, motion_models[lo:hi], *args, observer_mask[lo:hi], return_covariances, return_particles, lo)
         if dist is None:
             local = self._rerun_large_windows(local, *rerun)
@@ -260,11 +275,15 @@ class Tracker:
             # points are independent: the only collective of the data path is this gather of the result blocks (one call).
             # Every rank then sees every status, so all ranks agree without another collective on whether some points need
             # their second run (a search window that outgrew the plan's capacity) and a second gather.
-            merged = self._gather(dist, local, ntracks, world)
+            lap("local")
+            merged = local if self._gathered else self._gather(dist, local, ntracks, world)
             if self._can_rerun(seed) and (merged["status"] == _lib.GB_ST_WINDOW_TOO_LARGE).any():
+                if self._gathered:
+                    local = {k: np.array(v[lo:hi]) for k, v in merged.items()}
                 local = self._rerun_large_windows(local, *rerun)
                 merged = self._gather(dist, local, ntracks, world)
             local = merged
+            lap("gather")
 
         # materialise errors / warnings the way the reference reports them (tracker.py:358-368)
         errors: List[Optional[BaseException]] = [None] * ntracks
@@ -297,11 +316,14 @@ class Tracker:
         tracks = Tracks(**kwargs)
         if reduced is not None:
             tracks.reduced = reduced
+        lap("results")
+        if isinstance(self.last_run, dict):
+            self.last_run["host_ms"] = host_ms  # where the wall time of this call went (host view; the device runs under 'fetch')
         return tracks
 
     # ------------------------------------------------------------------ device plumbing
     def _track_local(self, models, image_index, taus, tile_size, observer_mask, return_covariances, return_particles,
-                     point_offset=0, dist=None, seed=None, n_particles=0) -> dict:
+                     point_offset=0, dist=None, seed=None, n_particles=0, gather=None) -> dict:
         """Run the filter for ``models`` on this process's GPU; returns host arrays for these points.  ``dist`` = the NCCL
         group the frames are shared over (only the first session of a call takes part in the shared upload).  Ranks may
         split their points into different numbers of sessions: no collective depends on it."""
@@ -317,8 +339,15 @@ class Tracker:
             session = Session(self, models[lo:lo + block], image_index, taus, tile_size, observer_mask[lo:lo + block],
                               return_covariances, return_particles, point_offset=point_offset + lo,
                               dist=dist if lo == 0 else None, seed=seed)
+            self._lap("session")
             session.run()
-            parts.append(session.fetch())
+            self._lap("enqueue")
+            if gather is not None and block >= len(models):
+                parts.append(session.fetch(gather))  # results of all ranks
+                self._gathered = True
+            else:
+                parts.append(session.fetch())
+            self._lap("fetch")
             st = session.stats
             if stats is None:
                 stats = dict(st, sessions=1) if block < len(models) else st
@@ -407,29 +436,25 @@ class Tracker:
         gathered buffers are unpacked on the host.  A rank without points contributes arrays of zero rows."""
         import torch
 
+        from .session import result_layout, unpack_results
+
         backend = dist.get_backend()
         device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         per = -(-ntracks // world)
-        keys = sorted(local)
-        layout, chunks = [], []
-        for key in keys:
-            arr = np.ascontiguousarray(local[key])
-            pad = np.zeros((per,) + arr.shape[1:], dtype=arr.dtype)
-            pad[: arr.shape[0]] = arr
-            layout.append((key, pad.shape, pad.dtype, pad.nbytes))
-            chunks.append(pad.view(np.uint8).reshape(-1))
-        mine = torch.from_numpy(np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)).to(device)
+        T, O = local["obs_flags"].shape[1:3]
+        cov, parts = local["sigmas"].ndim == 4, "particles" in local
+        layout, nbytes = result_layout(per, T, O, local["particles"].shape[2] if parts else 0, cov, parts)
+        packed = np.zeros(nbytes, dtype=np.uint8)
+        for key, tail, dtype, at, _ in layout:
+            arr = np.ascontiguousarray(local[key], dtype=dtype).reshape(-1).view(np.uint8)
+            packed[at:at + arr.size] = arr
+        mine = torch.from_numpy(packed).to(device)
         if backend == "nccl":
-            everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+            everyone = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
             dist.all_gather_into_tensor(everyone, mine)
-            everyone = everyone.cpu().numpy().reshape(world, -1)
+            everyone = everyone.cpu().numpy().reshape(world, nbytes)
         else:
-            parts = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(parts, mine)
-            everyone = np.stack([p.cpu().numpy() for p in parts])
-        merged, at = {}, 0
-        for key, shape, dtype, nbytes in layout:
-            block = np.ascontiguousarray(everyone[:, at:at + nbytes]).view(dtype).reshape((world * per,) + shape[1:])
-            merged[key] = block[:ntracks]
-            at += nbytes
-        return merged
+            blocks = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(blocks, mine)
+            everyone = np.stack([blk.cpu().numpy() for blk in blocks])
+        return unpack_results(everyone, layout, per, ntracks)

@@ -212,7 +212,7 @@ day = datetime.timedelta(days=1)
 models = [gb.CartesianMotion(xy=(float(i), 0), time_unit=day, dem=0.0, n=8) for i in range(5)]
 tracker = gb.Tracker([obs])
 seen = {}
-def fake_local(models, image_index, taus, tile_size, mask, cov, parts, point_offset=0, dist=None, seed=None, n_particles=0):
+def fake_local(models, image_index, taus, tile_size, mask, cov, parts, point_offset=0, dist=None, seed=None, n_particles=0, gather=None):
     # stands in for the GPU compute: encodes (global point index, time) so the gather can be checked
     from glimpse_b200.session import empty_result
     P, T, O = len(models), image_index.shape[0], image_index.shape[1]
