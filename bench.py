@@ -534,7 +534,8 @@ def run_gpu_arm(args):
 def side_records(gb, synthetic, main_scene, world, rank, device, max_over_ranks, barrier, peak, args):
     """Three records beside the headline (config 2) line:
     result_crc  CRC-32 of the means and sigmas of a fixed 64-point problem tracked through the public API, sharded over the
-                ranks of this run: the same number at every N (the device draws are keyed by the global point index).
+                ranks of this run: the same number at every N (the device draws are keyed by the global point index), and
+                the same as result_crc_one_gpu, the problem tracked on one GPU in the same run.
     strong      strong scaling: a fixed 8 000 points of the workload split over the ranks, end to end (frames uploaded once
                 per box and shared over NVLink, one gather of the results).
     configs     one end-to-end track() each of BASELINE.json's other single-GPU shapes (rank 0's GPU only), with the frames
@@ -546,9 +547,15 @@ def side_records(gb, synthetic, main_scene, world, rank, device, max_over_ranks,
     out = {}
     small = synthetic.nadir_scene(seed=77, n_points=64, n_particles=2000, n_frames=8, imgsz=(600, 400))
     observers, models = synthetic.build(small, gb)
-    tracks = gb.Tracker(observers, seed=777).track(models, tile_size=small.tile_size)
-    crc = zlib.crc32(np.ascontiguousarray(tracks.means).tobytes())
-    out["result_crc"] = "%08x" % zlib.crc32(np.ascontiguousarray(tracks.sigmas).tobytes(), crc)
+    def crc_of(tracks):
+        crc = zlib.crc32(np.ascontiguousarray(tracks.means).tobytes())
+        return "%08x" % zlib.crc32(np.ascontiguousarray(tracks.sigmas).tobytes(), crc)
+
+    out["result_crc"] = crc_of(gb.Tracker(observers, seed=777).track(models, tile_size=small.tile_size))
+    # the same problem on this rank's GPU alone, and a checksum of its (host-generated) frames: the three numbers of runs on
+    # different boxes can only be compared if the frames agree (SciPy's filter may round differently on another CPU)
+    out["result_crc_one_gpu"] = crc_of(gb.Tracker(observers, seed=777, distributed=False).track(models, tile_size=small.tile_size))
+    out["result_crc_frames"] = "%08x" % zlib.crc32(b"".join(np.ascontiguousarray(f).tobytes() for f in small.observers[0].frames))
     # ---- strong scaling
     total = 8000
     kw = dict(WORKLOAD)

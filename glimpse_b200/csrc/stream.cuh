@@ -952,7 +952,12 @@ __global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
 #ifndef GB_S4P_THREADS
 #define GB_S4P_THREADS 192
 #endif
+#ifndef GB_S4P_CAP
 #define GB_S4P_CAP 768
+#endif
+#ifndef GB_S4P_MINB
+#define GB_S4P_MINB 4
+#endif
 #define GB_S4P_PPT ((GB_S4P_CAP + GB_S4P_THREADS - 1) / GB_S4P_THREADS)
 constexpr int kS4pSmem = GB_S4P_CAP * 64;
 
@@ -971,7 +976,7 @@ __device__ __forceinline__ void s4p_project_child(const CamK& cam, const double 
 }
 
 template <bool COV, bool TAN>
-__global__ void __launch_bounds__(GB_S4P_THREADS, 4) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
+__global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_propagate(const __grid_constant__ StepParams prm,
                                                                                    const __grid_constant__ NextParams nxt) {
   constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16, PPT = GB_S4P_PPT, CAP = GB_S4P_CAP, NW = GB_S4P_THREADS / 32, TH = GB_S4P_THREADS;
   extern __shared__ __align__(128) unsigned char s4p_raw[];

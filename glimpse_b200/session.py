@@ -4,6 +4,7 @@ single teacher-forced steps (``gb_track_init`` / ``gb_track_step``)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -450,7 +451,7 @@ class Session:
         time a Tracker sees an upload of this size, remembered afterwards — ``track()`` is a collective call under
         ``torch.distributed`` (same arguments, same cache state on every rank), so later sessions need no agreement."""
         dist = self.dist
-        if dist is None or dist.get_backend() != "nccl":
+        if dist is None or dist.get_backend() != "nccl" or os.environ.get("GB_SHARED_UPLOAD", "1") == "0":
             return False
         agreed = self.tracker.__dict__.setdefault("_shared_upload_agreed", {})
         key = (int(n_frames), int(n_bytes))
@@ -580,8 +581,12 @@ class Session:
                     mine[at:at + src.numel()].copy_(src)
                 everyone = torch.empty(world * nbytes, dtype=torch.uint8, device=self.device)
                 dist.all_gather_into_tensor(everyone, mine)
-                host["everyone"] = torch.empty(everyone.shape, dtype=torch.uint8, pin_memory=True)
-                host["everyone"].copy_(everyone, non_blocking=True)
+                # (rank, array) -> (array, rank) on the device, so that the host side is a view of the pinned buffers
+                everyone = everyone.view(world, nbytes)
+                for key, tail, dtype, at, nb in layout:
+                    dev = everyone[:, at:at + nb].contiguous()
+                    host["all_" + key] = torch.empty(dev.shape, dtype=torch.uint8, pin_memory=True)
+                    host["all_" + key].copy_(dev, non_blocking=True)
                 names = ["obs_flags", "window"]
             for k in names:
                 src = b[k]
@@ -593,7 +598,8 @@ class Session:
         if self.return_particles:
             d2h += b["particles"].numel() * 8 + b["weights"].numel() * 8
         if gather is not None:
-            out = unpack_results(h["everyone"].reshape(world, nbytes), layout, per, ntracks)
+            out = {key: h["all_" + key].reshape(-1).view(dtype).reshape((world * per,) + tuple(tail))[:ntracks]
+                   for key, tail, dtype, at, nb in layout}
             d2h *= world
         else:
             n = h["means"].shape[0]
