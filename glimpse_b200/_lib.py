@@ -110,6 +110,7 @@ SIGNATURES = {
     "gb_version": (C.c_int, []),
     "gb_last_error": (C.c_char_p, []),
     "gb_struct_size": (C.c_int64, [C.c_int32]),
+    "gb_sample_surface": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gb_kernel_timing": (C.c_int, [C.c_int32]),
     "gb_kernel_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "gb_camera_from_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(gb_camera)]),

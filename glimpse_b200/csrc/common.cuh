@@ -51,6 +51,15 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global
                "l"(__cvta_generic_to_global(src_global)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 2-D tile of a tensor described by a CUtensorMap (the TMA engine's tiled mode: `cp.async.bulk.tensor.2d`, SASS UTMALDG):
+// the box of the map whose first element is (x, y) lands densely in shared memory (128-byte aligned), out-of-range elements
+// as zeros, and completes on the mbarrier with the box's full byte count.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"

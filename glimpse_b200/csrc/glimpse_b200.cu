@@ -3,6 +3,7 @@
 // The per-update kernels are in stream.cuh (one update = kernels over all points of a batch; batches of points advance
 // on their own streams); this file holds the kernel parameters, the first-frame / template kernels, the stand-alone
 // stage entry points and the host side of the C ABI.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -114,6 +115,13 @@ struct NextParams {
   double tau, tau2;
   int img[GB_MAX_OBS];
   CamK cam[GB_MAX_OBS];
+};
+
+// Tensor maps (TMA descriptors) of the frames the observers show at time t: a kernel parameter of k_s2_surface, so the
+// descriptors live in the constant bank of the launch.  ok[o] = 0: that frame is read with ordinary loads.
+struct alignas(64) FrameMaps {
+  CUtensorMap map[GB_MAX_OBS];
+  int ok[GB_MAX_OBS];
 };
 
 __device__ __forceinline__ double* state_buffer(const StepParams& prm, int t) { return (t & 1) ? prm.state_b : prm.state_a; }
@@ -637,6 +645,89 @@ static constexpr int kMaxSlots = 8;   // side streams / scratch slots of GB_MODE
 static constexpr int kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 static constexpr int kHeaderBytes = (int)((sizeof(SmemHeader) + 15) / 16 * 16);
 
+// ---------------------------------------------------------------------------------------------
+// Tensor maps of the frames (TMA): one CUtensorMap per image of the current descriptor, kept in a per-device table in
+// global memory.  A frame qualifies when its base and pitch are multiples of 16 bytes; the box is GB_TMA_BOXW bytes x
+// GB_TMA_BOXH rows of uint8.  cuTensorMapEncodeTiled is looked up at run time (no link-time dependency on the driver, so
+// the library still loads on a machine without one).
+// ---------------------------------------------------------------------------------------------
+struct TensorMapTable {
+  std::vector<CUtensorMap> host;
+  std::vector<gb_image> seen;   // what each entry was encoded from
+  std::vector<uint8_t> ok;
+};
+static thread_local TensorMapTable g_tmaps;
+static thread_local bool g_tmaps_on = false;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  });
+  return fn;
+}
+
+// Encode (or reuse) the maps of the images the descriptor references; GB_TMA=0 switches the TMA path off (A/B runs).
+static int ensure_tensor_maps(const gb_track_desc& d) {
+  TensorMapTable& tb = g_tmaps;
+  g_tmaps_on = false;
+  const char* env = getenv("GB_TMA");
+  EncodeTiledFn encode = (env && !strcmp(env, "0")) ? nullptr : encode_tiled_fn();
+  if (!encode || !d.images_host) return GB_OK;
+  int n_images = 0;
+  for (int64_t k = 0; k < (int64_t)d.T * d.O; ++k) {
+    const int o = (int)(k % d.O), idx = d.image_index_host[k];
+    if (idx >= 0 && d.image_offset_host[o] + idx + 1 > n_images) n_images = d.image_offset_host[o] + idx + 1;
+  }
+  if ((size_t)n_images > tb.host.size()) {
+    const size_t old = tb.host.size();
+    tb.host.resize(n_images);
+    tb.seen.resize(n_images);
+    tb.ok.resize(n_images, 0);
+    for (size_t k = old; k < (size_t)n_images; ++k) memset(&tb.seen[k], 0, sizeof(gb_image));
+  }
+  for (int k = 0; k < n_images; ++k) {
+    const gb_image& im = d.images_host[k];
+    if (tb.seen[k].pixels == im.pixels && tb.seen[k].width == im.width && tb.seen[k].height == im.height && tb.seen[k].pitch == im.pitch &&
+        tb.seen[k].nchan == im.nchan)
+      continue;
+    tb.seen[k] = im;
+    tb.ok[k] = 0;
+    if (!im.pixels || (reinterpret_cast<uintptr_t>(im.pixels) & 15) || (im.pitch & 15) || im.width <= 0 || im.height <= 0) continue;
+    const cuuint64_t dims[2] = {(cuuint64_t)im.width * (cuuint64_t)im.nchan, (cuuint64_t)im.height};
+    const cuuint64_t strides[1] = {(cuuint64_t)im.pitch};
+    const cuuint32_t box[2] = {GB_TMA_BOXW, GB_TMA_BOXH}, estr[2] = {1, 1};
+    if (encode(&tb.host[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(im.pixels), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      tb.ok[k] = 1;
+  }
+  g_tmaps_on = true;
+  return GB_OK;
+}
+
+// The maps of the frames of time prm.t, as k_s2_surface's kernel parameter.
+static void frame_maps(const StepParams& prm, FrameMaps& fm) {
+  memset(&fm, 0, sizeof(fm));
+  if (!g_tmaps_on) return;
+  for (int o = 0; o < prm.O; ++o) {
+    const int image = prm.img[o];
+    if (image >= 0 && (size_t)image < g_tmaps.ok.size() && g_tmaps.ok[image]) {
+      fm.map[o] = g_tmaps.host[image];
+      fm.ok[o] = 1;
+    }
+  }
+}
+
 static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   memset(&prm, 0, sizeof(prm));
   prm.P = d.P;
@@ -845,7 +936,9 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   const unsigned nb = (unsigned)(prm.pb * prm.s_nblk);
   k_s0_reset<<<grid_for(prm.pb * prm.O * 5, 256), 256, 0, stream>>>(prm);
   k_s1_propagate<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
-  k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, prm.s2_budget);
+  FrameMaps fm;
+  frame_maps(prm, fm);
+  k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, fm, prm.s2_budget);
   k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
   if (prm.resample_method == GB_RESAMPLE_CHOICE) {
     k_s4c_scan<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
@@ -1052,6 +1145,8 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
         nxt.cam[o] = pn.cam[o];
       }
     }
+    FrameMaps fm;
+    frame_maps(prm, fm);
     if (has_init[t] || has_tmpl[t]) {
       if ((rc = join_sides())) return rc;
       if ((rc = wait_images(stream, prm))) return rc;
@@ -1094,7 +1189,7 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
       }
       if (has_update[t]) {
         kt.begin(GB_K_SURFACE, ss);
-        k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, prm.s2_budget);
+        k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, fm, prm.s2_budget);
         kt.end(ss);
         kt.begin(GB_K_WEIGHTS, ss);
         k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);
@@ -1184,6 +1279,29 @@ __global__ void k_motion_log_likelihoods(const gb_motion* __restrict__ motion, c
     ll[p * N + i] = surface_log_likelihood(m, surfaces, s[i], s[N + i], s[2 * N + i], flags);
   }
   if (flags && status) atomicCAS(&status[p], 0, GB_ST_DEM_BOUNDS);
+}
+
+// Observer.sample_tile as a stand-alone call (observer.py:178-214): interpolating spline (degree 3 not-a-knot = FITPACK's, or
+// degree 1) through the cell centres of `tile` (Mv rows x Mu columns), evaluated at n points given relative to the first cell
+// centre in cell units.  One CTA: Hermite data (F, F_u, F_v, F_uv) in the caller's work area `herm` [Mv][Mu | 1] float4.
+__global__ void __launch_bounds__(256) k_sample_surface(const double* __restrict__ tile, int Mu, int Mv, int lin_u, int lin_v,
+                                                        const double* __restrict__ xy, int64_t n, float4* __restrict__ herm,
+                                                        double* __restrict__ out) {
+  const int tid = threadIdx.x, nthr = blockDim.x, Mp = Mu | 1;
+  for (int i = tid; i < Mu * Mv; i += nthr) {
+    const int r = i / Mu, c = i - r * Mu;
+    herm[r * Mp + c] = make_float4((float)tile[i], 0.0f, 0.0f, 0.0f);
+  }
+  __syncthreads();
+  float* base = reinterpret_cast<float*>(herm);
+  for (int line = tid; line < Mv + Mu; line += nthr) {
+    if (line < Mv) spline_slopes_line(base + (int64_t)line * Mp * 4, base + (int64_t)line * Mp * 4 + 1, 4, Mu, !lin_u);
+    else spline_slopes_line(base + (int64_t)(line - Mv) * 4, base + (int64_t)(line - Mv) * 4 + 2, Mp * 4, Mv, !lin_v);
+  }
+  __syncthreads();
+  for (int c = tid; c < Mu; c += nthr) spline_slopes_line(base + (int64_t)c * 4 + 1, base + (int64_t)c * 4 + 3, Mp * 4, Mv, !lin_v);
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += nthr) out[i] = (double)hermite_eval_sat(herm, Mp, Mu, Mv, xy[2 * i], xy[2 * i + 1], lin_u != 0, lin_v != 0);
 }
 
 }  // namespace gb
@@ -1357,6 +1475,7 @@ int gb_track_step(const gb_track_desc* d, int32_t t, const gb_stage_io* io, void
   if (rc) return rc;
   if (t < 1 || t >= d->T) return fail(GB_E_INVALID, "time index out of range%s");
   if ((rc = ensure_tables())) return rc;
+  if ((rc = ensure_tensor_maps(*d))) return rc;
   StepParams prm;
   fill_params(*d, t, prm);
   if (io) prm.io = *io;
@@ -1370,6 +1489,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   if (!d->mask_host || !d->first_host || !d->last_host) return fail(GB_E_INVALID, "host copies of mask/first/last required%s");
   if ((rc = ensure_tables())) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if ((rc = ensure_tensor_maps(*d))) return rc;
   const bool cov = d->covariances != nullptr;
   int64_t launches = 0;
   if (d->resample_method != GB_RESAMPLE_CHOICE) {  // (choice: step-by-step flow below)
@@ -1478,6 +1598,19 @@ int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surface
   if (!motion || !surfaces || !state || !ll || P <= 0 || N <= 0 || P > 65535) return fail(GB_E_INVALID, "bad arguments%s");
   dim3 grid((unsigned)grid_for(N, 256), (unsigned)P, 1);
   k_motion_log_likelihoods<<<grid, 256, 0, (cudaStream_t)stream>>>(motion, surfaces, N, state, ll, status);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_sample_surface(const double* tile, int32_t rows, int32_t cols, int32_t kx, int32_t ky, const double* xy, int64_t n, void* work,
+                      double* out, void* stream) {
+  if (!tile || !xy || !work || !out || n <= 0) return fail(GB_E_INVALID, "bad arguments%s");
+  if ((kx != 1 && kx != 3) || (ky != 1 && ky != 3)) return fail(GB_E_INVALID, "spline degrees 1 and 3 are supported%s");
+  if (rows < kx + 1 || cols < ky + 1 || rows > GB_MAX_SURFACE || cols > GB_MAX_SURFACE)
+    return fail(GB_E_INVALID, "tile must have between degree + 1 and 1024 cells per axis%s");
+  int rc = ensure_tables();
+  if (rc) return rc;
+  k_sample_surface<<<1, 256, 0, (cudaStream_t)stream>>>(tile, cols, rows, ky == 1, kx == 1, xy, n, reinterpret_cast<float4*>(work), out);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

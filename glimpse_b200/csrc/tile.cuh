@@ -35,6 +35,8 @@ struct TileWork {
   float2* tmpl;      // [th][tw] high-passed template, negated and duplicated (-t, -t): the packed FP32 SSD adds it to two pixels
   uint32_t* hist;    // [nbins]
   int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
+  const void* tmap = nullptr;  // CUtensorMap of the frame (global memory), or null: the window is read with ordinary loads
+  uint64_t* bar = nullptr;     // mbarrier of the CTA for the TMA loads (phase 0)
   int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
   bool cub_u = true, cub_v = true;  // cubic (default) or piecewise-linear interpolation along the columns / rows (Tracker.interpolation)
 };
@@ -237,12 +239,63 @@ __device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, i
 // Phases 1-5 of the surface of one search window: raw window -> high-passed, CDF-matched float tile `w.hp`
 // (plus the template in `w.tmpl`).  All threads of the CTA participate.  `box` = (left, top, right, bottom);
 // template data in global memory.  The caller has verified the capacity and carved `w`.
+// Frames are read through the TMA engine when the frame has a tensor map (`w.tmap`, built by the host for frames whose
+// pitch and base are 16-byte aligned): the window arrives as boxes of GB_TMA_BOXW bytes x GB_TMA_BOXH rows, staged where the
+// padded window copy (`w.packed`) is built afterwards.
+#define GB_TMA_BOXW 32
+#define GB_TMA_BOXH 8
+__device__ __forceinline__ bool tile_window_by_tma(const TileWork& w, int nchan) {
+  if (!w.tmap || !w.bar) return false;
+  const int nbx = (w.Su * nchan + GB_TMA_BOXW - 1) / GB_TMA_BOXW, nby = (w.Sv + GB_TMA_BOXH - 1) / GB_TMA_BOXH;
+  return (int64_t)nbx * nby * (GB_TMA_BOXW * GB_TMA_BOXH) <= (int64_t)(w.Sv + 4) * (w.Su + 4) * 4 && (smem_u32(w.packed) & 127u) == 0u &&
+         __isShared(w.packed);
+}
+
 __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitch, int nchan, const int* box, const double* __restrict__ g_tmpl,
                                     const double* __restrict__ g_tq, const double* __restrict__ g_tv, TileWork& w,
                                     float* dump_search, int64_t dump_cap, long long* clk) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int Su = w.Su, Sv = w.Sv, Sp = w.Sp;
   const int area = Su * Sv;
+  const bool by_tma = tile_window_by_tma(w, nchan);
+  if (by_tma) {
+    // 1. (TMA) one thread asks for every box of the window; everybody fills the tables meanwhile, then turns the staged
+    //    bytes into band sums and counts them (the histogram pass of phase 2 is folded into this one)
+    const int nbx = (Su * nchan + GB_TMA_BOXW - 1) / GB_TMA_BOXW, nby = (Sv + GB_TMA_BOXH - 1) / GB_TMA_BOXH;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(w.packed);
+    if (tid == 0) {
+      mbar_expect_tx(w.bar, (uint32_t)(nbx * nby * GB_TMA_BOXW * GB_TMA_BOXH));
+      for (int by = 0; by < nby; ++by)
+        for (int bx = 0; bx < nbx; ++bx)
+          tma_load_2d(stage + (by * nbx + bx) * (GB_TMA_BOXW * GB_TMA_BOXH), w.tmap, box[0] * nchan + bx * GB_TMA_BOXW,
+                      box[1] + by * GB_TMA_BOXH, w.bar);
+    }
+    const int ta = w.tw * w.th;
+    for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
+    for (int i = tid; i < ta; i += nthr) {
+      const float tv = -(float)g_tmpl[i];
+      w.tmpl[i] = make_float2(tv, tv);
+    }
+    for (int i = tid; i < w.nvals; i += nthr) {
+      w.tq[i] = g_tq[i];
+      w.tv[i] = g_tv[i];
+    }
+    __syncthreads();
+    mbar_wait(w.bar, 0);
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    for (int r = warp; r < Sv; r += nwarp) {
+      const uint8_t* rowb = stage + (r >> 3) * nbx * (GB_TMA_BOXW * GB_TMA_BOXH) + (r & 7) * GB_TMA_BOXW;
+      for (int c = lane; c < Su; c += 32) {
+        unsigned v = 0;
+        for (int ch = 0; ch < nchan; ++ch) {
+          const int x = c * nchan + ch;
+          v += rowb[(x >> 5) * (GB_TMA_BOXW * GB_TMA_BOXH) + (x & 31)];
+        }
+        w.raw[r * Su + c] = (uint16_t)v;
+        atomicAdd(&w.hist[v], 1u);
+      }
+    }
+  } else
   // 1. raw window, template and its CDF; clear the histogram.  Every global load a thread needs first is issued
   //    before anything waits on one (the template words, then four window pixels per trip): the phase costs about
   //    one memory round trip instead of one per loop.
@@ -283,7 +336,8 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   }
   __syncthreads();
   // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
-  for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
+  if (!by_tma)
+    for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
   const bool hp5 = w.mh == 5 && w.mw == 5;
   if (!hp5) {
     // other median sizes (Tracker.highpass): a plain copy of the window, since hp overwrites raw

@@ -337,6 +337,12 @@ int gb_init_particles(const gb_motion* motion, const gb_surface* surfaces, int64
  * sigma is 0, for SoA state [P][6][N].  (The tangent kinds return None in the reference, motion.py:77-89: the caller does not ask.) */
 int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* state, double* ll,
                               int32_t* status, void* stream);
+/* Observer.sample_tile (observer.py:178-214) as a stand-alone call: the interpolating spline RectBivariateSpline(rows, columns, tile,
+ * kx, ky, s = 0) of degree 3 (FITPACK's not-a-knot cubic) or 1 per axis, evaluated at n points.  tile[rows][cols] f64 (held as float32
+ * on the device, like the SSE surface it is used for); xy[n][2] = (column, row) coordinates measured from the first cell centre in cell
+ * units, clamped to the data sites like FITPACK's evaluation; work = rows * (cols | 1) * 16 bytes; out[n] f64.  All device pointers. */
+int gb_sample_surface(const double* tile, int32_t rows, int32_t cols, int32_t kx, int32_t ky, const double* xy, int64_t n, void* work,
+                      double* out, void* stream);
 /* Tracker.particle_mean / compute_particle_sigma / particle_covariance (tracker.py:72-104) on
  * row-major particles[n][6], weights[n]: mean[6], sigma[6] (or NULL), cov[36] (or NULL). */
 int gb_moments(const double* particles, const double* weights, int64_t n, double* mean, double* sigma, double* cov,

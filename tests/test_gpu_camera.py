@@ -81,3 +81,40 @@ def test_project_large_batch_against_oracle(cuda):
     got = cam.xyz_to_uv(xyz)
     want = orc.project(cam.vector, xyz, correction=(cam.correction["radius"], cam.correction["refraction"]))
     assert np.max(np.abs(got - want)) <= UV_TOL_PX
+
+
+def test_observer_sample_tile_and_shift_tile_match_fitpack(cuda):
+    """Observer.sample_tile / shift_tile (reference observer.py:146-214) through gb_sample_surface: the device's Hermite-form
+    not-a-knot spline against scipy's RectBivariateSpline (FITPACK) on a smooth tile — cubic, linear and mixed degrees, points
+    and grids, arguments up to half a cell outside the outermost centres (evaluated at the clamped coordinate)."""
+    import datetime
+
+    import scipy.interpolate
+
+    import glimpse_b200 as gb
+
+    rng = np.random.RandomState(5)
+    ny, nx = 23, 31
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    tile = np.sin(xx / 4.0) * np.cos(yy / 5.0) + 0.05 * rng.rand(ny, nx)
+    box = (100.0, 50.0, 100.0 + nx, 50.0 + ny)
+    day = datetime.timedelta(days=1)
+    cam = gb.Camera(imgsz=(200, 100), f=100.0)
+    obs = gb.Observer([gb.Image(f"i{k}", cam=cam, datetime=datetime.datetime(2020, 1, 1) + k * day) for k in range(2)])
+    uv = np.column_stack((box[0] + rng.rand(500) * nx, box[1] + rng.rand(500) * ny))
+    cu, cv = np.arange(box[0] + 0.5, box[2]), np.arange(box[1] + 0.5, box[3])
+    for kw in ({}, {"kx": 1, "ky": 1}, {"kx": 3, "ky": 1}):
+        f = scipy.interpolate.RectBivariateSpline(cv, cu, tile, **kw)
+        got = obs.sample_tile(uv, tile, box, **kw)
+        assert np.max(np.abs(got - f(uv[:, 1], uv[:, 0], grid=False))) < 2e-6  # the device holds the tile as float32
+        gu, gv = np.linspace(box[0], box[2], 17), np.linspace(box[1], box[3], 13)
+        grid = obs.sample_tile((gu, gv), tile, box, grid=True, **kw)
+        assert grid.shape == (13, 17) and np.max(np.abs(grid - f(gv, gu, grid=True))) < 2e-6
+    with pytest.raises(ValueError, match="outside box"):
+        obs.sample_tile(np.array([[box[0] - 0.1, box[1] + 1.0]]), tile, box)
+    duv = (0.3, -0.45)
+    f = scipy.interpolate.RectBivariateSpline(np.arange(0.5, ny), np.arange(0.5, nx), tile)
+    want = f(np.arange(0.5, ny) + duv[1], np.arange(0.5, nx) + duv[0], grid=True)
+    assert np.max(np.abs(obs.shift_tile(tile.copy(), duv) - want)) < 2e-6
+    rgb = np.dstack([tile, 2 * tile, -tile])
+    assert np.max(np.abs(obs.shift_tile(rgb, duv)[:, :, 1] - 2 * want)) < 4e-6

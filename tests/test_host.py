@@ -368,3 +368,36 @@ def test_blocks_and_second_runs_are_assembled_on_the_host(monkeypatch):
     tracks = tracker.track(models)
     assert [isinstance(e, MemoryError) for e in tracks.errors] == [False, True, False, False, True]
     assert len(created) == 1
+
+
+def test_observer_subset_split_and_select_datetimes():
+    """Observer.subset / split (reference observer.py:455-493) and helpers.select_datetimes / datetime_range with the known
+    answers of the reference's doctests (helpers.py:1870-1922)."""
+    import glimpse_b200 as gb
+    from glimpse_b200.observer import datetime_range, select_datetimes
+
+    t = [datetime.datetime(2020, 1, 1, 0, 0, x) for x in (0, 1, 2, 4, 5)]
+    assert select_datetimes(t).tolist() == [True] * 5
+    assert select_datetimes(t, start=t[1]).tolist() == [False, True, True, True, True]
+    assert select_datetimes(t, start=t[1], end=t[1]).tolist() == [False, True, False, False, False]
+    snap = datetime.timedelta(seconds=2)
+    assert select_datetimes(t, snap=snap).tolist() == [True, False, True, True, True]
+    assert select_datetimes(t, snap=snap, maxdt=0 * snap).tolist() == [True, False, True, True, False]
+    with pytest.raises(ValueError, match="Start datetime is after end datetime"):
+        select_datetimes(t, start=t[3], end=t[1])
+    base = (2020, 1, 1, 0, 0)
+    rng = datetime_range(datetime.datetime(*base, 0), datetime.datetime(*base, 2), datetime.timedelta(seconds=1))
+    assert list(rng) == [datetime.datetime(*base, s) for s in (0, 1, 2)]
+    obs = _observers(9)
+    sub = obs.subset(start=obs.datetimes[2], end=obs.datetimes[5])
+    assert [img is obs.images[2 + i] for i, img in enumerate(sub.images)] == [True] * 4 and sub.sigma == obs.sigma
+    parts = obs.split(2)  # two halves sharing one image (overlap = 1)
+    assert [len(p.images) for p in parts] == [5, 5] and parts[1].images[0] is parts[0].images[-1]
+    parts = obs.split(2, overlap=0)
+    assert [len(p.images) for p in parts] == [5, 4] and parts[1].images[0] is obs.images[5]
+    parts = obs.split([obs.datetimes[3]], overlap=2)
+    assert [len(p.images) for p in parts] == [4, 7] and parts[1].images[0] is obs.images[2]
+    with pytest.raises(ValueError, match="Shift larger than 0.5 pixels"):
+        obs.shift_tile(np.zeros((5, 5)), (0.6, 0.0))
+    with pytest.raises(NotImplementedError):
+        obs.sample_tile(np.zeros((1, 2)), np.zeros((5, 5)), (0, 0, 5, 5), kx=2)
