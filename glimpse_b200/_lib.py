@@ -27,6 +27,7 @@ GB_WINDOW_MARGIN, GB_WINDOW_MARGIN_MAX = 191, 1000  # default / retry capacity o
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
 GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2}
 GB_MODE_STREAM = 1
+GB_HP_MODES = {"reflect": 0, "grid-mirror": 0, "constant": 1, "grid-constant": 1, "nearest": 2, "mirror": 3, "wrap": 4, "grid-wrap": 4}
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 
 
@@ -89,6 +90,7 @@ class gb_track_desc(C.Structure):
         ("window_stats", C.c_void_p),
         ("resample_method", C.c_int32), ("highpass_size", C.c_int32),
         ("interp_rows", C.c_int32), ("interp_cols", C.c_int32),
+        ("highpass_mode", C.c_int32), ("highpass_origin", C.c_int32), ("highpass_cval", C.c_double),
         ("final_weights", C.c_void_p),
         ("plan", gb_plan),
     ]

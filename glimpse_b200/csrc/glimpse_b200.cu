@@ -47,6 +47,8 @@ struct StepParams {
   int n_slabs, hp_rows;       // hp_rows x hp_cols: size of the median high-pass (Tracker.highpass['size'], tracker.py:59, 530)
   int64_t slab_bytes, particle_scratch_bytes;
   int skip_evolve, viewshed, rng_mode, hp_cols;
+  int hp_mode, hp_org_r, hp_org_c;  // border mode (GB_HP_*) and origin of the median high-pass
+  double hp_cval;
   uint64_t seed;
   int64_t point_offset;
   double tau, tau2;
@@ -538,12 +540,25 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   // high-pass (tracker.py:530-531): value minus the reflected median (5x5 unless Tracker.highpass says otherwise), taken
   // on grey levels
   double* tile = prm.tmpl_tile + (p * prm.O + o) * (int64_t)(tw * th);
-  const bool hp5 = prm.hp_rows == 5 && prm.hp_cols == 5;
+  const bool hp_plain = prm.hp_mode == GB_HP_REFLECT && prm.hp_org_r == 0 && prm.hp_org_c == 0;
+  const bool hp5 = prm.hp_rows == 5 && prm.hp_cols == 5 && hp_plain;
+  // (general border mode: the constant beyond the border takes its place among the grey levels through the normalised values)
+  int cval_level = nbins;
+  if (!hp_plain)
+    for (int b = nbins - 1; b >= 0; --b)
+      if (!(mul(sub(quo((double)b, (double)nchan), mean), inv_std) < prm.hp_cval)) cval_level = b;
   for (int i = tid; i < area; i += blockDim.x) {
     const int r = i / bw, c = i - r * bw;
-    const int med = hp5 ? median5x5(s_raw, bw, bh, r, c) : median_window(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols);
     const double vn = mul(sub(quo((double)s_raw[i], (double)nchan), mean), inv_std);
-    const double vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
+    double vm;
+    if (hp_plain) {
+      const int med = hp5 ? median5x5(s_raw, bw, bh, r, c) : median_window(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols);
+      vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
+    } else {
+      const int code = median_window_codes(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols, prm.hp_mode, prm.hp_org_r, prm.hp_org_c,
+                                           2 * cval_level);
+      vm = (code & 1) ? mul(sub(quo((double)(code >> 1), (double)nchan), mean), inv_std) : prm.hp_cval;
+    }
     tile[i] = sub(vn, vm);
   }
 }
@@ -742,6 +757,10 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.interp_cols = d.interp_cols ? d.interp_cols : 3;
   prm.hp_rows = d.highpass_size ? (d.highpass_size & 0xffff) : 5;
   prm.hp_cols = d.highpass_size ? (d.highpass_size >> 16 & 0xffff) : 5;
+  prm.hp_mode = d.highpass_mode;
+  prm.hp_org_r = (int16_t)(d.highpass_origin & 0xffff);
+  prm.hp_org_c = (int16_t)(d.highpass_origin >> 16 & 0xffff);
+  prm.hp_cval = d.highpass_cval;
   prm.cluster = d.plan.cluster;
   prm.n_local = d.plan.n_local;
   prm.particles_in_smem = d.plan.particles_in_smem;
@@ -816,6 +835,14 @@ static int check_desc(const gb_track_desc& d) {
   if (d.highpass_size != 0 && ((d.highpass_size & 0xffff) < 1 || (d.highpass_size & 0xffff) > GB_MAX_HIGHPASS ||
                                (d.highpass_size >> 16 & 0xffff) < 1 || (d.highpass_size >> 16 & 0xffff) > GB_MAX_HIGHPASS))
     return fail(GB_E_INVALID, "highpass_size: rows and columns must be between 1 and 31%s");
+  {
+    const int rows = d.highpass_size ? (d.highpass_size & 0xffff) : 5, cols = d.highpass_size ? (d.highpass_size >> 16 & 0xffff) : 5;
+    const int org_r = (int16_t)(d.highpass_origin & 0xffff), org_c = (int16_t)(d.highpass_origin >> 16 & 0xffff);
+    if (d.highpass_mode < GB_HP_REFLECT || d.highpass_mode > GB_HP_WRAP) return fail(GB_E_INVALID, "highpass_mode: unknown border mode%s");
+    // scipy.ndimage: -(size // 2) <= origin <= (size - 1) // 2
+    if (org_r < -(rows / 2) || org_r > (rows - 1) / 2 || org_c < -(cols / 2) || org_c > (cols - 1) / 2)
+      return fail(GB_E_INVALID, "highpass_origin: the shifted window must still cover its pixel%s");
+  }
   if ((d.interp_rows != 0 && d.interp_rows != 1 && d.interp_rows != 3) || (d.interp_cols != 0 && d.interp_cols != 1 && d.interp_cols != 3))
     return fail(GB_E_INVALID, "interp_rows / interp_cols: spline degrees 1 and 3 are supported%s");
   if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");

@@ -38,6 +38,8 @@ struct TileWork {
   const void* tmap = nullptr;  // CUtensorMap of the frame (global memory), or null: the window is read with ordinary loads
   uint64_t* bar = nullptr;     // mbarrier of the CTA for the TMA loads (phase 0)
   int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
+  int hp_mode = 0, hp_org_r = 0, hp_org_c = 0;  // its border mode (GB_HP_*) and origin (Tracker.highpass['mode'], ['origin'])
+  double hp_cval = 0.0;                          // ... and the constant beyond the border for GB_HP_CONSTANT
   bool cub_u = true, cub_v = true;  // cubic (default) or piecewise-linear interpolation along the columns / rows (Tracker.interpolation)
 };
 
@@ -142,6 +144,52 @@ __device__ inline int median_window(const uint16_t* raw, int Su, int Sv, int r, 
       for (int a = 0; a < mh; ++a) {
         const uint16_t* row = raw + reflect_index_any(r0 + a, Sv) * Su;
         for (int b = 0; b < mw; ++b) below += (int)row[reflect_index_any(c0 + b, Su)] < cand;
+      }
+    }
+    if (below <= rank) level = cand;
+  }
+  return level;
+}
+
+// Border handling of scipy.ndimage filters for an index beyond [0, n): the index it maps to, or -1 for 'constant'.
+__device__ __forceinline__ int border_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case GB_HP_CONSTANT: return -1;
+    case GB_HP_NEAREST: return i < 0 ? 0 : n - 1;
+    case GB_HP_MIRROR: {  // d c b | a b c d | c b a: period 2 n - 2
+      if (n == 1) return 0;
+      const int period = 2 * n - 2;
+      i = i % period;
+      if (i < 0) i += period;
+      return i < n ? i : period - i;
+    }
+    case GB_HP_WRAP: {
+      i = i % n;
+      return i < 0 ? i + n : i;
+    }
+    default: return reflect_index_any(i, n);
+  }
+}
+
+// The general median high-pass (Tracker.highpass with `mode`, `cval`, `origin`): rank (mh mw) / 2 of the window that starts at
+// (r - mh / 2 - origin_r, c - mw / 2 - origin_c), borders by `mode`.  Works on CODES: a pixel of grey level g has code 2 g + 1,
+// the constant beyond the border has the even code `cval_code` = 2 x (number of grey levels whose filtered-tile value is below
+// cval) — the codes are ordered like the values, so the rank element is found on integers (bit by bit, as median_window does).
+// Returns the code of the median: odd = grey level (code - 1) / 2, even = the border constant.
+__device__ inline int median_window_codes(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw, int mode, int org_r, int org_c,
+                                          int cval_code) {
+  const int rank = (mh * mw) >> 1, r0 = r - (mh >> 1) - org_r, c0 = c - (mw >> 1) - org_c;
+  int level = 0;
+  for (int bit = 2048; bit; bit >>= 1) {
+    const int cand = level | bit;
+    int below = 0;
+    for (int a = 0; a < mh; ++a) {
+      const int rr = border_index(r0 + a, Sv, mode);
+      for (int b = 0; b < mw; ++b) {
+        const int cc = border_index(c0 + b, Su, mode);
+        const int code = (rr < 0 || cc < 0) ? cval_code : 2 * (int)raw[rr * Su + cc] + 1;
+        below += code < cand;
       }
     }
     if (below <= rank) level = cand;
@@ -338,9 +386,10 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
   if (!by_tma)
     for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
-  const bool hp5 = w.mh == 5 && w.mw == 5;
+  const bool hp_plain = w.hp_mode == GB_HP_REFLECT && w.hp_org_r == 0 && w.hp_org_c == 0;
+  const bool hp5 = w.mh == 5 && w.mw == 5 && hp_plain;
   if (!hp5) {
-    // other median sizes (Tracker.highpass): a plain copy of the window, since hp overwrites raw
+    // other median sizes / border modes (Tracker.highpass): a plain copy of the window, since hp overwrites raw
     uint16_t* copy = reinterpret_cast<uint16_t*>(w.packed);
     for (int i = tid; i < area; i += nthr) copy[i] = w.raw[i];
   } else {
@@ -382,7 +431,25 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   if (clk && threadIdx.x == 0) clk[0] = clock64();
   // 5. high-pass: matched value minus the matched 5x5 median (tracker.py:530-531), cast to float32
   //    as the reference does for matchTemplate (tracker.py:610).  One thread = pixels (r, c), (r+1, c).
-  if (!hp5) {
+  if (!hp5 && !hp_plain) {
+    // general border mode / origin: the border constant takes its place among the grey levels through the matched values
+    __shared__ int s_cval_level;
+    if (tid == 0) s_cval_level = w.nbins;
+    __syncthreads();
+    for (int b = tid; b < w.nbins; b += nthr)
+      if (w.hist[b] && !(w.lut[b] < w.hp_cval)) atomicMin(&s_cval_level, b);  // smallest occupied level whose value is >= cval
+    __syncthreads();
+    const int cval_code = 2 * s_cval_level;
+    const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
+    for (int i = tid; i < area; i += nthr) {
+      const int r = i / Su, c = i - r * Su;
+      const int code = median_window_codes(copy, Su, Sv, r, c, w.mh, w.mw, w.hp_mode, w.hp_org_r, w.hp_org_c, cval_code);
+      const double med = (code & 1) ? w.lut[code >> 1] : w.hp_cval;
+      const float o = (float)sub(w.lut[copy[i]], med);
+      w.hp[r * Sp + c] = o;
+      if (dump_search && i < dump_cap) dump_search[i] = o;
+    }
+  } else if (!hp5) {
     const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
     for (int i = tid; i < area; i += nthr) {
       const int r = i / Su, c = i - r * Su;

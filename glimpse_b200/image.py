@@ -107,8 +107,8 @@ class Raster:
     def constant(self) -> bool:
         return self.array.ndim != 2 or self.array.size == 1
 
-    def lower(self, torch, device) -> "tuple[_lib.gb_surface, object]":
-        """-> (``gb_surface``, device tensor kept alive by the caller)."""
+    def lower_host(self) -> "tuple[_lib.gb_surface, object]":
+        """-> (``gb_surface`` without its device pointer, the (nx, ny) array of cell values on increasing centres or None)."""
         s = _lib.gb_surface()
         s.xmin, s.xmax = float(min(self.xlim)), float(max(self.xlim))
         s.ymin, s.ymax = float(min(self.ylim)), float(max(self.ylim))
@@ -126,10 +126,17 @@ class Raster:
             z = z[:, ::-1]
         if nx < 2 or ny < 2:
             raise NotImplementedError("1-D rasters are not supported on device")
-        tensor = torch.as_tensor(np.ascontiguousarray(z)).to(device)
-        s.z = tensor.data_ptr()
         s.nx, s.ny = nx, ny
         s.dx, s.dy = abs(dx), abs(dy)
         s.x0, s.y0 = s.xmin + s.dx / 2, s.ymin + s.dy / 2
         s.value = 0.0
+        return s, np.ascontiguousarray(z)
+
+    def lower(self, torch, device) -> "tuple[_lib.gb_surface, object]":
+        """-> (``gb_surface``, device tensor kept alive by the caller)."""
+        s, z = self.lower_host()
+        if z is None:
+            return s, None
+        tensor = torch.as_tensor(z).to(device)
+        s.z = tensor.data_ptr()
         return s, tensor

@@ -133,6 +133,54 @@ def adopt_model(model):
     raise NotImplementedError(f"motion model {name} has no device kernel (no CPU fallback)")
 
 
+MOTION_DTYPE = np.dtype([("kind", "<i4"), ("dem", "<i4"), ("dem_sigma", "<i4"), ("pad_", "<i4"), ("xy", "<f8", 2),
+                         ("xy_sigma", "<f8", 2), ("v", "<f8", 3), ("v_sigma", "<f8", 3), ("a", "<f8", 3), ("a_sigma", "<f8", 3),
+                         ("slope_sigma", "<f8")])  # field layout of gb_motion (include/glimpse_b200.h)
+
+
+def lower_models(models, viewshed=None):
+    """Motion models (this package's or the reference's) -> the tables the kernels read, on the host:
+    ``(gb_motion table as a structured array, [(gb_surface, cell values or None)], index of the viewshed surface or -1)``.
+    Equal constant surfaces (the numbers the models wrap into 0-D rasters, motion.py:136-141) share one entry."""
+    assert MOTION_DTYPE.itemsize == C.sizeof(_lib.gb_motion)
+    rasters, table, memo = {}, [], {}
+
+    def index_of(raster):
+        hit = memo.get(id(raster))
+        if hit is not None:
+            return hit
+        key = getattr(raster, "_const_key", None)
+        if key is None or key not in rasters:
+            if not (hasattr(raster, "array") and hasattr(raster, "xlim")):
+                raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
+            arr = np.asarray(raster.array)
+            key = id(raster)
+            if arr.ndim != 2 or arr.size == 1:  # constant: share by value
+                key = ("const", float(arr.flat[0]), tuple(np.asarray(raster.xlim, dtype=float)),
+                       tuple(np.asarray(raster.ylim, dtype=float)))
+            if key not in rasters:
+                wrapped = raster if isinstance(raster, Raster) else Raster(raster.array, x=raster.xlim, y=raster.ylim)
+                rasters[key] = len(table)
+                table.append(wrapped.lower_host())
+        memo[id(raster)] = out = rasters[key]
+        return out
+
+    table_m = np.zeros(len(models), dtype=MOTION_DTYPE)
+    adopted = [adopt_model(m) for m in models]
+    vel = [m._velocity() for m in adopted]
+    table_m["kind"] = [m.kind for m in adopted]
+    table_m["dem"] = [index_of(m.dem) for m in adopted]
+    table_m["dem_sigma"] = [index_of(m.dem_sigma) for m in adopted]
+    table_m["xy"] = np.array([m.xy for m in adopted], dtype=float)
+    xs = np.array([m.xy_sigma for m in adopted], dtype=float)
+    table_m["xy_sigma"] = xs if xs.ndim == 2 else xs[:, None]
+    for k, name in enumerate(("v", "v_sigma", "a", "a_sigma")):
+        table_m[name] = np.array([v[k] for v in vel], dtype=float)
+    table_m["slope_sigma"] = [float(getattr(m, "slope_sigma", 0.0)) for m in adopted]
+    view = index_of(viewshed) if viewshed is not None else -1
+    return table_m, table, view
+
+
 def session_bytes(lib, mode: int, cluster: int, P: int, N: int, T: int, O: int, tw: int, th: int, return_covariances: bool,
                   return_particles: bool, window_margin: int = _lib.GB_WINDOW_MARGIN) -> int:
     """Device memory one :class:`Session` of ``P`` points allocates (the frames excluded): two particle-state buffers,
@@ -175,9 +223,9 @@ class Session:
         P, T, O = self.P, self.T, self.O
         N = self.N = int(models[0].n)
         if any(int(m.n) != N for m in models):
-            raise NotImplementedError("all motion models of one track() call must have the same number of particles")
+            raise ValueError("one device session holds models with the same number of particles (Tracker.track groups them)")
         if O > _lib.GB_MAX_OBS:
-            raise NotImplementedError(f"at most {_lib.GB_MAX_OBS} observers")
+            raise NotImplementedError(f"at most {_lib.GB_MAX_OBS} observers per track() call (GB_MAX_OBS, include/glimpse_b200.h)")
         self.tw, self.th = (int(v) for v in tile_size)
         self.return_covariances, self.return_particles = return_covariances, return_particles
         self.image_index = np.ascontiguousarray(image_index, dtype=np.int32)
@@ -254,10 +302,11 @@ class Session:
             method = getattr(tracker, "resample_method", "systematic")
             stratified = method in ("stratified", "choice")  # one uniform per particle and update
             d.resample_method = _lib.GB_RESAMPLE[method]
-            from .tracker import highpass_size, interpolation_degrees
+            from .tracker import highpass_params, interpolation_degrees
 
-            rows, cols = highpass_size(getattr(tracker, "highpass", {"size": (5, 5)}))
+            rows, cols, hp_mode, org_r, org_c, cval = highpass_params(getattr(tracker, "highpass", {"size": (5, 5)}))
             d.highpass_size = 0 if (rows, cols) == (5, 5) else rows | cols << 16
+            d.highpass_mode, d.highpass_origin, d.highpass_cval = hp_mode, (org_r & 0xffff) | (org_c & 0xffff) << 16, cval
             d.interp_rows, d.interp_cols = interpolation_degrees(getattr(tracker, "interpolation", {}))
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED
@@ -481,56 +530,16 @@ class Session:
 
     def _lower_models(self, models):
         torch, device = self.torch, self.device
-        rasters, table = {}, []
-
-        memo = {}
-
-        def index_of(raster):
-            hit = memo.get(id(raster))
-            if hit is not None:
-                return hit
-            memo[id(raster)] = out = _index_of(raster)
-            return out
-
-        def _index_of(raster):
-            key = getattr(raster, "_const_key", None)
-            if key is not None and key in rasters:
-                return rasters[key]
-            if not (hasattr(raster, "array") and hasattr(raster, "xlim")):
-                raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
-            arr = np.asarray(raster.array)
-            key = id(raster)
-            if arr.ndim != 2 or arr.size == 1:  # constant: share by value
-                key = ("const", float(arr.flat[0]), tuple(np.asarray(raster.xlim, dtype=float)),
-                       tuple(np.asarray(raster.ylim, dtype=float)))
-            if key not in rasters:
-                wrapped = raster if isinstance(raster, Raster) else Raster(raster.array, x=raster.xlim, y=raster.ylim)
-                s, tensor = wrapped.lower(torch, device)
-                rasters[key] = len(table)
-                table.append(s)
+        table_m, surfaces, viewshed = lower_models(models, self.tracker.viewshed)
+        table = []
+        for s, z in surfaces:
+            if z is not None:
+                tensor = torch.as_tensor(z).to(device)
+                s.z = tensor.data_ptr()
                 self.keep.append(tensor)
-            return rasters[key]
-
-        # gb_motion table as one structured array (field layout of include/glimpse_b200.h)
-        dt = np.dtype([("kind", "<i4"), ("dem", "<i4"), ("dem_sigma", "<i4"), ("pad_", "<i4"), ("xy", "<f8", 2),
-                       ("xy_sigma", "<f8", 2), ("v", "<f8", 3), ("v_sigma", "<f8", 3), ("a", "<f8", 3), ("a_sigma", "<f8", 3),
-                       ("slope_sigma", "<f8")])
-        assert dt.itemsize == C.sizeof(_lib.gb_motion)
-        table_m = np.zeros(len(models), dtype=dt)
-        adopted = [adopt_model(m) for m in models]
-        vel = [m._velocity() for m in adopted]
-        table_m["kind"] = [m.kind for m in adopted]
-        table_m["dem"] = [index_of(m.dem) for m in adopted]
-        table_m["dem_sigma"] = [index_of(m.dem_sigma) for m in adopted]
-        table_m["xy"] = np.array([m.xy for m in adopted], dtype=float)
-        xs = np.array([m.xy_sigma for m in adopted], dtype=float)
-        table_m["xy_sigma"] = xs if xs.ndim == 2 else xs[:, None]
-        for k, name in enumerate(("v", "v_sigma", "a", "a_sigma")):
-            table_m[name] = np.array([v[k] for v in vel], dtype=float)
-        table_m["slope_sigma"] = [float(getattr(m, "slope_sigma", 0.0)) for m in adopted]
+            table.append(s)
         self.tangent = table_m["kind"] >= _lib.GB_MOTION_TANGENT_CARTESIAN
         self.motion_kinds = int(np.bitwise_or.reduce(1 << table_m["kind"].astype(np.int64))) if len(models) else 0
-        viewshed = index_of(self.tracker.viewshed) if self.tracker.viewshed is not None else -1
         motion_dev = torch.from_numpy(table_m.view(np.uint8).reshape(-1)).to(device)
         surf_dev = _struct_array_to_device(torch, table, _lib.gb_surface, device)
         self.h2d += motion_dev.numel() + surf_dev.numel()

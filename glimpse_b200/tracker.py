@@ -21,9 +21,10 @@ Differences a user can see (all documented in DESIGN.md):
   (``rng="numpy"`` cannot replay its draws: such a point keeps its ``MemoryError`` in ``Tracks.errors``).
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
-* ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass={'size': ...}`` of any size up to 31 x 31 (the
-  default 5 x 5 has the fast kernel) and ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values
-  raise ``NotImplementedError`` (no CPU fallback).
+* ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass`` with ``size`` up to 31 x 31 (the default
+  5 x 5 'reflect' has the fast kernel), any border ``mode`` / ``cval`` / ``origin`` of ``scipy.ndimage.median_filter``, and
+  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values (``residual``, a median ``footprint``,
+  spline degrees 2 / 4 / 5) raise ``NotImplementedError`` (no CPU fallback).
 """
 from __future__ import annotations
 
@@ -50,19 +51,34 @@ def pairwise_distance_datetimes(x, y) -> np.ndarray:
 from .session import point_span  # noqa: E402,F401  (re-exported)
 
 
-def highpass_size(highpass: dict):
-    """(rows, columns) of ``scipy.ndimage.median_filter(tile, **highpass)`` (reference tracker.py:59, 530).
+def highpass_params(highpass: dict):
+    """``scipy.ndimage.median_filter(tile, **highpass)`` (reference tracker.py:59, 530) as the device kernels take it:
+    ``(rows, columns, mode, origin_rows, origin_columns, cval)``.
 
-    The device kernels implement ``size`` (one integer or a pair, 1..31 each) with the default ``mode='reflect'``
-    and ``origin=0``; anything else has no kernel and raises ``NotImplementedError`` (there is no CPU fallback)."""
-    extra = set(highpass) - {"size", "mode", "origin"}
-    if extra or "size" not in highpass or highpass.get("mode", "reflect") != "reflect" or np.any(np.asarray(highpass.get("origin", 0)) != 0):
-        raise NotImplementedError("highpass: only {'size': int or (rows, columns)} with mode='reflect', origin=0 has a device kernel")
+    ``size`` (one integer or a pair, 1..31 each), ``mode`` ('reflect' default, 'constant', 'nearest', 'mirror', 'wrap' and
+    their 'grid-' aliases), ``cval`` and ``origin`` (one integer or a pair) have kernels; a ``footprint`` does not and raises
+    ``NotImplementedError`` (there is no CPU fallback)."""
+    extra = set(highpass) - {"size", "mode", "origin", "cval"}
+    if extra or "size" not in highpass:
+        raise NotImplementedError("highpass: {'size', 'mode', 'cval', 'origin'} have a device kernel; a footprint does not")
     size = highpass["size"]
     rows, cols = (size, size) if np.ndim(size) == 0 else tuple(size)
     if int(rows) != rows or int(cols) != cols or not (1 <= rows <= 31 and 1 <= cols <= 31):
         raise NotImplementedError("highpass: 'size' must be integers between 1 and 31")
-    return int(rows), int(cols)
+    mode = highpass.get("mode", "reflect")
+    if mode not in _lib.GB_HP_MODES:
+        raise RuntimeError(f"boundary mode not supported: {mode}")  # scipy's own complaint
+    origin = highpass.get("origin", 0)
+    org_r, org_c = (origin, origin) if np.ndim(origin) == 0 else tuple(origin)
+    for org, m in ((org_r, rows), (org_c, cols)):
+        if int(org) != org or not (-(int(m) // 2) <= org <= (int(m) - 1) // 2):
+            raise ValueError("invalid origin")  # scipy's own complaint
+    return int(rows), int(cols), _lib.GB_HP_MODES[mode], int(org_r), int(org_c), float(highpass.get("cval", 0.0))
+
+
+def highpass_size(highpass: dict):
+    """(rows, columns) of the median high-pass (see :func:`highpass_params`)."""
+    return highpass_params(highpass)[:2]
 
 
 def interpolation_degrees(interpolation: dict):
@@ -211,6 +227,11 @@ class Tracker:
         for model in motion_models[1:]:
             if model.time_unit != time_unit:
                 raise ValueError("Motion models must have equal time units")
+        counts = sorted({int(m.n) for m in motion_models})
+        if len(counts) > 1:
+            # every motion model may carry its own number of particles (tracker.py:328): the device sessions are uniform in
+            # N, so the points are tracked group by group (one group per particle count) and put back in their order
+            return self._track_by_particle_count(counts, params)
         if self.resample_method not in _lib.GB_RESAMPLE:
             raise NotImplementedError("only resample_method='systematic', 'stratified' and 'choice' have device kernels")
         highpass_size(self.highpass)  # raises for what has no device kernel
@@ -319,6 +340,59 @@ class Tracker:
         lap("results")
         if isinstance(self.last_run, dict):
             self.last_run["host_ms"] = host_ms  # where the wall time of this call went (host view; the device runs under 'fetch')
+        return tracks
+
+    def _track_by_particle_count(self, counts, params) -> Tracks:
+        models = list(params["motion_models"])
+        ntracks, n_obs = len(models), len(self.observers)
+        mask = params["observer_mask"]
+        mask = np.ones((ntracks, n_obs), dtype=bool) if mask is None else np.asarray(mask, dtype=bool).reshape(ntracks, n_obs)
+        user_seed = base_seed = self.seed
+        if self.rng == "philox" and base_seed is None:
+            base_seed = int(np.random.randint(0, 2 ** 61))
+        parts = []
+        try:
+            for k, n in enumerate(counts):
+                idx = [i for i, m in enumerate(models) if int(m.n) == n]
+                if base_seed is not None:
+                    self.seed = base_seed + k
+                kw = dict(params, motion_models=[models[i] for i in idx], observer_mask=mask[idx])
+                try:
+                    part = self.track(**kw)
+                except Exception as exc:  # a group of one point raises instead of capturing: capture it here
+                    if ntracks < 2:
+                        raise
+                    part = exc
+                parts.append((idx, part))
+        finally:
+            self.seed = user_seed
+        first = next(part for _, part in parts if isinstance(part, Tracks))
+        T = first.means.shape[1]
+        cov = first.covariances is not None
+        means = np.full((ntracks, T, 6), np.nan)
+        sig = np.full((ntracks, T, 6, 6) if cov else (ntracks, T, 6), np.nan)
+        errors, warns = [None] * ntracks, [None] * ntracks
+        particles = [None] * ntracks if params["return_particles"] and not params["reduce_particles"] else None
+        weights = [None] * ntracks if particles is not None else None
+        reduced = [None] * ntracks if params["reduce_particles"] else None
+        for idx, part in parts:
+            for j, i in enumerate(idx):
+                if not isinstance(part, Tracks):
+                    errors[i] = part
+                    continue
+                means[i] = part.means[j]
+                sig[i] = (part.covariances if cov else part.sigmas)[j]
+                errors[i], warns[i] = part.errors[j], part.warnings[j]
+                if particles is not None:
+                    particles[i], weights[i] = part.particles[j], part.weights[j]
+                if reduced is not None:
+                    reduced[i] = part.reduced[j]
+        kwargs = dict(time_unit=first.time_unit, datetimes=first.datetimes, means=means, tracker=self, images=first.images, params=params,
+                      errors=errors, warnings=warns, particles=particles, weights=weights)
+        kwargs["covariances" if cov else "sigmas"] = sig
+        tracks = Tracks(**kwargs)
+        if reduced is not None:
+            tracks.reduced = reduced
         return tracks
 
     # ------------------------------------------------------------------ device plumbing

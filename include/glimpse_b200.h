@@ -193,6 +193,17 @@ typedef struct gb_plan {
   int32_t stream_slots;     /* GB_MODE_STREAM: batches in flight (side streams / scratch slots) */
 } gb_plan;
 
+/* Border modes of the median high-pass (Tracker.highpass['mode'], scipy.ndimage: d c b a | a b c d | d c b a is 'reflect'). */
+#define GB_HP_REFLECT 0
+#define GB_HP_CONSTANT 1
+#define GB_HP_NEAREST 2
+#define GB_HP_MIRROR 3
+#define GB_HP_WRAP 4
+
+/* Observers per gb_track call: the cameras of one time step travel as kernel launch parameters (operands straight from the
+ * constant bank), which bounds their number.  (The reference has no limit; its use cases have one to three stations.) */
+#define GB_MAX_OBSERVERS 8
+
 /* Size a launch plan for N particles per point, a w x h template, P points and O observers.
  * `prefer_cluster` is ignored (it sized the removed cluster-per-point organisation); `mode` must be GB_MODE_STREAM.
  * Plan fields that only that organisation used (cluster, particles_in_smem, n_slabs, slab_bytes, particle_scratch_bytes) are 1 / 0. */
@@ -273,6 +284,10 @@ typedef struct gb_track_desc {
   int32_t interp_rows, interp_cols; /* Tracker.interpolation (tracker.py:60, observer.py:210): degree of the interpolating spline along the rows
                                     * (kx) and the columns (ky) of the SSE surface, which also sets the minimum surface size (tracker.py:584-594).
                                     * 3 (cubic, not-a-knot) or 1 (piecewise linear); 0 = the default 3 */
+  int32_t highpass_mode;           /* border mode of the median high-pass (scipy.ndimage.median_filter's `mode`): GB_HP_* */
+  int32_t highpass_origin;         /* its `origin` as (rows & 0xffff) | (columns & 0xffff) << 16, each a signed 16-bit shift of the window:
+                                    * the window of pixel i spans i - size / 2 - origin ... (0 = centred, the default) */
+  double highpass_cval;            /* value beyond the border with GB_HP_CONSTANT (`cval`), in the units of the filtered tile */
   double* final_weights;           /* [N] or NULL: weights of point P - 1's resampled particles at its last time — what Tracker.weights holds
                                     * after track() in the reference (tracker.py:62-70, 216-223: the state of the last processed track);
                                     * the caller pre-fills it with ones (a point that is never updated keeps its initial weights) */

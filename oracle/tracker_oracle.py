@@ -377,13 +377,14 @@ def cdf_match(a: np.ndarray, cdf) -> np.ndarray:
     return mapped[inverse.ravel()].reshape(a.shape)
 
 
-def median_window(tile: np.ndarray, size=(5, 5), exact: bool = False) -> np.ndarray:
+def median_window(tile: np.ndarray, size=(5, 5), exact: bool = False, **filter_kwargs) -> np.ndarray:
     """``scipy.ndimage.median_filter(tile, size, mode='reflect')`` or, with ``exact``, a direct
-    restatement (edge pixel duplicated; rank ``n // 2`` of the window)."""
-    if not exact:
+    restatement (edge pixel duplicated; rank ``n // 2`` of the window).  ``filter_kwargs`` = the other entries of
+    ``Tracker.highpass`` (``mode``, ``cval``, ``origin``): always scipy's own filter."""
+    if not exact or filter_kwargs:
         import scipy.ndimage
 
-        return scipy.ndimage.median_filter(tile, size=size)
+        return scipy.ndimage.median_filter(tile, size=size, **filter_kwargs)
     hy, hx = size[0] // 2, size[1] // 2
     padded = np.pad(tile, ((hy, size[0] - 1 - hy), (hx, size[1] - 1 - hx)), mode="symmetric")
     windows = np.lib.stride_tricks.sliding_window_view(padded, size).reshape(tile.shape + (-1,))
@@ -391,14 +392,14 @@ def median_window(tile: np.ndarray, size=(5, 5), exact: bool = False) -> np.ndar
     return np.partition(windows, k, axis=2)[:, :, k]
 
 
-def prepare_tile(pixels: np.ndarray, histogram=None, size=(5, 5), exact_median: bool = False):
+def prepare_tile(pixels: np.ndarray, histogram=None, size=(5, 5), exact_median: bool = False, **filter_kwargs):
     """gray -> z-score -> (search: CDF match) -> (template: CDF) -> minus 5x5 median (tracker.py:522-534).
     Returns (tile, cdf of the pre-filter tile)."""
     tile = normalize(to_gray(pixels))
     if histogram is not None:
         tile = cdf_match(tile, histogram)
     cdf = value_cdf(tile)
-    tile = tile - median_window(tile, size=size, exact=exact_median)
+    tile = tile - median_window(tile, size=size, exact=exact_median, **filter_kwargs)
     return tile, cdf
 
 
@@ -618,6 +619,7 @@ def track(
     trace: bool = False,
     raise_errors: bool = False,
     highpass_size=(5, 5),
+    highpass_kwargs: Optional[Dict] = None,
     kx: int = 3,
     ky: int = 3,
 ) -> TrackResult:
@@ -627,12 +629,14 @@ def track(
     observer ``o`` matched to time ``t`` or -1 (tracker.py:466-492).  Draws come from the legacy
     global NumPy generator in the reference's order unless ``randn`` / ``random`` are supplied.
     ``exact`` switches the three library kernels to their closed-form restatements.
-    ``highpass_size`` = ``Tracker.highpass["size"]`` as (rows, columns) or one integer (tracker.py:59, 530).
+    ``highpass_size`` = ``Tracker.highpass["size"]`` as (rows, columns) or one integer (tracker.py:59, 530);
+    ``highpass_kwargs`` = its other entries (``mode``, ``cval``, ``origin`` of ``scipy.ndimage.median_filter``).
     ``kx``, ``ky`` = ``Tracker.interpolation`` (tracker.py:60): spline degree along the rows / columns of the SSE surface.
     """
     if np.ndim(highpass_size) == 0:
         highpass_size = (int(highpass_size),) * 2
     highpass_size = tuple(int(v) for v in highpass_size)
+    hp_kw = dict(highpass_kwargs or {})
     randn = randn or np.random.randn
     random = random or np.random.random
     T, O = image_index.shape
@@ -672,7 +676,7 @@ def track(
                     uv0 = project(cam, weighted_mean(ps, w)[None, 0:3], obs.correction(img)).ravel()
                     box = snap_tile_box(uv0, tile_size, cam[6:8].astype(int))
                     pixels = obs.frames[img][box[1]:box[3], box[0]:box[2]]
-                    tile, cdf = prepare_tile(pixels, size=highpass_size, exact_median=exact)
+                    tile, cdf = prepare_tile(pixels, size=highpass_size, exact_median=exact, **hp_kw)
                     templates[o] = {"tile": tile, "cdf": cdf, "box": box, "duv": uv0 - box.reshape(2, -1).mean(axis=0)}
                     if trace:
                         made.append({"p": p, "obs": int(o), "img": img, "box": box, "tile": tile, "values": cdf[0], "quantiles": cdf[1]})
@@ -693,7 +697,7 @@ def track(
                             skipped[p, t, o] = 2
                             continue
                         pixels = obs.frames[img][box[1]:box[3], box[0]:box[2]]
-                        search, _ = prepare_tile(pixels, histogram=tpl["cdf"], size=highpass_size, exact_median=exact)
+                        search, _ = prepare_tile(pixels, histogram=tpl["cdf"], size=highpass_size, exact_median=exact, **hp_kw)
                         sse = ssd_surface(search, tpl["tile"], exact=exact)
                         sbox = surface_box(box, size, tpl["duv"])
                         sampled = spline_sample(uv, sse, sbox, exact=exact, kx=kx, ky=ky)

@@ -114,6 +114,23 @@ def track_cases():
             scene_kwargs=dict(seed=19, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1919, post=add_second_observer, highpass={"size": 4},
         ),
+        # ... other border modes and origins of the median filter (scipy.ndimage.median_filter's mode / cval / origin)
+        "track_hp_mirror": dict(
+            scene_kwargs=dict(seed=29, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=2929, highpass={"size": 5, "mode": "mirror"},
+        ),
+        "track_hp_const": dict(
+            scene_kwargs=dict(seed=31, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=3131, post=add_second_observer, highpass={"size": (3, 5), "mode": "constant", "cval": 0.1, "origin": (1, -2)},
+        ),
+        "track_hp_wrap": dict(
+            scene_kwargs=dict(seed=33, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=3333, highpass={"size": (4, 6), "mode": "wrap", "origin": (-2, 2)},
+        ),
+        "track_hp_nearest": dict(
+            scene_kwargs=dict(seed=35, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=3535, highpass={"size": 7, "mode": "nearest", "origin": 3},
+        ),
         # ... and other spline degrees (Tracker.interpolation, tracker.py:60): bilinear; a 2 x 2 .. 3 x 3 surface (bilinear,
         # window widened to the minimum); cubic along the rows with linear along the columns, two observers
         "track_lin": dict(

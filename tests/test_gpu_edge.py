@@ -445,3 +445,24 @@ def test_points_that_outgrow_the_window_capacity_are_run_again(cuda):
     kept = gb.Tracker(observers, rng="numpy").track(models, tile_size=scene.tile_size)
     assert all(isinstance(e, MemoryError) for e in kept.errors)
     assert np.isfinite(kept.means[:, 1]).all() and np.isnan(kept.means[:, -1]).all()
+
+
+def test_models_with_their_own_particle_counts(cuda):
+    """tracker.py:328: every motion model carries its own n.  Points are tracked group by group (one device session per
+    particle count) and come back in their order; a group's results equal those of tracking that group alone."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=6, n_points=6, n_particles=500, n_frames=5, imgsz=(320, 240), margin_px=100)
+    observers, models = synthetic.build(scene, gb)
+    for i in (1, 4):
+        models[i].n = 800
+    tracker = gb.Tracker(observers, seed=21)
+    tracks = tracker.track(models, tile_size=scene.tile_size, return_particles=True)
+    assert all(e is None for e in tracks.errors) and tracks.means.shape == (6, 5, 6)
+    assert [p.shape for p in tracks.particles] == [(5, 800 if i in (1, 4) else 500, 6) for i in range(6)]
+    assert np.isfinite(tracks.means).all() and np.all(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0]) < 0.15)
+    first = gb.Tracker(observers, seed=21).track([models[i] for i in (0, 2, 3, 5)], tile_size=scene.tile_size)
+    np.testing.assert_array_equal(tracks.means[[0, 2, 3, 5]], first.means)
+    second = gb.Tracker(observers, seed=22).track([models[i] for i in (1, 4)], tile_size=scene.tile_size)
+    np.testing.assert_array_equal(tracks.means[[1, 4]], second.means)
+    assert tracker.seed == 21

@@ -159,7 +159,7 @@ def test_unsupported_options_raise_instead_of_falling_back():
     obs = _observers(3)
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
-    for kw in (dict(resample_method="residual"), dict(highpass={"size": (5, 5), "mode": "nearest"}),
+    for kw in (dict(resample_method="residual"),
                dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
                dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
         with pytest.raises(NotImplementedError):
@@ -173,6 +173,15 @@ def test_unsupported_options_raise_instead_of_falling_back():
 
     assert highpass_size({"size": (3, 7)}) == (3, 7)  # (rows, columns), as scipy.ndimage.median_filter reads it
     assert highpass_size({"size": 4, "mode": "reflect", "origin": 0}) == (4, 4)
+    from glimpse_b200 import _lib
+    from glimpse_b200.tracker import highpass_params
+
+    assert highpass_params({"size": (3, 5), "mode": "constant", "cval": 0.1, "origin": (1, -2)}) == (3, 5, _lib.GB_HP_MODES["constant"], 1, -2, 0.1)
+    assert highpass_params({"size": 5, "mode": "grid-wrap"})[2] == _lib.GB_HP_MODES["wrap"]
+    with pytest.raises(ValueError, match="invalid origin"):  # scipy: -(size // 2) <= origin <= (size - 1) // 2
+        highpass_params({"size": 4, "origin": 2})
+    with pytest.raises(RuntimeError, match="boundary mode not supported"):
+        highpass_params({"size": 5, "mode": "periodic"})
 
     class Custom:
         n, time_unit = 10, day
@@ -401,3 +410,37 @@ def test_observer_subset_split_and_select_datetimes():
         obs.shift_tile(np.zeros((5, 5)), (0.6, 0.0))
     with pytest.raises(NotImplementedError):
         obs.sample_tile(np.zeros((1, 2)), np.zeros((5, 5)), (0, 0, 5, 5), kx=2)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("kind", ["cartesian", "cylindrical", "tangent_cartesian", "tangent_cylindrical"])
+def test_reference_objects_lower_to_the_same_tables(kind):
+    """the reference's own Observer / Image / Camera / motion-model / Raster objects are accepted as they
+    are.  Built from one scene with both packages, they must lower to byte-identical gb_camera / gb_motion / gb_surface tables
+    (host side of the C ABI), including gridded DEMs, a viewshed raster and cameras with curvature / refraction corrections."""
+    import scenes
+    from glimpse_b200 import synthetic
+    from glimpse_b200.camera import lower_camera
+    from glimpse_b200.session import lower_models
+    from oracle.ref_shim import import_reference
+
+    import glimpse_b200 as gb
+
+    glimpse = import_reference()
+    scene = synthetic.nadir_scene(seed=5, n_points=4, n_particles=64, n_frames=3, imgsz=(320, 240), margin_px=90, kind=kind,
+                                  jitter_deg=0.05, world_offset=(4.99e5, 6.77e6))
+    if kind.startswith("tangent"):
+        scenes.add_gridded_dem(scene)
+    tables = []
+    for api in (glimpse, gb):
+        observers, models = synthetic.build(scene, api)
+        observers[0].images[1].cam.correction = {"radius": 6.3781e6, "refraction": 0.13}
+        cams = [bytes(lower_camera(img.cam)) for obs in observers for img in obs.images]
+        view = api.Raster(np.ones((6, 8)), x=(4.98e5, 5.0e5), y=(6.78e6, 6.76e6))
+        table_m, surfaces, vi = lower_models(models, view)
+        surf = [(bytes(s), None if z is None else z.tobytes()) for s, z in surfaces]
+        tables.append((cams, table_m.tobytes(), surf, vi))
+    assert tables[0][0] == tables[1][0]  # gb_camera of every image
+    assert tables[0][1] == tables[1][1]  # gb_motion of every point
+    assert tables[0][2] == tables[1][2] and tables[0][3] == tables[1][3]  # gb_surface table (structs and cell values), viewshed index
+    assert len(tables[0][2]) >= (3 if kind.startswith("tangent") else 2)
