@@ -25,7 +25,7 @@ GB_OBS_OUT_OF_FRAME = 2
 GB_ST_WINDOW_TOO_LARGE = 6
 GB_WINDOW_MARGIN, GB_WINDOW_MARGIN_MAX = 191, 1000  # default / retry capacity of the search windows beyond the template, px
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
-GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2}
+GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2, "residual": 3}
 GB_MODE_STREAM = 1
 GB_HP_MODES = {"reflect": 0, "grid-mirror": 0, "constant": 1, "grid-constant": 1, "nearest": 2, "mirror": 3, "wrap": 4, "grid-wrap": 4}
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3

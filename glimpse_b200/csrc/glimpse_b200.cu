@@ -970,6 +970,9 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   if (prm.resample_method == GB_RESAMPLE_CHOICE) {
     k_s4c_scan<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
     k_s4c_gather<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+  } else if (prm.resample_method == GB_RESAMPLE_RESIDUAL) {
+    k_s4r_residual<<<(unsigned)prm.pb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
+    k_s4c_gather<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   } else {
     k_s4_resample<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
   }
@@ -1519,7 +1522,7 @@ int gb_track(const gb_track_desc* d, void* stream_, int64_t* launches_out) {
   if ((rc = ensure_tensor_maps(*d))) return rc;
   const bool cov = d->covariances != nullptr;
   int64_t launches = 0;
-  if (d->resample_method != GB_RESAMPLE_CHOICE) {  // (choice: step-by-step flow below)
+  if (d->resample_method != GB_RESAMPLE_CHOICE && d->resample_method != GB_RESAMPLE_RESIDUAL) {  // (those two: step-by-step flow below)
     if ((rc = track_streaming(*d, stream, &launches))) return rc;
     if (launches_out) *launches_out = launches;
     return GB_OK;

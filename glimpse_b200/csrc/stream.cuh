@@ -819,6 +819,155 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_scan(const __grid_
   }
 }
 
+// np.add.reduce over a contiguous float64 vector = NumPy's pairwise summation (numpy/core/src/umath/loops_utils.h:
+// fewer than 8 elements in order; up to 128 with eight strided accumulators combined as ((r0 + r1) + (r2 + r3)) + ((r4 + r5) +
+// (r6 + r7)) and the remainder added in order; longer vectors split at n / 2 rounded down to a multiple of 8).  One thread.
+// `scale`, `shift`: the summand is a[i] * scale - shift[i] (shift may be null) — the residual resampler sums derived vectors.
+template <class F>
+__device__ __forceinline__ double numpy_pairwise_block(F a, int64_t lo, int64_t n) {  // n <= 128
+  if (n < 8) {
+    double res = 0.0;
+    for (int64_t i = 0; i < n; ++i) res += a(lo + i);
+    return res;
+  }
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = a(lo + k);
+  int64_t i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] += a(lo + i + k);
+  }
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res += a(lo + i);
+  return res;
+}
+template <class F>
+__device__ double numpy_pairwise_sum(F a, int64_t lo0, int64_t n0) {
+  // the recursion, unrolled on an explicit stack (post-order: left subtree, right subtree, add)
+  int64_t lo[40], n[40];
+  double left[40];
+  int phase[40];
+  int sp = 0;
+  lo[0] = lo0;
+  n[0] = n0;
+  phase[0] = 0;
+  double ret = 0.0;
+  while (sp >= 0) {
+    if (n[sp] <= 128) {
+      ret = numpy_pairwise_block(a, lo[sp], n[sp]);
+      --sp;
+      continue;
+    }
+    int64_t n2 = n[sp] / 2;
+    n2 -= n2 % 8;
+    if (phase[sp] == 0) {
+      phase[sp] = 1;
+      lo[sp + 1] = lo[sp];
+      n[sp + 1] = n2;
+      phase[sp + 1] = 0;
+      ++sp;
+    } else if (phase[sp] == 1) {
+      left[sp] = ret;
+      phase[sp] = 2;
+      lo[sp + 1] = lo[sp] + n2;
+      n[sp + 1] = n[sp] - n2;
+      phase[sp + 1] = 0;
+      ++sp;
+    } else {
+      ret = left[sp] + ret;
+      --sp;
+    }
+  }
+  return ret;
+}
+
+// Residual resampling exactly as the reference does it (tracker.py:188-203), including what a textbook version would not:
+// the residuals are taken of the NORMALISED weights minus the integer repetitions (not of n w), so their cumulative sum is not
+// monotone, and np.searchsorted's answers on it depend on NumPy's search, which keeps one bound from the previous key
+// (numpy/core/src/npysort/binsearch.cpp) — restated here operation by operation.  One CTA per point: the sums, the cumulative
+// sum and the search run on one thread in NumPy's order (this method is a compatibility path, not a fast one); repetitions and
+// their offsets on all threads.  Output: the parent of every child, int32 [N], behind the cumulative sums in the point's
+// projected-coordinate scratch (dead after k_s3) — k_s4c_gather copies the parents.
+__global__ void __launch_bounds__(GB_SBLOCK_THREADS) k_s4r_residual(const __grid_constant__ StepParams prm) {
+  __shared__ double s_tot[2];
+  __shared__ int s_scan[GB_SBLOCK_THREADS];
+  __shared__ int s_K;
+  const int64_t p = prm.p0 + blockIdx.x;
+  if (!stream_point_active(prm, p) || prm.s_pflags[p] != 0) return;
+  const int tid = threadIdx.x, N = (int)prm.N, t = prm.t;
+  const double* w = prm.s_w + (int64_t)p * N;
+  double* cs = prm.s_uv + p * prm.O * 2 * (int64_t)N;    // [N] normalised weights, then residuals, then their cumulative sum
+  int* ridx = reinterpret_cast<int*>(cs + N);           // [N] parent of every child
+  int* cum = ridx + N;                                  // [N] inclusive prefix of the repetitions
+  if (tid == 0) s_tot[0] = numpy_pairwise_sum([w](int64_t i) { return w[i]; }, 0, N);
+  __syncthreads();
+  const double total = s_tot[0], dn = (double)N;
+  // repetitions = (n * weights).astype(int); blocked layout so that one scan over the threads orders them
+  const int per = (N + GB_SBLOCK_THREADS - 1) / GB_SBLOCK_THREADS, i0 = tid * per, i1 = min(N, i0 + per);
+  int mine = 0;
+  for (int i = i0; i < i1; ++i) {
+    const double wn = quo(w[i], total);
+    const int reps = (int)mul(dn, wn);
+    cs[i] = sub(wn, (double)reps);  // residuals = weights - repetitions
+    mine += reps;
+    cum[i] = mine;
+  }
+  s_scan[tid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < GB_SBLOCK_THREADS; ++k) {
+      const int x = s_scan[k];
+      s_scan[k] = run;
+      run += x;
+    }
+    s_K = run;
+  }
+  __syncthreads();
+  for (int i = i0; i < i1; ++i) cum[i] += s_scan[tid];
+  __syncthreads();
+  const int K = min(s_K, N);
+  // initial_indexes = np.repeat(np.arange(n), repetitions): child j belongs to the first parent whose inclusive prefix exceeds j
+  for (int j = tid; j < K; j += GB_SBLOCK_THREADS) {
+    int lo = 0, hi = N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    ridx[j] = lo;
+  }
+  if (tid == 0) {
+    // residuals *= 1 / residuals.sum(); cumulative_sum = np.cumsum(residuals); cumulative_sum[-1] = 1.0
+    const double inv = quo(1.0, numpy_pairwise_sum([cs](int64_t i) { return cs[i]; }, 0, N));
+    double run = 0.0;
+    for (int i = 0; i < N; ++i) {
+      run = add(run, mul(cs[i], inv));
+      cs[i] = run;
+    }
+    cs[N - 1] = 1.0;
+    // additional_indexes = np.searchsorted(cumulative_sum, np.random.random(n - len(initial_indexes)))
+    const StratifiedDraws draws = stratified_draws(prm, p, t);  // one uniform per additional child, in order
+    int64_t lo = 0, hi = N;
+    double last = K < N ? draws.u(0) : 0.0;
+    for (int k = 0; k < N - K; ++k) {
+      const double key = draws.u(k);
+      if (last < key) {
+        hi = N;
+      } else {
+        lo = 0;
+        hi = hi < N ? hi + 1 : N;
+      }
+      last = key;
+      while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (cs[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      ridx[K + k] = (int)lo;
+    }
+  }
+}
+
 template <bool COV>
 __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_gather(const __grid_constant__ StepParams prm) {
   constexpr int NM = Moments<COV>::NM, KP = COV ? 32 : 16;
@@ -845,14 +994,21 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s4c_gather(const __gri
   double* fin = (prm.final_weights && p == prm.P - 1 && t == prm.last[p]) ? prm.final_weights : nullptr;
   Moments<COV> mom;
   mom.clear();
+  const bool given = prm.resample_method == GB_RESAMPLE_RESIDUAL;  // k_s4r_residual has written every child's parent
+  const int* ridx = reinterpret_cast<const int*>(cdf + N);
   for (int j = base + tid; j < end; j += GB_SBLOCK_THREADS) {
-    const double u = draws.u(j);
-    int lo = 0, hi = N;  // number of entries <= u (np.searchsorted side='right')
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    int idx;
+    if (given) {
+      idx = min(max(ridx[j], 0), N - 1);
+    } else {
+      const double u = draws.u(j);
+      int lo = 0, hi = N;  // number of entries <= u (np.searchsorted side='right')
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+      }
+      idx = min(lo, N - 1);
     }
-    const int idx = min(lo, N - 1);
     double s[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) s[c] = ev[c * (int64_t)N + idx];

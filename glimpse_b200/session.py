@@ -300,7 +300,10 @@ class Session:
             d.point_offset = int(point_offset)
             d.motion_kinds = self.motion_kinds
             method = getattr(tracker, "resample_method", "systematic")
-            stratified = method in ("stratified", "choice")  # one uniform per particle and update
+            stratified = method in ("stratified", "choice", "residual")  # (up to) one uniform per particle and update
+            if method == "residual" and draws is None and tracker.rng == "numpy":
+                raise NotImplementedError("resample_method='residual' draws a number of uniforms that depends on the weights: the "
+                                          "reference's draw sequence cannot be generated ahead of the run; use rng='philox'")
             d.resample_method = _lib.GB_RESAMPLE[method]
             from .tracker import highpass_params, interpolation_degrees
 

@@ -21,10 +21,11 @@ Differences a user can see (all documented in DESIGN.md):
   (``rng="numpy"`` cannot replay its draws: such a point keeps its ``MemoryError`` in ``Tracks.errors``).
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
-* ``resample_method`` 'systematic', 'stratified' and 'choice', ``highpass`` with ``size`` up to 31 x 31 (the default
+* every ``resample_method`` ('systematic', 'stratified', 'residual', 'choice'), ``highpass`` with ``size`` up to 31 x 31 (the default
   5 x 5 'reflect' has the fast kernel), any border ``mode`` / ``cval`` / ``origin`` of ``scipy.ndimage.median_filter``, and
-  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values (``residual``, a median ``footprint``,
-  spline degrees 2 / 4 / 5) raise ``NotImplementedError`` (no CPU fallback).
+  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values (a median ``footprint``, spline degrees
+  2 / 4 / 5) raise ``NotImplementedError`` (no CPU fallback).  'residual' with ``rng="numpy"`` cannot replay the reference's
+  draws (their number depends on the weights) and raises too.
 """
 from __future__ import annotations
 
@@ -233,7 +234,7 @@ class Tracker:
             # N, so the points are tracked group by group (one group per particle count) and put back in their order
             return self._track_by_particle_count(counts, params)
         if self.resample_method not in _lib.GB_RESAMPLE:
-            raise NotImplementedError("only resample_method='systematic', 'stratified' and 'choice' have device kernels")
+            raise ValueError(f"unknown resample_method {self.resample_method!r}")
         highpass_size(self.highpass)  # raises for what has no device kernel
         interpolation_degrees(self.interpolation)
         self.reset()

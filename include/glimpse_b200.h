@@ -56,6 +56,8 @@ extern "C" {
 #define GB_RESAMPLE_SYSTEMATIC 0 /* tracker.py:168-176: one uniform per update */
 #define GB_RESAMPLE_STRATIFIED 1 /* tracker.py:178-186: one uniform per particle and update */
 #define GB_RESAMPLE_CHOICE 2     /* tracker.py:205-209: np.random.choice with replacement = inverse-CDF sampling, one uniform per particle */
+#define GB_RESAMPLE_RESIDUAL 3   /* tracker.py:188-203: int(n w) copies of every particle, the rest by np.searchsorted on the cumulative
+                                  * residuals exactly as the reference computes them; uniforms [P][S][N], the first n - sum(int(n w)) used */
 
 #define GB_RNG_SUPPLIED 0 /* normals / uniforms provided in the reference's draw order */
 #define GB_RNG_PHILOX 1   /* counter-based Philox4x32-10 on device */

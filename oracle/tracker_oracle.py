@@ -552,6 +552,22 @@ def stratified_indices(weights: np.ndarray, u: np.ndarray) -> np.ndarray:
     return np.searchsorted(np.cumsum(wn), positions)
 
 
+def residual_indices(weights: np.ndarray, random: Callable = np.random.random):
+    """tracker.py:188-203, statement by statement (the residuals are those of the normalised weights, and np.searchsorted runs
+    on their — not monotone — cumulative sum).  Returns (indices, the uniforms drawn)."""
+    n = len(weights)
+    weights = weights / weights.sum()
+    repetitions = (n * weights).astype(int)
+    initial_indexes = np.repeat(np.arange(n), repetitions)
+    residuals = weights - repetitions
+    residuals *= 1 / residuals.sum()
+    cumulative_sum = np.cumsum(residuals)
+    cumulative_sum[-1] = 1.0
+    u = random(n - len(initial_indexes))
+    additional_indexes = np.searchsorted(cumulative_sum, u)
+    return np.hstack((initial_indexes, additional_indexes)), u
+
+
 def choice_indices(weights: np.ndarray, u: np.ndarray) -> np.ndarray:
     """(tracker.py:205-209): ``np.random.choice(arange(n), n, replace=True, p=w / w.sum())`` of the legacy generator =
     inverse-CDF sampling with ``random_sample(n)`` (numpy/random/mtrand.pyx, ``RandomState.choice``)."""
@@ -716,6 +732,8 @@ def track(
                     elif resample_method == "choice":
                         u = random(len(w))
                         idx = choice_indices(w, u)
+                    elif resample_method == "residual":
+                        idx, u = residual_indices(w, random)
                     else:
                         u = random()
                         idx = systematic_indices(w, u)

@@ -95,11 +95,21 @@ def run_reference(scene, seed, points=None, return_covariances=False, observer_m
             rec["indices"] = np.array(out)
             return out
 
+        orig_hstack = np.hstack
+
+        def hstack(tup, *a, **kw):  # residual resampling: the ancestors are hstack((repeated, searched))
+            out = orig_hstack(tup, *a, **kw)
+            rec["indices"] = np.array(out)
+            return out
+
         np.random.random, np.searchsorted, np.random.choice = random, searchsorted, choice
+        if (method or tracker.resample_method) == "residual":
+            np.hstack = hstack
         try:
             orig_resample(method)
         finally:
             np.random.random, np.searchsorted, np.random.choice = orig_random, orig_search, orig_choice
+            np.hstack = orig_hstack
         steps.append(rec)
         current["obs"] = {}
 

@@ -104,6 +104,11 @@ def track_cases():
             scene_kwargs=dict(seed=15, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1515, resample_method="choice",
         ),
+        # residual resampling as the reference computes it (tracker.py:188-203); wide velocity prior so that weights are uneven
+        "track_residual": dict(
+            scene_kwargs=dict(seed=37, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=3737, resample_method="residual",
+        ),
         # other sizes of the median high-pass (Tracker.highpass, tracker.py:59, 530):
         # rows != columns, and an even size given as one integer (window offsets -2 .. 1)
         "track_hp37": dict(

@@ -159,8 +159,7 @@ def test_unsupported_options_raise_instead_of_falling_back():
     obs = _observers(3)
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
-    for kw in (dict(resample_method="residual"),
-               dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
+    for kw in (dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
                dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
         with pytest.raises(NotImplementedError):
             gb.Tracker([obs], **kw).track(models)
