@@ -91,6 +91,7 @@ class gb_track_desc(C.Structure):
         ("resample_method", C.c_int32), ("highpass_size", C.c_int32),
         ("interp_rows", C.c_int32), ("interp_cols", C.c_int32),
         ("highpass_mode", C.c_int32), ("highpass_origin", C.c_int32), ("highpass_cval", C.c_double),
+        ("highpass_footprint_host", C.c_void_p),
         ("final_weights", C.c_void_p),
         ("plan", gb_plan),
     ]

@@ -49,6 +49,8 @@ struct StepParams {
   int skip_evolve, viewshed, rng_mode, hp_cols;
   int hp_mode, hp_org_r, hp_org_c;  // border mode (GB_HP_*) and origin of the median high-pass
   double hp_cval;
+  int hp_has_fp;
+  uint32_t hp_fp[GB_MAX_HIGHPASS];  // footprint of the median high-pass, one word per window row
   uint64_t seed;
   int64_t point_offset;
   double tau, tau2;
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   // high-pass (tracker.py:530-531): value minus the reflected median (5x5 unless Tracker.highpass says otherwise), taken
   // on grey levels
   double* tile = prm.tmpl_tile + (p * prm.O + o) * (int64_t)(tw * th);
-  const bool hp_plain = prm.hp_mode == GB_HP_REFLECT && prm.hp_org_r == 0 && prm.hp_org_c == 0;
+  const bool hp_plain = prm.hp_mode == GB_HP_REFLECT && prm.hp_org_r == 0 && prm.hp_org_c == 0 && !prm.hp_has_fp;
   const bool hp5 = prm.hp_rows == 5 && prm.hp_cols == 5 && hp_plain;
   // (general border mode: the constant beyond the border takes its place among the grey levels through the normalised values)
   int cval_level = nbins;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
       vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
     } else {
       const int code = median_window_codes(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols, prm.hp_mode, prm.hp_org_r, prm.hp_org_c,
-                                           2 * cval_level);
+                                           2 * cval_level, prm.hp_has_fp ? prm.hp_fp : nullptr);
       vm = (code & 1) ? mul(sub(quo((double)(code >> 1), (double)nchan), mean), inv_std) : prm.hp_cval;
     }
     tile[i] = sub(vn, vm);
@@ -761,6 +763,9 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
   prm.hp_org_r = (int16_t)(d.highpass_origin & 0xffff);
   prm.hp_org_c = (int16_t)(d.highpass_origin >> 16 & 0xffff);
   prm.hp_cval = d.highpass_cval;
+  prm.hp_has_fp = d.highpass_footprint_host != nullptr;
+  if (prm.hp_has_fp)
+    for (int a = 0; a < GB_MAX_HIGHPASS; ++a) prm.hp_fp[a] = a < prm.hp_rows ? d.highpass_footprint_host[a] : 0u;
   prm.cluster = d.plan.cluster;
   prm.n_local = d.plan.n_local;
   prm.particles_in_smem = d.plan.particles_in_smem;
@@ -839,6 +844,11 @@ static int check_desc(const gb_track_desc& d) {
     const int rows = d.highpass_size ? (d.highpass_size & 0xffff) : 5, cols = d.highpass_size ? (d.highpass_size >> 16 & 0xffff) : 5;
     const int org_r = (int16_t)(d.highpass_origin & 0xffff), org_c = (int16_t)(d.highpass_origin >> 16 & 0xffff);
     if (d.highpass_mode < GB_HP_REFLECT || d.highpass_mode > GB_HP_WRAP) return fail(GB_E_INVALID, "highpass_mode: unknown border mode%s");
+    if (d.highpass_footprint_host) {
+      uint32_t any = 0;
+      for (int a = 0; a < rows; ++a) any |= d.highpass_footprint_host[a] & (cols >= 32 ? 0xffffffffu : ((1u << cols) - 1u));
+      if (!any) return fail(GB_E_INVALID, "highpass_footprint_host: empty footprint%s");
+    }
     // scipy.ndimage: -(size // 2) <= origin <= (size - 1) // 2
     if (org_r < -(rows / 2) || org_r > (rows - 1) / 2 || org_c < -(cols / 2) || org_c > (cols - 1) / 2)
       return fail(GB_E_INVALID, "highpass_origin: the shifted window must still cover its pixel%s");

@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   w.hp_org_r = prm.hp_org_r;
   w.hp_org_c = prm.hp_org_c;
   w.hp_cval = prm.hp_cval;
+  w.hp_fp = prm.hp_has_fp ? prm.hp_fp : nullptr;
   w.cub_u = prm.interp_cols != 1;
   w.cub_v = prm.interp_rows != 1;
   w.th = prm.tile_h;

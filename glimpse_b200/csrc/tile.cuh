@@ -40,6 +40,7 @@ struct TileWork {
   int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
   int hp_mode = 0, hp_org_r = 0, hp_org_c = 0;  // its border mode (GB_HP_*) and origin (Tracker.highpass['mode'], ['origin'])
   double hp_cval = 0.0;                          // ... and the constant beyond the border for GB_HP_CONSTANT
+  const uint32_t* hp_fp = nullptr;               // ... and the footprint (one word per window row), or null: the full window
   bool cub_u = true, cub_v = true;  // cubic (default) or piecewise-linear interpolation along the columns / rows (Tracker.interpolation)
 };
 
@@ -177,9 +178,15 @@ __device__ __forceinline__ int border_index(int i, int n, int mode) {
 // the constant beyond the border has the even code `cval_code` = 2 x (number of grey levels whose filtered-tile value is below
 // cval) — the codes are ordered like the values, so the rank element is found on integers (bit by bit, as median_window does).
 // Returns the code of the median: odd = grey level (code - 1) / 2, even = the border constant.
+// `fp` = the footprint, one word per window row (bit b = column b takes part), or null for the full window.
 __device__ inline int median_window_codes(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw, int mode, int org_r, int org_c,
-                                          int cval_code) {
-  const int rank = (mh * mw) >> 1, r0 = r - (mh >> 1) - org_r, c0 = c - (mw >> 1) - org_c;
+                                          int cval_code, const uint32_t* fp = nullptr) {
+  int count = mh * mw;
+  if (fp) {
+    count = 0;
+    for (int a = 0; a < mh; ++a) count += __popc(fp[a]);
+  }
+  const int rank = count >> 1, r0 = r - (mh >> 1) - org_r, c0 = c - (mw >> 1) - org_c;
   int level = 0;
   for (int bit = 2048; bit; bit >>= 1) {
     const int cand = level | bit;
@@ -187,6 +194,7 @@ __device__ inline int median_window_codes(const uint16_t* raw, int Su, int Sv, i
     for (int a = 0; a < mh; ++a) {
       const int rr = border_index(r0 + a, Sv, mode);
       for (int b = 0; b < mw; ++b) {
+        if (fp && !(fp[a] >> b & 1u)) continue;
         const int cc = border_index(c0 + b, Su, mode);
         const int code = (rr < 0 || cc < 0) ? cval_code : 2 * (int)raw[rr * Su + cc] + 1;
         below += code < cand;
@@ -386,7 +394,7 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
   if (!by_tma)
     for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
-  const bool hp_plain = w.hp_mode == GB_HP_REFLECT && w.hp_org_r == 0 && w.hp_org_c == 0;
+  const bool hp_plain = w.hp_mode == GB_HP_REFLECT && w.hp_org_r == 0 && w.hp_org_c == 0 && !w.hp_fp;
   const bool hp5 = w.mh == 5 && w.mw == 5 && hp_plain;
   if (!hp5) {
     // other median sizes / border modes (Tracker.highpass): a plain copy of the window, since hp overwrites raw
@@ -443,7 +451,7 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
     const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
     for (int i = tid; i < area; i += nthr) {
       const int r = i / Su, c = i - r * Su;
-      const int code = median_window_codes(copy, Su, Sv, r, c, w.mh, w.mw, w.hp_mode, w.hp_org_r, w.hp_org_c, cval_code);
+      const int code = median_window_codes(copy, Su, Sv, r, c, w.mh, w.mw, w.hp_mode, w.hp_org_r, w.hp_org_c, cval_code, w.hp_fp);
       const double med = (code & 1) ? w.lut[code >> 1] : w.hp_cval;
       const float o = (float)sub(w.lut[copy[i]], med);
       w.hp[r * Sp + c] = o;

@@ -307,9 +307,13 @@ class Session:
             d.resample_method = _lib.GB_RESAMPLE[method]
             from .tracker import highpass_params, interpolation_degrees
 
-            rows, cols, hp_mode, org_r, org_c, cval = highpass_params(getattr(tracker, "highpass", {"size": (5, 5)}))
+            rows, cols, hp_mode, org_r, org_c, cval, masks = highpass_params(getattr(tracker, "highpass", {"size": (5, 5)}))
             d.highpass_size = 0 if (rows, cols) == (5, 5) else rows | cols << 16
             d.highpass_mode, d.highpass_origin, d.highpass_cval = hp_mode, (org_r & 0xffff) | (org_c & 0xffff) << 16, cval
+            if masks is not None:
+                self.footprint_h = np.zeros(31, dtype=np.uint32)
+                self.footprint_h[:rows] = masks
+                d.highpass_footprint_host = self.footprint_h.ctypes.data
             d.interp_rows, d.interp_cols = interpolation_degrees(getattr(tracker, "interpolation", {}))
             if draws is not None or tracker.rng == "numpy":
                 d.rng_mode = _lib.GB_RNG_SUPPLIED

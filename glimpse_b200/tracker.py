@@ -22,9 +22,9 @@ Differences a user can see (all documented in DESIGN.md):
 * ``parallel`` is accepted and ignored: points are spread over the GPU, and over ranks when
   ``torch.distributed`` is initialised (one contiguous block of points per rank, one final gather).
 * every ``resample_method`` ('systematic', 'stratified', 'residual', 'choice'), ``highpass`` with ``size`` up to 31 x 31 (the default
-  5 x 5 'reflect' has the fast kernel), any border ``mode`` / ``cval`` / ``origin`` of ``scipy.ndimage.median_filter``, and
-  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; other values (a median ``footprint``, spline degrees
-  2 / 4 / 5) raise ``NotImplementedError`` (no CPU fallback).  'residual' with ``rng="numpy"`` cannot replay the reference's
+  5 x 5 'reflect' has the fast kernel) or a ``footprint``, any border ``mode`` / ``cval`` / ``origin`` of
+  ``scipy.ndimage.median_filter``, and
+  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; spline degrees 2 / 4 / 5 raise ``NotImplementedError`` (no CPU fallback).  'residual' with ``rng="numpy"`` cannot replay the reference's
   draws (their number depends on the weights) and raises too.
 """
 from __future__ import annotations
@@ -54,18 +54,30 @@ from .session import point_span  # noqa: E402,F401  (re-exported)
 
 def highpass_params(highpass: dict):
     """``scipy.ndimage.median_filter(tile, **highpass)`` (reference tracker.py:59, 530) as the device kernels take it:
-    ``(rows, columns, mode, origin_rows, origin_columns, cval)``.
+    ``(rows, columns, mode, origin_rows, origin_columns, cval, footprint rows as bit masks or None)``.
 
-    ``size`` (one integer or a pair, 1..31 each), ``mode`` ('reflect' default, 'constant', 'nearest', 'mirror', 'wrap' and
-    their 'grid-' aliases), ``cval`` and ``origin`` (one integer or a pair) have kernels; a ``footprint`` does not and raises
-    ``NotImplementedError`` (there is no CPU fallback)."""
-    extra = set(highpass) - {"size", "mode", "origin", "cval"}
-    if extra or "size" not in highpass:
-        raise NotImplementedError("highpass: {'size', 'mode', 'cval', 'origin'} have a device kernel; a footprint does not")
-    size = highpass["size"]
-    rows, cols = (size, size) if np.ndim(size) == 0 else tuple(size)
+    ``size`` (one integer or a pair, 1..31 each) or a ``footprint`` (2-D, up to 31 x 31; it wins over ``size``, as in scipy),
+    ``mode`` ('reflect' default, 'constant', 'nearest', 'mirror', 'wrap' and their 'grid-' aliases), ``cval`` and ``origin``
+    (one integer or a pair)."""
+    extra = set(highpass) - {"size", "footprint", "mode", "origin", "cval"}
+    if extra:
+        raise TypeError(f"median_filter() got an unexpected keyword argument {sorted(extra)[0]!r}")
+    footprint = highpass.get("footprint")
+    masks = None
+    if footprint is not None:
+        footprint = np.asarray(footprint, dtype=bool)
+        if footprint.ndim != 2 or not footprint.any():
+            raise RuntimeError("footprint must be a non-empty 2-D array")
+        rows, cols = footprint.shape
+        if not footprint.all():
+            masks = [int(sum(1 << b for b in range(cols) if footprint[a, b])) for a in range(rows)]
+    elif "size" in highpass:
+        size = highpass["size"]
+        rows, cols = (size, size) if np.ndim(size) == 0 else tuple(size)
+    else:
+        raise RuntimeError("no footprint or filter size provided")  # scipy's own complaint
     if int(rows) != rows or int(cols) != cols or not (1 <= rows <= 31 and 1 <= cols <= 31):
-        raise NotImplementedError("highpass: 'size' must be integers between 1 and 31")
+        raise NotImplementedError("highpass: the window must have between 1 and 31 rows and columns")
     mode = highpass.get("mode", "reflect")
     if mode not in _lib.GB_HP_MODES:
         raise RuntimeError(f"boundary mode not supported: {mode}")  # scipy's own complaint
@@ -74,7 +86,7 @@ def highpass_params(highpass: dict):
     for org, m in ((org_r, rows), (org_c, cols)):
         if int(org) != org or not (-(int(m) // 2) <= org <= (int(m) - 1) // 2):
             raise ValueError("invalid origin")  # scipy's own complaint
-    return int(rows), int(cols), _lib.GB_HP_MODES[mode], int(org_r), int(org_c), float(highpass.get("cval", 0.0))
+    return int(rows), int(cols), _lib.GB_HP_MODES[mode], int(org_r), int(org_c), float(highpass.get("cval", 0.0)), masks
 
 
 def highpass_size(highpass: dict):

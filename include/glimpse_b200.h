@@ -290,6 +290,8 @@ typedef struct gb_track_desc {
   int32_t highpass_origin;         /* its `origin` as (rows & 0xffff) | (columns & 0xffff) << 16, each a signed 16-bit shift of the window:
                                     * the window of pixel i spans i - size / 2 - origin ... (0 = centred, the default) */
   double highpass_cval;            /* value beyond the border with GB_HP_CONSTANT (`cval`), in the units of the filtered tile */
+  const uint32_t* highpass_footprint_host; /* host, or NULL = the full window: `footprint` of the filter, one word per window row (bit b =
+                                    * column b takes part); highpass_size is then the footprint's shape and the rank is (cells set) / 2 */
   double* final_weights;           /* [N] or NULL: weights of point P - 1's resampled particles at its last time — what Tracker.weights holds
                                     * after track() in the reference (tracker.py:62-70, 216-223: the state of the last processed track);
                                     * the caller pre-fills it with ones (a point that is never updated keeps its initial weights) */

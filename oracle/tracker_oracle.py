@@ -649,9 +649,10 @@ def track(
     ``highpass_kwargs`` = its other entries (``mode``, ``cval``, ``origin`` of ``scipy.ndimage.median_filter``).
     ``kx``, ``ky`` = ``Tracker.interpolation`` (tracker.py:60): spline degree along the rows / columns of the SSE surface.
     """
-    if np.ndim(highpass_size) == 0:
-        highpass_size = (int(highpass_size),) * 2
-    highpass_size = tuple(int(v) for v in highpass_size)
+    if highpass_size is not None:  # (None: the window is given by highpass_kwargs['footprint'])
+        if np.ndim(highpass_size) == 0:
+            highpass_size = (int(highpass_size),) * 2
+        highpass_size = tuple(int(v) for v in highpass_size)
     hp_kw = dict(highpass_kwargs or {})
     randn = randn or np.random.randn
     random = random or np.random.random

@@ -136,6 +136,11 @@ def track_cases():
             scene_kwargs=dict(seed=35, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=3535, highpass={"size": 7, "mode": "nearest", "origin": 3},
         ),
+        "track_hp_footprint": dict(  # a plus-shaped footprint with a hole, shifted, on a wrapped border
+            scene_kwargs=dict(seed=39, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=3939, highpass={"footprint": [[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 0, 1, 1], [0, 1, 1, 1, 0]], "mode": "mirror",
+                                 "origin": (0, 1)},
+        ),
         # ... and other spline degrees (Tracker.interpolation, tracker.py:60): bilinear; a 2 x 2 .. 3 x 3 surface (bilinear,
         # window widened to the minimum); cubic along the rows with linear along the columns, two observers
         "track_lin": dict(

@@ -159,7 +159,7 @@ def test_unsupported_options_raise_instead_of_falling_back():
     obs = _observers(3)
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
-    for kw in (dict(highpass={"footprint": np.ones((3, 3))}), dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
+    for kw in (dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
                dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
         with pytest.raises(NotImplementedError):
             gb.Tracker([obs], **kw).track(models)
@@ -175,7 +175,10 @@ def test_unsupported_options_raise_instead_of_falling_back():
     from glimpse_b200 import _lib
     from glimpse_b200.tracker import highpass_params
 
-    assert highpass_params({"size": (3, 5), "mode": "constant", "cval": 0.1, "origin": (1, -2)}) == (3, 5, _lib.GB_HP_MODES["constant"], 1, -2, 0.1)
+    assert highpass_params({"size": (3, 5), "mode": "constant", "cval": 0.1, "origin": (1, -2)}) == (3, 5, _lib.GB_HP_MODES["constant"], 1, -2, 0.1, None)
+    cross = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    assert highpass_params({"footprint": cross, "size": 9})[:2] == (3, 3) and highpass_params({"footprint": cross})[6] == [2, 7, 2]
+    assert highpass_params({"footprint": np.ones((3, 7))})[6] is None  # a full footprint is a size
     assert highpass_params({"size": 5, "mode": "grid-wrap"})[2] == _lib.GB_HP_MODES["wrap"]
     with pytest.raises(ValueError, match="invalid origin"):  # scipy: -(size // 2) <= origin <= (size - 1) // 2
         highpass_params({"size": 4, "origin": 2})
