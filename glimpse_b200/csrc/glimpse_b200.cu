@@ -853,8 +853,8 @@ static int check_desc(const gb_track_desc& d) {
     if (org_r < -(rows / 2) || org_r > (rows - 1) / 2 || org_c < -(cols / 2) || org_c > (cols - 1) / 2)
       return fail(GB_E_INVALID, "highpass_origin: the shifted window must still cover its pixel%s");
   }
-  if ((d.interp_rows != 0 && d.interp_rows != 1 && d.interp_rows != 3) || (d.interp_cols != 0 && d.interp_cols != 1 && d.interp_cols != 3))
-    return fail(GB_E_INVALID, "interp_rows / interp_cols: spline degrees 1 and 3 are supported%s");
+  if (d.interp_rows < 0 || d.interp_rows > 5 || d.interp_cols < 0 || d.interp_cols > 5)
+    return fail(GB_E_INVALID, "interp_rows / interp_cols: spline degrees 1 to 5 (0 = the default 3)%s");
   if (!d.sigmas == !d.covariances) return fail(GB_E_INVALID, "exactly one of sigmas / covariances must be given%s");
   if (!d.images_host) return fail(GB_E_INVALID, "images_host is required%s");
   if (!d.images || !d.mask || !d.first || !d.last || !d.motion || !d.surfaces || !d.state_a || !d.state_b || !d.means ||
@@ -1324,16 +1324,30 @@ __global__ void k_motion_log_likelihoods(const gb_motion* __restrict__ motion, c
 // Observer.sample_tile as a stand-alone call (observer.py:178-214): interpolating spline (degree 3 not-a-knot = FITPACK's, or
 // degree 1) through the cell centres of `tile` (Mv rows x Mu columns), evaluated at n points given relative to the first cell
 // centre in cell units.  One CTA: Hermite data (F, F_u, F_v, F_uv) in the caller's work area `herm` [Mv][Mu | 1] float4.
-__global__ void __launch_bounds__(256) k_sample_surface(const double* __restrict__ tile, int Mu, int Mv, int lin_u, int lin_v,
+__global__ void __launch_bounds__(256) k_sample_surface(const double* __restrict__ tile, int Mu, int Mv, int ku, int kv,
                                                         const double* __restrict__ xy, int64_t n, float4* __restrict__ herm,
                                                         double* __restrict__ out) {
   const int tid = threadIdx.x, nthr = blockDim.x, Mp = Mu | 1;
+  const int lin_u = ku == 1, lin_v = kv == 1;
   for (int i = tid; i < Mu * Mv; i += nthr) {
     const int r = i / Mu, c = i - r * Mu;
     herm[r * Mp + c] = make_float4((float)tile[i], 0.0f, 0.0f, 0.0f);
   }
   __syncthreads();
   float* base = reinterpret_cast<float*>(herm);
+  if (!spline_is_hermite(ku, kv)) {  // degrees 2 / 4 / 5: B-spline coefficients (work area behind the Hermite array)
+    double* abu = reinterpret_cast<double*>(herm + (int64_t)Mv * Mp);
+    double* abv = abu + (int64_t)Mu * (2 * ku + 1);
+    if (tid == 0) bspline_factor(abu, Mu, ku);
+    if (tid == 32) bspline_factor(abv, Mv, kv);
+    __syncthreads();
+    for (int r = tid; r < Mv; r += nthr) bspline_solve_line(abu, Mu, ku, base + (int64_t)r * Mp * 4, 4);
+    __syncthreads();
+    for (int c = tid; c < Mu; c += nthr) bspline_solve_line(abv, Mv, kv, base + (int64_t)c * 4, Mp * 4);
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += nthr) out[i] = (double)bspline_eval(herm, Mp, Mu, Mv, xy[2 * i], xy[2 * i + 1], ku, kv);
+    return;
+  }
   for (int line = tid; line < Mv + Mu; line += nthr) {
     if (line < Mv) spline_slopes_line(base + (int64_t)line * Mp * 4, base + (int64_t)line * Mp * 4 + 1, 4, Mu, !lin_u);
     else spline_slopes_line(base + (int64_t)(line - Mv) * 4, base + (int64_t)(line - Mv) * 4 + 2, Mp * 4, Mv, !lin_v);
@@ -1645,12 +1659,12 @@ int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surface
 int gb_sample_surface(const double* tile, int32_t rows, int32_t cols, int32_t kx, int32_t ky, const double* xy, int64_t n, void* work,
                       double* out, void* stream) {
   if (!tile || !xy || !work || !out || n <= 0) return fail(GB_E_INVALID, "bad arguments%s");
-  if ((kx != 1 && kx != 3) || (ky != 1 && ky != 3)) return fail(GB_E_INVALID, "spline degrees 1 and 3 are supported%s");
+  if (kx < 1 || kx > 5 || ky < 1 || ky > 5) return fail(GB_E_INVALID, "spline degrees 1 to 5 are supported%s");
   if (rows < kx + 1 || cols < ky + 1 || rows > GB_MAX_SURFACE || cols > GB_MAX_SURFACE)
     return fail(GB_E_INVALID, "tile must have between degree + 1 and 1024 cells per axis%s");
   int rc = ensure_tables();
   if (rc) return rc;
-  k_sample_surface<<<1, 256, 0, (cudaStream_t)stream>>>(tile, cols, rows, ky == 1, kx == 1, xy, n, reinterpret_cast<float4*>(work), out);
+  k_sample_surface<<<1, 256, 0, (cudaStream_t)stream>>>(tile, cols, rows, ky, kx, xy, n, reinterpret_cast<float4*>(work), out);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

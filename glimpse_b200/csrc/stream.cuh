@@ -254,8 +254,9 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   const int* ib = s_ib;
   int box_l = ib[0], box_t = ib[1], box_r = -ib[2], box_b = -ib[3];
   const bool nan_any = ib[4] != 0;
-  if (!nan_any && ((box_r - box_l) - prm.tile_w < 5 || (box_b - box_t) - prm.tile_h < 5)) {
-    // cloud narrower than ~3 px: the reference widens the box from the exact extents (tracker.py:584-594)
+  if (!nan_any && ((box_r - box_l) - prm.tile_w < prm.interp_cols + 2 || (box_b - box_t) - prm.tile_h < prm.interp_rows + 2)) {
+    // cloud narrower than the spline degree (the integer box is at most 2 px wider than the exact extents): the reference
+    // widens the box from the exact extents (tracker.py:584-594)
     const double* uv = prm.s_uv + po * 2 * (int64_t)N;
     double mm[4] = {CUDART_INF, CUDART_INF, CUDART_INF, CUDART_INF};
     for (int i = tid; i < N; i += blockDim.x) {
@@ -321,6 +322,8 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   w.hp_fp = prm.hp_has_fp ? prm.hp_fp : nullptr;
   w.cub_u = prm.interp_cols != 1;
   w.cub_v = prm.interp_rows != 1;
+  w.ku = prm.interp_cols;
+  w.kv = prm.interp_rows;
   w.th = prm.tile_h;
   w.Mu = w.Su - w.tw + 1;
   w.Mv = w.Sv - w.th + 1;
@@ -345,7 +348,9 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   }
   char* region = prm.s_surf + po * prm.surf_bytes;
   const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
-  if (need > prm.surf_bytes || w.Mu > GB_MAX_SURFACE || w.Mv > GB_MAX_SURFACE) {
+  const bool gen = !spline_is_hermite(w.ku, w.kv);  // degrees 2 / 4 / 5: coefficients solved with a work area behind the tile's data
+  if (gen) w.band = reinterpret_cast<double*>(region + align16(need));
+  if (need + (gen ? bspline_band_bytes(w.Mu, w.Mv, w.ku, w.kv) + 16 : 0) > prm.surf_bytes || w.Mu > GB_MAX_SURFACE || w.Mv > GB_MAX_SURFACE) {
     if (tid == 0) atomicOr(&prm.s_pflags[p], (int)GB_F_WINDOW);
     return;
   }
@@ -355,8 +360,8 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   // (A negative budget skips the interleaved path: parity tests of the other paths.)
   const int64_t budget = smem_budget < 0 ? -smem_budget : smem_budget;
   const bool in_smem = smem_budget >= 0 && need <= budget;
-  const bool planar = !in_smem && tile_bytes_needed_planar(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
-  const bool staged = !in_smem && !planar && tile_bytes_needed_staged(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
+  const bool planar = !gen && !in_smem && tile_bytes_needed_planar(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
+  const bool staged = !gen && !in_smem && !planar && tile_bytes_needed_staged(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals) <= budget;
   // (TMA staging is used by the interleaved organisation only — windows up to ~82 px, 96 % of them on the bench scene; the
   //  planar / staged organisations of the largest windows read their pixels with ordinary loads)
   if (!in_smem) w.tmap = nullptr;
@@ -563,6 +568,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
   }
   const bool vec = (N & 1) == 0;
   const bool lin_u = prm.interp_cols == 1, lin_v = prm.interp_rows == 1;  // Tracker.interpolation: degree 1 along an axis
+  const bool gen = !spline_is_hermite(prm.interp_cols, prm.interp_rows);   // degrees 2 / 4 / 5: B-spline coefficients
   uint32_t flags = 0;
   double wacc = 0.0;
   const int blk_end = min(N, (b + 1) * prm.s_block);  // s_block is even: pairs never straddle CTAs
@@ -597,7 +603,8 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
         for (int q = 0; q < 2; ++q) {
           if (!((u[q] >= r.sl) & (u[q] <= r.sr) & (v[q] >= r.st) & (v[q] <= r.sb))) flags |= GB_F_SAMPLE_OUTSIDE;
           // FITPACK evaluates at the argument clamped to the first/last data site: the saturation inside hermite_eval_sat
-          const double val = (double)hermite_eval_sat(r.herm, r.Mp, r.Mu, r.Mv, u[q] - r.cu0, v[q] - r.cv0, lin_u, lin_v);
+          const double val = gen ? (double)bspline_eval(r.herm, r.Mp, r.Mu, r.Mv, u[q] - r.cu0, v[q] - r.cv0, prm.interp_cols, prm.interp_rows)
+                                 : (double)hermite_eval_sat(r.herm, r.Mp, r.Mu, r.Mv, u[q] - r.cu0, v[q] - r.cv0, lin_u, lin_v);
           ll[q] = add(ll[q], mul(val, r.scale));
           if (prm.io.dump_sampled && (q == 0 || vb)) prm.io.dump_sampled[(p * O + o) * N + ia + q] = val;
         }

@@ -42,6 +42,8 @@ struct TileWork {
   double hp_cval = 0.0;                          // ... and the constant beyond the border for GB_HP_CONSTANT
   const uint32_t* hp_fp = nullptr;               // ... and the footprint (one word per window row), or null: the full window
   bool cub_u = true, cub_v = true;  // cubic (default) or piecewise-linear interpolation along the columns / rows (Tracker.interpolation)
+  int ku = 3, kv = 3;               // the degrees themselves; other than 1 / 3: B-spline coefficients instead of Hermite data
+  double* band = nullptr;           // ... and the work area of their collocation solves (global memory)
 };
 
 __host__ __device__ inline int64_t align16(int64_t b) { return (b + 15) / 16 * 16; }
@@ -290,6 +292,105 @@ __device__ __forceinline__ float hermite_eval(const float4* __restrict__ herm, i
   const float top_v = a0 * h00.z + a2 * h01.z + a1 * h00.w + a3 * h01.w;
   const float bot_v = a0 * h10.z + a2 * h11.z + a1 * h10.w + a3 * h11.w;
   return b0 * top_f + b2 * bot_f + b1 * top_v + b3 * bot_v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolating splines of degree 2, 4 and 5 (Tracker.interpolation; RectBivariateSpline(kx, ky, s = 0) = FITPACK regrid).
+// The data sites are the cell centres 0 .. m - 1 (unit spacing), so FITPACK's knots (fpregr.f, interpolation case) are known
+// in closed form: k + 1 copies of 0 and of m - 1 at the ends and m - k - 1 interior knots — the sites (k + 1) / 2 ..
+// m - 1 - (k + 1) / 2 for an odd degree, the midpoints k / 2 + 1 / 2 .. m - 1 - k / 2 - 1 / 2 for an even one.  The surface
+// is kept as tensor-product B-spline coefficients (one float per cell, in the x component of the Hermite array): they solve
+// the two banded collocation systems, and a sample is a (kx + 1) x (ky + 1) sum over de Boor's basis values (fpbspl.f).
+// Any degree 1 .. 5 per axis can take this path; degrees 1 and 3 on both axes keep the cheaper Hermite form.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bspline_knot(int i, int m, int k) {
+  if (i <= k) return 0.0;
+  if (i >= m) return (double)(m - 1);
+  const int q = i - k - 1;
+  return (k & 1) ? (double)((k + 1) / 2 + q) : (double)(k / 2 + q) + 0.5;
+}
+// knot interval l (k <= l <= m - 1) with t[l] <= x < t[l + 1] for x in [0, m - 1] (the last interval is closed, fpbisp.f)
+__device__ __forceinline__ int bspline_span(double x, int m, int k) {
+  const double first = (k & 1) ? (double)((k + 1) / 2) : (double)(k / 2) + 0.5;
+  const int cnt = (int)floor(x - first) + 1;  // interior knots <= x
+  return k + max(0, min(cnt, m - k - 1));
+}
+// the k + 1 B-splines that do not vanish on interval l, at x (fpbspl.f)
+__device__ __forceinline__ void bspline_basis(double x, int l, int m, int k, double (&h)[6]) {
+  double hh[5];
+  h[0] = 1.0;
+  for (int j = 1; j <= k; ++j) {
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 0; i < j; ++i) {
+      const int li = l + 1 + i, lj = li - j;
+      const double tli = bspline_knot(li, m, k), tlj = bspline_knot(lj, m, k);
+      const double f = hh[i] / (tli - tlj);
+      h[i] += f * (tli - x);
+      h[i + 1] = f * (x - tlj);
+    }
+  }
+}
+// LU factors (no pivoting: B-spline collocation matrices are totally positive) of the m x m collocation matrix
+// A[i][j] = B_j(site i) in band storage ab[i][j - i + k], |j - i| <= k.  One thread.
+__device__ inline void bspline_factor(double* ab, int m, int k) {
+  const int W = 2 * k + 1;
+  for (int i = 0; i < m * W; ++i) ab[i] = 0.0;
+  for (int i = 0; i < m; ++i) {
+    const int l = bspline_span((double)i, m, k);
+    double h[6];
+    bspline_basis((double)i, l, m, k, h);
+    for (int a = 0; a <= k; ++a) {
+      const int j = l - k + a;
+      if (j - i >= -k && j - i <= k) ab[i * W + (j - i + k)] = h[a];
+    }
+  }
+  for (int c = 0; c < m; ++c) {
+    const double piv = ab[c * W + k];
+    const int last = min(m - 1, c + k);
+    for (int r = c + 1; r <= last; ++r) {
+      const double f = ab[r * W + (c - r + k)] / piv;
+      ab[r * W + (c - r + k)] = f;
+      for (int j = c + 1; j <= last; ++j) ab[r * W + (j - r + k)] -= f * ab[c * W + (j - c + k)];
+    }
+  }
+}
+// Solve A x = b in place along one line of floats (stride in floats) with the factors above.
+__device__ inline void bspline_solve_line(const double* __restrict__ ab, int m, int k, float* line, int stride) {
+  const int W = 2 * k + 1;
+  for (int r = 0; r < m; ++r) {  // L y = b (unit diagonal)
+    double y = (double)line[r * stride];
+    for (int c = max(0, r - k); c < r; ++c) y -= ab[r * W + (c - r + k)] * (double)line[c * stride];
+    line[r * stride] = (float)y;
+  }
+  for (int r = m - 1; r >= 0; --r) {  // U x = y
+    double x = (double)line[r * stride];
+    const int last = min(m - 1, r + k);
+    for (int c = r + 1; c <= last; ++c) x -= ab[r * W + (c - r + k)] * (double)line[c * stride];
+    line[r * stride] = (float)(x / ab[r * W + k]);
+  }
+}
+// Sample of the coefficient surface at (x, y) from the first cell centre in cell units (fpbisp.f): arguments clamped to the
+// data sites.  ku / kv = degree along the columns / rows.
+__device__ __noinline__ float bspline_eval(const float4* __restrict__ coef, int Mp, int Mu, int Mv, double x, double y, int ku, int kv) {
+  x = fmin(fmax(x, 0.0), (double)(Mu - 1));
+  y = fmin(fmax(y, 0.0), (double)(Mv - 1));
+  const int lu = bspline_span(x, Mu, ku), lv = bspline_span(y, Mv, kv);
+  double hu[6], hv[6];
+  bspline_basis(x, lu, Mu, ku, hu);
+  bspline_basis(y, lv, Mv, kv, hv);
+  double acc = 0.0;
+  for (int a = 0; a <= kv; ++a) {
+    const float4* row = coef + (lv - kv + a) * Mp + (lu - ku);
+    double r = 0.0;
+    for (int b = 0; b <= ku; ++b) r = fma(hu[b], (double)row[b].x, r);
+    acc = fma(hv[a], r, acc);
+  }
+  return (float)acc;
+}
+__host__ __device__ inline bool spline_is_hermite(int ku, int kv) { return (ku == 1 || ku == 3) && (kv == 1 || kv == 3); }
+__host__ __device__ inline int64_t bspline_band_bytes(int Mu, int Mv, int ku, int kv) {
+  return ((int64_t)Mu * (2 * ku + 1) + (int64_t)Mv * (2 * kv + 1)) * 8;
 }
 
 // Phases 1-5 of the surface of one search window: raw window -> high-passed, CDF-matched float tile `w.hp`
@@ -643,6 +744,20 @@ __device__ inline void tile_finish_interleaved(TileWork& w, float* dump_sse, int
   }
   __syncthreads();
   if (clk && threadIdx.x == 0) clk[2] = clock64();
+  if (!spline_is_hermite(w.ku, w.kv)) {
+    // 7'. B-spline coefficients of the interpolating spline of degrees (ku, kv): rows, then columns, in place
+    float* base = reinterpret_cast<float*>(w.herm);
+    double* abu = w.band;
+    double* abv = abu + (int64_t)Mu * (2 * w.ku + 1);
+    if (tid == 0) bspline_factor(abu, Mu, w.ku);
+    if (tid == 32) bspline_factor(abv, Mv, w.kv);
+    __syncthreads();
+    for (int r = tid; r < Mv; r += nthr) bspline_solve_line(abu, Mu, w.ku, base + (int64_t)r * Mp * 4, 4);
+    __syncthreads();
+    for (int c = tid; c < Mu; c += nthr) bspline_solve_line(abv, Mv, w.kv, base + (int64_t)c * 4, Mp * 4);
+    __syncthreads();
+    return;
+  }
   // 7. Hermite data: dF/du along rows and dF/dv along columns, then the cross derivative
   {
     float* base = reinterpret_cast<float*>(w.herm);

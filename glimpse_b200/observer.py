@@ -62,8 +62,8 @@ class Observer:
     @staticmethod
     def _spline_degrees(kwargs: dict):
         kx, ky = kwargs.get("kx", 3), kwargs.get("ky", 3)
-        if set(kwargs) - {"kx", "ky"} or kx not in (1, 3) or ky not in (1, 3):
-            raise NotImplementedError("only RectBivariateSpline(kx = 1 or 3, ky = 1 or 3, s = 0) has a device kernel")
+        if set(kwargs) - {"kx", "ky"} or kx not in (1, 2, 3, 4, 5) or ky not in (1, 2, 3, 4, 5):
+            raise NotImplementedError("only RectBivariateSpline(kx = 1..5, ky = 1..5, s = 0) has a device kernel")
         return int(kx), int(ky)
 
     @staticmethod
@@ -77,7 +77,7 @@ class Observer:
         dev = torch.device("cuda", torch.cuda.current_device())
         t = torch.as_tensor(np.ascontiguousarray(tile, dtype=float)).to(dev)
         xy = torch.as_tensor(np.ascontiguousarray(np.column_stack((cols, rows)), dtype=float)).to(dev)
-        work = torch.empty((tile.shape[0] * (tile.shape[1] | 1) * 16,), dtype=torch.uint8, device=dev)
+        work = torch.empty((tile.shape[0] * (tile.shape[1] | 1) * 16 + (tile.shape[0] + tile.shape[1]) * 88,), dtype=torch.uint8, device=dev)
         out = torch.empty((xy.shape[0],), dtype=torch.float64, device=dev)
         _lib.check(lib.gb_sample_surface(t.data_ptr(), tile.shape[0], tile.shape[1], kx, ky, xy.data_ptr(), xy.shape[0], work.data_ptr(),
                                          out.data_ptr(), torch.cuda.current_stream().cuda_stream))

@@ -380,9 +380,10 @@ class Session:
                 self.image_events[k] = event.cuda_event
             self._pending_copies = self._pending_copies[len(todo):]
             return
-        for k, event in self._pending_events:
-            self.image_events[k] = event.cuda_event
         if limit is not None or not self._pending_copies:
+            if not self._pending_copies:  # every frame was already on the device: their events are recorded
+                for k, event in self._pending_events:
+                    self.image_events[k] = event.cuda_event
             return  # the bulk groups go out once the small tables are queued (second call)
         dist = self.dist
         world, rank = dist.get_world_size(), dist.get_rank()
@@ -402,6 +403,9 @@ class Session:
                 dist.all_gather_into_tensor(arena[g0:g0 + span], staging)
                 for _, (dev, arr, event) in members:
                     event.record(copy_stream)
+        # (an event has its handle once it is recorded: the table the kernels wait on is filled afterwards)
+        for k, event in self._pending_events:
+            self.image_events[k] = event.cuda_event
         self._pending_copies = []
 
     # ---------------------------------------------------------------- uploads

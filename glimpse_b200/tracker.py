@@ -24,7 +24,8 @@ Differences a user can see (all documented in DESIGN.md):
 * every ``resample_method`` ('systematic', 'stratified', 'residual', 'choice'), ``highpass`` with ``size`` up to 31 x 31 (the default
   5 x 5 'reflect' has the fast kernel) or a ``footprint``, any border ``mode`` / ``cval`` / ``origin`` of
   ``scipy.ndimage.median_filter``, and
-  ``interpolation`` degrees 3 (default) and 1 per axis have kernels; spline degrees 2 / 4 / 5 raise ``NotImplementedError`` (no CPU fallback).  'residual' with ``rng="numpy"`` cannot replay the reference's
+  ``interpolation`` degrees 1 to 5 per axis have kernels (3 and 1: Hermite form; 2, 4, 5: B-spline coefficients); a smoothing
+  factor raises ``NotImplementedError`` (no CPU fallback).  'residual' with ``rng="numpy"`` cannot replay the reference's
   draws (their number depends on the weights) and raises too.
 """
 from __future__ import annotations
@@ -96,11 +97,14 @@ def highpass_size(highpass: dict):
 
 def interpolation_degrees(interpolation: dict):
     """(kx, ky) of ``RectBivariateSpline(rows, columns, sse, **interpolation)`` (reference tracker.py:60, 584-594,
-    observer.py:210): spline degree along the rows / columns of the SSE surface.  Degrees 3 (default) and 1 have device
-    kernels; 2, 4, 5 and the smoothing / bbox arguments raise ``NotImplementedError`` (there is no CPU fallback)."""
+    observer.py:210): spline degree along the rows / columns of the SSE surface, 1 to 5 each (3 and 1 keep the Hermite-form
+    kernels, the others go through B-spline coefficients).  A smoothing factor or a bounding box has no kernel and raises
+    ``NotImplementedError`` (there is no CPU fallback)."""
     kx, ky = interpolation.get("kx", 3), interpolation.get("ky", 3)
-    if set(interpolation) - {"kx", "ky"} or kx not in (1, 3) or ky not in (1, 3):
-        raise NotImplementedError("interpolation: only {'kx': 1 or 3, 'ky': 1 or 3} has a device kernel")
+    if set(interpolation) - {"kx", "ky", "s"} or interpolation.get("s", 0) != 0:
+        raise NotImplementedError("interpolation: only the degrees {'kx', 'ky'} of an interpolating spline (s = 0) have a device kernel")
+    if kx not in (1, 2, 3, 4, 5) or ky not in (1, 2, 3, 4, 5):
+        raise ValueError("kx, ky must be in [1, 5]")  # FITPACK's own complaint
     return int(kx), int(ky)
 
 
@@ -311,11 +315,22 @@ class Tracker:
             # their second run (a search window that outgrew the plan's capacity) and a second gather.
             lap("local")
             merged = local if self._gathered else self._gather(dist, local, ntracks, world)
-            if self._can_rerun(seed) and (merged["status"] == _lib.GB_ST_WINDOW_TOO_LARGE).any():
-                if self._gathered:
-                    local = {k: np.array(v[lo:hi]) for k, v in merged.items()}
-                local = self._rerun_large_windows(local, *rerun)
-                merged = self._gather(dist, local, ntracks, world)
+            failed = np.nonzero(merged["status"] == _lib.GB_ST_WINDOW_TOO_LARGE)[0]
+            if self._can_rerun(seed) and len(failed):
+                # every rank runs its own failed points again and the patched rows alone are gathered (padded to the largest
+                # count of any rank, which all ranks know from the gathered statuses)
+                merged = {k: (v if v.flags.writeable else np.array(v)) for k, v in merged.items()}
+                mine = failed[(failed >= lo) & (failed < hi)] - lo
+                rows = self._rerun_rows(mine, *rerun)
+                counts = [int(((failed >= r * per_rank) & (failed < (r + 1) * per_rank)).sum()) for r in range(world)]
+                most = max(counts)
+                if rows is None:  # (a rank without failed points contributes padding of the right shapes)
+                    rows = {k: v[:0] for k, v in merged.items()}
+                patched = self._gather(dist, rows, world * most, world, per=most)
+                for r in range(world):
+                    idx = failed[(failed >= r * per_rank) & (failed < (r + 1) * per_rank)]
+                    for key in merged:
+                        merged[key][idx] = patched[key][r * most:r * most + counts[r]]
             local = merged
             lap("gather")
 
@@ -455,32 +470,45 @@ class Tracker:
     def _can_rerun(self, seed) -> bool:
         return self.rng == "philox" and seed is not None and self.window_margin < _lib.GB_WINDOW_MARGIN_MAX
 
-    def _rerun_large_windows(self, out, seed, models, image_index, taus, tile_size, observer_mask, return_covariances,
-                             return_particles, point_offset) -> dict:
-        """Points that ended with GB_ST_WINDOW_TOO_LARGE (their particle cloud outgrew the plan's surface regions) are tracked
-        again with the largest window capacity; the counter-based device draws make the second run identical to the first up
-        to the time it stopped (``seed`` = the Philox key of the first run).  Runs of consecutive failed points share a
-        session (the draws are keyed by the global point number, which a session derives from its first point).  The rows of
-        ``out`` are replaced in place."""
+    def _rerun_runs(self, failed, seed, models, image_index, taus, tile_size, observer_mask, return_covariances, return_particles,
+                    point_offset):
+        """Local points ``failed`` (ascending) tracked again with the largest window capacity: yields (first, last + 1, results)
+        per run of consecutive points — a session derives the global point numbers its draws are keyed by from its first point.
+        The counter-based device draws make the second run identical to the first up to the time it stopped (``seed`` = the
+        Philox key of the first run)."""
         from .session import Session
 
-        failed = np.nonzero(out["status"] == _lib.GB_ST_WINDOW_TOO_LARGE)[0]
-        if len(failed) == 0 or not self._can_rerun(seed):
-            return out
-        runs, start = [], int(failed[0])
-        for a, b in zip(failed, list(failed[1:]) + [None]):
-            if b is None or int(b) != int(a) + 1:
-                runs.append((start, int(a) + 1))
-                start = int(b) if b is not None else 0
+        failed = [int(p) for p in failed]
+        runs, start = [], failed[0]
+        for a, b in zip(failed, failed[1:] + [None]):
+            if b is None or b != a + 1:
+                runs.append((start, a + 1))
+                start = b
         for lo, hi in runs:
             session = Session(self, models[lo:hi], image_index, taus, tile_size, observer_mask[lo:hi], return_covariances,
                               return_particles, point_offset=point_offset + lo, window_margin=_lib.GB_WINDOW_MARGIN_MAX, seed=seed)
             session.run()
             part = session.fetch()
+            del session
+            yield lo, hi, part
+        self.__dict__.setdefault("_rerun_points", []).extend(int(point_offset + p) for p in failed)
+
+    def _rerun_rows(self, failed, *args):
+        """Results of the local points ``failed`` after their second run, in that order (None if there are none)."""
+        if len(failed) == 0:
+            return None
+        parts = [part for _, _, part in self._rerun_runs(failed, *args)]
+        return {k: np.concatenate([part[k] for part in parts], axis=0) for k in parts[0]}
+
+    def _rerun_large_windows(self, out, seed, *args) -> dict:
+        """Points of ``out`` that ended with GB_ST_WINDOW_TOO_LARGE (their particle cloud outgrew the plan's surface regions)
+        are tracked again and their rows replaced in place."""
+        failed = np.nonzero(out["status"] == _lib.GB_ST_WINDOW_TOO_LARGE)[0]
+        if len(failed) == 0 or not self._can_rerun(seed):
+            return out
+        for lo, hi, part in self._rerun_runs(failed, seed, *args):
             for key, rows in out.items():
                 rows[lo:hi] = part[key]
-            del session
-        self.__dict__.setdefault("_rerun_points", []).extend(int(point_offset + p) for p in failed)
         return out
 
     def _points_per_session(self, models, image_index, tile_size, return_covariances, return_particles) -> int:
@@ -517,7 +545,7 @@ class Tracker:
 
     # ------------------------------------------------------------------ multi-GPU: one final gather
     @staticmethod
-    def _gather(dist, local: dict, ntracks: int, world: int) -> dict:
+    def _gather(dist, local: dict, ntracks: int, world: int, per: int = None) -> dict:
         """All-gather the per-rank result blocks in ONE collective (points are independent: no per-step collective): every
         array is padded to the block size ceil(ntracks / world), the blocks are packed into one byte buffer per rank, and the
         gathered buffers are unpacked on the host.  A rank without points contributes arrays of zero rows."""
@@ -527,7 +555,7 @@ class Tracker:
 
         backend = dist.get_backend()
         device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        per = -(-ntracks // world)
+        per = -(-ntracks // world) if per is None else per
         T, O = local["obs_flags"].shape[1:3]
         cov, parts = local["sigmas"].ndim == 4, "particles" in local
         layout, nbytes = result_layout(per, T, O, local["particles"].shape[2] if parts else 0, cov, parts)

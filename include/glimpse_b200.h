@@ -285,7 +285,8 @@ typedef struct gb_track_desc {
                                     * scipy.ndimage.median_filter(tile, size=(rows, columns)), 1..31 each); 0 = the default 5 x 5 */
   int32_t interp_rows, interp_cols; /* Tracker.interpolation (tracker.py:60, observer.py:210): degree of the interpolating spline along the rows
                                     * (kx) and the columns (ky) of the SSE surface, which also sets the minimum surface size (tracker.py:584-594).
-                                    * 3 (cubic, not-a-knot) or 1 (piecewise linear); 0 = the default 3 */
+                                    * 1 to 5 (3 = cubic not-a-knot and 1 = piecewise linear in Hermite form, 2 / 4 / 5 as B-spline coefficients on
+                                    * FITPACK's knots); 0 = the default 3 */
   int32_t highpass_mode;           /* border mode of the median high-pass (scipy.ndimage.median_filter's `mode`): GB_HP_* */
   int32_t highpass_origin;         /* its `origin` as (rows & 0xffff) | (columns & 0xffff) << 16, each a signed 16-bit shift of the window:
                                     * the window of pixel i spans i - size / 2 - origin ... (0 = centred, the default) */
@@ -357,9 +358,10 @@ int gb_init_particles(const gb_motion* motion, const gb_surface* surfaces, int64
 int gb_motion_log_likelihoods(const gb_motion* motion, const gb_surface* surfaces, int64_t P, int64_t N, const double* state, double* ll,
                               int32_t* status, void* stream);
 /* Observer.sample_tile (observer.py:178-214) as a stand-alone call: the interpolating spline RectBivariateSpline(rows, columns, tile,
- * kx, ky, s = 0) of degree 3 (FITPACK's not-a-knot cubic) or 1 per axis, evaluated at n points.  tile[rows][cols] f64 (held as float32
- * on the device, like the SSE surface it is used for); xy[n][2] = (column, row) coordinates measured from the first cell centre in cell
- * units, clamped to the data sites like FITPACK's evaluation; work = rows * (cols | 1) * 16 bytes; out[n] f64.  All device pointers. */
+ * kx, ky, s = 0) of degree 1 to 5 per axis (3 = FITPACK's not-a-knot cubic), evaluated at n points.  tile[rows][cols] f64 (held as
+ * float32 on the device, like the SSE surface it is used for); xy[n][2] = (column, row) coordinates measured from the first cell centre
+ * in cell units, clamped to the data sites like FITPACK's evaluation; work = rows * (cols | 1) * 16 + (rows + cols) * 88 bytes; out[n]
+ * f64.  All device pointers. */
 int gb_sample_surface(const double* tile, int32_t rows, int32_t cols, int32_t kx, int32_t ky, const double* xy, int64_t n, void* work,
                       double* out, void* stream);
 /* Tracker.particle_mean / compute_particle_sigma / particle_covariance (tracker.py:72-104) on

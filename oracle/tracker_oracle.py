@@ -470,6 +470,34 @@ def notaknot_slopes(y: np.ndarray) -> np.ndarray:
     return np.linalg.solve(A, rhs.reshape(m, -1)).reshape(y.shape)
 
 
+def fitpack_interpolation_knots(x: np.ndarray, k: int) -> np.ndarray:
+    """Knots of FITPACK's interpolating spline (s = 0) of degree k through the sites x (fpregr.f / fpcurf.f): k + 1 copies
+    of the end sites and m - k - 1 interior knots — the sites x[(k+1)/2 .. m-1-(k+1)/2] for an odd degree, the midpoints
+    (x[j-1] + x[j]) / 2, j = k/2+1 .. m-1-k/2, for an even one."""
+    m = len(x)
+    if k % 2:
+        interior = x[(k + 1) // 2: m - (k + 1) // 2]
+    else:
+        j = np.arange(k // 2 + 1, m - k // 2)
+        interior = (x[j - 1] + x[j]) * 0.5
+    return np.concatenate((np.repeat(x[0], k + 1), interior, np.repeat(x[-1], k + 1)))
+
+
+def _bspline_sample(uv, F, cu, cv, kx, ky):
+    """Tensor-product interpolating spline of degrees (kx along rows, ky along columns) restated with SciPy's B-spline
+    collocation solver on FITPACK's knots (independent of FITPACK's own regrid / bispev), evaluated at clamped arguments."""
+    import scipy.interpolate
+
+    tv, tu = fitpack_interpolation_knots(cv, kx), fitpack_interpolation_knots(cu, ky)
+    rows = scipy.interpolate.make_interp_spline(cu, F.T, k=ky, t=tu)      # along the columns, for every row: c[(nu), (nv)]
+    coef = scipy.interpolate.make_interp_spline(cv, rows.c.T, k=kx, t=tv)  # then along the rows: c[(nv), (nu)]
+    u = np.clip(uv[:, 0], cu[0], cu[-1])
+    v = np.clip(uv[:, 1], cv[0], cv[-1])
+    bu = scipy.interpolate.BSpline.design_matrix(u, tu, ky).toarray()  # (n, nu)
+    bv = scipy.interpolate.BSpline.design_matrix(v, tv, kx).toarray()  # (n, nv)
+    return np.einsum("nv,vu,nu->n", bv, coef.c, bu)
+
+
 def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: bool = False, kx: int = 3, ky: int = 3) -> np.ndarray:
     """Sample ``surface`` (cell centres inside ``box``) at ``uv`` with the interpolating spline of degree ``kx``
     along the rows (v) and ``ky`` along the columns (u) (observer.py:178-214; ``Tracker.interpolation``).
@@ -489,7 +517,7 @@ def spline_sample(uv: np.ndarray, surface: np.ndarray, box: np.ndarray, exact: b
         f = scipy.interpolate.RectBivariateSpline(cv, cu, surface, kx=kx, ky=ky)
         return f(uv[:, 1], uv[:, 0], grid=False)
     if kx not in (1, 3) or ky not in (1, 3):
-        raise NotImplementedError("closed-form restatement for degrees 1 and 3 only")
+        return _bspline_sample(uv, surface.astype(float), cu, cv, kx, ky)
     F = surface.astype(float)
     zero = np.zeros_like(F)
     Fv = notaknot_slopes(F) if kx == 3 else zero  # d/dv along rows axis

@@ -155,6 +155,19 @@ def track_cases():
             scene_kwargs=dict(seed=25, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=2525, post=add_second_observer, interpolation={"kx": 3, "ky": 1},
         ),
+        # degrees 2, 4, 5 (FITPACK's knots between the data sites for even degrees): B-spline coefficients on the device
+        "track_k22": dict(
+            scene_kwargs=dict(seed=41, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=4141, interpolation={"kx": 2, "ky": 2},
+        ),
+        "track_k45": dict(
+            scene_kwargs=dict(seed=43, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=4343, post=add_second_observer, interpolation={"kx": 4, "ky": 5},
+        ),
+        "track_k52_narrow": dict(  # surfaces of 6 x 3 cells
+            scene_kwargs=dict(seed=45, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=4545, post=narrow_cloud, interpolation={"kx": 5, "ky": 2},
+        ),
         "track_narrow": dict(  # the default cubic on a widened 4 x 4 surface
             scene_kwargs=dict(seed=27, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=2727, post=narrow_cloud,

@@ -103,7 +103,7 @@ def test_observer_sample_tile_and_shift_tile_match_fitpack(cuda):
     obs = gb.Observer([gb.Image(f"i{k}", cam=cam, datetime=datetime.datetime(2020, 1, 1) + k * day) for k in range(2)])
     uv = np.column_stack((box[0] + rng.rand(500) * nx, box[1] + rng.rand(500) * ny))
     cu, cv = np.arange(box[0] + 0.5, box[2]), np.arange(box[1] + 0.5, box[3])
-    for kw in ({}, {"kx": 1, "ky": 1}, {"kx": 3, "ky": 1}):
+    for kw in ({}, {"kx": 1, "ky": 1}, {"kx": 3, "ky": 1}, {"kx": 2, "ky": 2}, {"kx": 4, "ky": 5}, {"kx": 5, "ky": 2}):
         f = scipy.interpolate.RectBivariateSpline(cv, cu, tile, **kw)
         got = obs.sample_tile(uv, tile, box, **kw)
         assert np.max(np.abs(got - f(uv[:, 1], uv[:, 0], grid=False))) < 2e-6  # the device holds the tile as float32

@@ -159,8 +159,7 @@ def test_unsupported_options_raise_instead_of_falling_back():
     obs = _observers(3)
     day = datetime.timedelta(days=1)
     models = [gb.CartesianMotion(xy=(0, 0), time_unit=day, dem=0.0, n=10)]
-    for kw in (dict(highpass={"size": 33}), dict(interpolation={"kx": 2, "ky": 3}),
-               dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
+    for kw in (dict(highpass={"size": 33}), dict(interpolation={"kx": 3, "ky": 3, "s": 1.0})):
         with pytest.raises(NotImplementedError):
             gb.Tracker([obs], **kw).track(models)
     with pytest.raises(ValueError, match="equal time units"):
@@ -168,7 +167,9 @@ def test_unsupported_options_raise_instead_of_falling_back():
 
     from glimpse_b200.tracker import highpass_size, interpolation_degrees
 
-    assert interpolation_degrees({}) == (3, 3) and interpolation_degrees({"kx": 1}) == (1, 3)
+    assert interpolation_degrees({}) == (3, 3) and interpolation_degrees({"kx": 1}) == (1, 3) and interpolation_degrees({"kx": 2, "ky": 5}) == (2, 5)
+    with pytest.raises(ValueError, match="must be in"):
+        interpolation_degrees({"kx": 6})
 
     assert highpass_size({"size": (3, 7)}) == (3, 7)  # (rows, columns), as scipy.ndimage.median_filter reads it
     assert highpass_size({"size": 4, "mode": "reflect", "origin": 0}) == (4, 4)
@@ -251,6 +252,31 @@ for n in (3, 1):
     if n > 1:
         assert tracks.particles.shape == (3, 4, 8, 6) and tracks.weights.shape == (3, 4, 8)
         assert seen["block"] == ((0, 2) if dist.get_rank() == 0 else (2, 1)), seen
+# points that outgrew their search windows: every rank runs its own again, only the patched rows are gathered
+from glimpse_b200 import _lib
+from glimpse_b200.session import empty_result
+def failing_local(models, image_index, *a, point_offset=0, **kw):
+    out = fake_local(models, image_index, *a, point_offset=point_offset, **kw)
+    out["status"][:] = 0
+    for i in range(len(models)):
+        if point_offset + i in (1, 3, 4):
+            out["status"][i], out["means"][i] = _lib.GB_ST_WINDOW_TOO_LARGE, np.nan
+    return out
+def fake_rows(failed, seed, models, image_index, *a):
+    point_offset = a[-1]
+    if len(failed) == 0:
+        return None
+    rows = empty_result(len(failed), image_index.shape[0], image_index.shape[1], False, False)
+    for j, i in enumerate(failed):
+        rows["means"][j] = 1000 + point_offset + i
+        rows["sigmas"][j] = 7
+    return rows
+tracker._track_local, tracker._rerun_rows = failing_local, fake_rows
+tracks = tracker.track(models)
+assert all(e is None for e in tracks.errors), tracks.errors
+assert [float(tracks.means[i, 0, 0]) for i in range(5)] == [0.0, 1001.0, 200.0, 1003.0, 1004.0], tracks.means[:, 0, 0]
+assert np.all(tracks.sigmas[[1, 3, 4]] == 7)
+tracker._track_local = fake_local
 local = fake_local(models[:1] if dist.get_rank() == 0 else [], np.zeros((4, 1), dtype=np.int32), None, None, None, False, True,
                    point_offset=dist.get_rank(), n_particles=8)
 merged = gb.Tracker._gather(dist, local, 1, 2)
@@ -411,7 +437,7 @@ def test_observer_subset_split_and_select_datetimes():
     with pytest.raises(ValueError, match="Shift larger than 0.5 pixels"):
         obs.shift_tile(np.zeros((5, 5)), (0.6, 0.0))
     with pytest.raises(NotImplementedError):
-        obs.sample_tile(np.zeros((1, 2)), np.zeros((5, 5)), (0, 0, 5, 5), kx=2)
+        obs.sample_tile(np.zeros((1, 2)), np.zeros((5, 5)), (0, 0, 5, 5), kx=6)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference checkout (build container only)")

@@ -91,13 +91,21 @@ def run(config):
 
     import glimpse_b200 as gb
 
+    rank, world = 0, 1
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:  # torchrun: points sharded over the GPUs of the box
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+        rank, world = dist.get_rank(), dist.get_world_size()
     t0 = time.perf_counter()
     scene = scene_for(config)
     observers, models = synthetic.build(scene, gb)
     print(f"config {config}: scene built in {time.perf_counter() - t0:.1f} s", file=sys.stderr, flush=True)
     tracker = gb.Tracker(observers, seed=20260100 + config)
     best = None
-    for rep in range(1 if config == 5 else 2):  # the second call finds the frames on the device and the allocator warm
+    for rep in range(1 if (config == 5 and world == 1) else 2):  # the second call finds the frames on the device and the allocator warm
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         tracks = tracker.track(models, tile_size=scene.tile_size)
@@ -105,7 +113,12 @@ def run(config):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         print(f"config {config}: track call {rep} took {dt:.2f} s", file=sys.stderr, flush=True)
-    return check_and_report(config, scene, tracks, best, tracker.last_run)
+    if rank != 0:
+        return None
+    out = check_and_report(config, scene, tracks, best, tracker.last_run)
+    if world > 1:
+        print(json.dumps({"config": config, "n_gpus": world, "host_ms_rank0": tracker.last_run.get("host_ms")}), flush=True)
+    return out
 
 
 if __name__ == "__main__":
