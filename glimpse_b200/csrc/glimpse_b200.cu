@@ -976,7 +976,10 @@ static int launch_stream_batch(const StepParams& prm, cudaStream_t stream) {
   FrameMaps fm;
   frame_maps(prm, fm);
   k_s2_surface<<<(unsigned)(prm.pb * prm.O), GB_S2_THREADS, kSurfaceSmem, stream>>>(prm, fm, prm.s2_budget);
-  k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
+  if (spline_is_hermite(prm.interp_cols, prm.interp_rows))
+    k_s3_weights<false><<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
+  else
+    k_s3_weights<true><<<dim3((unsigned)prm.s_nblk, (unsigned)prm.pb), s3_threads(prm.s_block), 0, stream>>>(prm);
   if (prm.resample_method == GB_RESAMPLE_CHOICE) {
     k_s4c_scan<<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
     k_s4c_gather<COV><<<nb, GB_SBLOCK_THREADS, 0, stream>>>(prm);
@@ -1232,7 +1235,10 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
         k_s2_surface<<<(unsigned)(pb * prm.O), GB_S2_THREADS, kSurfaceSmem, ss>>>(prm, fm, prm.s2_budget);
         kt.end(ss);
         kt.begin(GB_K_WEIGHTS, ss);
-        k_s3_weights<<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);
+        if (spline_is_hermite(prm.interp_cols, prm.interp_rows))
+          k_s3_weights<false><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);
+        else
+          k_s3_weights<true><<<dim3((unsigned)prm.s_nblk, (unsigned)pb), s3_threads(prm.s_block), 0, ss>>>(prm);
         kt.end(ss);
         kt.begin(GB_K_PUBLISH, ss);
         k_s3b_publish<<<(unsigned)((pb + 7) / 8), 256, 0, ss>>>(prm);

@@ -515,6 +515,8 @@ __device__ __forceinline__ void s3_publish_prefix(const StepParams& prm, int64_t
     pre[nblk + 3] = quo(1.0, (double)prm.N);
   }
 }
+// GEN: spline degrees other than 1 / 3 (B-spline coefficients; its own instantiation keeps the default kernel's registers)
+template <bool GEN>
 __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ SurfaceRef s_ref[GB_MAX_OBS];
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
   }
   const bool vec = (N & 1) == 0;
   const bool lin_u = prm.interp_cols == 1, lin_v = prm.interp_rows == 1;  // Tracker.interpolation: degree 1 along an axis
-  const bool gen = !spline_is_hermite(prm.interp_cols, prm.interp_rows);   // degrees 2 / 4 / 5: B-spline coefficients
+  constexpr bool gen = GEN;
   uint32_t flags = 0;
   double wacc = 0.0;
   const int blk_end = min(N, (b + 1) * prm.s_block);  // s_block is even: pairs never straddle CTAs
