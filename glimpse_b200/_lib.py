@@ -27,6 +27,8 @@ GB_WINDOW_MARGIN, GB_WINDOW_MARGIN_MAX = 191, 1000  # default / retry capacity o
 GB_RNG_SUPPLIED, GB_RNG_PHILOX = 0, 1
 GB_RESAMPLE = {"systematic": 0, "stratified": 1, "choice": 2, "residual": 3}
 GB_MODE_STREAM = 1
+GB_PIX = {"uint8": 0, "uint16": 1, "float32": 2, "float64": 3}
+GB_PLAN_RANKED_FRAMES = 1
 GB_HP_MODES = {"reflect": 0, "grid-mirror": 0, "constant": 1, "grid-constant": 1, "nearest": 2, "mirror": 3, "wrap": 4, "grid-wrap": 4}
 GB_MOTION_CARTESIAN, GB_MOTION_CYLINDRICAL, GB_MOTION_TANGENT_CARTESIAN, GB_MOTION_TANGENT_CYLINDRICAL = 0, 1, 2, 3
 
@@ -42,6 +44,7 @@ class gb_camera(C.Structure):
 class gb_image(C.Structure):
     _fields_ = [
         ("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("nchan", C.c_int32),
+        ("dtype", C.c_int32), ("pad_", C.c_int32),
         ("cam", gb_camera),
     ]
 

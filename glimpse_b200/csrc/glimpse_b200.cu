@@ -57,7 +57,7 @@ struct StepParams {
   int img[GB_MAX_OBS];       // global image index of each observer at time t, -1 = none
   CamK cam[GB_MAX_OBS];      // that image's camera (constant bank: operands without loads)
   const uint8_t* pixels[GB_MAX_OBS];
-  int pitch[GB_MAX_OBS], nchan[GB_MAX_OBS];
+  int pitch[GB_MAX_OBS], nchan[GB_MAX_OBS], pixdtype[GB_MAX_OBS];
   int tmpl_frame[GB_MAX_OBS]; // time index at which each observer's template is cut
   double obs_scale[GB_MAX_OBS];
   const gb_image* images;
@@ -416,6 +416,8 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   __shared__ double s_stats[2];
   __shared__ uint16_t s_raw[GB_MAX_TEMPLATE];
   __shared__ uint32_t s_hist[GB_MAX_BINS];
+  __shared__ double s_vals[GB_MAX_TEMPLATE];  // frames other than uint8: the tile's grey values ...
+  __shared__ uint16_t s_rep[GB_MAX_TEMPLATE]; // ... and one pixel of every level
   const int64_t p = blockIdx.x / prm.O;
   const int o = (int)(blockIdx.x - p * prm.O);
   const int t = prm.t;
@@ -480,22 +482,42 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   // the snapped box always spans tile_w x tile_h pixels for integer sizes
   const int bw = s_box[2] - s_box[0], bh = s_box[3] - s_box[1];
   const int area = bw * bh;
-  const int nchan = img->nchan, nbins = 255 * nchan + 1;
+  const int nchan = img->nchan;
+  // uint8 frames: grey levels are the band sums (value = level / bands).  Other types: the tile's grey values are kept and every
+  // pixel's level is the number of tile pixels below it (same order, equal values share a level), one representative per level.
+  const bool ranked = img->dtype != GB_PIX_U8;
+  const int nbins = ranked ? area : 255 * nchan + 1;
   for (int i = tid; i < nbins; i += blockDim.x) s_hist[i] = 0u;
   for (int i = tid; i < area; i += blockDim.x) {
     const int r = i / bw, c = i - r * bw;
     // a box snapped onto the frame edge can reach one pixel outside only through rounding; clamp
     const int rr = min(max(s_box[1] + r, 0), img->height - 1), cc = min(max(s_box[0] + c, 0), img->width - 1);
-    const uint8_t* px = img->pixels + (int64_t)rr * img->pitch + (int64_t)cc * img->nchan;
-    unsigned sum = 0;
-    for (int k = 0; k < img->nchan; ++k) sum += px[k];
-    s_raw[i] = (uint16_t)sum;
+    if (ranked) {
+      s_vals[i] = pixel_gray(img->pixels, img->pitch, nchan, img->dtype, rr, cc);
+    } else {
+      const uint8_t* px = img->pixels + (int64_t)rr * img->pitch + (int64_t)cc * img->nchan;
+      unsigned sum = 0;
+      for (int k = 0; k < img->nchan; ++k) sum += px[k];
+      s_raw[i] = (uint16_t)sum;
+    }
   }
   __syncthreads();
+  if (ranked) {
+    for (int i = tid; i < area; i += blockDim.x) {
+      const double v = s_vals[i];
+      int below = 0;
+      for (int j = 0; j < area; ++j) below += s_vals[j] < v;
+      s_raw[i] = (uint16_t)below;
+      s_rep[below] = (uint16_t)i;  // (any pixel of the level: they hold the same value)
+    }
+    __syncthreads();
+  }
+  auto gray_of = [&](int i) { return ranked ? s_vals[i] : quo((double)s_raw[i], (double)nchan); };
+  auto level_value = [&](int b) { return ranked ? s_vals[s_rep[b]] : quo((double)b, (double)nchan); };
   // grey mean and population std (helpers.py:324-344)
   double sum = 0.0;
   for (int i = tid; i < area; i += blockDim.x) {
-    sum += quo((double)s_raw[i], (double)nchan);
+    sum += gray_of(i);
     atomicAdd(&s_hist[s_raw[i]], 1u);
   }
   sum = warp_sum(sum);
@@ -510,7 +532,7 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   const double mean = s_stats[0];
   double ss = 0.0;
   for (int i = tid; i < area; i += blockDim.x) {
-    const double d = sub(quo((double)s_raw[i], (double)nchan), mean);
+    const double d = sub(gray_of(i), mean);
     ss += mul(d, d);
   }
   ss = warp_sum(ss);
@@ -533,7 +555,7 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
     for (int b = 0; b < nbins; ++b) {
       if (!s_hist[b]) continue;
       run += s_hist[b];
-      vals[n] = mul(sub(quo((double)b, (double)nchan), mean), inv_std);
+      vals[n] = mul(sub(level_value(b), mean), inv_std);
       qs[n] = quo((double)run, (double)area);
       ++n;
     }
@@ -548,18 +570,18 @@ __global__ void __launch_bounds__(256) k_template(const __grid_constant__ StepPa
   int cval_level = nbins;
   if (!hp_plain)
     for (int b = nbins - 1; b >= 0; --b)
-      if (!(mul(sub(quo((double)b, (double)nchan), mean), inv_std) < prm.hp_cval)) cval_level = b;
+      if ((!ranked || s_hist[b]) && !(mul(sub(level_value(b), mean), inv_std) < prm.hp_cval)) cval_level = b;
   for (int i = tid; i < area; i += blockDim.x) {
     const int r = i / bw, c = i - r * bw;
-    const double vn = mul(sub(quo((double)s_raw[i], (double)nchan), mean), inv_std);
+    const double vn = mul(sub(gray_of(i), mean), inv_std);
     double vm;
     if (hp_plain) {
-      const int med = hp5 ? median5x5(s_raw, bw, bh, r, c) : median_window(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols);
-      vm = mul(sub(quo((double)med, (double)nchan), mean), inv_std);
+      const int med = hp5 ? median5x5(s_raw, bw, bh, r, c) : median_window(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols, nbins);
+      vm = mul(sub(level_value(med), mean), inv_std);
     } else {
       const int code = median_window_codes(s_raw, bw, bh, r, c, prm.hp_rows, prm.hp_cols, prm.hp_mode, prm.hp_org_r, prm.hp_org_c,
-                                           2 * cval_level, prm.hp_has_fp ? prm.hp_fp : nullptr);
-      vm = (code & 1) ? mul(sub(quo((double)(code >> 1), (double)nchan), mean), inv_std) : prm.hp_cval;
+                                           2 * cval_level, prm.hp_has_fp ? prm.hp_fp : nullptr, nbins);
+      vm = (code & 1) ? mul(sub(level_value(code >> 1), mean), inv_std) : prm.hp_cval;
     }
     tile[i] = sub(vn, vm);
   }
@@ -715,11 +737,12 @@ static int ensure_tensor_maps(const gb_track_desc& d) {
   for (int k = 0; k < n_images; ++k) {
     const gb_image& im = d.images_host[k];
     if (tb.seen[k].pixels == im.pixels && tb.seen[k].width == im.width && tb.seen[k].height == im.height && tb.seen[k].pitch == im.pitch &&
-        tb.seen[k].nchan == im.nchan)
+        tb.seen[k].nchan == im.nchan && tb.seen[k].dtype == im.dtype)
       continue;
     tb.seen[k] = im;
     tb.ok[k] = 0;
-    if (!im.pixels || (reinterpret_cast<uintptr_t>(im.pixels) & 15) || (im.pitch & 15) || im.width <= 0 || im.height <= 0) continue;
+    if (!im.pixels || im.dtype != GB_PIX_U8 || (reinterpret_cast<uintptr_t>(im.pixels) & 15) || (im.pitch & 15) || im.width <= 0 || im.height <= 0)
+      continue;
     const cuuint64_t dims[2] = {(cuuint64_t)im.width * (cuuint64_t)im.nchan, (cuuint64_t)im.height};
     const cuuint64_t strides[1] = {(cuuint64_t)im.pitch};
     const cuuint32_t box[2] = {GB_TMA_BOXW, GB_TMA_BOXH}, estr[2] = {1, 1};
@@ -790,6 +813,7 @@ static void fill_params(const gb_track_desc& d, int t, StepParams& prm) {
       prm.pixels[o] = im.pixels;
       prm.pitch[o] = im.pitch;
       prm.nchan[o] = im.nchan;
+      prm.pixdtype[o] = im.dtype;
     }
     prm.obs_scale[o] = d.obs_scale_host[o];
     int tf = -1;
@@ -1467,16 +1491,16 @@ int gb_state_to_rows(const double* state, int64_t npoints, int64_t n, double* ro
 }
 
 int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
-                 int32_t prefer_cluster, int32_t mode, gb_plan* plan) {
-  return gb_step_plan_ex(n_particles, tile_w, tile_h, npoints, n_observers, prefer_cluster, mode, 191, plan);
+                 int32_t flags, int32_t mode, gb_plan* plan) {
+  return gb_step_plan_ex(n_particles, tile_w, tile_h, npoints, n_observers, flags, mode, 191, plan);
 }
 
 int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
-                    int32_t prefer_cluster, int32_t mode, int32_t window_margin, gb_plan* plan) {
+                    int32_t flags, int32_t mode, int32_t window_margin, gb_plan* plan) {
   if (window_margin < 4 || window_margin > GB_MAX_SURFACE - 1) return fail(GB_E_INVALID, "window_margin must be between 4 and 1023%s");
   if (!plan || n_particles <= 0 || tile_w < 1 || tile_h < 1) return fail(GB_E_INVALID, "bad plan arguments%s");
   if ((int64_t)tile_w * tile_h > GB_MAX_TEMPLATE) return fail(GB_E_RESOURCE, "template larger than 1024 pixels%s");
-  (void)prefer_cluster;
+  if (flags & ~GB_PLAN_RANKED_FRAMES) return fail(GB_E_INVALID, "unknown plan flags%s");
   if (n_observers < 1 || n_observers > GB_MAX_OBS) return fail(GB_E_INVALID, "between 1 and 8 observers are supported%s");
   if (mode != GB_MODE_STREAM) return fail(GB_E_INVALID, "unknown mode (the cluster-per-point organisation of round 1 was removed)%s");
   memset(plan, 0, sizeof(*plan));
@@ -1496,7 +1520,17 @@ int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t
     plan->stream_block = (int32_t)(((n_particles + plan->stream_nblk - 1) / plan->stream_nblk + 1) / 2 * 2);
     plan->stream_nblk = (int32_t)((n_particles + plan->stream_block - 1) / plan->stream_block);
     // surface regions sized for search windows up to `window_margin` (191 by default) px larger than the template
-    plan->surf_bytes = (tile_bytes_needed(tile_w + window_margin, tile_h + window_margin, tile_w, tile_h, GB_MAX_BINS, tile_w * tile_h) + 255) / 256 * 256;
+    {
+      // largest window + (ranked frames: rank histograms with one bin per window pixel, and the window's grey values) +
+      // the collocation factors of spline degrees 2 / 4 / 5
+      const int64_t Su = tile_w + window_margin, Sv = tile_h + window_margin;
+      const bool ranked = (flags & GB_PLAN_RANKED_FRAMES) != 0;
+      const int64_t bins = ranked ? (Su * Sv < 65535 ? Su * Sv : 65535) : GB_MAX_BINS;
+      int64_t bytes = tile_bytes_needed((int)Su, (int)Sv, tile_w, tile_h, (int)bins, tile_w * tile_h) + 16;
+      bytes += bspline_band_bytes((int)(Su - tile_w + 1), (int)(Sv - tile_h + 1), 5, 5) + 16;
+      if (ranked) bytes += bins * 8 + 16;
+      plan->surf_bytes = (bytes + 255) / 256 * 256;
+    }
     // Points are independent: they are cut into `slots` batches that advance on their own side streams, so the
     // low-occupancy tails of one batch's kernels (a few very large search windows) overlap the other batches' work.
     // (Batches small enough to keep the intermediates L2-resident were measured slower: launch-bound.)

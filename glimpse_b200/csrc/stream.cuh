@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   w.th = prm.tile_h;
   w.Mu = w.Su - w.tw + 1;
   w.Mv = w.Sv - w.th + 1;
-  w.nbins = 255 * prm.nchan[o] + 1;
+  w.dtype = prm.pixdtype[o];
+  w.nbins = w.dtype == GB_PIX_U8 ? 255 * prm.nchan[o] + 1 : w.Su * w.Sv;  // grey levels, or ranks of the window's pixels
   w.nvals = n_values;
   w.tmap = fm.ok[o] ? &fm.map[o] : nullptr;
   w.bar = &s_tma_bar;
@@ -349,8 +350,17 @@ __global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_co
   char* region = prm.s_surf + po * prm.surf_bytes;
   const int64_t need = tile_bytes_needed(w.Su, w.Sv, w.tw, w.th, w.nbins, w.nvals);
   const bool gen = !spline_is_hermite(w.ku, w.kv);  // degrees 2 / 4 / 5: coefficients solved with a work area behind the tile's data
-  if (gen) w.band = reinterpret_cast<double*>(region + align16(need));
-  if (need + (gen ? bspline_band_bytes(w.Mu, w.Mv, w.ku, w.kv) + 16 : 0) > prm.surf_bytes || w.Mu > GB_MAX_SURFACE || w.Mv > GB_MAX_SURFACE) {
+  const bool ranked = w.dtype != GB_PIX_U8;          // frames other than uint8: the window's grey values, likewise
+  int64_t tail = align16(need);
+  if (gen) {
+    w.band = reinterpret_cast<double*>(region + tail);
+    tail += align16(bspline_band_bytes(w.Mu, w.Mv, w.ku, w.kv));
+  }
+  if (ranked) {
+    w.vals = reinterpret_cast<double*>(region + tail);
+    tail += (int64_t)w.Su * w.Sv * 8;
+  }
+  if (tail > prm.surf_bytes || w.Mu > GB_MAX_SURFACE || w.Mv > GB_MAX_SURFACE || (ranked && w.Su * w.Sv > 65535)) {
     if (tid == 0) atomicOr(&prm.s_pflags[p], (int)GB_F_WINDOW);
     return;
   }

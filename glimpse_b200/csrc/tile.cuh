@@ -35,6 +35,8 @@ struct TileWork {
   float2* tmpl;      // [th][tw] high-passed template, negated and duplicated (-t, -t): the packed FP32 SSD adds it to two pixels
   uint32_t* hist;    // [nbins]
   int Su, Sv, Mu, Mv, Mp, Sp, Tp, nbins, nvals, tw, th;
+  int dtype = 0;               // GB_PIX_* of the frame: other than uint8, the window goes through `vals` and becomes ranks
+  double* vals = nullptr;      // [Sv][Su] grey values of the window (global work area behind the tile's data), frames other than uint8
   const void* tmap = nullptr;  // CUtensorMap of the frame (global memory), or null: the window is read with ordinary loads
   uint64_t* bar = nullptr;     // mbarrier of the CTA for the TMA loads (phase 0)
   int mh = 5, mw = 5;  // rows x columns of the median high-pass (Tracker.highpass['size'])
@@ -131,11 +133,17 @@ __device__ __forceinline__ int reflect_index_any(int i, int n) {
 // places the window at offsets -(m / 2) .. m - 1 - m / 2 along each axis and returns the element of rank
 // (mh * mw) / 2.  Grey levels are integers below 1024 (band sums of uint8), so the element is found bit by bit:
 // it is >= L exactly when at most `rank` neighbours are < L.  (The 5x5 default never comes here.)
-__device__ inline int median_window(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw) {
+// `nlevels` = number of grey levels (sets the first bit tried).
+__device__ __forceinline__ int top_bit_below(int n) {
+  int top = 1;
+  while (2 * top < n) top *= 2;
+  return top;
+}
+__device__ inline int median_window(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw, int nlevels = 1024) {
   const int rank = (mh * mw) >> 1, r0 = r - (mh >> 1), c0 = c - (mw >> 1);
   const bool inside = r0 >= 0 && r0 + mh <= Sv && c0 >= 0 && c0 + mw <= Su;
   int level = 0;
-  for (int bit = 512; bit; bit >>= 1) {
+  for (int bit = top_bit_below(nlevels); bit; bit >>= 1) {
     const int cand = level | bit;
     int below = 0;
     if (inside) {
@@ -182,7 +190,7 @@ __device__ __forceinline__ int border_index(int i, int n, int mode) {
 // Returns the code of the median: odd = grey level (code - 1) / 2, even = the border constant.
 // `fp` = the footprint, one word per window row (bit b = column b takes part), or null for the full window.
 __device__ inline int median_window_codes(const uint16_t* raw, int Su, int Sv, int r, int c, int mh, int mw, int mode, int org_r, int org_c,
-                                          int cval_code, const uint32_t* fp = nullptr) {
+                                          int cval_code, const uint32_t* fp = nullptr, int nlevels = 1024) {
   int count = mh * mw;
   if (fp) {
     count = 0;
@@ -190,7 +198,7 @@ __device__ inline int median_window_codes(const uint16_t* raw, int Su, int Sv, i
   }
   const int rank = count >> 1, r0 = r - (mh >> 1) - org_r, c0 = c - (mw >> 1) - org_c;
   int level = 0;
-  for (int bit = 2048; bit; bit >>= 1) {
+  for (int bit = top_bit_below(2 * nlevels + 2); bit; bit >>= 1) {
     const int cand = level | bit;
     int below = 0;
     for (int a = 0; a < mh; ++a) {
@@ -396,6 +404,39 @@ __host__ __device__ inline int64_t bspline_band_bytes(int Mu, int Mv, int ku, in
 // Phases 1-5 of the surface of one search window: raw window -> high-passed, CDF-matched float tile `w.hp`
 // (plus the template in `w.tmpl`).  All threads of the CTA participate.  `box` = (left, top, right, bottom);
 // template data in global memory.  The caller has verified the capacity and carved `w`.
+// Grey value of pixel (row, col) of a frame of any supported type, as the reference sees it after to_gray (tracker.py:522-524):
+// the pixel itself for one band, else tile.mean(axis=2) — NumPy sums the few bands in order, in float64 for integer types and in
+// float32 for float32 frames, and divides by their number.
+__device__ __forceinline__ double pixel_gray(const uint8_t* pixels, int64_t pitch, int nchan, int dtype, int row, int col) {
+  const uint8_t* base = pixels + (int64_t)row * pitch;
+  switch (dtype) {
+    case GB_PIX_U16: {
+      const uint16_t* q = reinterpret_cast<const uint16_t*>(base) + (int64_t)col * nchan;
+      double sum = (double)q[0];
+      for (int ch = 1; ch < nchan; ++ch) sum += (double)q[ch];
+      return nchan > 1 ? quo(sum, (double)nchan) : sum;
+    }
+    case GB_PIX_F32: {
+      const float* q = reinterpret_cast<const float*>(base) + (int64_t)col * nchan;
+      float sum = q[0];
+      for (int ch = 1; ch < nchan; ++ch) sum = __fadd_rn(sum, q[ch]);
+      return nchan > 1 ? (double)__fdiv_rn(sum, (float)nchan) : (double)sum;
+    }
+    case GB_PIX_F64: {
+      const double* q = reinterpret_cast<const double*>(base) + (int64_t)col * nchan;
+      double sum = q[0];
+      for (int ch = 1; ch < nchan; ++ch) sum = add(sum, q[ch]);
+      return nchan > 1 ? quo(sum, (double)nchan) : sum;
+    }
+    default: {
+      const uint8_t* q = base + (int64_t)col * nchan;
+      double sum = (double)q[0];
+      for (int ch = 1; ch < nchan; ++ch) sum += (double)q[ch];
+      return nchan > 1 ? quo(sum, (double)nchan) : sum;
+    }
+  }
+}
+
 // Frames are read through the TMA engine when the frame has a tensor map (`w.tmap`, built by the host for frames whose
 // pitch and base are 16-byte aligned): the window arrives as boxes of GB_TMA_BOXW bytes x GB_TMA_BOXH rows, staged where the
 // padded window copy (`w.packed`) is built afterwards.
@@ -414,8 +455,34 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int Su = w.Su, Sv = w.Sv, Sp = w.Sp;
   const int area = Su * Sv;
-  const bool by_tma = tile_window_by_tma(w, nchan);
-  if (by_tma) {
+  const bool by_tma = w.dtype == GB_PIX_U8 && tile_window_by_tma(w, nchan);
+  const bool ranked = w.dtype != GB_PIX_U8;
+  if (ranked) {
+    // 1. (frames other than uint8) grey values of the window, then every pixel becomes the number of window pixels below it:
+    //    equal values get equal levels and the order is kept, which is all CDF matching and the median need (nbins = Su Sv)
+    const int ta = w.tw * w.th;
+    for (int e = tid; e < area; e += nthr) {
+      const int r = e / Su, c = e - r * Su;
+      w.vals[e] = pixel_gray(pixels, pitch, nchan, w.dtype, box[1] + r, box[0] + c);
+    }
+    for (int i = tid; i < w.nbins; i += nthr) w.hist[i] = 0u;
+    for (int i = tid; i < ta; i += nthr) {
+      const float tv = -(float)g_tmpl[i];
+      w.tmpl[i] = make_float2(tv, tv);
+    }
+    for (int i = tid; i < w.nvals; i += nthr) {
+      w.tq[i] = g_tq[i];
+      w.tv[i] = g_tv[i];
+    }
+    __syncthreads();
+    for (int e = tid; e < area; e += nthr) {
+      const double v = w.vals[e];
+      int below = 0;
+      for (int j = 0; j < area; ++j) below += w.vals[j] < v;
+      w.raw[e] = (uint16_t)below;
+      atomicAdd(&w.hist[below], 1u);
+    }
+  } else if (by_tma) {
     // 1. (TMA) one thread asks for every box of the window; everybody fills the tables meanwhile, then turns the staged
     //    bytes into band sums and counts them (the histogram pass of phase 2 is folded into this one)
     const int nbx = (Su * nchan + GB_TMA_BOXW - 1) / GB_TMA_BOXW, nby = (Sv + GB_TMA_BOXH - 1) / GB_TMA_BOXH;
@@ -493,7 +560,7 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
   }
   __syncthreads();
   // 2. histogram of grey levels + reflect-padded, row-paired copy of the window for the median
-  if (!by_tma)
+  if (!by_tma && !ranked)
     for (int i = tid; i < area; i += nthr) atomicAdd(&w.hist[w.raw[i]], 1u);
   const bool hp_plain = w.hp_mode == GB_HP_REFLECT && w.hp_org_r == 0 && w.hp_org_c == 0 && !w.hp_fp;
   const bool hp5 = w.mh == 5 && w.mw == 5 && hp_plain;
@@ -552,7 +619,7 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
     const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
     for (int i = tid; i < area; i += nthr) {
       const int r = i / Su, c = i - r * Su;
-      const int code = median_window_codes(copy, Su, Sv, r, c, w.mh, w.mw, w.hp_mode, w.hp_org_r, w.hp_org_c, cval_code, w.hp_fp);
+      const int code = median_window_codes(copy, Su, Sv, r, c, w.mh, w.mw, w.hp_mode, w.hp_org_r, w.hp_org_c, cval_code, w.hp_fp, w.nbins);
       const double med = (code & 1) ? w.lut[code >> 1] : w.hp_cval;
       const float o = (float)sub(w.lut[copy[i]], med);
       w.hp[r * Sp + c] = o;
@@ -562,7 +629,7 @@ __device__ inline void tile_prepare(const uint8_t* __restrict__ pixels, int pitc
     const uint16_t* copy = reinterpret_cast<const uint16_t*>(w.packed);
     for (int i = tid; i < area; i += nthr) {
       const int r = i / Su, c = i - r * Su;
-      const int med = median_window(copy, Su, Sv, r, c, w.mh, w.mw);
+      const int med = median_window(copy, Su, Sv, r, c, w.mh, w.mw, w.nbins);
       const float o = (float)sub(w.lut[copy[i]], w.lut[med]);
       w.hp[r * Sp + c] = o;
       if (dump_search && i < dump_cap) dump_search[i] = o;

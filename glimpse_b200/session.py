@@ -41,6 +41,32 @@ def empty_result(P, T, O, return_covariances, return_particles, N=0) -> dict:
     return out
 
 
+def device_frame(array: np.ndarray) -> np.ndarray:
+    """A frame as it is copied to the device: uint8 (the integer tile pipeline), uint16, float32 or float64 (the rank pipeline)
+    with 1-8 bands, C-contiguous.  Other integer types go to float64 (exact) and float16 to float32, as NumPy would promote them
+    in ``tile.mean(axis=2)`` / ``normalize`` (reference tracker.py:522-526)."""
+    if array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 8):
+        raise NotImplementedError("device frames must be (rows, columns) or (rows, columns, 1-8 bands) arrays")
+    if array.dtype.name not in _lib.GB_PIX:
+        if array.dtype.kind in "iub":
+            array = array.astype(np.float64)
+        elif array.dtype == np.float16:
+            array = array.astype(np.float32)
+        else:
+            raise NotImplementedError(f"frames of type {array.dtype} have no device kernel")
+    return array if array.flags.c_contiguous else np.ascontiguousarray(array)
+
+
+def frames_need_ranks(observers, image_index) -> bool:
+    """Whether some frame a track will read is not uint8 (the surface regions are then sized for rank histograms)."""
+    for o, obs in enumerate(observers):
+        for i in {int(v) for v in image_index[:, o] if v >= 0}:
+            array = getattr(obs.images[i], "array", None)
+            if array is not None and array.dtype != np.uint8:
+                return True
+    return False
+
+
 def result_layout(per: int, T: int, O: int, N: int, return_covariances: bool, return_particles: bool):
     """Byte layout of one rank's block of results in the gather of a multi-GPU track: ``per`` points per rank (the last
     rank's block is zero-padded), one 16-byte aligned section per array, keys in sorted order.  Returns
@@ -239,7 +265,8 @@ class Session:
             mode = _lib.GB_MODE_STREAM
             if window_margin is None:
                 window_margin = getattr(tracker, "window_margin", _lib.GB_WINDOW_MARGIN)
-            _lib.check(self.lib.gb_step_plan_ex(N, self.tw, self.th, P, O, 0, mode, int(window_margin),
+            flags = _lib.GB_PLAN_RANKED_FRAMES if frames_need_ranks(tracker.observers, self.image_index) else 0
+            _lib.check(self.lib.gb_step_plan_ex(N, self.tw, self.th, P, O, flags, mode, int(window_margin),
                                                 C.byref(self.plan)))
             self.h2d = 0
             # the first two frames' uploads start right away (the first kernels wait for them); the other big copies are
@@ -374,7 +401,7 @@ class Session:
             todo = self._pending_copies if limit is None else self._pending_copies[:limit]
             with torch.cuda.stream(copy_stream):
                 for dev, arr, event in todo:
-                    dev.copy_(torch.from_numpy(arr), non_blocking=True)
+                    dev.copy_(torch.from_numpy(arr).view(torch.uint8).reshape(-1), non_blocking=True)
                     event.record(copy_stream)
             for k, event in self._pending_events:
                 self.image_events[k] = event.cuda_event
@@ -447,9 +474,7 @@ class Session:
                 key = (o, i, id(array))
                 cached = tracker._frame_cache.get(key) if use_cache else None
                 if cached is None:
-                    if array.dtype != np.uint8 or array.ndim not in (2, 3) or (array.ndim == 3 and not 1 <= array.shape[2] <= 4):
-                        raise NotImplementedError("device frames must be uint8 with 1-4 bands")
-                    arr = array if array.flags.c_contiguous else np.ascontiguousarray(array)
+                    arr = device_frame(array)
                     fresh.append((k, key, use_cache, arr))
                     continue
                 placed.append((k, cached))
@@ -478,7 +503,7 @@ class Session:
                 self._arena = arena
                 free = tracker.__dict__.setdefault("_event_free", [])  # events handed back by clear_device_cache()
                 for n_f, ((k, key, use_cache, arr), off) in enumerate(zip(fresh, offsets_b)):
-                    dev = arena[off:off + arr.nbytes].view(arr.shape)
+                    dev = arena[off:off + arr.nbytes]  # (bytes: the frame keeps its own pixel type)
                     event = free.pop() if free else torch.cuda.Event()
                     self._pending_copies.append((dev, arr, event))
                     if self._shared_upload:
@@ -486,18 +511,19 @@ class Session:
                         self._upload_groups[group][2].append((off, (dev, arr, event)))
                     else:
                         self.h2d += arr.nbytes
-                    cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event)
+                    cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event,
+                              _lib.GB_PIX[arr.dtype.name])
                     if use_cache:
                         tracker._frame_cache[key] = cached
                     placed.append((k, cached))
             for k, cached in sorted(placed, key=lambda kc: order_of[kc[0]]):
                 o, i, img, _used = structs[k]
-                dev, w, h, pitch, nchan, event = cached
+                dev, w, h, pitch, nchan, event, pix = cached
                 self.keep.append(dev)
                 self.keep_events.append(event)
                 g = out[k]
                 g.pixels = dev.data_ptr()
-                g.width, g.height, g.pitch, g.nchan = w, h, pitch, nchan
+                g.width, g.height, g.pitch, g.nchan, g.dtype = w, h, pitch, nchan, pix
                 g.cam = self._lower_camera_memo(img.cam)
                 self._pending_events.append((k, event))
         self.images_host = (_lib.gb_image * len(out))(*out)

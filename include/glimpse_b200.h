@@ -80,13 +80,20 @@ typedef struct gb_camera {
   int32_t pad_;
 } gb_camera;
 
-/* One cached frame (image.py:137-214 with cache=True): the uint8 pixel array exactly as the host holds
- * it, (height, width, nchan) row-major with `pitch` BYTES per row.  The tile loaders sum the `nchan`
- * bands on the fly, so tile.mean(axis=2) (tracker.py:523-524) is that sum / nchan; no converted copy
- * of the frame is ever written. */
+/* One cached frame (image.py:137-214 with cache=True): the pixel array exactly as the host holds it, (height, width, nchan)
+ * row-major with `pitch` BYTES per row, of type `dtype`.  uint8 frames (the usual case) are summed over their bands on the fly
+ * (tile.mean(axis=2), tracker.py:523-524, is that sum / nchan) and take the integer tile pipeline; the other types take a rank
+ * pipeline (every window pixel is replaced by the number of window pixels below it — CDF matching and the median only depend on
+ * the order).  No converted copy of a frame is ever written. */
+#define GB_PIX_U8 0
+#define GB_PIX_U16 1
+#define GB_PIX_F32 2
+#define GB_PIX_F64 3
 typedef struct gb_image {
   const uint8_t* pixels;
   int32_t width, height, pitch, nchan;
+  int32_t dtype;                   /* GB_PIX_* */
+  int32_t pad_;
   gb_camera cam;
 } gb_image;
 
@@ -207,15 +214,17 @@ typedef struct gb_plan {
 #define GB_MAX_OBSERVERS 8
 
 /* Size a launch plan for N particles per point, a w x h template, P points and O observers.
- * `prefer_cluster` is ignored (it sized the removed cluster-per-point organisation); `mode` must be GB_MODE_STREAM.
+ * `flags`: GB_PLAN_RANKED_FRAMES = some frame is not uint8 (the surface regions are sized for rank histograms of the largest window);
+ * `mode` must be GB_MODE_STREAM.
  * Plan fields that only that organisation used (cluster, particles_in_smem, n_slabs, slab_bytes, particle_scratch_bytes) are 1 / 0. */
+#define GB_PLAN_RANKED_FRAMES 1
 int gb_step_plan(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
-                 int32_t prefer_cluster, int32_t mode, gb_plan* plan_host);
+                 int32_t flags, int32_t mode, gb_plan* plan_host);
 /* The same with the capacity of the search windows chosen by the caller: in GB_MODE_STREAM every (point, observer) owns a surface
  * region sized for windows up to `window_margin` px larger than the template per axis (gb_step_plan: 191; 4..1023).  A point whose
  * particle cloud outgrows it ends with GB_ST_WINDOW_TOO_LARGE; the Tracker then re-runs that point with the largest margin. */
 int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t npoints, int32_t n_observers,
-                    int32_t prefer_cluster, int32_t mode, int32_t window_margin, gb_plan* plan_host);
+                    int32_t flags, int32_t mode, int32_t window_margin, gb_plan* plan_host);
 
 /* Everything one Tracker.track call needs (track/tracker.py:225-417).  Shapes use P points,
  * N particles, T times, O observers, S = T - 1 update steps, w x h template. */

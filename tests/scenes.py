@@ -71,6 +71,32 @@ def narrow_cloud(scene):
     return scene
 
 
+def frames_as(dtype):
+    """Post-processing of a scene: the same frames in another pixel type, with sub-grey-level detail so that a window holds far
+    more distinct values than the 256 of the uint8 frames (uint16: 200 sub-levels; float32 / float64: grey / 255 plus noise)."""
+    def convert(scene):
+        rng = np.random.RandomState(17)
+        for obs in scene.observers:
+            frames = []
+            for f in obs.frames:
+                if dtype == np.uint16:
+                    g = f.astype(np.uint16) * 200 + rng.randint(0, 200, f.shape).astype(np.uint16)
+                else:
+                    g = ((f.astype(np.float64) + rng.rand(*f.shape)) / 255.0).astype(dtype)
+                frames.append(np.ascontiguousarray(g))
+            obs.frames = frames
+        return scene
+    return convert
+
+
+def chain(*steps):
+    def run(scene):
+        for step in steps:
+            scene = step(scene)
+        return scene
+    return run
+
+
 def track_cases():
     return {
         # config-1 shape, shrunk: 1 observer, Cartesian, full distortion
@@ -103,6 +129,24 @@ def track_cases():
         "track_choice": dict(
             scene_kwargs=dict(seed=15, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=1515, resample_method="choice",
+        ),
+        # frames other than uint8 (tracker.py:522-524 takes any dtype): the rank pipeline of the device
+        "track_u16": dict(
+            scene_kwargs=dict(seed=47, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=4747, post=frames_as(np.uint16),
+        ),
+        "track_u16_rgb": dict(  # second observer with three uint16 bands, covariances
+            scene_kwargs=dict(seed=49, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              kind="cylindrical", velocity_sigma=0.2),
+            seed=4949, post=chain(frames_as(np.uint16), add_second_observer), return_covariances=True,
+        ),
+        "track_f32": dict(
+            scene_kwargs=dict(seed=51, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=5151, post=frames_as(np.float32),
+        ),
+        "track_f64_hp3": dict(  # float64 frames, 3 x 3 median on a 'nearest' border
+            scene_kwargs=dict(seed=53, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=5353, post=frames_as(np.float64), highpass={"size": 3, "mode": "nearest"},
         ),
         # residual resampling as the reference computes it (tracker.py:188-203); wide velocity prior so that weights are uneven
         "track_residual": dict(

@@ -472,3 +472,24 @@ def test_reference_objects_lower_to_the_same_tables(kind):
     assert tables[0][1] == tables[1][1]  # gb_motion of every point
     assert tables[0][2] == tables[1][2] and tables[0][3] == tables[1][3]  # gb_surface table (structs and cell values), viewshed index
     assert len(tables[0][2]) >= (3 if kind.startswith("tangent") else 2)
+
+
+def test_frames_of_other_types_are_accepted_as_numpy_would_promote_them():
+    """tracker.py:522-526 takes frames of any dtype: uint8 keeps the integer tile pipeline, uint16 / float32 / float64 go to the
+    device as they are (rank pipeline), other integer types as float64 (exact), float16 as float32."""
+    from glimpse_b200 import _lib
+    from glimpse_b200.session import device_frame, frames_need_ranks
+
+    for dtype, want in ((np.uint8, "uint8"), (np.uint16, "uint16"), (np.float32, "float32"), (np.float64, "float64"), (np.int16, "float64"),
+                        (np.int32, "float64"), (np.uint32, "float64"), (np.bool_, "float64"), (np.float16, "float32")):
+        out = device_frame(np.ones((4, 6, 3), dtype=dtype)[:, ::2])  # (a non-contiguous view is copied)
+        assert out.dtype.name == want and out.flags.c_contiguous and out.shape == (4, 3, 3) and want in _lib.GB_PIX
+    with pytest.raises(NotImplementedError):
+        device_frame(np.ones((4, 6), dtype=complex))
+    with pytest.raises(NotImplementedError):
+        device_frame(np.ones((4, 6, 9), dtype=np.uint8))
+    obs = _observers(3)
+    index = np.array([[0], [1], [2]])
+    assert not frames_need_ranks([obs], index)
+    obs.images[1].array = np.zeros((10, 20), dtype=np.uint16)
+    assert frames_need_ranks([obs], index) and not frames_need_ranks([obs], np.array([[0], [-1], [2]]))
