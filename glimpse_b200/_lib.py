@@ -37,7 +37,7 @@ class gb_camera(C.Structure):
     _fields_ = [
         ("R", C.c_double * 9), ("xyz", C.c_double * 3), ("f", C.c_double * 2), ("cc", C.c_double * 2),
         ("k", C.c_double * 6), ("p", C.c_double * 2), ("corr_c1", C.c_double), ("corr_c2", C.c_double),
-        ("imgsz", C.c_int32 * 2), ("has_corr", C.c_int32), ("pad_", C.c_int32),
+        ("imgsz", C.c_int32 * 2), ("has_corr", C.c_int32), ("affine", C.c_int32),
     ]
 
 

@@ -44,6 +44,11 @@ __device__ __forceinline__ void distort(const gb_camera& c, double x, double y, 
 
 // Camera.xyz_to_uv (camera.py:591-628): NaN behind the camera (camera.py:1466-1467).
 __device__ __forceinline__ void project(const gb_camera& c, double px, double py, double pz, double& u, double& v) {
+  if (c.affine) {  // raster observer (raster.py:423-445): (xy - (xlim[0], ylim[0])) / d, z unused
+    u = quo(sub(px, c.xyz[0]), c.f[0]);
+    v = quo(sub(py, c.xyz[1]), c.f[1]);
+    return;
+  }
   const double dx = sub(px, c.xyz[0]);
   const double dy = sub(py, c.xyz[1]);
   double dz = sub(pz, c.xyz[2]);
@@ -88,6 +93,11 @@ __host__ inline void camk_from(const gb_camera& c, CamK& out) {
 __device__ __forceinline__ void project_fast(const CamK& k, double px, double py, double pz, double& u, double& v) {
   const gb_camera& c = k.c;
   const double dx = px - c.xyz[0], dy = py - c.xyz[1];
+  if (c.affine) {  // raster observer: (xy - origin) / cell size, as the reference divides (raster.py:445)
+    u = dx / c.f[0];
+    v = dy / c.f[1];
+    return;
+  }
   double dz = pz - c.xyz[2];
   if (c.has_corr) dz = add(dz, quo(mul(c.corr_c1, add(mul(dx, dx), mul(dy, dy))), c.corr_c2));
   const double xc = fma(c.R[2], dz, fma(c.R[1], dy, c.R[0] * dx));
@@ -190,6 +200,12 @@ __device__ inline void undistort(const gb_camera& c, double x, double y, double&
 
 // Camera.uv_to_xyz (camera.py:630-663): ray direction with unit depth along the optical axis.
 __device__ inline void unproject(const gb_camera& c, double u, double v, double& dx, double& dy, double& dz) {
+  if (c.affine) {  // Grid.uv_to_xyz (raster.py:447-459): uv * d + origin, z is NaN; the caller adds xyz = origin when asked for points
+    dx = mul(u, c.f[0]);
+    dy = mul(v, c.f[1]);
+    dz = CUDART_NAN;
+    return;
+  }
   // (uv - (imgsz * 0.5 + c)) * (1 / f)   (camera.py:1517)
   const double x = mul(sub(u, c.cc[0]), quo(1.0, c.f[0]));
   const double y = mul(sub(v, c.cc[1]), quo(1.0, c.f[1]));

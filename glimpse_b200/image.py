@@ -1,4 +1,5 @@
-"""Frame holders: ``Image`` (photograph + per-frame Camera) and ``Raster`` (DEM / viewshed grid).
+"""Frame holders: ``Image`` (photograph + per-frame Camera) and ``Raster`` (DEM / viewshed grid, or an
+orthoimage with a datetime that an ``Observer`` tracks through like an ``Image``).
 
 Mirrors the parts of reference ``image.py:86-119,137-214,279-299`` and ``raster.py:30-421,891-1027``
 that the Tracker touches.  File decoding is host I/O and out of scope; in-memory arrays are the
@@ -70,7 +71,9 @@ class Image:
 
 
 class Raster:
-    """Regular grid of values (reference ``raster.py:523-560``): DEM, DEM uncertainty or viewshed.
+    """Regular grid of values (reference ``raster.py:523-560``): DEM, DEM uncertainty, viewshed — or, with a
+    ``datetime``, one frame of an Observer made of orthoimages (the reference Tracker only needs ``xyz_to_uv``,
+    ``inbounds``, ``size`` and ``read`` of a frame: tracker.py:580-607, observer.py:115-130).
 
     ``x`` / ``y`` are the outer limits (left, right) / (top, bottom) or cell-centre vectors, exactly
     as the reference accepts them; a scalar ``array`` is the constant surface the motion models build
@@ -78,9 +81,10 @@ class Raster:
     """
 
     def __init__(self, array, x=None, y=None, datetime: _dt.datetime = None) -> None:
-        self.array = np.atleast_2d(np.asarray(array, dtype=float)) if np.ndim(array) else np.asarray(array, dtype=float)
+        # values keep their type (an orthoimage is tracked in the type it has, like Image.array); surfaces are lowered as float64
+        self.array = np.atleast_2d(np.asarray(array)) if np.ndim(array) else np.asarray(array, dtype=float)
         self.datetime = datetime
-        shape = self.array.shape if self.array.ndim == 2 else (1, 1)
+        shape = self.array.shape[0:2] if self.array.ndim >= 2 else (1, 1)
         self.xlim = self._limits(x, shape[1])
         self.ylim = self._limits(y, shape[0])
         # identity used to share one device surface between equal constant rasters
@@ -99,13 +103,55 @@ class Raster:
 
     @property
     def size(self) -> np.ndarray:
-        if self.array.ndim != 2:
+        if self.array.ndim < 2:
             return np.array((1, 1))
-        return np.array(self.array.shape[::-1])
+        return np.array(self.array.shape[0:2][::-1])
+
+    @property
+    def d(self) -> np.ndarray:
+        """Signed cell size (dx, dy) (reference raster.py:119-122)."""
+        return np.hstack((np.diff(self.xlim), np.diff(self.ylim))) / self.size
+
+    def xyz_to_uv(self, xyz) -> np.ndarray:
+        """World -> image coordinates of the grid; z is optional and unused (reference raster.py:423-445)."""
+        xyz = np.asarray(xyz)
+        return (xyz[:, 0:2] - (self.xlim[0], self.ylim[0])) / self.d
+
+    def uv_to_xyz(self, uv) -> np.ndarray:
+        """Image -> world coordinates, z = NaN (reference raster.py:447-459)."""
+        uv = np.asarray(uv)
+        xy = uv * self.d + (self.xlim[0], self.ylim[0])
+        return np.column_stack((xy, np.full((xy.shape[0], 1), np.nan)))
+
+    def inbounds(self, uv) -> np.ndarray:
+        """Whether image coordinates are in or on the bounds (reference raster.py:339-341)."""
+        uv = np.asarray(uv)
+        return np.all((uv >= 0) & (uv <= self.size), axis=1)
+
+    def read(self, box: Iterable[int] = None, cache: bool = True) -> np.ndarray:
+        """Values, optionally cropped to (left, top, right, bottom) (reference raster.py:763-836; in-memory arrays only)."""
+        if box is None:
+            return self.array
+        box = np.asarray(box).reshape(-1, 2)
+        if not np.issubdtype(box.dtype, np.integer):
+            raise ValueError("Box must be integers")
+        if not np.all(self.inbounds(box)):
+            raise ValueError("Box is out of bounds")
+        return self.array[box[0, 1]:box[1, 1], box[0, 0]:box[1, 0]]
+
+    def lower_grid_camera(self) -> "_lib.gb_camera":
+        """The frame's world -> image map as an affine ``gb_camera`` (``affine = 1``: origin in ``xyz``, cell size in ``f``)."""
+        out = _lib.gb_camera()
+        d = self.d
+        out.affine = 1
+        out.xyz[:] = [float(self.xlim[0]), float(self.ylim[0]), 0.0]
+        out.f[:] = [float(d[0]), float(d[1])]
+        out.imgsz[:] = [int(v) for v in self.size]
+        return out
 
     @property
     def constant(self) -> bool:
-        return self.array.ndim != 2 or self.array.size == 1
+        return self.array.ndim < 2 or self.array.size == 1
 
     def lower_host(self) -> "tuple[_lib.gb_surface, object]":
         """-> (``gb_surface`` without its device pointer, the (nx, ny) array of cell values on increasing centres or None)."""
@@ -119,7 +165,7 @@ class Raster:
         ny, nx = self.array.shape
         dx = (self.xlim[1] - self.xlim[0]) / nx
         dy = (self.ylim[1] - self.ylim[0]) / ny
-        z = self.array.T  # (nx, ny)
+        z = self.array.T.astype(float, copy=False)  # (nx, ny)
         if dx < 0:
             z = z[::-1, :]
         if dy < 0:

@@ -164,6 +164,20 @@ MOTION_DTYPE = np.dtype([("kind", "<i4"), ("dem", "<i4"), ("dem_sigma", "<i4"), 
                          ("slope_sigma", "<f8")])  # field layout of gb_motion (include/glimpse_b200.h)
 
 
+def lower_grid_camera(frame) -> "_lib.gb_camera":
+    """Affine ``gb_camera`` of a raster frame: this package's Raster or any object with the reference Grid's ``xlim`` /
+    ``ylim`` / ``size`` (raster.py:30-132)."""
+    if not (hasattr(frame, "xlim") and hasattr(frame, "ylim") and hasattr(frame, "size")):
+        raise NotImplementedError("observer frames must be Image (with .cam) or Raster (with .xlim, .ylim, .size) objects")
+    if not isinstance(frame, Raster):
+        size = tuple(int(v) for v in frame.size)
+        grid = Raster.__new__(Raster)
+        grid.array = np.empty((size[1], size[0], 0))  # only the shape is used
+        grid.xlim, grid.ylim = np.asarray(frame.xlim, dtype=float), np.asarray(frame.ylim, dtype=float)
+        frame = grid
+    return frame.lower_grid_camera()
+
+
 def lower_models(models, viewshed=None):
     """Motion models (this package's or the reference's) -> the tables the kernels read, on the host:
     ``(gb_motion table as a structured array, [(gb_surface, cell values or None)], index of the viewshed surface or -1)``.
@@ -524,7 +538,7 @@ class Session:
                 g = out[k]
                 g.pixels = dev.data_ptr()
                 g.width, g.height, g.pitch, g.nchan, g.dtype = w, h, pitch, nchan, pix
-                g.cam = self._lower_camera_memo(img.cam)
+                g.cam = self._lower_frame_camera(img)
                 self._pending_events.append((k, event))
         self.images_host = (_lib.gb_image * len(out))(*out)
         images_dev = torch.frombuffer(bytearray(bytes(self.images_host)), dtype=torch.uint8).to(device)
@@ -548,6 +562,14 @@ class Session:
             sig = sig.tolist()
             agreed[key] = bool(sig[0] == -sig[2] and sig[1] == -sig[3])
         return agreed[key] and n_frames > 0
+
+    def _lower_frame_camera(self, img):
+        """``gb_camera`` of one frame: the Image's Camera, or the affine grid map of a Raster frame (an Observer of
+        orthoimages: anything with ``xlim`` / ``ylim`` / ``size`` and no ``cam``, reference raster.py:423-445)."""
+        cam = getattr(img, "cam", None)
+        if cam is not None:
+            return self._lower_camera_memo(cam)
+        return lower_grid_camera(img)
 
     def _lower_camera_memo(self, cam):
         """``lower_camera`` once per distinct camera (a sequence of frames usually shares one)."""

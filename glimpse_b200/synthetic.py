@@ -141,6 +141,21 @@ def nadir_scene(
     )
 
 
+def as_raster_frames(scene: Scene, observer: int = 0) -> Scene:
+    """Turn one observer of a distortion-free nadir scene into a sequence of orthoimages (``Raster`` frames with a
+    datetime): pixel (u, v) of the nadir camera is the ground cell at x = ox + (u - W/2) m, y = oy - (v - H/2) m."""
+    obs = scene.observers[observer]
+    m = scene.meta["metres_per_px"]
+    for vec in obs.cams:
+        W, H = (int(v) for v in vec[6:8])
+        ox, oy = vec[0], vec[1]
+        grid = np.zeros(20)
+        grid[0:6] = (ox - W / 2 * m, oy + H / 2 * m, np.nan, ox + W / 2 * m, oy - H / 2 * m, np.nan)
+        grid[6:8] = (W, H)
+        vec[:] = grid
+    return scene
+
+
 def build(scene: Scene, api, points: Optional[Sequence[int]] = None):
     """Instantiate ``api.Camera/Image/Observer/<Motion>`` objects (``api`` = this package or the
     reference package).  Returns ``(observers, motion_models)``."""
@@ -148,6 +163,9 @@ def build(scene: Scene, api, points: Optional[Sequence[int]] = None):
     for o, obs in enumerate(scene.observers):
         images = []
         for i, (frame, vec, dt) in enumerate(zip(obs.frames, obs.cams, obs.datetimes)):
+            if np.isnan(vec[2]):  # a raster frame: [xlim[0], ylim[0], NaN, xlim[1], ylim[1], NaN, nx, ny, ...] (as_raster_frames)
+                images.append(api.Raster(frame, x=(vec[0], vec[3]), y=(vec[1], vec[4]), datetime=dt))
+                continue
             cam = api.Camera(imgsz=tuple(int(v) for v in vec[6:8]), f=tuple(vec[8:10]), c=tuple(vec[10:12]),
                              k=tuple(vec[12:18]), p=tuple(vec[18:20]), xyz=tuple(vec[0:3]), viewdir=tuple(vec[3:6]))
             img = api.Image(f"obs{o}_frame{i}", cam=cam, datetime=dt)

@@ -77,7 +77,9 @@ typedef struct gb_camera {
   double corr_c1, corr_c2;
   int32_t imgsz[2];
   int32_t has_corr;
-  int32_t pad_;
+  int32_t affine;                  /* 1 = a raster observer (an orthoimage on a regular grid, raster.py:423-459):
+                                    * u = (x - xyz[0]) / f[0], v = (y - xyz[1]) / f[1] with xyz = (xlim[0], ylim[0], -) and
+                                    * f = the signed cell size d; z, R, cc, k, p are unused */
 } gb_camera;
 
 /* One cached frame (image.py:137-214 with cache=True): the pixel array exactly as the host holds it, (height, width, nchan)

@@ -127,6 +127,24 @@ def undistort(cam: np.ndarray, xy: np.ndarray, iterations: int = 20) -> np.ndarr
     return est
 
 
+def grid_vector(xlim: Sequence[float], ylim: Sequence[float], size: Sequence[int]) -> np.ndarray:
+    """A raster frame (an orthoimage: ``Raster`` with a datetime as an Observer's image) in the 20 slots of a camera vector:
+    ``[xlim[0], ylim[0], NaN, xlim[1], ylim[1], NaN, nx, ny, 0...]`` — the NaN camera height marks it."""
+    out = np.zeros(20)
+    out[0:6] = (xlim[0], ylim[0], np.nan, xlim[1], ylim[1], np.nan)
+    out[6:8] = size
+    return out
+
+
+def is_grid_vector(cam: np.ndarray) -> bool:
+    return bool(np.isnan(cam[2]))
+
+
+def grid_cell_size(cam: np.ndarray) -> np.ndarray:
+    """``Grid.d`` (raster.py:119-122): signed cell size from the outer limits and the size."""
+    return np.hstack((np.diff(cam[[0, 3]]), np.diff(cam[[1, 4]]))) / cam[6:8].astype(int)
+
+
 def project(cam: np.ndarray, xyz: np.ndarray, correction: Optional[Tuple[float, float]] = None) -> np.ndarray:
     """World -> image coordinates (camera.py:591-628, 1435-1470, 1499-1508).
 
@@ -134,6 +152,8 @@ def project(cam: np.ndarray, xyz: np.ndarray, correction: Optional[Tuple[float, 
     (helpers.py:1771-1790).  Points behind the camera give NaN.
     """
     cam = np.asarray(cam, dtype=float)
+    if is_grid_vector(cam):  # a raster frame: (xy - (xlim[0], ylim[0])) / d, z unused (raster.py:423-445)
+        return (np.asarray(xyz, dtype=float)[:, 0:2] - (cam[0], cam[1])) / grid_cell_size(cam)
     d = np.asarray(xyz, dtype=float) - cam[0:3]
     if correction is not None:
         radius, refraction = correction

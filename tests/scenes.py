@@ -148,6 +148,17 @@ def track_cases():
             scene_kwargs=dict(seed=53, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
             seed=5353, post=frames_as(np.float64), highpass={"size": 3, "mode": "nearest"},
         ),
+        # Raster observers: an Observer whose frames are orthoimages (Raster with a datetime; xyz_to_uv is the grid's affine map,
+        # raster.py:423-445) — alone, and as a float32 orthoimage next to an RGB camera station
+        "track_raster": dict(
+            scene_kwargs=dict(seed=55, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),
+            seed=5555, post=synthetic.as_raster_frames,
+        ),
+        "track_raster_mixed": dict(
+            scene_kwargs=dict(seed=57, n_points=2, n_particles=256, n_frames=5, imgsz=(320, 240), margin_px=100,
+                              kind="cylindrical", velocity_sigma=0.2),
+            seed=5757, post=chain(frames_as(np.float32), add_second_observer, synthetic.as_raster_frames), return_covariances=True,
+        ),
         # residual resampling as the reference computes it (tracker.py:188-203); wide velocity prior so that weights are uneven
         "track_residual": dict(
             scene_kwargs=dict(seed=37, n_points=2, n_particles=300, n_frames=5, imgsz=(320, 240), margin_px=100),

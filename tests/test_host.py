@@ -474,6 +474,42 @@ def test_reference_objects_lower_to_the_same_tables(kind):
     assert len(tables[0][2]) >= (3 if kind.startswith("tangent") else 2)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference checkout (build container only)")
+def test_reference_raster_frames_lower_to_the_same_affine_camera():
+    """An Observer of orthoimages: the reference's Raster frames and this package's lower to the same affine gb_camera, and
+    both packages' Raster agree on xyz_to_uv / uv_to_xyz / inbounds / read / d / size (raster.py:119-122, 339-341, 423-459, 763-836)."""
+    import scenes
+    from glimpse_b200 import synthetic
+    from glimpse_b200.session import lower_grid_camera
+    from oracle.ref_shim import import_reference
+
+    import glimpse_b200 as gb
+
+    glimpse = import_reference()
+    scene = synthetic.as_raster_frames(synthetic.nadir_scene(seed=5, n_points=4, n_particles=64, n_frames=3, imgsz=(320, 240), margin_px=90,
+                                                             world_offset=(4.99e5, 6.77e6)))
+    built = [synthetic.build(scene, api)[0][0] for api in (glimpse, gb)]
+    for a, b in zip(built[0].images, built[1].images):
+        ca, cb = lower_grid_camera(a), lower_grid_camera(b)
+        assert bytes(ca) == bytes(cb) and cb.affine == 1 and tuple(cb.imgsz) == (320, 240)
+        assert cb.f[0] > 0 > cb.f[1]  # north-up: y decreases with the row
+        xyz = np.column_stack((4.99e5 + np.linspace(-40, 40, 7), 6.77e6 + np.linspace(-30, 30, 7), np.zeros(7)))
+        np.testing.assert_array_equal(a.xyz_to_uv(xyz), b.xyz_to_uv(xyz))
+        uv = a.xyz_to_uv(xyz)
+        np.testing.assert_array_equal(a.uv_to_xyz(uv), b.uv_to_xyz(uv))
+        np.testing.assert_array_equal(a.inbounds(uv - 150), b.inbounds(uv - 150))
+        np.testing.assert_array_equal(a.d, b.d)
+        np.testing.assert_array_equal(a.size, b.size)
+        np.testing.assert_array_equal(a.read(box=(3, 4, 30, 20)), b.read(box=(3, 4, 30, 20)))
+        assert b.read().dtype == np.uint8
+        with pytest.raises(ValueError):
+            b.read(box=(-1, 0, 5, 5))
+        with pytest.raises(ValueError):
+            b.read(box=(0.5, 0, 5, 5))
+    with pytest.raises(NotImplementedError):
+        lower_grid_camera(object())
+
+
 def test_frames_of_other_types_are_accepted_as_numpy_would_promote_them():
     """tracker.py:522-526 takes frames of any dtype: uint8 keeps the integer tile pipeline, uint16 / float32 / float64 go to the
     device as they are (rank pipeline), other integer types as float64 (exact), float16 as float32."""
