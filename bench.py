@@ -460,22 +460,30 @@ def run_gpu_arm(args):
         return tracker.track(models, tile_size=scene.tile_size)
 
     e2e_steps = max(1, min(args.steps, 8))
-    # (the warm-up calls keep their result like the timed ones do: with the previous Tracks still alive a call needs a second
-    #  set of pinned result buffers, whose first allocation — 78 MB at 8 GPUs — would otherwise land in the second timed step)
-    tracks = None
-    for _ in range(max(2, min(args.warmup, 3))):
-        tracks = e2e_once()
+    # (the warm-up calls keep ALL their results until the last one is done: a call needs a fresh set of pinned result buffers
+    #  whenever every cached set is still referenced, and a first cudaHostAlloc of that set — 2 x 38 MB at 8 GPUs, 8 processes
+    #  at once — costs ~50 ms (tools/e2e_steps.py: host_alloc 2 in exactly the slow calls).  Three sets cached here cover the
+    #  steady state of a loop that keeps its previous result; `host_alloc_each_rank0` below shows that no timed step allocated.)
+    held = [e2e_once() for _ in range(max(3, min(args.warmup, 3)))]
+    tracks = held[-1]
+    del held
     barrier()
+
+    def host_allocs():
+        stats = torch.cuda.host_memory_stats() if hasattr(torch.cuda, "host_memory_stats") else {}
+        return int(stats.get("num_host_alloc", 0))
+
     import gc
 
     gc.collect()
     gc.disable()  # as timeit does: a cyclic collection over the scene's objects would land in one of the steps
     t0 = time.perf_counter()
-    e2e_each, e2e_host = [], []
+    e2e_each, e2e_host, e2e_allocs = [], [], []
     for _ in range(e2e_steps):
-        t1 = time.perf_counter()
+        t1, a1 = time.perf_counter(), host_allocs()
         tracks = e2e_once()
         e2e_each.append(1e3 * (time.perf_counter() - t1))  # track() returns host arrays: the device is idle again
+        e2e_allocs.append(host_allocs() - a1)
         e2e_host.append({k: round(v, 2) for k, v in tracker.last_run.get("host_ms", {}).items()})
     torch.cuda.synchronize()
     # the mean of the steps is the value (what a user sees); every step time is in ms_each, the median beside it
@@ -487,7 +495,7 @@ def run_gpu_arm(args):
            "d2h_bytes_per_step": int(tracker.last_run["d2h_bytes"]), "ms_per_step": 1e3 * e2e_mean_s, "steps": e2e_steps,
            "ms_each": e2e_each, "median_ms_per_step": 1e3 * e2e_median_s, "aggregate": "mean of steps (max over ranks)",
            "host_ms_last_step": {k: round(v, 2) for k, v in tracker.last_run.get("host_ms", {}).items()},
-           "host_ms_each_rank0": e2e_host}
+           "host_ms_each_rank0": e2e_host, "host_alloc_each_rank0": e2e_allocs}
     v_err = float(np.nanmedian(np.abs(tracks.vxyz[:, -1, 0] - scene.truth_velocity[0])))
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload ------------

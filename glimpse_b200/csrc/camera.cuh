@@ -42,6 +42,8 @@ __device__ __forceinline__ void distort(const gb_camera& c, double x, double y, 
   }
 }
 
+__device__ __forceinline__ void project_direction(const gb_camera& c, double dx, double dy, double dz, double& u, double& v);
+
 // Camera.xyz_to_uv (camera.py:591-628): NaN behind the camera (camera.py:1466-1467).
 __device__ __forceinline__ void project(const gb_camera& c, double px, double py, double pz, double& u, double& v) {
   if (c.affine) {  // raster observer (raster.py:423-445): (xy - (xlim[0], ylim[0])) / d, z unused
@@ -57,6 +59,11 @@ __device__ __forceinline__ void project(const gb_camera& c, double px, double py
     const double d2 = add(mul(dx, dx), mul(dy, dy));
     dz = add(dz, quo(mul(c.corr_c1, d2), c.corr_c2));
   }
+  project_direction(c, dx, dy, dz, u, v);
+}
+
+// Camera.xyz_to_uv(directions=True) (camera.py:1448-1449): a ray from the camera, no translation and no correction.
+__device__ __forceinline__ void project_direction(const gb_camera& c, double dx, double dy, double dz, double& u, double& v) {
   const double xc = fma(c.R[2], dz, fma(c.R[1], dy, c.R[0] * dx));
   const double yc = fma(c.R[5], dz, fma(c.R[4], dy, c.R[3] * dx));
   const double zc = fma(c.R[8], dz, fma(c.R[7], dy, c.R[6] * dx));

@@ -245,6 +245,80 @@ __global__ void k_unproject(const __grid_constant__ gb_camera cam, const double*
   }
 }
 
+// Image.project (image.py:301-361): one thread per pixel of the target camera.  The pixel centre is cast out through the
+// target camera, projected into the source camera as a direction, and every band of the source frame is sampled there the
+// way scipy.interpolate.RegularGridInterpolator does on the pixel-centre grid (bounds_error=False: NaN outside, which an
+// integer frame stores as 0).  Arithmetic per band type as restated in oracle/tracker_oracle.py::project_image.
+__device__ __forceinline__ double band_value(const uint8_t* pixels, int64_t pitch, int nchan, int dtype, int row, int col, int ch) {
+  const uint8_t* base = pixels + (int64_t)row * pitch;
+  const int64_t e = (int64_t)col * nchan + ch;
+  switch (dtype) {
+    case GB_PIX_U16: return (double)reinterpret_cast<const uint16_t*>(base)[e];
+    case GB_PIX_F32: return (double)reinterpret_cast<const float*>(base)[e];
+    case GB_PIX_F64: return reinterpret_cast<const double*>(base)[e];
+    default: return (double)base[e];
+  }
+}
+
+__device__ __forceinline__ void grid_interval(double x, int n, int& i, double& y) {
+  double f = floor(x - 0.5);
+  if (!(f >= 0.0)) f = 0.0;  // (NaN too: the distance below stays NaN)
+  i = (int)fmin(f, (double)(n - 2));
+  y = sub(x, (double)i + 0.5);
+}
+
+__global__ void k_project_image(const __grid_constant__ gb_image src, const __grid_constant__ gb_camera dst, int method,
+                                uint8_t* __restrict__ out) {
+  const int W = dst.imgsz[0], H = dst.imgsz[1], C = src.nchan, sw = src.width, sh = src.height;
+  const int64_t total = (int64_t)W * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / W), col = (int)(i - (int64_t)row * W);
+    double dx, dy, dz, pu, pv;
+    unproject(dst, (double)col + 0.5, (double)row + 0.5, dx, dy, dz);
+    project_direction(src.cam, dx, dy, dz, pu, pv);
+    const bool nan = isnan(pu) || isnan(pv);
+    const bool outside = pv < 0.5 || pv > (double)sh - 0.5 || pu < 0.5 || pu > (double)sw - 0.5;
+    int i0 = 0, i1 = 0;
+    double y0 = 0.0, y1 = 0.0;
+    if (!nan && !outside) {
+      grid_interval(pv, sh, i0, y0);
+      grid_interval(pu, sw, i1, y1);
+    }
+    for (int ch = 0; ch < C; ++ch) {
+      double val = CUDART_NAN;
+      if (!nan && !outside) {
+        if (method == 0) {
+          val = band_value(src.pixels, src.pitch, C, src.dtype, y0 <= 0.5 ? i0 : i0 + 1, y1 <= 0.5 ? i1 : i1 + 1, ch);
+        } else {
+          const double v00 = band_value(src.pixels, src.pitch, C, src.dtype, i0, i1, ch);
+          const double v01 = band_value(src.pixels, src.pitch, C, src.dtype, i0, i1 + 1, ch);
+          const double v10 = band_value(src.pixels, src.pitch, C, src.dtype, i0 + 1, i1, ch);
+          const double v11 = band_value(src.pixels, src.pitch, C, src.dtype, i0 + 1, i1 + 1, ch);
+          const double a0 = sub(1.0, y0), a1 = sub(1.0, y1);
+          if (src.dtype == GB_PIX_F32) {  // generic form: value * (wy * wx), summed in corner order
+            val = mul(v00, mul(a0, a1));
+            val = add(val, mul(v01, mul(a0, y1)));
+            val = add(val, mul(v10, mul(y0, a1)));
+            val = add(val, mul(v11, mul(y0, y1)));
+          } else {  // integer and float64 bands: v * wy * wx, left to right
+            val = mul(mul(v00, a0), a1);
+            val = add(val, mul(mul(v01, a0), y1));
+            val = add(val, mul(mul(v10, y0), a1));
+            val = add(val, mul(mul(v11, y0), y1));
+          }
+        }
+      }
+      const int64_t e = i * C + ch;
+      switch (src.dtype) {
+        case GB_PIX_U16: reinterpret_cast<uint16_t*>(out)[e] = isnan(val) ? (uint16_t)0 : (uint16_t)(int)val; break;
+        case GB_PIX_F32: reinterpret_cast<float*>(out)[e] = (float)val; break;
+        case GB_PIX_F64: reinterpret_cast<double*>(out)[e] = val; break;
+        default: out[e] = isnan(val) ? (uint8_t)0 : (uint8_t)(int)val; break;
+      }
+    }
+  }
+}
+
 __global__ void k_state_from_rows(const double* __restrict__ rows, int64_t npoints, int64_t n, double* __restrict__ state) {
   const int64_t total = npoints * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1472,6 +1546,21 @@ int gb_unproject(const gb_camera* cam, const double* uv, int64_t n, int directio
   if (!cam || (n > 0 && (!xyz || !uv))) return fail(GB_E_INVALID, "null argument%s");
   if (n <= 0) return GB_OK;
   k_unproject<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*cam, uv, n, directions, depth, xyz);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int gb_project_image(const gb_image* src, const gb_camera* dst, int32_t method, void* out, void* stream) {
+  if (!src || !dst || !out || !src->pixels) return fail(GB_E_INVALID, "null argument%s");
+  if (method != 0 && method != 1) return fail(GB_E_INVALID, "project_image: method must be 0 (nearest) or 1 (linear)%s");
+  if (src->cam.affine || dst->affine) return fail(GB_E_INVALID, "project_image: both cameras must be frame cameras%s");
+  if (src->cam.xyz[0] != dst->xyz[0] || src->cam.xyz[1] != dst->xyz[1] || src->cam.xyz[2] != dst->xyz[2])
+    return fail(GB_E_INVALID, "Source and target cameras have different positions ('xyz')%s");
+  if (src->width < 2 || src->height < 2 || src->nchan < 1 || dst->imgsz[0] < 1 || dst->imgsz[1] < 1 || src->dtype < GB_PIX_U8 ||
+      src->dtype > GB_PIX_F64)
+    return fail(GB_E_INVALID, "project_image: the source frame needs two pixels per axis and a supported pixel type%s");
+  const int64_t total = (int64_t)dst->imgsz[0] * dst->imgsz[1];
+  k_project_image<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, *dst, method, reinterpret_cast<uint8_t*>(out));
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

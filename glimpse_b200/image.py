@@ -60,6 +60,42 @@ class Image:
             array = array[box[1]:box[3], box[0]:box[2]]
         return array
 
+    def project(self, cam: Camera, method: str = "linear") -> np.ndarray:
+        """Project the image into another camera at the same position (reference image.py:301-361): (cam.imgsz[1],
+        cam.imgsz[0], bands) of the image's pixel type, NaN (0 in an integer image) where the target sees nothing of the
+        source.  One thread per target pixel on the device (``gb_project_image``)."""
+        import ctypes as C
+
+        from .camera import lower_camera
+        from .session import device_frame
+
+        if method not in ("linear", "nearest"):
+            raise ValueError(f"Method '{method}' is not defined")
+        if not all(np.asarray(cam.xyz) == np.asarray(self.cam.xyz)):
+            raise ValueError("Source and target cameras have different positions ('xyz')")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        array = self.read()
+        frame = device_frame(array)  # uint8 / uint16 / float32 / float64 as they are, other types as NumPy promotes them
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pixels = torch.from_numpy(frame.reshape(-1).view(np.uint8)).to(dev)  # (bytes: the frame keeps its own pixel type)
+        src = _lib.gb_image()
+        src.pixels = pixels.data_ptr()
+        src.width, src.height, src.pitch = frame.shape[1], frame.shape[0], frame.strides[0]
+        src.nchan = 1 if frame.ndim == 2 else frame.shape[2]
+        src.dtype = _lib.GB_PIX[frame.dtype.name]
+        src.cam = lower_camera(self.cam)
+        dst = lower_camera(cam)
+        w, h = (int(v) for v in cam.imgsz)
+        out = torch.empty(h * w * src.nchan * frame.dtype.itemsize, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gb_project_image(C.byref(src), C.byref(dst), 1 if method == "linear" else 0, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+        result = out.cpu().numpy().view(frame.dtype).reshape(h, w, src.nchan)
+        if result.dtype != array.dtype:  # a type the device holds promoted: back to the image's own, as the reference assigns it
+            with np.errstate(invalid="ignore"):
+                result = result.astype(array.dtype)
+        return result
+
     def xyz_to_uv(self, xyz, **kwargs):
         return self.cam.xyz_to_uv(xyz, **kwargs)
 

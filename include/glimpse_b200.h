@@ -163,6 +163,13 @@ int gb_project(const gb_camera* cam_host, const double* xyz, int64_t n, double* 
 int gb_unproject(const gb_camera* cam_host, const double* uv, int64_t n, int directions, const double* depth,
                  double* xyz, void* stream);
 
+/* Image.project (image.py:301-361): resample a frame into the frame of another camera at the same position (sequence
+ * stabilisation warps; also optimize.project_images, optimize.py:2776-2872).  src_host->pixels is device memory; out is device
+ * memory of dst_cam_host->imgsz[1] x imgsz[0] x src nchan pixels of the source's type.  method 0 = 'nearest', 1 = 'linear'
+ * (scipy.interpolate.RegularGridInterpolator on pixel centres); pixels that fall outside the source are NaN (0 in an integer
+ * frame).  GB_E_INVALID if the cameras' positions differ (the reference's ValueError). */
+int gb_project_image(const gb_image* src_host, const gb_camera* dst_cam_host, int32_t method, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * State layout helpers
  * ------------------------------------------------------------------------------------------ */

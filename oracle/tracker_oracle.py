@@ -145,17 +145,18 @@ def grid_cell_size(cam: np.ndarray) -> np.ndarray:
     return np.hstack((np.diff(cam[[0, 3]]), np.diff(cam[[1, 4]]))) / cam[6:8].astype(int)
 
 
-def project(cam: np.ndarray, xyz: np.ndarray, correction: Optional[Tuple[float, float]] = None) -> np.ndarray:
+def project(cam: np.ndarray, xyz: np.ndarray, correction: Optional[Tuple[float, float]] = None, directions: bool = False) -> np.ndarray:
     """World -> image coordinates (camera.py:591-628, 1435-1470, 1499-1508).
 
     ``correction`` = (radius, refraction) enables the curvature/refraction term
-    (helpers.py:1771-1790).  Points behind the camera give NaN.
+    (helpers.py:1771-1790).  Points behind the camera give NaN.  ``directions``: ``xyz`` are ray directions from the
+    camera (no translation, no correction: camera.py:1448-1449).
     """
     cam = np.asarray(cam, dtype=float)
     if is_grid_vector(cam):  # a raster frame: (xy - (xlim[0], ylim[0])) / d, z unused (raster.py:423-445)
         return (np.asarray(xyz, dtype=float)[:, 0:2] - (cam[0], cam[1])) / grid_cell_size(cam)
-    d = np.asarray(xyz, dtype=float) - cam[0:3]
-    if correction is not None:
+    d = np.asarray(xyz, dtype=float) if directions else np.asarray(xyz, dtype=float) - cam[0:3]
+    if correction is not None and not directions:
         radius, refraction = correction
         d[:, 2] += (refraction - 1) * (d[:, 0:2] ** 2).sum(axis=1) / (2 * radius)
     R = rotation_matrix(cam[3:6])
@@ -182,6 +183,73 @@ def unproject(cam: np.ndarray, uv: np.ndarray, directions: bool = True, depth=1)
     if not directions:
         xyz += cam[0:3]
     return xyz
+
+
+def _grid_intervals(x: np.ndarray, n: int):
+    """Cell index and normalised distance of ``x`` on the pixel-centre grid 0.5, 1.5, .., n - 0.5 the way
+    scipy.interpolate.RegularGridInterpolator finds them (``find_indices``: grid[i] <= x < grid[i + 1], clipped to
+    [0, n - 2]; NaN stays NaN in the distance)."""
+    with np.errstate(invalid="ignore"):
+        i = np.floor(x - 0.5)
+    i = np.where(np.isnan(i), 0, i).astype(np.int64)
+    i = np.clip(i, 0, n - 2)
+    return i, (x - (i + 0.5)) / 1.0
+
+
+def project_image(frame: np.ndarray, src_cam: np.ndarray, dst_cam: np.ndarray, method: str = "linear") -> np.ndarray:
+    """``Image.project`` (image.py:301-361): the frame resampled into another camera at the same position.
+
+    Every pixel centre of the target camera is cast out as a ray (``uv_to_xyz``), projected into the source camera
+    (``xyz_to_uv(directions=True)``) and the source band sampled there with ``scipy.interpolate.RegularGridInterpolator``
+    on the pixel-centre grid (``bounds_error=False``: NaN outside), band by band; the result takes the frame's dtype
+    (NaN becomes 0 in an integer frame).  The interpolator's arithmetic, restated from scipy 1.18 (the container's; the
+    reference pins 1.4.1, whose linear form is the generic one below for every dtype):
+      integer and float64 bands (integers are converted to float64): ``v00 * (1 - y0) * (1 - y1) + v01 * (1 - y0) * y1
+      + v10 * y0 * (1 - y1) + v11 * y0 * y1`` left to right (``_rgi_cython.evaluate_linear_2d``);
+      other floating bands: ``sum(v * ((1 * wy) * wx))`` over the same four corners in the same order (``_evaluate_linear``);
+      nearest: the lower index where the normalised distance is <= 0.5, else the upper (``_evaluate_nearest``)."""
+    src_cam, dst_cam = np.asarray(src_cam, dtype=float), np.asarray(dst_cam, dtype=float)
+    if not all(src_cam[0:3] == dst_cam[0:3]):
+        raise ValueError("Source and target cameras have different positions ('xyz')")
+    W, H = (int(v) for v in dst_cam[6:8])
+    sw, sh = (int(v) for v in src_cam[6:8])
+    u = np.linspace(0.5, W - 0.5, W)
+    v = np.linspace(0.5, H - 0.5, H)
+    U, V = np.meshgrid(u, v)
+    uv = np.column_stack((U.flatten(), V.flatten()))
+    pvu = np.fliplr(project(src_cam, unproject(dst_cam, uv), directions=True))
+    array = frame if frame.ndim == 3 else frame[:, :, None]
+    out = np.empty((H, W, array.shape[2]), dtype=array.dtype)
+    pv, pu = pvu[:, 0], pvu[:, 1]
+    with np.errstate(invalid="ignore"):
+        outside = (pv < 0.5) | (pv > sh - 0.5) | (pu < 0.5) | (pu > sw - 0.5)
+    nans = np.isnan(pv) | np.isnan(pu)
+    i0, y0 = _grid_intervals(pv, sh)
+    i1, y1 = _grid_intervals(pu, sw)
+    for b in range(array.shape[2]):
+        band = array[:, :, b]
+        if not np.issubdtype(band.dtype, np.inexact):
+            band = band.astype(float)
+        if method == "nearest":
+            with np.errstate(invalid="ignore"):
+                r = np.where(y0 <= 0.5, i0, i0 + 1)
+                c = np.where(y1 <= 0.5, i1, i1 + 1)
+            val = band[r, c].astype(float)
+        elif method == "linear":
+            if band.dtype == np.float64:
+                val = (band[i0, i1] * (1 - y0) * (1 - y1) + band[i0, i1 + 1] * (1 - y0) * y1
+                       + band[i0 + 1, i1] * y0 * (1 - y1) + band[i0 + 1, i1 + 1] * y0 * y1)
+            else:
+                val = np.zeros(len(pv))
+                for (r, wy), (c, wx) in (((i0, 1 - y0), (i1, 1 - y1)), ((i0, 1 - y0), (i1 + 1, y1)),
+                                         ((i0 + 1, y0), (i1, 1 - y1)), ((i0 + 1, y0), (i1 + 1, y1))):
+                    val = val + band[r, c] * ((1.0 * wy) * wx)
+        else:
+            raise ValueError(f"Method '{method}' is not defined")
+        val = np.where(outside | nans, np.nan, val)
+        with np.errstate(invalid="ignore"):
+            out[:, :, b] = val.reshape(H, W)
+    return out
 
 
 def inframe(cam: np.ndarray, uv: np.ndarray) -> np.ndarray:

@@ -236,10 +236,29 @@ def camera_vectors():
     print("camera", len(configs), "configs")
 
 
+def project_image_vectors():
+    """``Image.project`` outputs of the reference for the cases of ``scenes.project_image_cases``."""
+    out = {}
+    for name, (dtype, bands, method, src, dst) in scenes.project_image_cases().items():
+        def cam_of(v):
+            return glimpse.Camera(imgsz=tuple(int(x) for x in v[6:8]), f=tuple(v[8:10]), c=tuple(v[10:12]), k=tuple(v[12:18]),
+                                  p=tuple(v[18:20]), xyz=tuple(v[0:3]), viewdir=tuple(v[3:6]))
+        img = glimpse.Image(name, cam=cam_of(src), datetime=synthetic.T0)
+        img.array = scenes.project_image_frame(name)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out[name] = img.project(cam_of(dst), method=method)
+    path = os.path.join(OUT, "project_image.npz")
+    np.savez_compressed(path, **out)
+    print("project_image", len(out), "cases", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]  # optional: names of the track cases to (re)generate
     if not only:
         camera_vectors()
+    if not only or "project_image" in only:
+        project_image_vectors()
     for name, case in scenes.track_cases().items():
         if not only or name in only:
             save_track_case(name, **case)

@@ -32,6 +32,43 @@ def camera_configs():
     }
 
 
+def project_image_cases():
+    """``Image.project`` (image.py:301-361) cases: name -> (frame dtype, bands, method, source camera vector, target camera vector).
+    The frames are ``project_image_frame(name)``; the goldens (tests/golden/project_image.npz) hold the reference's output."""
+    v = synthetic.camera_vector
+    pos = (10.0, 20.0, 30.0)
+    src = v(imgsz=(160, 120), f=(300.0, 295.0), xyz=pos, viewdir=(30.0, -10.0, 2.0), c=(1.5, -2.0), k=synthetic.FULL_K, p=synthetic.FULL_P)
+    dst = v(imgsz=(140, 100), f=(280.0, 280.0), xyz=pos, viewdir=(32.0, -9.0, 0.0), k=(0.1, 0, 0, 0, 0, 0))
+    same = v(imgsz=(160, 120), f=(300.0, 295.0), xyz=pos, viewdir=(31.0, -10.5, 1.0))  # same frame size: the grids are shared
+    wide = v(imgsz=(200, 90), f=(150.0, 150.0), xyz=pos, viewdir=(30.0, -10.0, 2.0))   # sees far beyond the source: NaN border
+    return {
+        "u8_rgb_linear": (np.uint8, 3, "linear", src, dst),
+        "u8_gray_nearest": (np.uint8, 1, "nearest", src, dst),
+        "u8_gray_linear_same": (np.uint8, 1, "linear", src, same),
+        "u16_rgb_linear": (np.uint16, 3, "linear", src, dst),
+        "f32_gray_linear": (np.float32, 1, "linear", src, wide),
+        "f32_rgb_nearest": (np.float32, 3, "nearest", src, same),
+        "f64_rgb_linear": (np.float64, 3, "linear", src, dst),
+        "f64_gray_nearest_wide": (np.float64, 1, "nearest", src, wide),
+        "i16_gray_linear": (np.int16, 1, "linear", src, dst),  # a type the device holds promoted to float64
+    }
+
+
+def project_image_frame(name):
+    dtype, bands, _, src, _ = project_image_cases()[name]
+    rng = np.random.RandomState(sum(map(ord, name)))
+    w, h = (int(x) for x in src[6:8])
+    tex = rng.rand(h, w, bands) * 250
+    if dtype == np.int16:
+        tex = tex * 40 - 3000
+    elif dtype == np.uint16:
+        tex = tex * 200
+    elif np.issubdtype(dtype, np.floating):
+        tex = tex / 250
+    frame = tex.astype(dtype)
+    return frame if bands > 1 else frame[:, :, 0]
+
+
 def add_second_observer(scene):
     """Second station: same place, rolled 180 deg (image flipped both ways), RGB frames, radial-only
     distortion, and images starting one frame later (staggered template start)."""
