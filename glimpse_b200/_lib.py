@@ -122,6 +122,9 @@ SIGNATURES = {
     "gb_camera_from_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(gb_camera)]),
     "gb_project": (C.c_int, [C.POINTER(gb_camera), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_project_image": (C.c_int, [C.POINTER(gb_image), C.POINTER(gb_camera), C.c_int32, C.c_void_p, C.c_void_p]),
+    "gb_viewshed_work_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "gb_viewshed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double),
+                              C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_unproject": (C.c_int, [C.POINTER(gb_camera), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gb_state_from_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_state_to_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "glimpse_b200.cu")
 OUT = os.path.join(HERE, "libglimpse_b200.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("glimpse_b200.cu", "common.cuh", "camera.cuh", "motion.cuh", "tile.cuh",
-                                                 "median25.cuh", "stream.cuh")] + [os.path.join(HERE, "..", "include", "glimpse_b200.h")]
+                                                 "median25.cuh", "stream.cuh", "viewshed.cuh")] + [os.path.join(HERE, "..", "include", "glimpse_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "--use_fast_math=false" if False else "-Xptxas=-v"]
 

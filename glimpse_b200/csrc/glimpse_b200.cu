@@ -721,6 +721,7 @@ __device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
 }
 
 #include "stream.cuh"
+#include "viewshed.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -1546,6 +1547,57 @@ int gb_unproject(const gb_camera* cam, const double* uv, int64_t n, int directio
   if (!cam || (n > 0 && (!xyz || !uv))) return fail(GB_E_INVALID, "null argument%s");
   if (n <= 0) return GB_OK;
   k_unproject<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*cam, uv, n, directions, depth, xyz);
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int64_t gb_viewshed_work_bytes(int32_t nx, int32_t ny, int32_t max_rings) {
+  if (nx < 1 || ny < 1 || max_rings < 1) return 0;
+  return viewshed_layout((int64_t)nx * ny, max_rings, nullptr, nullptr);
+}
+
+int gb_viewshed(const double* z, int32_t nx, int32_t ny, const double* x_centres, const double* y_centres, double cell,
+                const double* origin, const double* corr, int32_t max_rings, void* work, int64_t work_bytes, uint8_t* visible,
+                void* stream) {
+  if (!z || !x_centres || !y_centres || !origin || !work || !visible) return fail(GB_E_INVALID, "null argument%s");
+  if (nx < 1 || ny < 1 || max_rings < 1 || !(cell > 0.0)) return fail(GB_E_INVALID, "viewshed: empty raster or cell size%s");
+  if ((int64_t)nx * ny > 0x7fffffff) return fail(GB_E_RESOURCE, "viewshed: more than 2^31 cells%s");
+  ViewshedParams q;
+  memset(&q, 0, sizeof(q));
+  const int64_t n = (int64_t)nx * ny;
+  if (viewshed_layout(n, max_rings, reinterpret_cast<unsigned char*>(work), &q.w) > work_bytes)
+    return fail(GB_E_INVALID, "viewshed: work buffer smaller than gb_viewshed_work_bytes%s");
+  q.z = z;
+  q.xc = x_centres;
+  q.yc = y_centres;
+  q.nx = nx;
+  q.ny = ny;
+  q.R = max_rings;
+  q.ox = origin[0];
+  q.oy = origin[1];
+  q.oz = origin[2];
+  q.inv_cell = 1.0 / cell;
+  if (corr) {
+    q.has_corr = 1;
+    q.corr_c1 = corr[1] - 1.0;
+    q.corr_c2 = 2.0 * corr[0];
+  }
+  q.visible = visible;
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool attr_set = false;
+  const int sort_smem = GB_VS_MAX_RING * 12, sweep_smem = (GB_VS_MAX_RING + 2) * 8;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(k_vs_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
+    GB_CUDA(cudaFuncSetAttribute(k_vs_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+    attr_set = true;
+  }
+  k_vs_init<<<grid_for(max_rings + 1, 256), 256, 0, s>>>(q);
+  k_vs_cells<<<grid_for(n, 256), 256, 0, s>>>(q);
+  k_vs_count<<<grid_for(n, 256), 256, 0, s>>>(q);
+  k_vs_scan<<<1, 1024, 0, s>>>(q);
+  k_vs_scatter<<<grid_for(n, 256), 256, 0, s>>>(q);
+  k_vs_sort<<<max_rings, GB_VS_SORT_THREADS, sort_smem, s>>>(q);
+  k_vs_sweep<<<1, GB_VS_SWEEP_THREADS, sweep_smem, s>>>(q);
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }

@@ -175,6 +175,64 @@ class Raster:
             raise ValueError("Box is out of bounds")
         return self.array[box[0, 1]:box[1, 1], box[0, 0]:box[1, 0]]
 
+    @property
+    def x(self) -> np.ndarray:
+        """Cell-centre x coordinates in array order (reference raster.py:139-156)."""
+        return self._centres(self.xlim, self.size[0])
+
+    @property
+    def y(self) -> np.ndarray:
+        """Cell-centre y coordinates in array order (reference raster.py:161-174)."""
+        return self._centres(self.ylim, self.size[1])
+
+    @staticmethod
+    def _centres(lim, n) -> np.ndarray:
+        half = abs((lim[1] - lim[0]) / n) / 2
+        value = np.linspace(start=min(lim) + half, stop=max(lim) - half, num=int(n))
+        return value[::-1] if lim[1] < lim[0] else value
+
+    def viewshed(self, origin, correction=False) -> np.ndarray:
+        """Boolean array of the cells visible from ``origin`` (x, y, z) (reference raster.py:1293-1389): rings of cells by
+        rounded distance, swept outwards on the device against the previous ring's interpolated horizon (``gb_viewshed``).
+        ``correction``: arguments of ``helpers.elevation_corrections`` (``radius``, ``refraction``), ``True`` for its
+        defaults, or ``False`` / ``None``."""
+        import ctypes as C
+        import warnings
+
+        d = np.abs(self.d)
+        if not all(d[0] == d):
+            warnings.warn("DEM cells not square " + str(tuple(d)) + " - may lead to unexpected results")
+        origin = np.asarray(origin, dtype=float)
+        if not (min(self.xlim) <= origin[0] <= max(self.xlim) and min(self.ylim) <= origin[1] <= max(self.ylim)):
+            warnings.warn("Origin not in DEM - may lead to unexpected results")
+        if correction is True:
+            correction = {}
+        corr = None
+        if isinstance(correction, dict):
+            corr = (C.c_double * 2)(float(correction.get("radius", 6.3781e6)), float(correction.get("refraction", 0.13)))
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        z = np.ascontiguousarray(self.array, dtype=float)
+        ny, nx = z.shape
+        x, y = self.x, self.y
+        # rings between the nearest and the farthest cell: from the bounding box of the cell centres
+        near = np.hypot(np.clip(origin[0], x.min(), x.max()) - origin[0], np.clip(origin[1], y.min(), y.max()) - origin[1])
+        far = max(np.hypot(cx - origin[0], cy - origin[1]) for cx in (x.min(), x.max()) for cy in (y.min(), y.max()))
+        max_rings = int(far / d[0]) - int(near / d[0]) + 4
+        nbytes = int(lib.gb_viewshed_work_bytes(nx, ny, max_rings))
+        work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        z_d, x_d, y_d = (torch.from_numpy(np.array(v, dtype=float, order="C", copy=True)).to(dev) for v in (z, x, y))
+        out = torch.empty(ny * nx, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gb_viewshed(z_d.data_ptr(), nx, ny, x_d.data_ptr(), y_d.data_ptr(), float(d[0]), (C.c_double * 3)(*origin[:3]),
+                                   corr, max_rings, work.data_ptr(), nbytes, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        status = int(work[:4].cpu().numpy().view(np.int32)[0])  # (synchronises)
+        if status == 3:
+            raise NotImplementedError("viewshed: a ring of more than 16384 cells (rasters beyond ~2600 cells of radius)")
+        if status != 0:
+            raise RuntimeError(f"viewshed: device status {status}")
+        return out.cpu().numpy().reshape(ny, nx).astype(bool)
+
     def lower_grid_camera(self) -> "_lib.gb_camera":
         """The frame's world -> image map as an affine ``gb_camera`` (``affine = 1``: origin in ``xyz``, cell size in ``f``)."""
         out = _lib.gb_camera()

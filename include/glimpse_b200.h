@@ -170,6 +170,18 @@ int gb_unproject(const gb_camera* cam_host, const double* uv, int64_t n, int dir
  * frame).  GB_E_INVALID if the cameras' positions differ (the reference's ValueError). */
 int gb_project_image(const gb_image* src_host, const gb_camera* dst_cam_host, int32_t method, void* out, void* stream);
 
+/* Raster.viewshed (raster.py:1293-1389): cells of the DEM z (ny x nx doubles, row-major, device memory) visible from
+ * origin_host = (x, y, z).  x_centres[nx] / y_centres[ny] (device) are the cell-centre coordinates in array order (Grid.x, Grid.y,
+ * raster.py:139-174), cell = |d[0]|, corr_host = {radius, refraction} or NULL (helpers.elevation_corrections).  max_rings bounds
+ * the number of distance rings between the nearest and the farthest cell (the host knows it from the raster's corners); work =
+ * gb_viewshed_work_bytes(nx, ny, max_rings) bytes of device scratch whose first int32 is the status the caller reads back after
+ * the stream: 0 ok, 2 more rings than max_rings, 3 a ring of more than 16 384 cells (rasters beyond ~2 600 cells of radius).
+ * visible[ny * nx] = 1 / 0. */
+int64_t gb_viewshed_work_bytes(int32_t nx, int32_t ny, int32_t max_rings);
+int gb_viewshed(const double* z, int32_t nx, int32_t ny, const double* x_centres, const double* y_centres, double cell,
+                const double* origin_host, const double* corr_host, int32_t max_rings, void* work, int64_t work_bytes,
+                uint8_t* visible, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * State layout helpers
  * ------------------------------------------------------------------------------------------ */

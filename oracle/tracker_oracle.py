@@ -252,6 +252,75 @@ def project_image(frame: np.ndarray, src_cam: np.ndarray, dst_cam: np.ndarray, m
     return out
 
 
+def grid_centres(lim: Sequence[float], n: int) -> np.ndarray:
+    """``Grid.x`` / ``Grid.y`` (raster.py:139-174): cell centres in array order from the outer limits (first, last)."""
+    lo, hi = min(lim), max(lim)
+    half = abs((lim[1] - lim[0]) / n) / 2
+    centres = np.linspace(start=lo + half, stop=hi - half, num=n)
+    return centres[::-1] if lim[1] < lim[0] else centres
+
+
+def viewshed(z: np.ndarray, xlim: Sequence[float], ylim: Sequence[float], origin: Sequence[float],
+             correction: Optional[Tuple[float, float]] = None) -> np.ndarray:
+    """``Raster.viewshed`` (raster.py:1293-1389): cells of the (ny, nx) surface ``z`` visible from ``origin`` (x, y, z).
+
+    Cells are binned into rings by their rounded distance in cells and swept outwards: within a ring every cell's
+    elevation ratio dz / distance is compared with the highest ratio seen so far along its heading, which is the
+    previous ring's running maximum linearly interpolated (periodically) at the cell's heading.  Cells closer than half a
+    cell to the origin (ring 0) are skipped when other rings exist — the reference starts at the first ring boundary —
+    and a raster that is one ring only is all visible if that ring is ring 0.  ``correction`` = (radius, refraction)."""
+    z = np.asarray(z, dtype=float)
+    ny, nx = z.shape
+    x, y = grid_centres(xlim, nx), grid_centres(ylim, ny)
+    dx = np.tile(x - origin[0], ny)
+    dy = np.repeat(y - origin[1], nx)
+    dz = z.ravel() - origin[2]
+    d2 = dx ** 2 + dy ** 2
+    if correction is not None:
+        radius, refraction = correction
+        dz = dz + (refraction - 1) * d2 / (2 * radius)
+    dist = np.sqrt(d2)
+    cell = abs((xlim[1] - xlim[0]) / nx)
+    ring = (dist * (1 / cell) + 0.5).astype(int)
+    heading = np.arctan2(dy, dx)
+    order = np.lexsort((heading, ring))
+    ring_sorted = ring[order]
+    starts = np.flatnonzero(ring_sorted[1:] != ring_sorted[:-1]) + 1  # first sorted position of every ring but the first
+    if ring_sorted[0] != 0:
+        starts = np.concatenate(([0], starts))
+    elif len(starts) == 0:
+        return np.ones(z.shape, dtype=bool)
+    bounds = np.concatenate((starts, [len(order)]))
+    first = order[bounds[0]:bounds[1]]
+    dist[first[dist[first] == 0]] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ratio = dz / dist
+    visible = np.zeros(z.size, dtype=bool)
+    horizon_heading = horizon = None
+    horizon_has_nan = False
+    for k in range(len(bounds) - 1):
+        cells = order[bounds[k]:bounds[k + 1]]
+        h, r = heading[cells], ratio[cells]
+        if k == 0:
+            seen = ~np.isnan(r)
+            horizon = r
+            horizon_has_nan = bool(np.isnan(r).any())
+        else:
+            horizon = np.interp(h, horizon_heading, horizon, period=2 * np.pi)
+            with np.errstate(invalid="ignore"):
+                seen = r > horizon
+            if horizon_has_nan:
+                unknown = np.isnan(horizon)
+                opened = unknown & ~np.isnan(r)
+                seen |= opened
+                if np.count_nonzero(unknown) == np.count_nonzero(opened):
+                    horizon_has_nan = False
+            horizon[seen] = r[seen]
+        visible[cells] = seen
+        horizon_heading = h
+    return visible.reshape(z.shape)
+
+
 def inframe(cam: np.ndarray, uv: np.ndarray) -> np.ndarray:
     """(camera.py:700-718)."""
     imgsz = np.asarray(cam)[6:8].astype(int)

@@ -253,10 +253,35 @@ def project_image_vectors():
     print("project_image", len(out), "cases", os.path.getsize(path) // 1024, "KiB")
 
 
+def viewshed_vectors():
+    """``Raster.viewshed`` outputs of the reference for the cases of ``scenes.viewshed_cases`` (bit-packed)."""
+    out = {}
+    for name, case in scenes.viewshed_cases().items():
+        raster = glimpse.Raster(case["z"].copy(), x=case["xlim"], y=case["ylim"])
+        corr = case["correction"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vis = raster.viewshed(case["origin"], correction=dict(radius=corr[0], refraction=corr[1]) if corr else False)
+        out[name] = np.packbits(vis)
+        print("  ", name, vis.shape, "visible %.3f" % vis.mean())
+    case = scenes.viewshed_large_case()
+    raster = glimpse.Raster(case["z"].copy(), x=case["xlim"], y=case["ylim"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vis = raster.viewshed(case["origin"], correction=dict(radius=case["correction"][0], refraction=case["correction"][1]))
+    out["large_2000"] = np.packbits(vis)
+    print("  ", "large_2000", vis.shape, "visible %.4f" % vis.mean())
+    path = os.path.join(OUT, "viewshed.npz")
+    np.savez_compressed(path, **out)
+    print("viewshed", len(out), "cases", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]  # optional: names of the track cases to (re)generate
     if not only:
         camera_vectors()
+    if not only or "viewshed" in only:
+        viewshed_vectors()
     if not only or "project_image" in only:
         project_image_vectors()
     for name, case in scenes.track_cases().items():

@@ -32,6 +32,55 @@ def camera_configs():
     }
 
 
+def viewshed_cases():
+    """``Raster.viewshed`` (raster.py:1293-1389) cases: name -> dict(z (ny, nx), xlim, ylim, origin, correction = (radius, refraction)
+    or None).  Bumpy seeded DEMs; the goldens (tests/golden/viewshed.npz) hold the reference's boolean arrays."""
+    from scipy.ndimage import gaussian_filter
+
+    def dem(seed, ny, nx, relief=200.0):
+        rng = np.random.RandomState(seed)
+        return gaussian_filter(rng.rand(ny, nx), 3) * relief * 8 + np.linspace(0, 30, nx)[None, :]
+
+    def above(z, xlim, ylim, x, y, h):  # an eye h above the cell under (x, y)
+        col = int((x - xlim[0]) / ((xlim[1] - xlim[0]) / z.shape[1]))
+        row = int((y - ylim[0]) / ((ylim[1] - ylim[0]) / z.shape[0]))
+        return (x, y, float(np.nanmax(z[max(row - 1, 0):row + 2, max(col - 1, 0):col + 2])) + h)
+
+    xl, yl = (100.0, 900.0), (700.0, 100.0)
+    z = dem(3, 60, 80)
+    holes = z.copy()
+    holes[10:14, 20:30] = np.nan
+    holes[40, 5] = np.nan
+    holes[29:32, 38:41] = np.nan  # around the eye: the first ring has NaN cells
+    big = dem(5, 300, 420, relief=120.0)
+    return {
+        "interior": dict(z=z, xlim=xl, ylim=yl, origin=above(z, xl, yl, 483.3, 391.2, 3.0), correction=None),
+        "corner": dict(z=z, xlim=xl, ylim=yl, origin=above(z, xl, yl, 105.0, 695.0, 2.0), correction=None),
+        "on_cell_corner_corrected": dict(z=z, xlim=xl, ylim=yl, origin=above(z, xl, yl, 500.0, 400.0, 5.0), correction=(6.3781e6, 0.13)),
+        "on_cell_centre": dict(z=z, xlim=xl, ylim=yl, origin=above(z, xl, yl, 505.0, 395.0, 1.5), correction=None),  # a ring 0 of one cell
+        "nan_cells": dict(z=holes, xlim=xl, ylim=yl, origin=above(z, xl, yl, 483.3, 391.2, 3.0), correction=None),
+        "single_cell": dict(z=z[:1, :1], xlim=(0.0, 10.0), ylim=(10.0, 0.0), origin=(5.0, 5.0, 1000.0), correction=None),
+        "outside_flipped": dict(z=z[:30, :40], xlim=(900.0, 100.0), ylim=(100.0, 700.0), origin=(-50.0, 50.0, float(z.max()) + 40.0), correction=None),
+        "one_row": dict(z=z[:1, :], xlim=xl, ylim=(110.0, 100.0), origin=(300.0, 105.0, float(z[0].max()) - 5.0), correction=None),
+        "big": dict(z=big, xlim=(0.0, 4200.0), ylim=(3000.0, 0.0), origin=above(big, (0.0, 4200.0), (3000.0, 0.0), 1711.0, 1203.0, 150.0),
+                    correction=(6.3781e6, 0.13)),
+    }
+
+
+def viewshed_large_case(side=2000):
+    """A ``side`` x ``side`` DEM (bilinear blow-up of seeded noise, 900 m of relief, 10 m cells) seen from 30 m above a point
+    near its middle, curvature / refraction corrected: the full-size parity and timing case (golden ``viewshed_2000``)."""
+    rng = np.random.RandomState(7)
+    coarse = rng.rand(side // 50 + 2, side // 50 + 2)
+    yy, xx = np.mgrid[0:side, 0:side] / 50.0
+    i, j = yy.astype(int), xx.astype(int)
+    fy, fx = yy - i, xx - j
+    z = ((coarse[i, j] * (1 - fy) + coarse[i + 1, j] * fy) * (1 - fx) + (coarse[i, j + 1] * (1 - fy) + coarse[i + 1, j + 1] * fy) * fx) * 900.0
+    mid = side // 2
+    origin = (side * 5.0 + 3.0, side * 5.0 - 4.0, float(z[mid - 2:mid + 3, mid - 2:mid + 3].max()) + 30.0)
+    return dict(z=z, xlim=(0.0, side * 10.0), ylim=(side * 10.0, 0.0), origin=origin, correction=(6.3781e6, 0.13))
+
+
 def project_image_cases():
     """``Image.project`` (image.py:301-361) cases: name -> (frame dtype, bands, method, source camera vector, target camera vector).
     The frames are ``project_image_frame(name)``; the goldens (tests/golden/project_image.npz) hold the reference's output."""

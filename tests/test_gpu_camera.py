@@ -136,6 +136,49 @@ def test_project_image_errors(cuda):
         img.project(_camera_from_vector(gb, dst), method="cubic")
 
 
+@pytest.mark.parametrize("name", list(scenes.viewshed_cases()))
+def test_viewshed_matches_reference(cuda, name):
+    """Raster.viewshed (raster.py:1293-1389) through gb_viewshed against the reference's boolean array: equal cell for cell
+    (the device's atan2 may differ from NumPy's in the last bit, which could only flip a cell whose elevation ratio sits within
+    rounding of the interpolated horizon — none does in these cases)."""
+    import warnings
+
+    import glimpse_b200 as gb
+
+    case = scenes.viewshed_cases()[name]
+    ref = np.unpackbits(helpers.load_golden("viewshed")[name])[: case["z"].size].reshape(case["z"].shape).astype(bool)
+    raster = gb.Raster(case["z"], x=case["xlim"], y=case["ylim"])
+    corr = case["correction"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vis = raster.viewshed(case["origin"], correction=dict(radius=corr[0], refraction=corr[1]) if corr else False)
+    assert vis.dtype == bool and vis.shape == ref.shape
+    assert int((vis != ref).sum()) == 0, f"{int((vis != ref).sum())} of {ref.size} cells differ"
+
+
+def test_viewshed_full_size_matches_reference(cuda):
+    """2000 x 2000 cells, 1 400 rings of up to 8 900 cells: every one of the 4 000 000 cells as the reference has it."""
+    import glimpse_b200 as gb
+
+    case = scenes.viewshed_large_case()
+    ref = np.unpackbits(helpers.load_golden("viewshed")["large_2000"])[: case["z"].size].reshape(case["z"].shape).astype(bool)
+    raster = gb.Raster(case["z"], x=case["xlim"], y=case["ylim"])
+    vis = raster.viewshed(case["origin"], correction=dict(radius=case["correction"][0], refraction=case["correction"][1]))
+    assert int((vis != ref).sum()) == 0 and 0.005 < vis.mean() < 0.5
+
+
+def test_viewshed_warnings_and_limits(cuda):
+    import glimpse_b200 as gb
+
+    z = scenes.viewshed_cases()["interior"]["z"]
+    with pytest.warns(UserWarning, match="not square"):
+        gb.Raster(z, x=(0.0, 800.0), y=(300.0, 0.0)).viewshed((400.0, 150.0, 5000.0))
+    with pytest.warns(UserWarning, match="not in DEM"):
+        gb.Raster(z, x=(0.0, 800.0), y=(600.0, 0.0)).viewshed((-10.0, 150.0, 5000.0))
+    # from far above everything is visible; with the curvature correction too
+    assert gb.Raster(z, x=(0.0, 800.0), y=(600.0, 0.0)).viewshed((400.0, 300.0, 1e6), correction=True).all()
+
+
 def test_observer_sample_tile_and_shift_tile_match_fitpack(cuda):
     """Observer.sample_tile / shift_tile (reference observer.py:146-214) through gb_sample_surface: the device's Hermite-form
     not-a-knot spline against scipy's RectBivariateSpline (FITPACK) on a smooth tile — cubic, linear and mixed degrees, points
