@@ -117,6 +117,7 @@ struct StepParams {
 // What k_s4p needs to know about the NEXT time to advance the particles to it.
 struct NextParams {
   double tau, tau2;
+  int spec_update, pad_;  // no point starts at this time: every active point is resampled, k_s4p may request its parents early
   int img[GB_MAX_OBS];
   CamK cam[GB_MAX_OBS];
 };
@@ -1277,6 +1278,8 @@ static int track_streaming(const gb_track_desc& d, cudaStream_t stream, int64_t*
     NextParams nxt;
     memset(&nxt, 0, sizeof(nxt));
     for (int o = 0; o < GB_MAX_OBS; ++o) nxt.img[o] = -1;
+    nxt.spec_update = has_init[t] ? 0 : 1;
+    if (const char* e = getenv("GB_S4P_SPEC")) nxt.spec_update = nxt.spec_update && atoi(e) != 0;
     if (t + 1 < T) {
       StepParams pn;
       fill_params(d, t + 1, pn);

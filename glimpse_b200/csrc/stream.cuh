@@ -534,7 +534,8 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
   const int64_t p = prm.p0 + blockIdx.y;
   const int b = (int)blockIdx.x;
   const int act = prm.s_act[p];
-  if (!(act & GB_ACT_ACTIVE) || prm.s_pflags[p] != 0) return;
+  const int failed_at_t = prm.s_pflags[p];  // (both scalars are requested before the branch: one memory round trip)
+  if (!(act & GB_ACT_ACTIVE) || failed_at_t != 0) return;
   const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = (int)prm.N, O = prm.O;
@@ -1151,6 +1152,7 @@ __global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
 #endif
 #define GB_S4P_PPT ((GB_S4P_CAP + GB_S4P_THREADS - 1) / GB_S4P_THREADS)
 constexpr int kS4pSmem = GB_S4P_CAP * 64;
+static_assert(GB_S4P_THREADS >= 96 + GB_MAX_OBS, "k_s4p's prologue spreads its scalar loads over the first 104 threads");
 
 // One projected child: image coordinates of time t + 1 and its contribution to the integer cloud box.
 __device__ __forceinline__ void s4p_project_child(const CamK& cam, const double (&s)[6], double* uv, int64_t N, int j, double hw,
@@ -1183,35 +1185,60 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   __shared__ gb_motion s_motion;
   __shared__ int s_box[GB_MAX_OBS][5];
   __shared__ unsigned s_or;
+  __shared__ double s_refv[6];            // moment origin of the point (read in the prologue, used after the parents arrive)
+  __shared__ uint8_t s_mask[GB_MAX_OBS];  // observers that see the point
   const int64_t p = prm.p0 + blockIdx.y;  // grid: (blocks of a point, points of the batch)
   const int b = (int)blockIdx.x;
-  const int act = prm.s_act[p];
-  const bool update = (act & GB_ACT_ACTIVE) != 0, propagate = (act & GB_ACT_PROPAGATE) != 0;
-  if ((!update && !propagate) || prm.s_pflags[p] != 0) return;  // a point that failed at t is neither resampled nor advanced
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = prm.t;
   const int N = (int)prm.N, O = prm.O;
   const int base = b * prm.s_block;
   const int n_here = max(0, min(N, base + prm.s_block) - base);  // parents of this CTA (<= CAP)
-  // source of the particles that are resampled: the evolved particles of time t, or — at a point's first
-  // time — the initial particles, taken one to one
-  const double* src6 = (update ? prm.s_ev : state_buffer(prm, t)) + p * 6 * (int64_t)N + base;
   const double* wsrc = prm.s_w + (int64_t)p * N + base;
-  const bool bulk = n_here > 0 && ((N | n_here) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src6) | reinterpret_cast<uintptr_t>(wsrc)) & 15) == 0;
+  // When no point starts at this time every point that is processed is resampled from its evolved particles: the bulk
+  // copies of the CTA's parents are requested before the point's activity byte is even read (one memory round trip less
+  // in the prologue).  A point that turns out inactive or failed waits for the copies to land and leaves.
+  const double* spec6 = prm.s_ev + p * 6 * (int64_t)N + base;
+  const bool spec = nxt.spec_update && n_here > 0 && ((N | n_here) & 1) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(spec6) | reinterpret_cast<uintptr_t>(wsrc)) & 15) == 0;
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     mbar_fence_init();
+    if (spec) {
+      const uint32_t row = (uint32_t)n_here * 8u;
+      mbar_expect_tx(&s_bar[0], row);
+      bulk_load(s_w, wsrc, row, &s_bar[0]);
+      mbar_expect_tx(&s_bar[1], 6u * row);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) bulk_load(s_st + c * CAP, spec6 + c * (int64_t)N, row, &s_bar[1]);
+    }
   }
+  const int act = prm.s_act[p];
+  const int failed_at_t = prm.s_pflags[p];
+  const bool update = (act & GB_ACT_ACTIVE) != 0, propagate = (act & GB_ACT_PROPAGATE) != 0;
+  if ((!update && !propagate) || failed_at_t != 0) {  // a point that failed at t is neither resampled nor advanced
+    if (spec && tid == 0) {
+      mbar_wait(&s_bar[0], 0);
+      mbar_wait(&s_bar[1], 0);
+    }
+    return;
+  }
+  // source of the particles that are resampled: the evolved particles of time t, or — at a point's first
+  // time — the initial particles, taken one to one
+  const double* src6 = (update ? prm.s_ev : state_buffer(prm, t)) + p * 6 * (int64_t)N + base;
+  const bool bulk = n_here > 0 && ((N | n_here) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src6) | reinterpret_cast<uintptr_t>(wsrc)) & 15) == 0;
   if (propagate) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
     for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
     if (tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
   }
+  if (tid >= 64 && tid < 70) s_refv[tid - 64] = prm.s_ref[p * 6 + (tid - 64)];
+  if (tid >= 96 && tid < 96 + O) s_mask[tid - 96] = prm.mask[p * O + (tid - 96)];
   __syncthreads();
   if (bulk) {
     // weights first (the prefix needs them), then the six state rows: all in flight while the prefix is computed
-    if (tid == 0) {
+    if (tid == 0 && !spec) {
       const uint32_t row = (uint32_t)n_here * 8u;
       if (update) {
         mbar_expect_tx(&s_bar[0], row);
@@ -1277,7 +1304,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   if (update) {
     double ref[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) ref[c] = prm.s_ref[p * 6 + c];
+    for (int c = 0; c < 6; ++c) ref[c] = s_refv[c];
     Moments<COV> mom;
     mom.clear();
 #pragma unroll
@@ -1326,7 +1353,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   unsigned obs_on = 0;  // observers that see this point at t + 1 (block-uniform)
   if (propagate)
     for (int o = 0; o < O; ++o)
-      if (nxt.img[o] >= 0 && prm.mask[p * O + o]) obs_on |= 1u << o;
+      if (nxt.img[o] >= 0 && s_mask[o]) obs_on |= 1u << o;
   int carry = 0;  // parent of the last child of the previous chunk
   for (int Jc = J0; Jc < J1; Jc += CAP) {
     const int nch = min(CAP, J1 - Jc);
