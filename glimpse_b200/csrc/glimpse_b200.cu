@@ -1587,13 +1587,10 @@ int gb_viewshed(const double* z, int32_t nx, int32_t ny, const double* x_centres
   }
   q.visible = visible;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_set = false;
   const int sort_smem = GB_VS_MAX_RING * 12, sweep_smem = (GB_VS_MAX_RING + 2) * 8;
-  if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(k_vs_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
-    GB_CUDA(cudaFuncSetAttribute(k_vs_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
-    attr_set = true;
-  }
+  // (per device and cheap: set on every call rather than remembered per process)
+  GB_CUDA(cudaFuncSetAttribute(k_vs_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
+  GB_CUDA(cudaFuncSetAttribute(k_vs_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
   k_vs_init<<<grid_for(max_rings + 1, 256), 256, 0, s>>>(q);
   k_vs_cells<<<grid_for(n, 256), 256, 0, s>>>(q);
   k_vs_count<<<grid_for(n, 256), 256, 0, s>>>(q);
