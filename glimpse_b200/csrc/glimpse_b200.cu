@@ -975,7 +975,10 @@ static int check_desc(const gb_track_desc& d) {
 
 // dynamic shared memory of k_s2_surface: windows up to ~66 px with the interleaved surface, up to ~80 px on planes;
 // larger ones work in their global region
-static constexpr int kSurfaceSmem = 110 * 1024;
+#ifndef GB_S2_SMEM_KB
+#define GB_S2_SMEM_KB 110
+#endif
+static constexpr int kSurfaceSmem = GB_S2_SMEM_KB * 1024;
 
 struct StreamLayout {
   int64_t ev[2], uv, w, bsum, pre, pm, ibox, pflags[2], act, meta, ref, surf, total;

@@ -209,8 +209,13 @@ __global__ void __launch_bounds__(GB_SBLOCK_THREADS, 4) k_s1_propagate(const __g
   }
 }
 
+#ifndef GB_S2_THREADS
 #define GB_S2_THREADS 512
-__global__ void __launch_bounds__(GB_S2_THREADS, 2) k_s2_surface(const __grid_constant__ StepParams prm, const __grid_constant__ FrameMaps fm,
+#endif
+#ifndef GB_S2_MINB
+#define GB_S2_MINB 2
+#endif
+__global__ void __launch_bounds__(GB_S2_THREADS, GB_S2_MINB) k_s2_surface(const __grid_constant__ StepParams prm, const __grid_constant__ FrameMaps fm,
                                                                  int smem_budget) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_mm[GB_S2_THREADS / 32][4];
