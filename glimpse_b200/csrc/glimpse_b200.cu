@@ -1678,7 +1678,12 @@ int gb_step_plan_ex(int64_t n_particles, int32_t tile_w, int32_t tile_h, int64_t
     // Points are independent: they are cut into `slots` batches that advance on their own side streams, so the
     // low-occupancy tails of one batch's kernels (a few very large search windows) overlap the other batches' work.
     // (Batches small enough to keep the intermediates L2-resident were measured slower: launch-bound.)
-    int slots = 4;
+    // Fewer batches for few points, where a batch no longer fills the device and every extra launch shows: measured (40
+    // frames, ms per track, 1 / 2 / 4 batches) 10 points 1.31 / 1.36 / 2.40 (20 frames), 100 points 5.96 / 5.67 / 5.74,
+    // 250 points 8.76 / 7.99 / 7.85, 500 points 14.3 / 12.8 / 12.7 — a batch should hold at least ~50 points.
+    int slots = (int)(npoints / 50);
+    if (slots < 1) slots = 1;
+    if (slots > 4) slots = 4;
     int64_t batch = (npoints + slots - 1) / slots;
     if (const char* e = getenv("GB_STREAM_BATCH")) batch = atoll(e);   // tuning overrides
     if (const char* e = getenv("GB_STREAM_SLOTS")) slots = atoi(e);

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import helpers
+import scenes
 from glimpse_b200 import synthetic
 from oracle import tracker_oracle as orc
 
@@ -354,6 +355,33 @@ def test_blocks_of_points_give_the_same_track(cuda, rng):
         np.testing.assert_array_equal(tracker.particles, runs[0][1].particles)  # state of the last point, as the reference leaves it
     np.testing.assert_array_equal(runs[1][0].particles, runs[0][0].particles)
     assert len(runs[1][1].last_run["window_width"]) == len(runs[0][1].last_run["window_width"])
+
+
+@pytest.mark.parametrize("slots,batch", [(1, 7), (4, 2), (4, 1), (2, 5)])
+def test_the_batch_plan_does_not_change_the_track(cuda, monkeypatch, slots, batch):
+    """gb_track cuts the points into batches that advance on their own streams (one batch for few points, up to four): points are
+    independent and Philox counters are global, so every plan gives bit-identical results — also with an observer that starts
+    later (templates join the batches) and a point that fails on the way."""
+    import glimpse_b200 as gb
+
+    scene = synthetic.nadir_scene(seed=31, n_points=7, n_particles=700, n_frames=7, imgsz=(400, 300), margin_px=100)
+    scenes.add_second_observer(scene)
+    scene.points[3] = (1.0e4, 1.0e4)  # far outside every frame: fails at its template
+    observers, models = synthetic.build(scene, gb)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = gb.Tracker(observers, seed=9).track(models, tile_size=scene.tile_size, return_covariances=True, return_particles=True)
+        monkeypatch.setenv("GB_STREAM_SLOTS", str(slots))
+        monkeypatch.setenv("GB_STREAM_BATCH", str(batch))
+        tracker = gb.Tracker(observers, seed=9)
+        other = tracker.track(models, tile_size=scene.tile_size, return_covariances=True, return_particles=True)
+    plan = tracker.last_run["plan"]
+    assert plan["stream_slots"] == slots and plan["stream_batch"] == batch
+    assert base.errors[3] is not None and sum(e is not None for e in base.errors) == 1
+    assert [type(e) for e in other.errors] == [type(e) for e in base.errors]
+    np.testing.assert_array_equal(other.means, base.means)
+    np.testing.assert_array_equal(other.covariances, base.covariances)
+    np.testing.assert_array_equal(other.particles, base.particles)
 
 
 @pytest.mark.parametrize("kind", ["cartesian", "cylindrical", "tangent_cartesian", "tangent_cylindrical"])
