@@ -538,12 +538,24 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
   __shared__ double s_warp[GB_S3_MAX_THREADS / 32];
   const int64_t p = prm.p0 + blockIdx.y;
   const int b = (int)blockIdx.x;
-  const int act = prm.s_act[p];
-  const int failed_at_t = prm.s_pflags[p];  // (both scalars are requested before the branch: one memory round trip)
-  if (!(act & GB_ACT_ACTIVE) || failed_at_t != 0) return;
-  const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = (int)prm.N, O = prm.O;
+  const int act = prm.s_act[p];
+  const int failed_at_t = prm.s_pflags[p];
+  // every scalar of the prologue is requested before the first branch: one memory round trip instead of two
+  int meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double du_t = 0.0, dv_t = 0.0, obs_scale = 0.0;
+  if (tid < O) {
+    const int64_t po = p * O + tid;
+    const int4 m0 = *reinterpret_cast<const int4*>(prm.s_meta + po * 8), m1 = *reinterpret_cast<const int4*>(prm.s_meta + po * 8 + 4);
+    meta[0] = m0.x; meta[1] = m0.y; meta[2] = m0.z; meta[3] = m0.w;
+    meta[4] = m1.x; meta[5] = m1.y; meta[6] = m1.z; meta[7] = m1.w;
+    du_t = prm.tmpl_duv[po * 2];
+    dv_t = prm.tmpl_duv[po * 2 + 1];
+    obs_scale = prm.obs_scale[tid];
+  }
+  if (!(act & GB_ACT_ACTIVE) || failed_at_t != 0) return;
+  const bool surface_ll = (act & GB_ACT_SURFACE_LL) != 0;
   {
     if (surface_ll) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
@@ -553,14 +565,12 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
     if (tid < O) {
       const int o = tid;
       const int64_t po = p * O + o;
-      const int* meta = prm.s_meta + po * 8;
       SurfaceRef r;
       r.ok = meta[7];
       r.Mu = meta[4];
       r.Mv = meta[5];
       r.Mp = meta[6];
       const double eu = sub(mul((double)prm.tile_w, 0.5), 0.5), evv = sub(mul((double)prm.tile_h, 0.5), 0.5);
-      const double du_t = prm.tmpl_duv[po * 2], dv_t = prm.tmpl_duv[po * 2 + 1];
       r.sl = add(add((double)meta[0], eu), du_t);
       r.st = add(add((double)meta[1], evv), dv_t);
       r.sr = add(add((double)meta[2], -eu), du_t);
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __gr
       r.cv0 = add(r.st, mul(quo(sub(r.sb, r.st), (double)max(r.Mv, 1)), 0.5));
       r.cu1 = add(r.cu0, (double)(r.Mu - 1));
       r.cv1 = add(r.cv0, (double)(r.Mv - 1));
-      r.scale = prm.obs_scale[o];
+      r.scale = obs_scale;
       r.herm = reinterpret_cast<const float4*>(prm.s_surf + po * prm.surf_bytes);
       s_ref[o] = r;
     }
@@ -1157,7 +1167,7 @@ __global__ void k_s0p_reset(const __grid_constant__ StepParams prm) {
 #endif
 #define GB_S4P_PPT ((GB_S4P_CAP + GB_S4P_THREADS - 1) / GB_S4P_THREADS)
 constexpr int kS4pSmem = GB_S4P_CAP * 64;
-static_assert(GB_S4P_THREADS >= 96 + GB_MAX_OBS, "k_s4p's prologue spreads its scalar loads over the first 104 threads");
+static_assert(GB_S4P_THREADS >= 134, "k_s4p's prologue spreads its scalar loads over the first 134 threads");
 
 // One projected child: image coordinates of time t + 1 and its contribution to the integer cloud box.
 __device__ __forceinline__ void s4p_project_child(const CamK& cam, const double (&s)[6], double* uv, int64_t N, int j, double hw,
@@ -1190,6 +1200,7 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   __shared__ gb_motion s_motion;
   __shared__ int s_box[GB_MAX_OBS][5];
   __shared__ unsigned s_or;
+  __shared__ double s_pre6[6];            // the point's published prefix record, as far as this CTA needs it
   __shared__ double s_refv[6];            // moment origin of the point (read in the prologue, used after the parents arrive)
   __shared__ uint8_t s_mask[GB_MAX_OBS];  // observers that see the point
   const int64_t p = prm.p0 + blockIdx.y;  // grid: (blocks of a point, points of the batch)
@@ -1220,6 +1231,20 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   }
   const int act = prm.s_act[p];
   const int failed_at_t = prm.s_pflags[p];
+  // the point's motion model, moment origin and observer mask are requested in the same breath (one word per thread):
+  // they are needed by everybody who stays, and asking before the activity is known costs nothing
+  static_assert(sizeof(gb_motion) / 4 <= 64, "one motion word per thread of the first two warps");
+  uint32_t motion_word = 0;
+  double ref_word = 0.0;
+  uint8_t mask_byte = 0;
+  if (tid < (int)(sizeof(gb_motion) / 4)) motion_word = reinterpret_cast<const uint32_t*>(prm.motion + p)[tid];
+  if (tid >= 64 && tid < 70) ref_word = prm.s_ref[p * 6 + (tid - 64)];
+  if (tid >= 96 && tid < 96 + O) mask_byte = prm.mask[p * O + (tid - 96)];
+  if (tid >= 128 && tid < 134) {
+    // written by k_s3b_publish: prefix of this and the next CTA, total, 1 / total, the uniform draw, 1 / N
+    const int k = tid - 128;
+    ref_word = prm.s_pre[p * (prm.s_nblk + 4) + (k < 2 ? b + k : prm.s_nblk + (k - 2))];
+  }
   const bool update = (act & GB_ACT_ACTIVE) != 0, propagate = (act & GB_ACT_PROPAGATE) != 0;
   if ((!update && !propagate) || failed_at_t != 0) {  // a point that failed at t is neither resampled nor advanced
     if (spec && tid == 0) {
@@ -1232,14 +1257,11 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   // time — the initial particles, taken one to one
   const double* src6 = (update ? prm.s_ev : state_buffer(prm, t)) + p * 6 * (int64_t)N + base;
   const bool bulk = n_here > 0 && ((N | n_here) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src6) | reinterpret_cast<uintptr_t>(wsrc)) & 15) == 0;
-  if (propagate) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.motion + p);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_motion);
-    for (int k = tid; k < (int)(sizeof(gb_motion) / 4); k += blockDim.x) dst[k] = src[k];
-    if (tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
-  }
-  if (tid >= 64 && tid < 70) s_refv[tid - 64] = prm.s_ref[p * 6 + (tid - 64)];
-  if (tid >= 96 && tid < 96 + O) s_mask[tid - 96] = prm.mask[p * O + (tid - 96)];
+  if (tid < (int)(sizeof(gb_motion) / 4)) reinterpret_cast<uint32_t*>(&s_motion)[tid] = motion_word;
+  if (propagate && tid < GB_MAX_OBS * 5) s_box[tid / 5][tid % 5] = (tid % 5 == 4) ? 0 : 0x7fffffff;
+  if (tid >= 64 && tid < 70) s_refv[tid - 64] = ref_word;
+  if (tid >= 96 && tid < 96 + O) s_mask[tid - 96] = mask_byte;
+  if (tid >= 128 && tid < 134) s_pre6[tid - 128] = ref_word;
   __syncthreads();
   if (bulk) {
     // weights first (the prefix needs them), then the six state rows: all in flight while the prefix is computed
@@ -1263,10 +1285,8 @@ __global__ void __launch_bounds__(GB_S4P_THREADS, GB_S4P_MINB) k_s4p_resample_pr
   // ---- child ranges of the CTA's parents ----
   int J0, J1;
   if (update) {
-    // written by k_s3b_publish: every thread reads the same few words (one broadcast line)
-    const double* pre = prm.s_pre + p * (prm.s_nblk + 4);
-    const double prefix = pre[b], next_prefix = pre[b + 1], total = pre[prm.s_nblk], inv_total = pre[prm.s_nblk + 1],
-                 u01 = pre[prm.s_nblk + 2], inv_n = pre[prm.s_nblk + 3];
+    const double prefix = s_pre6[0], next_prefix = s_pre6[1], total = s_pre6[2], inv_total = s_pre6[3], u01 = s_pre6[4],
+                 inv_n = s_pre6[5];
     const bool stratified = prm.resample_method == GB_RESAMPLE_STRATIFIED;
     const double dN = (double)N;
     if (bulk) mbar_wait(&s_bar[0], 0);
