@@ -124,7 +124,8 @@ class Raster:
         self.xlim = self._limits(x, shape[1])
         self.ylim = self._limits(y, shape[0])
         # identity used to share one device surface between equal constant rasters
-        self._const_key = (("const", float(self.array.flat[0]), tuple(self.xlim.tolist()), tuple(self.ylim.tolist()))
+        # (a string: its hash is computed once, and a thousand models each wrap the same number into a raster of their own)
+        self._const_key = ("const|%r|%r|%r" % (float(self.array.flat[0]), tuple(self.xlim.tolist()), tuple(self.ylim.tolist()))
                            if self.constant else None)
 
     @staticmethod

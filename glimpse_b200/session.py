@@ -9,6 +9,8 @@ from typing import Optional
 
 import numpy as np
 
+from itertools import chain as _chain
+
 from . import _lib
 from .camera import lower_camera
 from .image import Raster
@@ -195,9 +197,9 @@ def lower_models(models, viewshed=None):
                 raise NotImplementedError("motion-model surfaces must be numbers or Raster objects")
             arr = np.asarray(raster.array)
             key = id(raster)
-            if arr.ndim != 2 or arr.size == 1:  # constant: share by value
-                key = ("const", float(arr.flat[0]), tuple(np.asarray(raster.xlim, dtype=float)),
-                       tuple(np.asarray(raster.ylim, dtype=float)))
+            if arr.ndim != 2 or arr.size == 1:  # constant: share by value (the same key glimpse_b200.Raster gives itself)
+                key = "const|%r|%r|%r" % (float(arr.flat[0]), tuple(np.asarray(raster.xlim, dtype=float).tolist()),
+                                          tuple(np.asarray(raster.ylim, dtype=float).tolist()))
             if key not in rasters:
                 wrapped = raster if isinstance(raster, Raster) else Raster(raster.array, x=raster.xlim, y=raster.ylim)
                 rasters[key] = len(table)
@@ -211,11 +213,24 @@ def lower_models(models, viewshed=None):
     table_m["kind"] = [m.kind for m in adopted]
     table_m["dem"] = [index_of(m.dem) for m in adopted]
     table_m["dem_sigma"] = [index_of(m.dem_sigma) for m in adopted]
-    table_m["xy"] = np.array([m.xy for m in adopted], dtype=float)
-    xs = np.array([m.xy_sigma for m in adopted], dtype=float)
-    table_m["xy_sigma"] = xs if xs.ndim == 2 else xs[:, None]
+    n = len(adopted)
+
+    def rows(values, width):
+        """(n, width) float64 from n sequences of `width` numbers (flattened through one iterator: several times faster than
+        np.array on a list of tuples); anything else — scalars to broadcast, ragged input — takes NumPy's general path."""
+        try:
+            if isinstance(values[0], np.ndarray):  # (iterating arrays element by element is the slow way round)
+                raise TypeError
+            out = np.fromiter(_chain.from_iterable(values), dtype=float, count=n * width).reshape(n, width)
+        except (TypeError, ValueError):
+            out = np.array(values, dtype=float)
+            out = np.broadcast_to(out[:, None] if out.ndim == 1 else out, (n, width))
+        return out
+
+    table_m["xy"] = rows([m.xy for m in adopted], 2)
+    table_m["xy_sigma"] = rows([m.xy_sigma for m in adopted], 2)
     for k, name in enumerate(("v", "v_sigma", "a", "a_sigma")):
-        table_m[name] = np.array([v[k] for v in vel], dtype=float)
+        table_m[name] = rows([v[k] for v in vel], 3)
     table_m["slope_sigma"] = [float(getattr(m, "slope_sigma", 0.0)) for m in adopted]
     view = index_of(viewshed) if viewshed is not None else -1
     return table_m, table, view
