@@ -500,7 +500,12 @@ struct SurfaceRef {
 
 // s3: spline sample + surface likelihood -> weight; two consecutive particles per thread.  Grid: blocks of a
 // point x points; launched with s3_threads(s_block) threads so that full trips cover the CTA's particle pairs.
+#ifndef GB_S3_MAX_THREADS
 #define GB_S3_MAX_THREADS 64
+#endif
+#ifndef GB_S3_MINB
+#define GB_S3_MINB 16
+#endif
 __host__ __device__ inline int s3_threads(int s_block) {
   const int pairs = (s_block + 1) / 2;
   const int trips = (pairs + GB_S3_MAX_THREADS - 1) / GB_S3_MAX_THREADS;
@@ -532,7 +537,7 @@ __device__ __forceinline__ void s3_publish_prefix(const StepParams& prm, int64_t
 }
 // GEN: spline degrees other than 1 / 3 (B-spline coefficients; its own instantiation keeps the default kernel's registers)
 template <bool GEN>
-__global__ void __launch_bounds__(GB_S3_MAX_THREADS, 16) k_s3_weights(const __grid_constant__ StepParams prm) {
+__global__ void __launch_bounds__(GB_S3_MAX_THREADS, GB_S3_MINB) k_s3_weights(const __grid_constant__ StepParams prm) {
   __shared__ gb_motion s_motion;
   __shared__ SurfaceRef s_ref[GB_MAX_OBS];
   __shared__ double s_warp[GB_S3_MAX_THREADS / 32];
