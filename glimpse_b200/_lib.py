@@ -125,6 +125,8 @@ SIGNATURES = {
     "gb_viewshed_work_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "gb_viewshed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double),
                               C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "gb_jpeg_info": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gb_decode_jpeg": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "gb_unproject": (C.c_int, [C.POINTER(gb_camera), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gb_state_from_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "gb_state_to_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

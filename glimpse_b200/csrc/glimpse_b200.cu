@@ -5,7 +5,9 @@
 // stage entry points and the host side of the C ABI.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
+#include <nvjpeg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1554,6 +1556,86 @@ int gb_unproject(const gb_camera* cam, const double* uv, int64_t n, int directio
   if (n <= 0) return GB_OK;
   k_unproject<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*cam, uv, n, directions, depth, xyz);
   GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame ingest: JPEG bytes -> pixels in device memory through nvJPEG (a library call, like the reference's own decode through
+// GDAL / libjpeg, image.py:137-214).  The library is opened at run time, so libglimpse_b200.so itself does not depend on it.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NvJpeg {
+  void* lib = nullptr;
+  nvjpegStatus_t (*create)(nvjpegHandle_t*) = nullptr;
+  nvjpegStatus_t (*state_create)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+  nvjpegStatus_t (*info)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+  nvjpegStatus_t (*decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*,
+                           cudaStream_t) = nullptr;
+  nvjpegHandle_t handle = nullptr;
+  nvjpegJpegState_t state = nullptr;
+  int device = -1;
+  bool tried = false;
+};
+thread_local NvJpeg t_nvjpeg;
+
+int nvjpeg_ready(NvJpeg** out) {
+  NvJpeg& j = t_nvjpeg;
+  if (!j.tried) {
+    j.tried = true;
+    for (const char* name : {"libnvjpeg.so.12", "/usr/local/cuda/lib64/libnvjpeg.so.12", "libnvjpeg.so"}) {
+      j.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (j.lib) break;
+    }
+    if (j.lib) {
+      j.create = reinterpret_cast<decltype(j.create)>(dlsym(j.lib, "nvjpegCreateSimple"));
+      j.state_create = reinterpret_cast<decltype(j.state_create)>(dlsym(j.lib, "nvjpegJpegStateCreate"));
+      j.info = reinterpret_cast<decltype(j.info)>(dlsym(j.lib, "nvjpegGetImageInfo"));
+      j.decode = reinterpret_cast<decltype(j.decode)>(dlsym(j.lib, "nvjpegDecode"));
+    }
+  }
+  if (!j.lib || !j.create || !j.state_create || !j.info || !j.decode)
+    return fail(GB_E_RESOURCE, "decode_jpeg: libnvjpeg.so.12 could not be opened%s");
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (!j.handle || j.device != dev) {  // (one handle per calling thread; a thread that changes device gets a new one)
+    if (j.create(&j.handle) != NVJPEG_STATUS_SUCCESS || j.state_create(j.handle, &j.state) != NVJPEG_STATUS_SUCCESS)
+      return fail(GB_E_RESOURCE, "decode_jpeg: nvjpegCreateSimple failed%s");
+    j.device = dev;
+  }
+  *out = &j;
+  return GB_OK;
+}
+}  // namespace
+
+int gb_jpeg_info(const uint8_t* jpeg, int64_t nbytes, int32_t* width, int32_t* height, int32_t* nchan) {
+  if (!jpeg || nbytes <= 0 || !width || !height || !nchan) return fail(GB_E_INVALID, "null argument%s");
+  NvJpeg* j = nullptr;
+  if (int rc = nvjpeg_ready(&j)) return rc;
+  int ncomp = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+  nvjpegChromaSubsampling_t sub;
+  if (j->info(j->handle, jpeg, (size_t)nbytes, &ncomp, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS)
+    return fail(GB_E_INVALID, "decode_jpeg: not a JPEG stream nvJPEG can read%s");
+  *width = ws[0];
+  *height = hs[0];
+  *nchan = ncomp >= 3 ? 3 : 1;
+  return GB_OK;
+}
+
+int gb_decode_jpeg(const uint8_t* jpeg, int64_t nbytes, int32_t width, int32_t height, int32_t nchan, uint8_t* out, void* stream) {
+  if (!jpeg || nbytes <= 0 || !out) return fail(GB_E_INVALID, "null argument%s");
+  if (nchan != 1 && nchan != 3) return fail(GB_E_INVALID, "decode_jpeg: 1 (grey) or 3 (RGB) output bands%s");
+  int32_t w = 0, h = 0, c = 0;
+  if (int rc = gb_jpeg_info(jpeg, nbytes, &w, &h, &c)) return rc;
+  if (w != width || h != height) return fail(GB_E_INVALID, "decode_jpeg: the stream's size differs from the frame's%s");
+  NvJpeg* j = nullptr;
+  if (int rc = nvjpeg_ready(&j)) return rc;
+  nvjpegImage_t img;
+  memset(&img, 0, sizeof(img));
+  img.channel[0] = out;
+  img.pitch[0] = (size_t)width * nchan;
+  const nvjpegStatus_t st = j->decode(j->handle, j->state, jpeg, (size_t)nbytes, nchan == 3 ? NVJPEG_OUTPUT_RGBI : NVJPEG_OUTPUT_Y, &img,
+                                      (cudaStream_t)stream);
+  if (st != NVJPEG_STATUS_SUCCESS) return fail(GB_E_CUDA, "decode_jpeg: nvjpegDecode failed%s");
   return GB_OK;
 }
 

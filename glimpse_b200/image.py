@@ -17,6 +17,24 @@ from . import _lib
 from .camera import Camera
 
 
+def decode_jpeg(data: bytes, gray: bool = None):
+    """JPEG bytes -> uint8 tensor on the current device, (rows, columns, 3) RGB or (rows, columns) luma (``gray``; default: as the
+    stream is encoded), decoded by nvJPEG through ``gb_decode_jpeg``."""
+    import ctypes as C
+
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    w, h, c = C.c_int32(), C.c_int32(), C.c_int32()
+    _lib.check(lib.gb_jpeg_info(data, len(data), C.byref(w), C.byref(h), C.byref(c)))
+    bands = 1 if (gray or (gray is None and c.value == 1)) else 3
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty((h.value, w.value, bands) if bands == 3 else (h.value, w.value), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    _lib.check(lib.gb_decode_jpeg(data, len(data), w.value, h.value, bands, out.data_ptr(), stream.cuda_stream))
+    stream.synchronize()  # (the bytes object must outlive the decode)
+    return out
+
+
 class Image:
     """Photograph taken by a :class:`Camera` at a known time (reference ``image.py:17-119``)."""
 
@@ -32,6 +50,7 @@ class Image:
         self.datetime = datetime
         self.exif = exif
         self.array: Optional[np.ndarray] = None
+        self.device_array = None  # the frame in device memory (read_device)
 
     @property
     def size(self) -> np.ndarray:
@@ -59,6 +78,26 @@ class Image:
         if box is not None:
             array = array[box[1]:box[3], box[0]:box[2]]
         return array
+
+    def read_device(self, cache: bool = True):
+        """The image as a uint8 tensor in device memory, decoded there from its JPEG file by nvJPEG (``gb_decode_jpeg``; the
+        reference decodes on the host through GDAL, image.py:137-214): (rows, columns, 3) RGB or (rows, columns) for a grey file.
+        With ``cache`` it is kept in ``device_array`` and a Tracker reads the frame from there instead of uploading ``array``.
+        Decoders differ in the last grey levels (IDCT, chroma upsampling): use ``read`` / ``array`` where the exact pixels of one
+        decoder matter.  The file must have the camera's image size (no resampling on the way)."""
+        held = getattr(self, "device_array", None)
+        if held is not None:
+            return held
+        with open(self.path, "rb") as f:
+            data = f.read()
+        tensor = decode_jpeg(data)
+        w, h = (int(v) for v in self.cam.imgsz)
+        if (tensor.shape[1], tensor.shape[0]) != (w, h):
+            raise NotImplementedError(f"{self.path}: {tensor.shape[1]} x {tensor.shape[0]} pixels, the camera has {w} x {h} "
+                                      "(resampling while decoding is not implemented: use read())")
+        if cache:
+            self.device_array = tensor
+        return tensor
 
     def project(self, cam: Camera, method: str = "linear") -> np.ndarray:
         """Project the image into another camera at the same position (reference image.py:301-361): (cam.imgsz[1],

@@ -50,13 +50,20 @@ class Observer:
     def extract_tile(self, box: Iterable[int], img: int) -> np.ndarray:
         return self.images[img].read(box=box, cache=self.cache)
 
-    def cache_images(self, index=slice(None)) -> None:
+    def cache_images(self, index=slice(None), device: bool = False) -> None:
+        """Read the images ahead of tracking (reference observer.py:260-268).  ``device=True``: JPEG files are decoded by
+        nvJPEG straight into device memory (``Image.read_device``) and tracked from there without an upload."""
         for img in np.asarray(self.images, dtype=object)[index]:
-            img.read(cache=True)
+            if device and hasattr(img, "read_device"):
+                img.read_device(cache=True)
+            else:
+                img.read(cache=True)
 
     def clear_images(self, index=slice(None)) -> None:
         for img in np.asarray(self.images, dtype=object)[index]:
             img.array = None
+            if hasattr(img, "device_array"):
+                img.device_array = None
 
     # ------------------------------------------------------------------ sub-pixel sampling (device spline)
     @staticmethod

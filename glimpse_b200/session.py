@@ -59,6 +59,19 @@ def device_frame(array: np.ndarray) -> np.ndarray:
     return array if array.flags.c_contiguous else np.ascontiguousarray(array)
 
 
+class DeviceFrame:
+    """A frame that already lies in device memory (``Image.read_device``: decoded there by nvJPEG), dressed like the host
+    arrays the upload code handles: shape / dtype / strides / nbytes of the (rows, columns[, bands]) uint8 pixels."""
+
+    def __init__(self, tensor) -> None:
+        self.tensor = tensor.contiguous()
+        self.shape = tuple(self.tensor.shape)
+        self.ndim = self.tensor.dim()
+        self.dtype = np.dtype(np.uint8)
+        self.nbytes = int(self.tensor.numel())
+        self.strides = tuple(int(s) for s in self.tensor.stride())
+
+
 def frames_need_ranks(observers, image_index) -> bool:
     """Whether some frame a track will read is not uint8 (the surface regions are then sized for rank histograms)."""
     for o, obs in enumerate(observers):
@@ -430,7 +443,8 @@ class Session:
             todo = self._pending_copies if limit is None else self._pending_copies[:limit]
             with torch.cuda.stream(copy_stream):
                 for dev, arr, event in todo:
-                    dev.copy_(torch.from_numpy(arr).view(torch.uint8).reshape(-1), non_blocking=True)
+                    src = arr.tensor.reshape(-1) if isinstance(arr, DeviceFrame) else torch.from_numpy(arr).view(torch.uint8).reshape(-1)
+                    dev.copy_(src, non_blocking=True)
                     event.record(copy_stream)
             for k, event in self._pending_events:
                 self.image_events[k] = event.cuda_event
@@ -499,18 +513,21 @@ class Session:
                 o, i, img, _used = structs[k]
                 obs = tracker.observers[o]
                 use_cache = bool(getattr(obs, "cache", True))
-                array = img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache)
+                on_device = getattr(img, "device_array", None) if getattr(img, "array", None) is None else None
+                array = on_device if on_device is not None else (img.array if getattr(img, "array", None) is not None else img.read(cache=use_cache))
                 key = (o, i, id(array))
                 cached = tracker._frame_cache.get(key) if use_cache else None
                 if cached is None:
-                    arr = device_frame(array)
+                    arr = DeviceFrame(array) if on_device is not None else device_frame(array)
                     fresh.append((k, key, use_cache, arr))
                     continue
                 placed.append((k, cached))
             # frames not on the device yet: one allocation (on the copy stream) carved into 256-byte aligned slices.
             # Shared upload (NCCL group): the frames form a few time-ordered groups, each padded to a multiple of
             # world x 256 bytes so that every rank contributes an equal slice to the group's all-gather.
-            self._shared_upload = self._agree_on_shared_upload(len(fresh), sum(arr.nbytes for _, _, _, arr in fresh))
+            # (frames decoded on the device are copied device to device by every rank itself: nothing to share)
+            any_on_device = any(isinstance(arr, DeviceFrame) for _, _, _, arr in fresh)
+            self._shared_upload = (not any_on_device) and self._agree_on_shared_upload(len(fresh), sum(arr.nbytes for _, _, _, arr in fresh))
             self._upload_groups = []
             if fresh:
                 world = self.dist.get_world_size() if self._shared_upload else 1
@@ -538,7 +555,7 @@ class Session:
                     if self._shared_upload:
                         group = max(g for g in range(len(self._upload_groups)) if self._upload_groups[g][0] <= off)
                         self._upload_groups[group][2].append((off, (dev, arr, event)))
-                    else:
+                    elif not isinstance(arr, DeviceFrame):
                         self.h2d += arr.nbytes
                     cached = (dev, arr.shape[1], arr.shape[0], arr.strides[0], 1 if arr.ndim == 2 else arr.shape[2], event,
                               _lib.GB_PIX[arr.dtype.name])

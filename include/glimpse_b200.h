@@ -170,6 +170,14 @@ int gb_unproject(const gb_camera* cam_host, const double* uv, int64_t n, int dir
  * frame).  GB_E_INVALID if the cameras' positions differ (the reference's ValueError). */
 int gb_project_image(const gb_image* src_host, const gb_camera* dst_cam_host, int32_t method, void* out, void* stream);
 
+/* Frame ingest (Image.read, image.py:137-214: the reference decodes through GDAL / libjpeg on the host): a JPEG stream in HOST
+ * memory decoded by nvJPEG straight into device memory, `out` = height x width x nchan uint8 (nchan 3: interleaved RGB, 1: luma),
+ * the layout gb_image describes.  The library is opened at run time (GB_E_RESOURCE if it is not installed); decoders differ in
+ * their IDCT and chroma upsampling, so the pixels are within a few grey levels of libjpeg's, not identical.  gb_jpeg_info reads the
+ * size and the number of bands (1 or 3) of a stream.  The decode is asynchronous on `stream`; jpeg_host must stay valid until then. */
+int gb_jpeg_info(const uint8_t* jpeg_host, int64_t nbytes, int32_t* width, int32_t* height, int32_t* nchan);
+int gb_decode_jpeg(const uint8_t* jpeg_host, int64_t nbytes, int32_t width, int32_t height, int32_t nchan, uint8_t* out, void* stream);
+
 /* Raster.viewshed (raster.py:1293-1389): cells of the DEM z (ny x nx doubles, row-major, device memory) visible from
  * origin_host = (x, y, z).  x_centres[nx] / y_centres[ny] (device) are the cell-centre coordinates in array order (Grid.x, Grid.y,
  * raster.py:139-174), cell = |d[0]|, corr_host = {radius, refraction} or NULL (helpers.elevation_corrections).  max_rings bounds

@@ -214,3 +214,91 @@ def test_observer_sample_tile_and_shift_tile_match_fitpack(cuda):
     assert np.max(np.abs(obs.shift_tile(tile.copy(), duv) - want)) < 2e-6
     rgb = np.dstack([tile, 2 * tile, -tile])
     assert np.max(np.abs(obs.shift_tile(rgb, duv)[:, :, 1] - 2 * want)) < 4e-6
+
+
+def _jpeg_bytes(array, quality=92, full_chroma=False):
+    import cv2
+
+    params = [int(cv2.IMWRITE_JPEG_QUALITY), quality]
+    if full_chroma:  # 4:4:4: no chroma subsampling, so that decoders only differ in their IDCT and colour conversion
+        params += [int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR), int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444)]
+    ok, buf = cv2.imencode(".jpg", array[:, :, ::-1] if array.ndim == 3 else array, params)
+    assert ok
+    return buf.tobytes()
+
+
+def _decode_or_skip(data, **kw):
+    from glimpse_b200.image import decode_jpeg
+
+    try:
+        return decode_jpeg(data, **kw)
+    except Exception as exc:  # the library is opened at run time
+        if "libnvjpeg" in str(exc):
+            pytest.skip("nvJPEG is not installed on this box")
+        raise
+
+
+@pytest.mark.parametrize("bands", [3, 1])
+def test_jpeg_decode_on_the_device_is_close_to_libjpeg(cuda, bands):
+    """Frame ingest (image.py:137-214): JPEG bytes decoded by nvJPEG straight into device memory.  Decoders differ in IDCT and
+    chroma upsampling, so the check is closeness to libjpeg-turbo's decode of the same stream (OpenCV), not identity."""
+    import cv2
+    from glimpse_b200 import synthetic
+
+    rng = np.random.RandomState(5)
+    tex = synthetic.smooth_texture((240, 320), rng)
+    frame = np.stack([tex, np.roll(tex, 5, axis=1), np.roll(tex, -3, axis=0)], axis=2) if bands == 3 else tex
+    data = _jpeg_bytes(np.ascontiguousarray(frame), full_chroma=True)
+    got = _decode_or_skip(data).cpu().numpy()
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_UNCHANGED)
+    ref = ref[:, :, ::-1] if ref.ndim == 3 else ref
+    assert got.shape == ref.shape == frame.shape and got.dtype == np.uint8
+    diff = np.abs(got.astype(int) - ref.astype(int))
+    assert diff.max() <= 4 and diff.mean() < 0.75, (diff.max(), diff.mean())
+    assert np.abs(got.astype(int) - frame.astype(int)).mean() < 3.0  # and both are the picture that was encoded
+    if bands == 3:
+        # a subsampled (4:2:0) stream of a picture whose colour changes from pixel to pixel: the decoders interpolate the
+        # chroma planes differently (libjpeg's triangle filter, nvJPEG's replication), the luma they agree on
+        sub = _jpeg_bytes(np.ascontiguousarray(frame))
+        y = _decode_or_skip(sub, gray=True).cpu().numpy()
+        y_ref = cv2.cvtColor(cv2.imdecode(np.frombuffer(sub, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2YCrCb)[:, :, 0]
+        assert y.shape == frame.shape[:2]
+        d = np.abs(y.astype(int) - y_ref.astype(int))
+        assert d.max() <= 4 and d.mean() < 0.75, (d.max(), d.mean())
+
+
+def test_tracking_from_device_decoded_frames(cuda, tmp_path):
+    """Observer.cache_images(device=True): the JPEG files are decoded on the device and tracked from there (no upload of pixel
+    arrays) — the same track, bit for bit, as from host arrays holding those very pixels."""
+    import glimpse_b200 as gb
+    from glimpse_b200 import synthetic
+
+    scene = synthetic.nadir_scene(seed=8, n_points=4, n_particles=600, n_frames=6, imgsz=(320, 240), margin_px=90, bands=3)
+    observers, models = synthetic.build(scene, gb)
+    images = observers[0].images
+    for i, img in enumerate(images):
+        path = tmp_path / f"frame{i}.jpg"
+        path.write_bytes(_jpeg_bytes(np.ascontiguousarray(img.array), quality=95))
+        img.path, img.array = str(path), None
+    try:
+        observers[0].cache_images(device=True)
+    except Exception as exc:
+        if "libnvjpeg" in str(exc):
+            pytest.skip("nvJPEG is not installed on this box")
+        raise
+    assert all(img.device_array is not None and img.array is None for img in images)
+    on_device = gb.Tracker(observers, seed=3)
+    a = on_device.track(models, tile_size=scene.tile_size)
+    assert all(e is None for e in a.errors)
+    # the same pixels as host arrays
+    for img in images:
+        img.array = img.device_array.cpu().numpy()
+        img.device_array = None
+    from_host = gb.Tracker(observers, seed=3)
+    b = from_host.track(models, tile_size=scene.tile_size)
+    np.testing.assert_array_equal(a.means, b.means)
+    np.testing.assert_array_equal(a.sigmas, b.sigmas)
+    assert on_device.last_run["h2d_bytes"] < from_host.last_run["h2d_bytes"] - 5 * 320 * 240 * 3
+    # and the decoded sequence still carries the motion
+    v = a.vxyz[:, -1, 0]
+    assert np.all(np.abs(v - scene.truth_velocity[0]) < 0.1)
